@@ -1,0 +1,311 @@
+/* mpt.h — C-ABI of libmpt.so, the B200-native path tracer behind merian-graph's `pt` node.
+ *
+ * This is the drop-in boundary. The reference has no FFI for this path: its
+ * `Render (Path-traced)` node records ONE `vkCmdTraceRaysKHR` per iteration
+ * (src/merian-graph/nodes/render_pt/render_pt.cpp:94-124) over tables owned by `merian::Scene`.
+ * The entry points below are what a merian node adapter binds instead; each cites
+ * the reference interface it replaces. Plain pointers and sizes only — no C++/torch types, no
+ * exceptions; every call returns an `mpt_status` and `mpt_last_error()` explains failures.
+ *
+ * All pointers named `d_*` are device pointers on the context's device, everything else is host
+ * memory. `stream` is a `cudaStream_t` passed as `void*` (0 = legacy default stream).
+ */
+#ifndef MPT_H
+#define MPT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define MPT_API __declspec(dllexport)
+#else
+#define MPT_API __attribute__((visibility("default")))
+#endif
+
+#define MPT_ABI_VERSION 1u
+
+typedef enum mpt_status {
+    MPT_OK = 0,
+    MPT_ERR_INVALID_ARGUMENT = 1,
+    MPT_ERR_CUDA = 2,
+    MPT_ERR_NOT_READY = 3, /* scene / materials not uploaded yet (render_pt.cpp:98: !scene->is_ready()) */
+    MPT_ERR_UNSUPPORTED = 4,
+    MPT_ERR_LIMIT = 5
+} mpt_status;
+
+typedef struct mpt_context mpt_context;
+
+/* ---- data formats shared with the reference ------------------------------------------------ */
+
+/* GeometryDataFlags, include/merian-shaders/scene/scene-data.slangh:15-42 (same values). */
+enum {
+    MPT_GEOM_PRETRANSFORMED = 0x1,
+    MPT_GEOM_HAS_PREV_VERTICES = 0x2,
+    MPT_GEOM_IS_ANIMATED = 0x4,
+    MPT_GEOM_FLIP_FACING = 0x8,
+    MPT_GEOM_INDEX_U8 = 0x10,
+    MPT_GEOM_INDEX_U16 = 0x20,
+    MPT_GEOM_INDEX_U32 = 0x40,
+    MPT_GEOM_FLAT_SHADING = 0x80,
+    MPT_GEOM_HAS_TANGENTS = 0x100,
+    MPT_GEOM_USE_ENV_MAP = 0x200,
+    MPT_GEOM_TWO_SIDED = 0x400
+};
+
+/* VkGeometryInstanceFlagBitsKHR as set by Scene::build_tlas (src/merian-shaders/scene/scene.cpp:1836-1847). */
+enum {
+    MPT_INSTANCE_FACING_CULL_DISABLE = 0x1, /* eTriangleFacingCullDisable (TwoSided groups) */
+    MPT_INSTANCE_FLIP_FACING = 0x2,         /* eTriangleFlipFacing                          */
+    MPT_INSTANCE_FORCE_OPAQUE = 0x4         /* eForceOpaque (group.all_opaque)              */
+};
+
+/* PackedVertexData, scene-data.slangh:75-80: 24 bytes, 4-byte aligned.
+ *   float3 position; uint32 encoded_normal (oct 2x snorm16); half2 uv; uint32 encoded_tangent. */
+typedef struct mpt_packed_vertex {
+    float position[3];
+    uint32_t encoded_normal;
+    uint16_t uv[2]; /* IEEE binary16 bits */
+    uint32_t encoded_tangent;
+} mpt_packed_vertex;
+
+/* One mesh = one BLAS geometry: vertex + index arrays as Scene::upload_meshes stores them
+ * (scene.cpp:1377-1670), i.e. AFTER the transform_vertex pass (transform_vertex.slang:12-40). */
+typedef struct mpt_mesh_desc {
+    const mpt_packed_vertex* vertices;
+    const void* indices;      /* u8/u16/u32 triples, or NULL for sequential (IndexType::None) */
+    uint32_t vertex_count;
+    uint32_t primitive_count;
+    uint32_t index_flag;      /* 0 | MPT_GEOM_INDEX_U8 | _U16 | _U32 */
+    uint32_t opaque;          /* VK_GEOMETRY_OPAQUE_BIT: 0 => candidates run the alpha test (scene.slang:500-519) */
+} mpt_mesh_desc;
+
+/* One mesh group = one BLAS (scene.hpp:401-436). geometry_index of a hit = position in `meshes`. */
+typedef struct mpt_blas_desc {
+    const uint32_t* meshes;
+    uint32_t mesh_count;
+} mpt_blas_desc;
+
+/* GeometryData, scene-data.slangh:119-129, in GeometryID order (scene.cpp:1236-1291), with the three
+ * buffer device addresses replaced by a mesh index. */
+typedef struct mpt_geometry_desc {
+    uint32_t mesh;
+    uint16_t material_id;
+    uint16_t flags; /* MPT_GEOM_* */
+    uint32_t primitive_count;
+} mpt_geometry_desc;
+
+/* VkAccelerationStructureInstanceKHR as filled by Scene::build_tlas (scene.cpp:1808-1857), in TLAS
+ * order: InstanceIndex() = position in the array, InstanceID() = instance_custom_index. */
+typedef struct mpt_instance_desc {
+    float transform[12]; /* row-major 3x4 object->world (VkTransformMatrixKHR) */
+    uint32_t instance_custom_index;
+    uint32_t mask;  /* 8 bit */
+    uint32_t flags; /* MPT_INSTANCE_* */
+    uint32_t blas;
+} mpt_instance_desc;
+
+typedef struct mpt_scene_desc {
+    const mpt_mesh_desc* meshes;
+    uint32_t mesh_count;
+    const mpt_blas_desc* blas;
+    uint32_t blas_count;
+    const mpt_geometry_desc* geometries;
+    uint32_t geometry_count;
+    const mpt_instance_desc* instances;
+    uint32_t instance_count;
+    /* Scene::instance_transforms / inverse_transposed_instance_transforms (scene.slang:33-38), one
+     * row-major float4x4 per TLAS instance; may be NULL when every geometry is Pretransformed. */
+    const float* instance_transforms;
+    const float* inverse_transposed_instance_transforms;
+} mpt_scene_desc;
+
+/* Material model dispatch (material-system.slang:51-72): material_model_type_id -> model. The ids are
+ * assigned at run time in registration order (material_system.cpp:124-139), so the adapter passes the table. */
+enum { MPT_MATERIAL_DIFFUSE = 0, MPT_MATERIAL_GLTF = 1 };
+enum { /* GltfMaterial<TRANSMISSION, VOLUME, CLEARCOAT, SHEEN, IRIDESCENCE, ANISOTROPY>, gltf-material.slang:64-69 */
+    MPT_GLTF_TRANSMISSION = 1, MPT_GLTF_VOLUME = 2, MPT_GLTF_CLEARCOAT = 4,
+    MPT_GLTF_SHEEN = 8, MPT_GLTF_IRIDESCENCE = 16, MPT_GLTF_ANISOTROPY = 32
+};
+typedef struct mpt_material_type {
+    uint32_t model;    /* MPT_MATERIAL_* */
+    uint32_t features; /* MPT_GLTF_* bits, 0 for diffuse */
+} mpt_material_type;
+
+/* Texture formats accepted by mpt_texture_upload (texture_manager.cpp:207-243 creates RGBA8 sRGB/UNORM;
+ * the env map is RGBA32F, scene.cpp:780-795). */
+enum { MPT_TEX_RGBA8_UNORM = 0, MPT_TEX_RGBA8_SRGB = 1, MPT_TEX_RGBA32F = 2 };
+enum { MPT_WRAP_REPEAT = 0, MPT_WRAP_CLAMP_TO_EDGE = 1, MPT_WRAP_MIRRORED_REPEAT = 2 };
+enum { MPT_FILTER_NEAREST = 0, MPT_FILTER_LINEAR = 1 };
+#define MPT_TEXTURE_NONE 0xFFFFu
+
+/* Camera, include/merian-shaders/scene/camera.slang:6-24, as written by Camera::write_to
+ * (src/merian/utils/camera/camera.cpp:349-368). */
+typedef struct mpt_camera {
+    float position[3];
+    float target[3];
+    float up[3];
+    float U[3];
+    float V[3];
+    float W[3];
+    float near_plane;
+    float far_plane;
+    float aspect_ratio;
+    float aperture_radius; /* must be 0 (pinhole); thin lens is out of scope */
+    float jitter[2];
+} mpt_camera;
+
+enum { MPT_ENV_EMPTY = 0, MPT_ENV_LATLONG = 1 };
+
+/* Render flags: the compile-time constants of render_pt.slang:11-16 become run-time parameters. */
+enum {
+    MPT_RENDER_EMISSION_ON_PRIMARY = 0x1, /* merian_render_emission_on_primary */
+    MPT_RENDER_DEMODULATE_ALBEDO = 0x2,   /* merian_render_demodulate_albedo (needs d_albedo) */
+    MPT_RENDER_OUTPUT_SUM = 0x4,          /* write sums over the samples instead of means (multi-GPU reduce) */
+    MPT_RENDER_NEE = 0x8                  /* env-map next event estimation with MIS (addition; same expectation) */
+};
+
+typedef struct mpt_render_params {
+    uint32_t width, height;
+    uint32_t frame;            /* Scene::frame (scene.slang:48), = info.get_total_iteration() */
+    int32_t spp;               /* "samples per pixel"  (render_pt.cpp:151) */
+    int32_t max_path_length;   /* "max path length"    (render_pt.cpp:154) */
+    uint32_t instance_mask;    /* properties "0".."7"  (render_pt.cpp:127-131) */
+    uint32_t flags;            /* MPT_RENDER_* */
+    /* Sample sharding: this call renders sample indices s = sample_offset + i*sample_stride,
+     * i in [0, spp). RNG seed is pcg4d16(px, py, frame, s) (render_pt.slang:114), so any partition of
+     * the sample indices over GPUs yields the same set of paths. Single GPU: offset 0, stride 1. */
+    uint32_t sample_offset;
+    uint32_t sample_stride;
+    float scene_time;          /* Scene::time (unused by the supported material models) */
+} mpt_render_params;
+
+/* Ray / hit records of mpt_trace. Ray = HLSL RayDesc (origin, tmin, direction, tmax). */
+typedef struct mpt_ray {
+    float origin[3];
+    float tmin;
+    float direction[3];
+    float tmax;
+} mpt_ray;
+
+/* Hit = merian::Hit (hit.slang:25-66); miss = all ids 0xFFFFFFFF, barycentrics 0. */
+typedef struct mpt_hit {
+    uint32_t instance_id;
+    uint32_t instance_index;
+    uint32_t primitive_id;
+    uint32_t geometry_index;
+    float barycentrics[2];
+} mpt_hit;
+
+/* Work counters accumulated over calls since the last reset (bench.py: Mrays/s, roofline bytes). */
+typedef struct mpt_stats {
+    uint64_t rays_primary;      /* closest-hit queries issued for camera rays          */
+    uint64_t rays_continuation; /* closest-hit queries issued for BSDF-sampled rays    */
+    uint64_t rays_shadow;       /* any-hit (visibility) queries issued by NEE          */
+    uint64_t shaded_hits;       /* shading points with geometry (get_shading_point)    */
+    uint64_t samples;           /* paths started (pixels * spp)                        */
+    uint64_t kernel_launches;   /* libmpt kernels launched                             */
+    uint64_t nodes_visited;     /* BVH8 nodes popped   (only counted when profiling counters are on) */
+    uint64_t tris_tested;       /* triangles tested    (only counted when profiling counters are on) */
+    double extend_ms;           /* device time of the extend (traversal) kernels, CUDA events (when timing is on) */
+    double shade_ms;            /* device time of the shade kernels                                            */
+    uint64_t extend_launches;
+    uint64_t shade_launches;
+} mpt_stats;
+
+/* ---- entry points -------------------------------------------------------------------------- */
+
+MPT_API uint32_t mpt_abi_version(void);
+
+/* Context per device; replaces RenderPT::initialize (render_pt.cpp:21-25). Fails (no CPU fallback)
+ * when the device is not sm_100. */
+MPT_API mpt_status mpt_create(int device, mpt_context** out_ctx);
+MPT_API void mpt_destroy(mpt_context* ctx);
+MPT_API const char* mpt_last_error(const mpt_context* ctx); /* ctx may be NULL: last create error */
+
+/* Replaces Scene::upload_meshes / upload_geometry_data / build_blas / build_tlas
+ * (scene.cpp:1377-1670, 1230-1311, 1672-1892): copies the tables into HBM and builds one compressed
+ * 8-wide BVH per BLAS plus one over the TLAS instances. */
+MPT_API mpt_status mpt_scene_upload(mpt_context* ctx, const mpt_scene_desc* scene);
+
+/* Replaces MaterialSystem::update (material_system.cpp:234-273): `entries` is the reference's host
+ * buffer, entry = MaterialHeader (4 B) + payload, entry_size bytes each (material_system.cpp:140-195). */
+MPT_API mpt_status mpt_materials_upload(mpt_context* ctx, const void* entries, uint32_t entry_size,
+                                        uint32_t material_count, const mpt_material_type* types,
+                                        uint32_t type_count);
+
+/* Replaces TextureManager texture creation (texture_manager.cpp:207-243). */
+MPT_API mpt_status mpt_texture_upload(mpt_context* ctx, uint32_t texture_id, uint32_t width,
+                                      uint32_t height, uint32_t format, uint32_t wrap_u,
+                                      uint32_t wrap_v, uint32_t filter, const void* pixels);
+
+/* Replaces LatLongEnvMap::write_to (env_map.hpp:112-118). `to_local` row-major 4x4; pixels RGBA32F,
+ * repeat addressing, bilinear (scene.cpp:786-789). type MPT_ENV_EMPTY ignores the rest. Also builds the
+ * alias table used by MPT_RENDER_NEE. */
+MPT_API mpt_status mpt_env_set(mpt_context* ctx, uint32_t type, const float* to_local,
+                               float intensity, uint32_t width, uint32_t height,
+                               const float* rgba32f);
+
+/* Replaces the gbuffer_rt raygen for the hit texture (gbuffer_rt.slang:18-31, gbuffer.slang:40-61):
+ * writes one PackedHitInfo (uint4) per pixel into d_tex1 (row-major, width*height*16 bytes). */
+MPT_API mpt_status mpt_primary_visibility(mpt_context* ctx, const mpt_camera* camera, uint32_t width,
+                                          uint32_t height, uint32_t instance_mask, void* d_tex1,
+                                          void* stream);
+
+/* Closest-hit queries for arbitrary rays (Scene::trace_ray, scene.slang:62-76) with
+ * RAY_FLAG_CULL_BACK_FACING_TRIANGLES (acceleration-structure.slang:64). d_rays: mpt_ray[n], d_hits: mpt_hit[n]. */
+MPT_API mpt_status mpt_trace(mpt_context* ctx, const void* d_rays, uint64_t n, uint32_t instance_mask,
+                             void* d_hits, void* stream);
+
+/* Replaces RenderPT::process (render_pt.cpp:94-124) = the raygen shader render_pt.slang:92-130.
+ * d_tex1: GBuffer hit texture (PackedHitInfo per pixel) or NULL to trace primary rays internally.
+ * d_albedo: GBuffer tex3 (float4 per pixel) or NULL; d_irradiance: float4 per pixel (rgb, second moment). */
+MPT_API mpt_status mpt_render(mpt_context* ctx, const mpt_camera* camera,
+                              const mpt_render_params* params, const void* d_tex1,
+                              const void* d_albedo, void* d_irradiance, void* stream);
+
+/* Same, end to end from HOST memory (pinned or pageable): copies tex1 (if given) host->device, renders,
+ * copies the irradiance image device->host, synchronises the stream. */
+MPT_API mpt_status mpt_render_host(mpt_context* ctx, const mpt_camera* camera,
+                                   const mpt_render_params* params, const void* h_tex1,
+                                   const void* h_albedo, void* h_irradiance, void* stream);
+
+/* Counters. profile_flags: bit0 = count BVH nodes/triangles per ray (slower kernels), bit1 = CUDA-event
+ * timing of every extend/shade launch. */
+MPT_API mpt_status mpt_set_profiling(mpt_context* ctx, uint32_t profile_flags);
+MPT_API mpt_status mpt_get_stats(mpt_context* ctx, mpt_stats* out);
+MPT_API mpt_status mpt_reset_stats(mpt_context* ctx);
+
+/* Introspection used by tests and DESIGN.md figures. */
+typedef struct mpt_bvh_info {
+    uint64_t node_count;     /* 80-byte BVH8 nodes over all BLAS + TLAS */
+    uint64_t triangle_count; /* 48-byte triangle records */
+    uint64_t node_bytes;
+    uint64_t triangle_bytes;
+    double build_ms;
+} mpt_bvh_info;
+MPT_API mpt_status mpt_bvh_get_info(mpt_context* ctx, mpt_bvh_info* out);
+
+/* Test hook for the BSDF property suite (tests/test_bsdf.cpp of the reference restated): runs
+ * sample_eval / eval / pdf of one BSDF on the device. See merian_b200/csrc/bsdf_check.cu. */
+typedef struct mpt_bsdf_check_params {
+    uint32_t bsdf;        /* 0 Lambert, 1 GGX, 2 GGX aniso, 3 FresnelMix, 4 IridescentFresnelMix, 5 IridescentRoughDielectric, 6 Sheen, 7 glTF full */
+    float wi[3];
+    uint32_t n_samples;
+    uint32_t seed;
+    float albedo[3];
+    float alpha;
+    float f0[3];
+    float ior_f0;
+    float alpha_bitangent;
+    float iridescence;
+} mpt_bsdf_check_params;
+MPT_API mpt_status mpt_bsdf_check(mpt_context* ctx, const mpt_bsdf_check_params* p, float* out16);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPT_H */

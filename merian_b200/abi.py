@@ -1,0 +1,135 @@
+"""ctypes mirror of include/mpt.h (data formats only; no algorithm lives here).
+
+Shared by the product loader (merian_b200._lib) and by the test-side oracle loader (oracle/oracle_py.py):
+both sides consume the same scene tables, exactly as the reference's renderer and its Scene do.
+"""
+import ctypes as C
+
+MPT_ABI_VERSION = 1
+
+# mpt_status
+MPT_OK, MPT_ERR_INVALID_ARGUMENT, MPT_ERR_CUDA, MPT_ERR_NOT_READY, MPT_ERR_UNSUPPORTED, MPT_ERR_LIMIT = range(6)
+
+# GeometryDataFlags, include/merian-shaders/scene/scene-data.slangh:15-42
+GEOM_PRETRANSFORMED = 0x1
+GEOM_HAS_PREV_VERTICES = 0x2
+GEOM_IS_ANIMATED = 0x4
+GEOM_FLIP_FACING = 0x8
+GEOM_INDEX_U8 = 0x10
+GEOM_INDEX_U16 = 0x20
+GEOM_INDEX_U32 = 0x40
+GEOM_FLAT_SHADING = 0x80
+GEOM_HAS_TANGENTS = 0x100
+GEOM_USE_ENV_MAP = 0x200
+GEOM_TWO_SIDED = 0x400
+
+INSTANCE_FACING_CULL_DISABLE = 0x1
+INSTANCE_FLIP_FACING = 0x2
+INSTANCE_FORCE_OPAQUE = 0x4
+
+MATERIAL_DIFFUSE, MATERIAL_GLTF = 0, 1
+GLTF_TRANSMISSION, GLTF_VOLUME, GLTF_CLEARCOAT, GLTF_SHEEN, GLTF_IRIDESCENCE, GLTF_ANISOTROPY = 1, 2, 4, 8, 16, 32
+
+TEX_RGBA8_UNORM, TEX_RGBA8_SRGB, TEX_RGBA32F = 0, 1, 2
+WRAP_REPEAT, WRAP_CLAMP_TO_EDGE, WRAP_MIRRORED_REPEAT = 0, 1, 2
+FILTER_NEAREST, FILTER_LINEAR = 0, 1
+TEXTURE_NONE = 0xFFFF
+
+ENV_EMPTY, ENV_LATLONG = 0, 1
+
+RENDER_EMISSION_ON_PRIMARY = 0x1
+RENDER_DEMODULATE_ALBEDO = 0x2
+RENDER_OUTPUT_SUM = 0x4
+RENDER_NEE = 0x8
+
+
+class PackedVertex(C.Structure):  # scene-data.slangh:75-80, 24 bytes
+    _pack_ = 4
+    _fields_ = [("position", C.c_float * 3), ("encoded_normal", C.c_uint32), ("uv", C.c_uint16 * 2),
+                ("encoded_tangent", C.c_uint32)]
+
+
+class MeshDesc(C.Structure):
+    _fields_ = [("vertices", C.c_void_p), ("indices", C.c_void_p), ("vertex_count", C.c_uint32),
+                ("primitive_count", C.c_uint32), ("index_flag", C.c_uint32), ("opaque", C.c_uint32)]
+
+
+class BlasDesc(C.Structure):
+    _fields_ = [("meshes", C.c_void_p), ("mesh_count", C.c_uint32)]
+
+
+class GeometryDesc(C.Structure):
+    _fields_ = [("mesh", C.c_uint32), ("material_id", C.c_uint16), ("flags", C.c_uint16), ("primitive_count", C.c_uint32)]
+
+
+class InstanceDesc(C.Structure):
+    _fields_ = [("transform", C.c_float * 12), ("instance_custom_index", C.c_uint32), ("mask", C.c_uint32),
+                ("flags", C.c_uint32), ("blas", C.c_uint32)]
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [("meshes", C.c_void_p), ("mesh_count", C.c_uint32),
+                ("blas", C.c_void_p), ("blas_count", C.c_uint32),
+                ("geometries", C.c_void_p), ("geometry_count", C.c_uint32),
+                ("instances", C.c_void_p), ("instance_count", C.c_uint32),
+                ("instance_transforms", C.c_void_p), ("inverse_transposed_instance_transforms", C.c_void_p)]
+
+
+class MaterialType(C.Structure):
+    _fields_ = [("model", C.c_uint32), ("features", C.c_uint32)]
+
+
+class Camera(C.Structure):  # camera.slang:6-24
+    _fields_ = [("position", C.c_float * 3), ("target", C.c_float * 3), ("up", C.c_float * 3),
+                ("U", C.c_float * 3), ("V", C.c_float * 3), ("W", C.c_float * 3),
+                ("near_plane", C.c_float), ("far_plane", C.c_float), ("aspect_ratio", C.c_float),
+                ("aperture_radius", C.c_float), ("jitter", C.c_float * 2)]
+
+
+class RenderParams(C.Structure):
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("frame", C.c_uint32), ("spp", C.c_int32),
+                ("max_path_length", C.c_int32), ("instance_mask", C.c_uint32), ("flags", C.c_uint32),
+                ("sample_offset", C.c_uint32), ("sample_stride", C.c_uint32), ("scene_time", C.c_float)]
+
+
+class Ray(C.Structure):
+    _fields_ = [("origin", C.c_float * 3), ("tmin", C.c_float), ("direction", C.c_float * 3), ("tmax", C.c_float)]
+
+
+class Hit(C.Structure):
+    _fields_ = [("instance_id", C.c_uint32), ("instance_index", C.c_uint32), ("primitive_id", C.c_uint32),
+                ("geometry_index", C.c_uint32), ("barycentrics", C.c_float * 2)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("rays_primary", C.c_uint64), ("rays_continuation", C.c_uint64), ("rays_shadow", C.c_uint64),
+                ("shaded_hits", C.c_uint64), ("samples", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("nodes_visited", C.c_uint64), ("tris_tested", C.c_uint64), ("extend_ms", C.c_double),
+                ("shade_ms", C.c_double), ("extend_launches", C.c_uint64), ("shade_launches", C.c_uint64)]
+
+
+class BvhInfo(C.Structure):
+    _fields_ = [("node_count", C.c_uint64), ("triangle_count", C.c_uint64), ("node_bytes", C.c_uint64),
+                ("triangle_bytes", C.c_uint64), ("build_ms", C.c_double)]
+
+
+class BsdfCheckParams(C.Structure):
+    _fields_ = [("bsdf", C.c_uint32), ("wi", C.c_float * 3), ("n_samples", C.c_uint32), ("seed", C.c_uint32),
+                ("albedo", C.c_float * 3), ("alpha", C.c_float), ("f0", C.c_float * 3), ("ior_f0", C.c_float),
+                ("alpha_bitangent", C.c_float), ("iridescence", C.c_float)]
+
+
+# numpy dtypes of the wire formats
+import numpy as np  # noqa: E402
+
+PACKED_VERTEX_DTYPE = np.dtype([("position", "<f4", 3), ("encoded_normal", "<u4"), ("uv", "<u2", 2),
+                                ("encoded_tangent", "<u4")])
+assert PACKED_VERTEX_DTYPE.itemsize == 24 and C.sizeof(PackedVertex) == 24
+# PackedHitInfo, include/merian-shaders/gbuffer.slang:40-61 (one R32G32B32A32_UINT texel of GBuffer tex1)
+PACKED_HIT_DTYPE = np.dtype([("instance_id", "<u4"), ("primitive_id", "<u4"), ("geometry_index", "<u2"),
+                             ("instance_index", "<u2"), ("barycentrics", "<f2", 2)])
+assert PACKED_HIT_DTYPE.itemsize == 16
+RAY_DTYPE = np.dtype([("origin", "<f4", 3), ("tmin", "<f4"), ("direction", "<f4", 3), ("tmax", "<f4")])
+HIT_DTYPE = np.dtype([("instance_id", "<u4"), ("instance_index", "<u4"), ("primitive_id", "<u4"),
+                      ("geometry_index", "<u4"), ("barycentrics", "<f4", 2)])
+assert RAY_DTYPE.itemsize == 32 and HIT_DTYPE.itemsize == 24
