@@ -1,0 +1,52 @@
+"""ctypes binding of libmpt.so (built in-tree from merian_b200/csrc). No fallback: a missing library or a
+non-sm_100 device raises."""
+import ctypes as C
+import os
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libmpt.so")
+_lib = None
+
+EXPORTS = ["mpt_abi_version", "mpt_create", "mpt_destroy", "mpt_last_error", "mpt_scene_upload", "mpt_materials_upload",
+           "mpt_texture_upload", "mpt_env_set", "mpt_primary_visibility", "mpt_trace", "mpt_render", "mpt_render_host",
+           "mpt_set_profiling", "mpt_get_stats", "mpt_reset_stats", "mpt_bvh_get_info", "mpt_bsdf_check"]
+
+
+class MptError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"libmpt status {status}: {message}")
+        self.status = status
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU or PyTorch fallback for the path tracer)")
+        l = C.CDLL(LIB_PATH)
+        l.mpt_abi_version.restype = C.c_uint32
+        l.mpt_last_error.restype = C.c_char_p
+        l.mpt_last_error.argtypes = [C.c_void_p]
+        l.mpt_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        l.mpt_destroy.argtypes = [C.c_void_p]
+        l.mpt_destroy.restype = None
+        l.mpt_scene_upload.argtypes = [C.c_void_p, C.POINTER(abi.SceneDesc)]
+        l.mpt_materials_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
+        l.mpt_texture_upload.argtypes = [C.c_void_p] + [C.c_uint32] * 7 + [C.c_void_p]
+        l.mpt_env_set.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_float, C.c_uint32, C.c_uint32, C.c_void_p]
+        l.mpt_primary_visibility.argtypes = [C.c_void_p, C.POINTER(abi.Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        l.mpt_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
+        l.mpt_render.argtypes = [C.c_void_p, C.POINTER(abi.Camera), C.POINTER(abi.RenderParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        l.mpt_render_host.argtypes = l.mpt_render.argtypes
+        l.mpt_set_profiling.argtypes = [C.c_void_p, C.c_uint32]
+        l.mpt_get_stats.argtypes = [C.c_void_p, C.POINTER(abi.Stats)]
+        l.mpt_reset_stats.argtypes = [C.c_void_p]
+        l.mpt_bvh_get_info.argtypes = [C.c_void_p, C.POINTER(abi.BvhInfo)]
+        l.mpt_bsdf_check.argtypes = [C.c_void_p, C.POINTER(abi.BsdfCheckParams), C.c_void_p]
+        if l.mpt_abi_version() != abi.MPT_ABI_VERSION:
+            raise RuntimeError("libmpt.so ABI version mismatch")
+        _lib = l
+    return _lib

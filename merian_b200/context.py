@@ -1,0 +1,136 @@
+"""Context: the Python face of the C-ABI (include/mpt.h). PyTorch supplies device memory and the stream; every
+computation happens in libmpt.so."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import abi
+from ._lib import MptError, lib
+
+
+def _hp(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("merian_b200.Context needs a CUDA device (B200); there is no CPU path")
+        self.l = lib()
+        self.device = device
+        self.torch_device = torch.device("cuda", device)
+        torch.cuda.init()
+        self.h = C.c_void_p()
+        st = self.l.mpt_create(device, C.byref(self.h))
+        if st != abi.MPT_OK:
+            raise MptError(st, self.l.mpt_last_error(None).decode())
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, st):
+        if st != abi.MPT_OK:
+            raise MptError(st, self.l.mpt_last_error(self.h).decode())
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.torch_device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.l.mpt_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ uploads (host arrays)
+    def scene_upload(self, scene_desc):
+        self._check(self.l.mpt_scene_upload(self.h, C.byref(scene_desc)))
+
+    def materials_upload(self, entries, entry_size, count, types, type_count):
+        self._check(self.l.mpt_materials_upload(self.h, entries, entry_size, count, C.cast(types, C.c_void_p), type_count))
+
+    def texture_upload(self, tid, w, h, fmt, wrap_u, wrap_v, filt, pixels):
+        self._check(self.l.mpt_texture_upload(self.h, tid, w, h, fmt, wrap_u, wrap_v, filt, _hp(pixels)))
+
+    def env_set(self, typ, to_local, intensity, w, h, pixels):
+        self._check(self.l.mpt_env_set(self.h, typ, _hp(to_local), intensity, w, h, _hp(pixels)))
+
+    # ------------------------------------------------------------------ device entry points (torch tensors)
+    def primary_visibility_device(self, cam, w, h, mask=0xFF, out=None):
+        if out is None:
+            out = torch.empty((h, w, 4), dtype=torch.int32, device=self.torch_device)
+        self._check(self.l.mpt_primary_visibility(self.h, C.byref(cam), w, h, mask, C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def primary_visibility(self, cam, w, h, mask=0xFF):
+        t = self.primary_visibility_device(cam, w, h, mask)
+        return t.cpu().numpy().view(abi.PACKED_HIT_DTYPE).reshape(h, w)
+
+    def trace_device(self, rays, mask=0xFF, hits=None):
+        n = rays.shape[0]
+        if hits is None:
+            hits = torch.empty((n, 6), dtype=torch.int32, device=self.torch_device)
+        self._check(self.l.mpt_trace(self.h, C.c_void_p(rays.data_ptr()), n, mask, C.c_void_p(hits.data_ptr()), self._stream()))
+        return hits
+
+    def trace(self, rays_np, mask=0xFF):
+        rays = torch.from_numpy(np.ascontiguousarray(rays_np).view(np.float32).reshape(-1, 8)).to(self.torch_device)
+        hits = self.trace_device(rays, mask)
+        return hits.cpu().numpy().view(abi.HIT_DTYPE).reshape(-1)
+
+    def render_device(self, cam, params, tex1=None, albedo=None, out=None):
+        if out is None:
+            out = torch.empty((params.height, params.width, 4), dtype=torch.float32, device=self.torch_device)
+        self._check(self.l.mpt_render(self.h, C.byref(cam), C.byref(params), C.c_void_p(tex1.data_ptr()) if tex1 is not None else None,
+                                      C.c_void_p(albedo.data_ptr()) if albedo is not None else None, C.c_void_p(out.data_ptr()), self._stream()))
+        return out
+
+    def render(self, cam, params, tex1=None, albedo=None):
+        t1 = torch.from_numpy(np.ascontiguousarray(tex1).view(np.int32).reshape(params.height, params.width, 4)).to(self.torch_device) if tex1 is not None else None
+        al = torch.from_numpy(np.ascontiguousarray(albedo, dtype=np.float32)).to(self.torch_device) if albedo is not None else None
+        return self.render_device(cam, params, t1, al).cpu().numpy()
+
+    def render_host(self, cam, params, h_tex1=None, h_albedo=None, h_out=None):
+        """End-to-end call on HOST tensors (pinned recommended): H2D tex1, render, D2H irradiance, stream sync."""
+        if h_out is None:
+            h_out = torch.empty((params.height, params.width, 4), dtype=torch.float32).pin_memory()
+        self._check(self.l.mpt_render_host(self.h, C.byref(cam), C.byref(params), C.c_void_p(h_tex1.data_ptr()) if h_tex1 is not None else None,
+                                           C.c_void_p(h_albedo.data_ptr()) if h_albedo is not None else None, C.c_void_p(h_out.data_ptr()),
+                                           self._stream()))
+        return h_out
+
+    # ------------------------------------------------------------------ counters
+    def set_profiling(self, flags):
+        self._check(self.l.mpt_set_profiling(self.h, flags))
+
+    def stats(self) -> abi.Stats:
+        s = abi.Stats()
+        self._check(self.l.mpt_get_stats(self.h, C.byref(s)))
+        return s
+
+    def reset_stats(self):
+        self._check(self.l.mpt_reset_stats(self.h))
+
+    def bvh_info(self) -> abi.BvhInfo:
+        b = abi.BvhInfo()
+        self._check(self.l.mpt_bvh_get_info(self.h, C.byref(b)))
+        return b
+
+    def bsdf_check(self, **kw):
+        p = abi.BsdfCheckParams()
+        p.bsdf = kw["bsdf"]
+        p.wi[:] = kw["wi"]
+        p.n_samples = kw.get("n_samples", 1 << 18)
+        p.seed = kw.get("seed", 0x1234567)
+        p.albedo[:] = kw.get("albedo", (1, 1, 1))
+        p.alpha = kw.get("alpha", 0.3)
+        p.f0[:] = kw.get("f0", (1, 1, 1))
+        p.ior_f0 = kw.get("ior_f0", 0.04)
+        p.alpha_bitangent = kw.get("alpha_bitangent", 0.3)
+        p.iridescence = kw.get("iridescence", 0.0)
+        out = np.zeros(16, np.float32)
+        self._check(self.l.mpt_bsdf_check(self.h, C.byref(p), _hp(out)))
+        return out

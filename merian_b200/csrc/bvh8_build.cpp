@@ -1,0 +1,278 @@
+// bvh8_build.cpp — host builder: binned-SAH BVH2 -> greedy 8-wide collapse -> quantised 80-byte nodes.
+// Replaces the driver BLAS/TLAS build of the reference (src/merian-shaders/scene/scene.cpp:1672-1892).
+#include "bvh8.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+namespace mpt {
+namespace {
+
+struct B3 {
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    void grow(const Box& b) {
+        for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); }
+    }
+    void grow(const B3& b) {
+        for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); }
+    }
+    void grow_pt(const float* p) {
+        for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); }
+    }
+    float half_area() const {
+        const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (dx < 0) return 0.f;
+        return dx * dy + dy * dz + dz * dx;
+    }
+};
+
+struct Node2 {
+    B3 box;
+    uint32_t left = 0, right = 0; // internal children
+    uint32_t first = 0, count = 0; // leaf range into prim index array (count > 0 => leaf)
+};
+
+constexpr int NBINS = 16;
+
+struct Builder2 {
+    const Box* boxes;
+    std::vector<float> cent; // 3 per prim
+    std::vector<uint32_t> idx;
+    std::vector<Node2> nodes;
+    int max_leaf;
+
+    void build(uint32_t n) {
+        idx.resize(n);
+        std::iota(idx.begin(), idx.end(), 0u);
+        cent.resize(size_t(n) * 3);
+        for (uint32_t i = 0; i < n; i++)
+            for (int a = 0; a < 3; a++) cent[size_t(i) * 3 + a] = 0.5f * (boxes[i].lo[a] + boxes[i].hi[a]);
+        nodes.reserve(size_t(n) * 2);
+        nodes.emplace_back();
+        struct Job { uint32_t node, first, count; };
+        std::vector<Job> stack;
+        stack.push_back({0, 0, n});
+        while (!stack.empty()) {
+            const Job j = stack.back();
+            stack.pop_back();
+            B3 box, cbox;
+            for (uint32_t i = j.first; i < j.first + j.count; i++) {
+                box.grow(boxes[idx[i]]);
+                cbox.grow_pt(&cent[size_t(idx[i]) * 3]);
+            }
+            nodes[j.node].box = box;
+            if (j.count <= 1) { make_leaf(j.node, j.first, j.count); continue; }
+
+            // binned SAH over the 3 axes
+            float best_cost = FLT_MAX;
+            int best_axis = -1, best_bin = -1;
+            for (int a = 0; a < 3; a++) {
+                const float cmin = cbox.lo[a], cmax = cbox.hi[a];
+                if (!(cmax > cmin)) continue;
+                B3 bb[NBINS];
+                uint32_t bc[NBINS] = {0};
+                const float k = float(NBINS) * (1.0f - 1e-6f) / (cmax - cmin);
+                for (uint32_t i = j.first; i < j.first + j.count; i++) {
+                    const uint32_t p = idx[i];
+                    int b = int((cent[size_t(p) * 3 + a] - cmin) * k);
+                    b = std::min(std::max(b, 0), NBINS - 1);
+                    bb[b].grow(boxes[p]);
+                    bc[b]++;
+                }
+                float ra[NBINS];
+                uint32_t rc[NBINS];
+                B3 acc;
+                uint32_t cnt = 0;
+                for (int b = NBINS - 1; b > 0; b--) {
+                    acc.grow(bb[b]);
+                    cnt += bc[b];
+                    ra[b] = acc.half_area();
+                    rc[b] = cnt;
+                }
+                acc = B3();
+                cnt = 0;
+                for (int b = 0; b < NBINS - 1; b++) {
+                    acc.grow(bb[b]);
+                    cnt += bc[b];
+                    if (cnt == 0 || rc[b + 1] == 0) continue;
+                    const float cost = acc.half_area() * float(cnt) + ra[b + 1] * float(rc[b + 1]);
+                    if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = b; }
+                }
+            }
+            const float parent_area = box.half_area();
+            const float leaf_cost = float(j.count);
+            const float split_cost = (parent_area > 0.f && best_axis >= 0) ? 1.0f + best_cost / parent_area : FLT_MAX;
+            if (int(j.count) <= max_leaf && split_cost >= leaf_cost) { make_leaf(j.node, j.first, j.count); continue; }
+
+            uint32_t mid;
+            if (best_axis >= 0) {
+                const int a = best_axis;
+                const float cmin = cbox.lo[a], cmax = cbox.hi[a];
+                const float k = float(NBINS) * (1.0f - 1e-6f) / (cmax - cmin);
+                auto it = std::partition(idx.begin() + j.first, idx.begin() + j.first + j.count, [&](uint32_t p) {
+                    int b = int((cent[size_t(p) * 3 + a] - cmin) * k);
+                    b = std::min(std::max(b, 0), NBINS - 1);
+                    return b <= best_bin;
+                });
+                mid = uint32_t(it - idx.begin()) - j.first;
+            } else {
+                mid = 0;
+            }
+            if (mid == 0 || mid == j.count) { // all centroids coincide: split the index range in half
+                if (int(j.count) <= max_leaf) { make_leaf(j.node, j.first, j.count); continue; }
+                mid = j.count / 2;
+            }
+            const uint32_t l = uint32_t(nodes.size());
+            nodes.emplace_back();
+            nodes.emplace_back();
+            nodes[j.node].left = l;
+            nodes[j.node].right = l + 1;
+            nodes[j.node].count = 0;
+            stack.push_back({l + 1, j.first + mid, j.count - mid});
+            stack.push_back({l, j.first, mid});
+        }
+    }
+    void make_leaf(uint32_t node, uint32_t first, uint32_t count) {
+        nodes[node].first = first;
+        nodes[node].count = count;
+    }
+};
+
+inline uint8_t exponent_for(float extent) {
+    // smallest e with extent / 2^e <= 255
+    if (!(extent > 0.f)) return 1;
+    int e = int(std::ceil(std::log2(double(extent) / 255.0)));
+    while (double(extent) / std::ldexp(1.0, e) > 255.0) e++;
+    e = std::min(std::max(e + 127, 1), 254);
+    return uint8_t(e);
+}
+
+} // namespace
+
+void build_bvh8(const Box* boxes, uint32_t n, Bvh8& out, int max_leaf) {
+    out.nodes.clear();
+    out.prim_order.clear();
+    B3 all;
+    for (uint32_t i = 0; i < n; i++) all.grow(boxes[i]);
+    for (int a = 0; a < 3; a++) { out.bounds.lo[a] = n ? all.lo[a] : 0.f; out.bounds.hi[a] = n ? all.hi[a] : 0.f; }
+    if (n == 0) {
+        Bvh8Node root;
+        std::memset(&root, 0, sizeof(root));
+        root.ex = root.ey = root.ez = 1;
+        out.nodes.push_back(root);
+        return;
+    }
+    Builder2 b2;
+    b2.boxes = boxes;
+    b2.max_leaf = std::min(std::max(max_leaf, 1), 3);
+    b2.build(n);
+    const std::vector<Node2>& n2 = b2.nodes;
+
+    out.prim_order.reserve(n);
+    out.nodes.reserve(n / 3 + 16);
+    struct Task { uint32_t wide, root2; };
+    std::vector<Task> queue;
+    out.nodes.emplace_back();
+    queue.push_back({0, 0});
+    for (size_t qi = 0; qi < queue.size(); qi++) {
+        const Task t = queue[qi];
+        // ---- gather up to 8 children: repeatedly open the internal child with the largest area
+        uint32_t ch[8];
+        int nch = 0;
+        if (n2[t.root2].count > 0) {
+            ch[nch++] = t.root2; // the BVH2 root itself is a leaf
+        } else {
+            ch[nch++] = n2[t.root2].left;
+            ch[nch++] = n2[t.root2].right;
+            while (nch < 8) {
+                int best = -1;
+                float best_area = -1.f;
+                for (int i = 0; i < nch; i++) {
+                    if (n2[ch[i]].count > 0) continue;
+                    const float a = n2[ch[i]].box.half_area();
+                    if (a > best_area) { best_area = a; best = i; }
+                }
+                if (best < 0) break;
+                const uint32_t open = ch[best];
+                ch[best] = n2[open].left;
+                ch[nch++] = n2[open].right;
+            }
+        }
+        // ---- slot assignment: slot s is visited first by rays with octant s (direction sign bit set = negative),
+        // so it should hold the child that is nearest along d_s: minimise sum of dot(centroid_c - centroid_p, d_s).
+        const B3& pb = n2[t.root2].box;
+        float pc[3];
+        for (int a = 0; a < 3; a++) pc[a] = 0.5f * (pb.lo[a] + pb.hi[a]);
+        float cost[8][8];
+        for (int c = 0; c < nch; c++) {
+            const B3& cb = n2[ch[c]].box;
+            float d[3];
+            for (int a = 0; a < 3; a++) d[a] = 0.5f * (cb.lo[a] + cb.hi[a]) - pc[a];
+            for (int s = 0; s < 8; s++)
+                cost[c][s] = ((s & 1) ? -d[0] : d[0]) + ((s & 2) ? -d[1] : d[1]) + ((s & 4) ? -d[2] : d[2]);
+        }
+        int slot_of[8], child_in_slot[8];
+        for (int i = 0; i < 8; i++) { slot_of[i] = -1; child_in_slot[i] = -1; }
+        for (int k = 0; k < nch; k++) {
+            float bc = FLT_MAX;
+            int bi = -1, bs = -1;
+            for (int c = 0; c < nch; c++) {
+                if (slot_of[c] >= 0) continue;
+                for (int s = 0; s < 8; s++) {
+                    if (child_in_slot[s] >= 0) continue;
+                    if (cost[c][s] < bc) { bc = cost[c][s]; bi = c; bs = s; }
+                }
+            }
+            slot_of[bi] = bs;
+            child_in_slot[bs] = bi;
+        }
+        // ---- encode
+        Bvh8Node node;
+        std::memset(&node, 0, sizeof(node));
+        node.px = pb.lo[0]; node.py = pb.lo[1]; node.pz = pb.lo[2];
+        node.ex = exponent_for(pb.hi[0] - pb.lo[0]);
+        node.ey = exponent_for(pb.hi[1] - pb.lo[1]);
+        node.ez = exponent_for(pb.hi[2] - pb.lo[2]);
+        const double sc[3] = {std::ldexp(1.0, int(node.ex) - 127), std::ldexp(1.0, int(node.ey) - 127), std::ldexp(1.0, int(node.ez) - 127)};
+        node.child_base = uint32_t(out.nodes.size());
+        node.prim_base = uint32_t(out.prim_order.size());
+        uint32_t n_internal = 0, prim_off = 0;
+        uint8_t* qlo[3] = {node.qlox, node.qloy, node.qloz};
+        uint8_t* qhi[3] = {node.qhix, node.qhiy, node.qhiz};
+        for (int s = 0; s < 8; s++) {
+            const int c = child_in_slot[s];
+            if (c < 0) continue;
+            const Node2& cn = n2[ch[c]];
+            for (int a = 0; a < 3; a++) {
+                const double lo = std::floor((double(cn.box.lo[a]) - double(pb.lo[a])) / sc[a]);
+                const double hi = std::ceil((double(cn.box.hi[a]) - double(pb.lo[a])) / sc[a]);
+                qlo[a][s] = uint8_t(std::min(std::max(lo, 0.0), 255.0));
+                qhi[a][s] = uint8_t(std::min(std::max(hi, 0.0), 255.0));
+            }
+            if (cn.count == 0) {
+                node.imask |= uint8_t(1u << s);
+                node.meta[s] = uint8_t((1u << 5) | (24u + uint32_t(s)));
+                n_internal++;
+            } else {
+                const uint32_t unary = (1u << cn.count) - 1u; // 1, 3, 7
+                node.meta[s] = uint8_t((unary << 5) | prim_off);
+                for (uint32_t k = 0; k < cn.count; k++) out.prim_order.push_back(b2.idx[cn.first + k]);
+                prim_off += cn.count;
+            }
+        }
+        out.nodes[t.wide] = node;
+        out.nodes.resize(out.nodes.size() + n_internal);
+        uint32_t j = 0;
+        for (int s = 0; s < 8; s++) {
+            const int c = child_in_slot[s];
+            if (c < 0 || n2[ch[c]].count != 0) continue;
+            queue.push_back({node.child_base + j, ch[c]});
+            j++;
+        }
+    }
+}
+
+} // namespace mpt

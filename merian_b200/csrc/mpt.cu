@@ -1,0 +1,1086 @@
+// mpt.cu — libmpt.so: wavefront path tracer kernels for sm_100a and the C-ABI of include/mpt.h.
+//
+// Pipeline per pass (K samples per pixel in flight, slots = K * pixels):
+//   k_shade_primary   one thread per pixel: primary shading point from the GBuffer hit (render_pt.slang:99-103),
+//                     then for each of the K samples: seed RNG, BSDF sample, continuation ray -> queue
+//   for bounce = 1 .. L-1:
+//     k_extend        persistent warps fetch batches of 32 rays from the queue (atomic counter), BVH8 closest hit
+//     k_shade_bounce  shading point, Beer-Lambert, emission accumulate, next BSDF sample; survivors are compacted
+//                     into the next queue with warp ballot + prefix popcount + one atomicAdd per warp
+//   k_resolve         per pixel: NaN/Inf rejection, sum of the K sample radiances and luminance^2 (render_pt.slang:116-129)
+// Queues are double-buffered SoA (origin|slot, direction|tmax); per-path state lives in fixed slots.
+#include "../../include/mpt.h"
+#include "bvh8.h"
+#include "shading.cuh"
+
+#include <chrono>
+#include <cstddef>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace mpt;
+
+// ======================================================================================= device side
+namespace {
+
+constexpr int kMaxBounces = 64;
+constexpr int kThreads = 128;
+
+struct Counters {
+    uint32_t qcount[kMaxBounces + 2]; // qcount[b] = rays queued for the extend of bounce b
+    uint32_t fetch[kMaxBounces + 2];  // persistent-thread fetch cursors
+    unsigned long long rays_continuation, rays_primary, shaded_hits, nodes_visited, tris_tested;
+};
+
+struct PackedHitInfo { // gbuffer.slang:40-61
+    uint32_t instance_id, primitive_id;
+    uint16_t geometry_index, instance_index;
+    __half2 bary;
+};
+static_assert(sizeof(PackedHitInfo) == 16, "PackedHitInfo is one uint4 texel");
+
+struct PathBuffers {
+    float4* q_o[2];   // origin.xyz | slot (bits)
+    float4* q_d[2];   // direction.xyz | tmax
+    HitRec* hits;
+    float4* thr;      // throughput.rgb | current_ior
+    float4* rad;      // radiance.rgb | rng state (bits)
+    float4* med;      // medium mu_t.rgb | -   (only touched when the scene has transmissive materials)
+};
+
+struct RenderConst {
+    uint32_t width, height, npix;
+    uint32_t frame;
+    int32_t max_path_length;
+    uint32_t instance_mask;
+    uint32_t flags;
+    uint32_t sample_offset, sample_stride;
+    uint32_t pass_first; // index (within this call) of the first sample of the pass
+    uint32_t pass_k;     // samples per pixel in this pass
+    int32_t spp;
+    uint32_t first_pass, last_pass;
+};
+
+MPT_DEV uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// Warp-aggregated queue append: one atomicAdd per warp. All 32 lanes must call.
+MPT_DEV uint32_t queue_push_index(bool alive, uint32_t* counter) {
+    const uint32_t m = __ballot_sync(0xFFFFFFFFu, alive);
+    uint32_t base = 0;
+    if (lane_id() == 0 && m) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    return base + __popc(m & ((1u << lane_id()) - 1u));
+}
+
+// One scattering step of trace_path (render_pt.slang:35-76): BSDF sample, throughput, medium bookkeeping, make_ray.
+template <uint32_t FEAT>
+MPT_DEV bool scatter(const ShadingPoint& sp, f3 ray_d, Rng& rng, f3& throughput, float& current_ior, f3& medium, f3& out_o, f3& out_d) {
+    if (!sp.has_material || all_below(throughput, kThroughputCut)) return false;
+    const f3 wi_world = -ray_d;
+    const f3 wi = sp.frame.to_local(wi_world);
+    f3 wo_l, weight;
+    float pdf;
+    if (!bsdf_sample_eval<FEAT>(sp.bsdf, wi, rng, wo_l, pdf, weight)) return false;
+    const f3 wo = sp.frame.to_world(wo_l);
+    throughput *= weight;
+    const bool transmission = wi.z * wo_l.z < 0.f;
+    const f3 ng = sp.face_normal_dec;
+    if (transmission) {
+        const float eta = sp.bsdf.gltf ? sp.bsdf.eta : 1.0f; // MaterialSample::get_interior_volume
+        current_ior /= eta;
+        medium = (dot(wi_world, ng) >= 0.f) ? sp.absorption : mk3(0.f);
+    }
+    // ShadingPoint::make_ray, hit.slang:134-147
+    const float wo_ng = dot(wo, ng);
+    if (((dot(wi_world, ng) < 0.f) != (wo_ng < 0.f)) != transmission) return false;
+    out_o = offset_ray_origin(sp.pos, wo_ng < 0.f ? -ng : ng);
+    out_d = wo;
+    return true;
+}
+
+// --------------------------------------------------------------------------------------- primary visibility
+template <bool COUNT>
+__global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ SceneView S, CameraParams cam, uint32_t w, uint32_t h, uint32_t mask, PackedHitInfo* out,
+                                                      Counters* ctr) {
+    // 8x4 pixel tiles per warp keep primary rays of a warp spatially coherent
+    const uint32_t tiles_x = (w + 7) / 8;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t tx = warp % tiles_x, ty = warp / tiles_x;
+    const uint32_t x = tx * 8 + (lane_id() & 7u), y = ty * 4 + (lane_id() >> 3);
+    if (x >= w || y >= h) return;
+    f3 o, d;
+    float tmin, tmax;
+    camera_ray(cam, x, y, w, h, o, d, tmin, tmax);
+    uint32_t nn = 0, nt = 0;
+    MaterialAlphaTest at{&S};
+    const HitRec hr = trace_closest<COUNT>(S.accel, o, d, tmin, tmax, mask, at, nn, nt);
+    PackedHitInfo p;
+    if (hr.tri == kMiss) {
+        p.instance_id = kMiss;
+        p.primitive_id = kMiss;
+        p.geometry_index = 0xFFFF;
+        p.instance_index = 0xFFFF;
+        p.bary = __floats2half2_rn(0.f, 0.f);
+    } else {
+        const float4* tp = S.accel.tris + size_t(hr.tri) * 3;
+        p.instance_id = S.accel.instances[hr.instance].custom_index;
+        p.primitive_id = __float_as_uint(__ldg(tp).w);
+        p.geometry_index = uint16_t(__float_as_uint(__ldg(tp + 1).w));
+        p.instance_index = uint16_t(hr.instance);
+        p.bary = __floats2half2_rn(hr.u, hr.v);
+    }
+    out[size_t(y) * w + x] = p;
+    if (COUNT) {
+        atomicAdd(&ctr->nodes_visited, (unsigned long long)nn);
+        atomicAdd(&ctr->tris_tested, (unsigned long long)nt);
+    }
+}
+
+// --------------------------------------------------------------------------------------- arbitrary rays
+template <bool COUNT>
+__global__ void __launch_bounds__(kThreads) k_trace(const __grid_constant__ SceneView S, const float4* rays, uint64_t n, uint32_t mask, uint32_t* hits6, Counters* ctr) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 ro = __ldg(rays + 2 * i), rd = __ldg(rays + 2 * i + 1);
+    uint32_t nn = 0, nt = 0;
+    MaterialAlphaTest at{&S};
+    const HitRec hr = trace_closest<COUNT>(S.accel, xyz(ro), xyz(rd), ro.w, rd.w, mask, at, nn, nt);
+    uint32_t* o = hits6 + 6 * i;
+    if (hr.tri == kMiss) {
+        o[0] = o[1] = o[2] = o[3] = kMiss;
+        o[4] = o[5] = 0u;
+    } else {
+        const float4* tp = S.accel.tris + size_t(hr.tri) * 3;
+        o[0] = S.accel.instances[hr.instance].custom_index;
+        o[1] = hr.instance;
+        o[2] = __float_as_uint(__ldg(tp).w);
+        o[3] = __float_as_uint(__ldg(tp + 1).w);
+        o[4] = __float_as_uint(hr.u);
+        o[5] = __float_as_uint(hr.v);
+    }
+    if (COUNT) {
+        atomicAdd(&ctr->nodes_visited, (unsigned long long)nn);
+        atomicAdd(&ctr->tris_tested, (unsigned long long)nt);
+    }
+}
+
+// --------------------------------------------------------------------------------------- wavefront: primary shade
+template <uint32_t FEAT>
+__global__ void __launch_bounds__(kThreads) k_shade_primary(const __grid_constant__ SceneView S, CameraParams cam, RenderConst rc, const PackedHitInfo* tex1, PathBuffers pb,
+                                                            Counters* ctr) {
+    const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = pix < rc.npix;
+    const uint32_t x = valid ? pix % rc.width : 0, y = valid ? pix / rc.width : 0;
+    f3 o, d;
+    float tmin, tmax;
+    camera_ray(cam, x, y, rc.width, rc.height, o, d, tmin, tmax);
+    ShadingPoint sp;
+    sp.has_material = false;
+    sp.emission = mk3(0.f);
+    sp.pos = o;
+    bool shaded = false;
+    if (valid) {
+        const PackedHitInfo ph = tex1[pix];
+        if (ph.instance_id != kMiss) { // Hit::is_valid, hit.slang:53-55
+            const uint4 gd = __ldg(S.geometries + ph.instance_id + uint32_t(ph.geometry_index));
+            HitRec hr;
+            hr.tri = __ldg(S.prim_to_tri + gd.z + ph.primitive_id);
+            hr.instance = ph.instance_index;
+            const float2 b = __half22float2(ph.bary);
+            hr.u = b.x;
+            hr.v = b.y;
+            surface_shading_point<FEAT>(S, o, d, hr, 1.0f, true, sp);
+            shaded = sp.has_material;
+        } else {
+            env_shading_point(S, o, d, sp);
+        }
+    }
+    // trace_path prologue, render_pt.slang:29-33 (exterior volume = Vacuum: transmittance 1)
+    const f3 radiance0 = (rc.flags & MPT_RENDER_EMISSION_ON_PRIMARY) ? sp.emission : mk3(0.f);
+    const uint32_t ms = __ballot_sync(0xFFFFFFFFu, shaded);
+    if (lane_id() == 0 && ms) atomicAdd(&ctr->shaded_hits, (unsigned long long)__popc(ms));
+
+    for (uint32_t k = 0; k < rc.pass_k; k++) {
+        const uint32_t slot = k * rc.npix + pix;
+        const uint32_t sidx = rc.sample_offset + (rc.pass_first + k) * rc.sample_stride;
+        Rng rng = make_pcg(pcg4d16(x, y, rc.frame, sidx)); // render_pt.slang:114
+        f3 throughput = mk3(1.f), medium = mk3(0.f), no, nd;
+        float ior = 1.0f;
+        bool alive = false;
+        if (valid && rc.max_path_length > 1) alive = scatter<FEAT>(sp, d, rng, throughput, ior, medium, no, nd);
+        const uint32_t qi = queue_push_index(alive, &ctr->qcount[1]);
+        if (alive) {
+            pb.q_o[0][qi] = make_float4(no.x, no.y, no.z, __uint_as_float(slot));
+            pb.q_d[0][qi] = make_float4(nd.x, nd.y, nd.z, kRayTMax);
+        }
+        if (valid) {
+            pb.rad[slot] = make_float4(radiance0.x, radiance0.y, radiance0.z, __uint_as_float(rng.state));
+            if (alive) {
+                pb.thr[slot] = make_float4(throughput.x, throughput.y, throughput.z, ior);
+                if (FEAT & F_TRANSMISSION) pb.med[slot] = make_float4(medium.x, medium.y, medium.z, 0.f);
+            }
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------- wavefront: extend
+template <bool COUNT>
+__global__ void __launch_bounds__(kThreads) k_extend(const __grid_constant__ SceneView S, const float4* __restrict__ q_o, const float4* __restrict__ q_d, HitRec* __restrict__ hits,
+                                                     uint32_t bounce, uint32_t mask, Counters* ctr) {
+    const uint32_t n = ctr->qcount[bounce];
+    uint32_t nn = 0, nt = 0;
+    MaterialAlphaTest at{&S};
+    while (true) {
+        uint32_t base = 0;
+        if (lane_id() == 0) base = atomicAdd(&ctr->fetch[bounce], 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= n) break;
+        const uint32_t j = base + lane_id();
+        if (j < n) {
+            const float4 ro = __ldg(q_o + j), rd = __ldg(q_d + j);
+            const HitRec hr = trace_closest<COUNT>(S.accel, xyz(ro), xyz(rd), 0.f /* SCENE_RAY_TMIN */, rd.w, mask, at, nn, nt);
+            *reinterpret_cast<uint4*>(hits + j) = make_uint4(hr.tri, hr.instance, __float_as_uint(hr.u), __float_as_uint(hr.v));
+        }
+    }
+    if (COUNT) {
+        atomicAdd(&ctr->nodes_visited, (unsigned long long)nn);
+        atomicAdd(&ctr->tris_tested, (unsigned long long)nt);
+    }
+}
+
+// --------------------------------------------------------------------------------------- wavefront: shade after extend
+template <uint32_t FEAT>
+__global__ void __launch_bounds__(kThreads) k_shade_bounce(const __grid_constant__ SceneView S, RenderConst rc, PathBuffers pb, uint32_t bounce, Counters* ctr) {
+    const uint32_t n = ctr->qcount[bounce];
+    const uint32_t in = (bounce - 1) & 1u, out = bounce & 1u;
+    const bool more = int32_t(bounce) + 1 < rc.max_path_length; // with_material, render_pt.slang:80
+    const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t n_shaded = 0;
+    for (uint32_t base = warp * 32u; base < n; base += warps_total * 32u) {
+        const uint32_t j = base + lane_id();
+        const bool valid = j < n;
+        bool alive = false;
+        f3 no, nd, throughput, medium = mk3(0.f);
+        float ior = 1.f;
+        uint32_t slot = 0;
+        if (valid) {
+            const float4 ro = __ldg(pb.q_o[in] + j), rd = __ldg(pb.q_d[in] + j);
+            const uint4 hw = *reinterpret_cast<const uint4*>(pb.hits + j);
+            HitRec hr;
+            hr.tri = hw.x;
+            hr.instance = hw.y;
+            hr.u = __uint_as_float(hw.z);
+            hr.v = __uint_as_float(hw.w);
+            slot = __float_as_uint(ro.w);
+            const float4 th = pb.thr[slot];
+            float4 ra = pb.rad[slot];
+            throughput = mk3(th.x, th.y, th.z);
+            ior = th.w;
+            if (FEAT & F_TRANSMISSION) { const float4 m = pb.med[slot]; medium = mk3(m.x, m.y, m.z); }
+            const f3 o = xyz(ro), d = xyz(rd);
+            ShadingPoint sp;
+            if (hr.tri != kMiss) {
+                surface_shading_point<FEAT>(S, o, d, hr, ior, more, sp);
+                n_shaded++;
+            } else {
+                env_shading_point(S, o, d, sp);
+            }
+            // Beer-Lambert over the segment just travelled, render_pt.slang:84 (Vacuum: mu_t = 0 -> exactly 1)
+            if (FEAT & F_TRANSMISSION) {
+                if (medium.x != 0.f || medium.y != 0.f || medium.z != 0.f) throughput *= vexp(-length(o - sp.pos) * medium);
+            }
+            f3 radiance = mk3(ra.x, ra.y, ra.z) + throughput * sp.emission; // :86
+            Rng rng = make_pcg(__float_as_uint(ra.w));
+            if (more) alive = scatter<FEAT>(sp, d, rng, throughput, ior, medium, no, nd);
+            pb.rad[slot] = make_float4(radiance.x, radiance.y, radiance.z, __uint_as_float(rng.state));
+            if (alive) {
+                pb.thr[slot] = make_float4(throughput.x, throughput.y, throughput.z, ior);
+                if (FEAT & F_TRANSMISSION) pb.med[slot] = make_float4(medium.x, medium.y, medium.z, 0.f);
+            }
+        }
+        const uint32_t qi = queue_push_index(alive, &ctr->qcount[bounce + 1]);
+        if (alive) {
+            pb.q_o[out][qi] = make_float4(no.x, no.y, no.z, __uint_as_float(slot));
+            pb.q_d[out][qi] = make_float4(nd.x, nd.y, nd.z, kRayTMax);
+        }
+    }
+    // one atomic per warp for the statistics
+    for (int off = 16; off > 0; off >>= 1) n_shaded += __shfl_down_sync(0xFFFFFFFFu, n_shaded, off);
+    if (lane_id() == 0 && n_shaded) atomicAdd(&ctr->shaded_hits, (unsigned long long)n_shaded);
+}
+
+// --------------------------------------------------------------------------------------- resolve
+__global__ void __launch_bounds__(kThreads) k_resolve(RenderConst rc, PathBuffers pb, const float4* albedo, float4* out, Counters* ctr) {
+    const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix == 0) {
+        unsigned long long rays = 0;
+        for (int b = 1; b < rc.max_path_length && b < kMaxBounces; b++) rays += ctr->qcount[b];
+        atomicAdd(&ctr->rays_continuation, rays);
+    }
+    if (pix >= rc.npix) return;
+    f3 demod = mk3(1.f);
+    if ((rc.flags & MPT_RENDER_DEMODULATE_ALBEDO) && albedo) {
+        const float4 a = albedo[pix];
+        demod = vmax(mk3(a.x, a.y, a.z), 1e-2f); // gbuffer.slang:146-148
+    }
+    f3 irr = mk3(0.f);
+    float m2 = 0.f;
+    if (!rc.first_pass) {
+        const float4 prev = out[pix];
+        irr = mk3(prev.x, prev.y, prev.z);
+        m2 = prev.w;
+    }
+    for (uint32_t k = 0; k < rc.pass_k; k++) {
+        const float4 r = pb.rad[k * rc.npix + pix];
+        const f3 contrib = mk3(r.x, r.y, r.z) / demod;
+        if (finite3(contrib)) { // !any(isnan) && !any(isinf), render_pt.slang:117
+            irr += contrib;
+            const float l = yuv_luminance(contrib);
+            m2 += l * l;
+        }
+    }
+    if (rc.last_pass && rc.spp > 0 && !(rc.flags & MPT_RENDER_OUTPUT_SUM)) {
+        irr = irr / float(rc.spp);
+        m2 /= float(rc.spp);
+    }
+    out[pix] = make_float4(irr.x, irr.y, irr.z, m2);
+}
+
+// --------------------------------------------------------------------------------------- BSDF property suite on the device
+// tests/bsdf/bsdf-checks.slang:30-135 restated: one thread, XorShift32 stream, Welford means, 256x512 quadrature.
+template <uint32_t FEAT> MPT_DEV bool check_sample(const Bsdf& b, f3 wi, Rng& rng, f3& wo, float& pdf, f3& w) {
+    return bsdf_sample_eval<FEAT>(b, wi, rng, wo, pdf, w);
+}
+__global__ void k_bsdf_check(mpt_bsdf_check_params P, float* out) {
+    constexpr uint32_t FEAT = 0x3F;
+    Bsdf b;
+    b.gltf = 1u;
+    b.base = mk3(P.albedo[0], P.albedo[1], P.albedo[2]);
+    b.ax = P.alpha; b.ay = P.alpha; b.alpha = P.alpha;
+    b.metallic = 0.f; b.f0 = P.ior_f0; b.eta = 1.0f / 1.5f; b.tw = 0.f;
+    b.coat_w = 0.f; b.coat_alpha = sq(kMinRoughness);
+    b.sheen_col = mk3(0.f); b.sheen_alpha = 0.f; b.max_sheen = 0.f;
+    b.iri = 0.f; b.iri_ior = 1.3f; b.iri_thick = 400.0f;
+    switch (P.bsdf) {
+    case 0: b.gltf = 0u; break;                                                    // Lambert
+    case 1: b.metallic = 1.f; b.base = mk3(1.f); break;                            // GGX = conductor with F0 = 1
+    case 2: b.metallic = 1.f; b.base = mk3(1.f); b.ay = P.alpha_bitangent; break;  // anisotropic GGX
+    case 4: b.iri = P.iridescence; break;                                          // IridescentFresnelMix<GGX, Lambert>, eta 1/1.5
+    case 5: b.tw = 1.f; b.f0 = 0.04f; b.iri = P.iridescence; break;                // IridescentRoughDielectric
+    case 8: b.metallic = 1.f; b.base = mk3(P.f0[0], P.f0[1], P.f0[2]); break;      // Conductor: Schlick(f0) * GGX
+    default: break;
+    }
+    const f3 wi = mk3(P.wi[0], P.wi[1], P.wi[2]);
+    Rng rng;
+    rng.state = P.seed | 1u;
+    rng.xorshift = true;
+    f3 mean_w = mk3(0.f), m2_w = mk3(0.f);
+    float mean_c = 0.f, m2_c = 0.f, max_w_err = 0.f, max_p_err = 0.f;
+    uint32_t valid = 0;
+    for (uint32_t i = 0; i < P.n_samples; ++i) {
+        f3 weight = mk3(0.f), wo;
+        float c = 0.f, pdf;
+        f3 w;
+        if (check_sample<FEAT>(b, wi, rng, wo, pdf, w)) {
+            valid++;
+            weight = w;
+            c = wo.z / pdf;
+            f3 e;
+            float pr;
+            bsdf_eval_pdf<FEAT>(b, wi, wo, e, pr);
+            const float pe = fabsf(pdf - pr) / (fmaxf(fabsf(pdf), fabsf(pr)) + 1e-6f);
+            max_p_err = isfinite(pe) ? fmaxf(max_p_err, pe) : 1e30f;
+            if (pr > 0.f) {
+                const float we = length(w - e / pr);
+                max_w_err = isfinite(we) ? fmaxf(max_w_err, we) : 1e30f;
+            }
+        }
+        const float inv_i = 1.0f / float(i + 1);
+        const f3 dw = weight - mean_w;
+        mean_w += dw * inv_i;
+        m2_w += dw * (weight - mean_w);
+        const float dc = c - mean_c;
+        mean_c += dc * inv_i;
+        m2_c += dc * (c - mean_c);
+    }
+    const float inv_n = 1.0f / float(P.n_samples);
+    const uint32_t NT = 256, NP = 512;
+    const float dtheta = (kPi * 0.5f) / float(NT), dphi = kTwoPi / float(NP);
+    float pdf_int = 0.f, max_recip = 0.f;
+    for (uint32_t ti = 0; ti < NT; ++ti) {
+        const float theta = (float(ti) + 0.5f) * dtheta, ct = cosf(theta), st = sinf(theta);
+        for (uint32_t pi = 0; pi < NP; ++pi) {
+            const float phi = (float(pi) + 0.5f) * dphi;
+            const f3 wo = mk3(st * cosf(phi), st * sinf(phi), ct);
+            f3 e1, e2;
+            float p1, p2;
+            bsdf_eval_pdf<FEAT>(b, wi, wo, e1, p1);
+            bsdf_eval_pdf<FEAT>(b, wo, wi, e2, p2);
+            pdf_int += p1 * st * dtheta * dphi;
+            const f3 fio = e1 / wo.z, foi = e2 / wi.z;
+            const f3 dd = mk3(fabsf(fio.x - foi.x), fabsf(fio.y - foi.y), fabsf(fio.z - foi.z));
+            const f3 mm = mk3(fmaxf(fabsf(fio.x), fabsf(foi.x)), fmaxf(fabsf(fio.y), fabsf(foi.y)), fmaxf(fabsf(fio.z), fabsf(foi.z))) + 1e-6f;
+            const float r = fmaxf(fmaxf(dd.x / mm.x, dd.y / mm.y), dd.z / mm.z);
+            max_recip = isfinite(r) ? fmaxf(max_recip, r) : 1e30f;
+        }
+    }
+    out[0] = mean_w.x; out[1] = mean_w.y; out[2] = mean_w.z;
+    out[3] = sqrtf(m2_w.x) * inv_n; out[4] = sqrtf(m2_w.y) * inv_n; out[5] = sqrtf(m2_w.z) * inv_n;
+    out[6] = mean_c; out[7] = sqrtf(m2_c) * inv_n; out[8] = float(valid);
+    out[9] = max_w_err; out[10] = max_p_err; out[11] = pdf_int; out[12] = max_recip;
+    out[13] = out[14] = out[15] = 0.f; // get_albedo is a denoiser guide, not on the pt path
+}
+
+} // namespace
+
+// ======================================================================================= host side
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    cudaError_t ensure(size_t n) {
+        if (n <= bytes) return cudaSuccess;
+        release();
+        if (n == 0) return cudaSuccess;
+        const cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) bytes = n;
+        return e;
+    }
+    cudaError_t upload(const void* src, size_t n) {
+        const cudaError_t e = ensure(n ? n : 16);
+        if (e != cudaSuccess || n == 0) return e;
+        return cudaMemcpy(p, src, n, cudaMemcpyHostToDevice);
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct TextureSlot {
+    cudaArray_t array = nullptr;
+    cudaTextureObject_t obj = 0;
+};
+
+} // namespace
+
+struct mpt_context {
+    int device = 0;
+    int sm_count = 148;
+    std::string error;
+    // scene
+    DevBuf nodes, tris, tri_attr, geometries, prim_to_tri, instances, tlas_prims, xform, xform_it;
+    DevBuf materials, material_types, texture_table, env_pixels;
+    std::vector<TextureSlot> textures;
+    SceneView view{};
+    uint32_t feature_union = 0;
+    bool scene_ready = false, materials_ready = false;
+    mpt_bvh_info bvh_info{};
+    // wavefront pool
+    DevBuf q_o[2], q_d[2], hits, thr, rad, med, counters, tex1_internal, stage_tex1, stage_albedo, stage_out;
+    size_t pool_slots = 0;
+    // stats / profiling
+    uint32_t profile_flags = 0;
+    mpt_stats stats{};
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_extend, ev_shade;
+    size_t ev_extend_used = 0, ev_shade_used = 0;
+};
+
+namespace {
+
+mpt_status fail(mpt_context* c, mpt_status s, const std::string& msg) {
+    if (c) c->error = msg;
+    else g_create_error = msg;
+    return s;
+}
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        const cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) return fail(ctx, MPT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+CameraParams to_device_camera(const mpt_camera& c) {
+    CameraParams p;
+    p.position = {c.position[0], c.position[1], c.position[2]};
+    p.U = {c.U[0], c.U[1], c.U[2]};
+    p.V = {c.V[0], c.V[1], c.V[2]};
+    p.W = {c.W[0], c.W[1], c.W[2]};
+    p.near_plane = c.near_plane;
+    p.far_plane = c.far_plane;
+    p.jitter_x = c.jitter[0];
+    p.jitter_y = c.jitter[1];
+    return p;
+}
+
+void invert_affine(const float* m, float* o) { // row-major 3x4
+    const double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], i = m[10];
+    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    const double id = 1.0 / det;
+    const double r[9] = {(e * i - f * h) * id, (c * h - b * i) * id, (b * f - c * e) * id, (f * g - d * i) * id, (a * i - c * g) * id,
+                         (c * d - a * f) * id, (d * h - e * g) * id, (b * g - a * h) * id, (a * e - b * d) * id};
+    for (int row = 0; row < 3; row++) {
+        for (int col = 0; col < 3; col++) o[row * 4 + col] = float(r[row * 3 + col]);
+        o[row * 4 + 3] = float(-(r[row * 3] * m[3] + r[row * 3 + 1] * m[7] + r[row * 3 + 2] * m[11]));
+    }
+}
+
+inline uint32_t fbits(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline float bitsf(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+
+template <class F> void time_launch(mpt_context* ctx, bool is_extend, cudaStream_t st, F&& launch) {
+    if (!(ctx->profile_flags & 2u)) { launch(); return; }
+    auto& pool = is_extend ? ctx->ev_extend : ctx->ev_shade;
+    size_t& used = is_extend ? ctx->ev_extend_used : ctx->ev_shade_used;
+    if (used == pool.size()) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        pool.emplace_back(a, b);
+    }
+    cudaEventRecord(pool[used].first, st);
+    launch();
+    cudaEventRecord(pool[used].second, st);
+    used++;
+}
+
+void harvest_events(mpt_context* ctx) {
+    for (int which = 0; which < 2; which++) {
+        auto& pool = which ? ctx->ev_shade : ctx->ev_extend;
+        size_t& used = which ? ctx->ev_shade_used : ctx->ev_extend_used;
+        for (size_t i = 0; i < used; i++) {
+            cudaEventSynchronize(pool[i].second);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, pool[i].first, pool[i].second);
+            if (which) { ctx->stats.shade_ms += ms; ctx->stats.shade_launches++; }
+            else { ctx->stats.extend_ms += ms; ctx->stats.extend_launches++; }
+        }
+        used = 0;
+    }
+}
+
+mpt_status ensure_pool(mpt_context* ctx, size_t slots, bool need_medium) {
+    if (slots > ctx->pool_slots) {
+        for (int i = 0; i < 2; i++) {
+            CU(ctx->q_o[i].ensure(slots * sizeof(float4)));
+            CU(ctx->q_d[i].ensure(slots * sizeof(float4)));
+        }
+        CU(ctx->hits.ensure(slots * sizeof(HitRec)));
+        CU(ctx->thr.ensure(slots * sizeof(float4)));
+        CU(ctx->rad.ensure(slots * sizeof(float4)));
+        ctx->pool_slots = slots;
+    }
+    if (need_medium) CU(ctx->med.ensure(ctx->pool_slots * sizeof(float4)));
+    if (!ctx->counters.p) {
+        CU(ctx->counters.ensure(sizeof(Counters)));
+        CU(cudaMemset(ctx->counters.p, 0, sizeof(Counters)));
+    }
+    return MPT_OK;
+}
+
+template <uint32_t FEAT>
+mpt_status run_passes(mpt_context* ctx, const CameraParams& cam, const mpt_render_params& P, const PackedHitInfo* tex1, const float4* albedo,
+                      float4* out, cudaStream_t st) {
+    const uint32_t npix = P.width * P.height;
+    const uint32_t K = uint32_t(std::max<size_t>(1, std::min<size_t>(size_t(std::max(P.spp, 1)), ctx->pool_slots / npix)));
+    PathBuffers pb;
+    for (int i = 0; i < 2; i++) { pb.q_o[i] = ctx->q_o[i].as<float4>(); pb.q_d[i] = ctx->q_d[i].as<float4>(); }
+    pb.hits = ctx->hits.as<HitRec>();
+    pb.thr = ctx->thr.as<float4>();
+    pb.rad = ctx->rad.as<float4>();
+    pb.med = ctx->med.as<float4>();
+    Counters* ctr = ctx->counters.as<Counters>();
+    const bool count = ctx->profile_flags & 1u;
+    const int L = std::min(P.max_path_length, kMaxBounces);
+    const uint32_t persistent_blocks = uint32_t(ctx->sm_count) * 8u;
+    const uint32_t pix_blocks = (npix + kThreads - 1) / kThreads;
+
+    RenderConst rc{};
+    rc.width = P.width; rc.height = P.height; rc.npix = npix; rc.frame = P.frame; rc.max_path_length = L;
+    rc.instance_mask = P.instance_mask; rc.flags = P.flags; rc.sample_offset = P.sample_offset; rc.sample_stride = P.sample_stride;
+    rc.spp = P.spp;
+
+    const uint32_t total = uint32_t(std::max(P.spp, 0));
+    uint32_t done = 0;
+    bool first = true;
+    do {
+        const uint32_t k = std::min(K, total - done);
+        rc.pass_first = done;
+        rc.pass_k = k;
+        rc.first_pass = first;
+        rc.last_pass = (done + k >= total);
+        CU(cudaMemsetAsync(ctr, 0, offsetof(Counters, rays_continuation), st));
+        time_launch(ctx, false, st, [&] { k_shade_primary<FEAT><<<pix_blocks, kThreads, 0, st>>>(ctx->view, cam, rc, tex1, pb, ctr); });
+        ctx->stats.kernel_launches++;
+        for (int b = 1; b < L; b++) {
+            const uint32_t in = uint32_t(b - 1) & 1u;
+            time_launch(ctx, true, st, [&] {
+                if (count) k_extend<true><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, pb.q_o[in], pb.q_d[in], pb.hits, uint32_t(b), P.instance_mask, ctr);
+                else k_extend<false><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, pb.q_o[in], pb.q_d[in], pb.hits, uint32_t(b), P.instance_mask, ctr);
+            });
+            time_launch(ctx, false, st, [&] { k_shade_bounce<FEAT><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, rc, pb, uint32_t(b), ctr); });
+            ctx->stats.kernel_launches += 2;
+        }
+        k_resolve<<<pix_blocks, kThreads, 0, st>>>(rc, pb, albedo, out, ctr);
+        ctx->stats.kernel_launches++;
+        done += k;
+        first = false;
+    } while (done < total);
+    CU(cudaGetLastError());
+    ctx->stats.samples += uint64_t(npix) * total;
+    return MPT_OK;
+}
+
+} // namespace
+
+// ======================================================================================= C-ABI
+extern "C" {
+
+MPT_API uint32_t mpt_abi_version(void) { return MPT_ABI_VERSION; }
+
+MPT_API const char* mpt_last_error(const mpt_context* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+MPT_API mpt_status mpt_create(int device, mpt_context** out_ctx) {
+    mpt_context* ctx = nullptr;
+    if (!out_ctx) return fail(nullptr, MPT_ERR_INVALID_ARGUMENT, "out_ctx is NULL");
+    *out_ctx = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) return fail(nullptr, MPT_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, MPT_ERR_INVALID_ARGUMENT, "device index out of range");
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) // the library carries sm_100a code only; there is no fallback path
+        return fail(nullptr, MPT_ERR_UNSUPPORTED, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", libmpt needs sm_100 (B200)");
+    CU(cudaSetDevice(device));
+    ctx = new mpt_context();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->view.env_type = 0;
+    *out_ctx = ctx;
+    return MPT_OK;
+}
+
+MPT_API void mpt_destroy(mpt_context* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& t : ctx->textures) {
+        if (t.obj) cudaDestroyTextureObject(t.obj);
+        if (t.array) cudaFreeArray(t.array);
+    }
+    for (auto* pool : {&ctx->ev_extend, &ctx->ev_shade})
+        for (auto& p : *pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
+    delete ctx;
+}
+
+MPT_API mpt_status mpt_scene_upload(mpt_context* ctx, const mpt_scene_desc* d) {
+    if (!ctx || !d) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    ctx->scene_ready = false;
+    if (d->instance_count == 0 || d->blas_count == 0) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "scene has no instances");
+    if (d->instance_count > 0xFFFFu) return fail(ctx, MPT_ERR_LIMIT, "more than 65535 TLAS instances (PackedHitInfo.instance_index is 16 bit, gbuffer.slang:44)");
+    const auto t_start = std::chrono::steady_clock::now();
+
+    std::vector<Bvh8Node> nodes;
+    std::vector<float4> tris;
+    std::vector<uint4> attrs;
+    std::vector<uint32_t> prim_to_tri;
+    std::vector<uint32_t> blas_root(d->blas_count);
+    std::vector<Box> blas_bounds(d->blas_count);
+    std::vector<std::vector<uint32_t>> blas_geom_offset(d->blas_count);
+
+    for (uint32_t bi = 0; bi < d->blas_count; bi++) {
+        const mpt_blas_desc& bd = d->blas[bi];
+        if (bd.mesh_count > 0xFFFFu) return fail(ctx, MPT_ERR_LIMIT, "more than 65535 geometries in one BLAS (PackedHitInfo.geometry_index is 16 bit)");
+        struct Ref { uint32_t geom, prim; };
+        std::vector<Ref> refs;
+        std::vector<Box> boxes;
+        blas_geom_offset[bi].resize(bd.mesh_count);
+        for (uint32_t g = 0; g < bd.mesh_count; g++) {
+            if (bd.meshes[g] >= d->mesh_count) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "BLAS references a mesh out of range");
+            const mpt_mesh_desc& m = d->meshes[bd.meshes[g]];
+            blas_geom_offset[bi][g] = uint32_t(prim_to_tri.size() + refs.size());
+            for (uint32_t p = 0; p < m.primitive_count; p++) {
+                uint32_t ia, ib, ic;
+                if (m.index_flag == MPT_GEOM_INDEX_U32) { const uint32_t* ix = (const uint32_t*)m.indices + size_t(p) * 3; ia = ix[0]; ib = ix[1]; ic = ix[2]; }
+                else if (m.index_flag == MPT_GEOM_INDEX_U16) { const uint16_t* ix = (const uint16_t*)m.indices + size_t(p) * 3; ia = ix[0]; ib = ix[1]; ic = ix[2]; }
+                else if (m.index_flag == MPT_GEOM_INDEX_U8) { const uint8_t* ix = (const uint8_t*)m.indices + size_t(p) * 3; ia = ix[0]; ib = ix[1]; ic = ix[2]; }
+                else { ia = p * 3; ib = ia + 1; ic = ia + 2; }
+                if (ia >= m.vertex_count || ib >= m.vertex_count || ic >= m.vertex_count) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "vertex index out of range");
+                Box bx;
+                for (int a = 0; a < 3; a++) {
+                    const float x0 = m.vertices[ia].position[a], x1 = m.vertices[ib].position[a], x2 = m.vertices[ic].position[a];
+                    bx.lo[a] = std::min(x0, std::min(x1, x2));
+                    bx.hi[a] = std::max(x0, std::max(x1, x2));
+                }
+                boxes.push_back(bx);
+                refs.push_back({g, p});
+            }
+        }
+        Bvh8 bvh;
+        build_bvh8(boxes.data(), uint32_t(boxes.size()), bvh);
+        const uint32_t node_off = uint32_t(nodes.size()), tri_off = uint32_t(tris.size() / 3);
+        blas_root[bi] = node_off;
+        blas_bounds[bi] = bvh.bounds;
+        for (Bvh8Node nd : bvh.nodes) {
+            nd.child_base += node_off;
+            nd.prim_base += tri_off;
+            nodes.push_back(nd);
+        }
+        const size_t p2t_base = prim_to_tri.size();
+        prim_to_tri.resize(p2t_base + refs.size());
+        for (uint32_t k = 0; k < bvh.prim_order.size(); k++) {
+            const uint32_t ri = bvh.prim_order[k];
+            const Ref r = refs[ri];
+            const mpt_mesh_desc& m = d->meshes[bd.meshes[r.geom]];
+            uint32_t ix[3];
+            if (m.index_flag == MPT_GEOM_INDEX_U32) { const uint32_t* q = (const uint32_t*)m.indices + size_t(r.prim) * 3; ix[0] = q[0]; ix[1] = q[1]; ix[2] = q[2]; }
+            else if (m.index_flag == MPT_GEOM_INDEX_U16) { const uint16_t* q = (const uint16_t*)m.indices + size_t(r.prim) * 3; ix[0] = q[0]; ix[1] = q[1]; ix[2] = q[2]; }
+            else if (m.index_flag == MPT_GEOM_INDEX_U8) { const uint8_t* q = (const uint8_t*)m.indices + size_t(r.prim) * 3; ix[0] = q[0]; ix[1] = q[1]; ix[2] = q[2]; }
+            else { ix[0] = r.prim * 3; ix[1] = ix[0] + 1; ix[2] = ix[0] + 2; }
+            const uint32_t w[3] = {r.prim, r.geom, m.opaque ? 0u : kTriNonOpaque};
+            uint32_t aw[12] = {0};
+            for (int c = 0; c < 3; c++) {
+                const mpt_packed_vertex& v = m.vertices[ix[c]];
+                tris.push_back(make_float4(v.position[0], v.position[1], v.position[2], bitsf(w[c])));
+                aw[c * 3 + 0] = v.encoded_normal;
+                aw[c * 3 + 1] = uint32_t(v.uv[0]) | (uint32_t(v.uv[1]) << 16);
+                aw[c * 3 + 2] = v.encoded_tangent;
+            }
+            attrs.push_back(make_uint4(aw[0], aw[1], aw[2], aw[3]));
+            attrs.push_back(make_uint4(aw[4], aw[5], aw[6], aw[7]));
+            attrs.push_back(make_uint4(aw[8], 0, 0, 0));
+            prim_to_tri[p2t_base + ri] = tri_off + k;
+        }
+    }
+
+    // ---- instances + TLAS
+    std::vector<InstanceRec> inst(d->instance_count);
+    std::vector<Box> ibox(d->instance_count);
+    bool identity_single = d->instance_count == 1;
+    for (uint32_t i = 0; i < d->instance_count; i++) {
+        const mpt_instance_desc& in = d->instances[i];
+        if (in.blas >= d->blas_count) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "instance references a BLAS out of range");
+        float inv[12];
+        invert_affine(in.transform, inv);
+        inst[i].inv0 = make_float4(inv[0], inv[1], inv[2], inv[3]);
+        inst[i].inv1 = make_float4(inv[4], inv[5], inv[6], inv[7]);
+        inst[i].inv2 = make_float4(inv[8], inv[9], inv[10], inv[11]);
+        inst[i].blas_root = blas_root[in.blas];
+        inst[i].custom_index = in.instance_custom_index;
+        inst[i].mask_flags = (in.mask & 0xFFu) | ((in.flags & 0xFFu) << 8);
+        inst[i].pad = 0;
+        static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+        if (std::memcmp(in.transform, ident, sizeof(ident)) != 0) identity_single = false;
+        const Box& ob = blas_bounds[in.blas];
+        Box wb;
+        for (int a = 0; a < 3; a++) { wb.lo[a] = 3e38f; wb.hi[a] = -3e38f; }
+        for (int k = 0; k < 8; k++) {
+            const float p[3] = {(k & 1) ? ob.hi[0] : ob.lo[0], (k & 2) ? ob.hi[1] : ob.lo[1], (k & 4) ? ob.hi[2] : ob.lo[2]};
+            for (int a = 0; a < 3; a++) {
+                const float* m = in.transform + a * 4;
+                const float v = m[0] * p[0] + m[1] * p[1] + m[2] * p[2] + m[3];
+                wb.lo[a] = std::min(wb.lo[a], v);
+                wb.hi[a] = std::max(wb.hi[a], v);
+            }
+        }
+        for (int a = 0; a < 3; a++) { // the object-space test is exact; the world box only prunes
+            const float pad = (wb.hi[a] - wb.lo[a]) * 1e-5f + 1e-6f;
+            wb.lo[a] -= pad;
+            wb.hi[a] += pad;
+        }
+        ibox[i] = wb;
+    }
+    std::vector<uint32_t> tlas_prims;
+    uint32_t root = blas_root[d->instances[0].blas];
+    if (!identity_single) {
+        Bvh8 tl;
+        build_bvh8(ibox.data(), d->instance_count, tl);
+        const uint32_t node_off = uint32_t(nodes.size());
+        root = node_off;
+        for (Bvh8Node nd : tl.nodes) {
+            nd.child_base += node_off;
+            nodes.push_back(nd); // prim_base indexes tlas_prims directly
+        }
+        tlas_prims = tl.prim_order;
+    }
+
+    // ---- geometry table
+    std::vector<uint4> geoms(d->geometry_count);
+    for (uint32_t g = 0; g < d->geometry_count; g++)
+        geoms[g] = make_uint4(uint32_t(d->geometries[g].material_id) | (uint32_t(d->geometries[g].flags) << 16), d->geometries[g].primitive_count, 0u, 0u);
+    for (uint32_t i = 0; i < d->instance_count; i++) {
+        const mpt_instance_desc& in = d->instances[i];
+        const mpt_blas_desc& bd = d->blas[in.blas];
+        for (uint32_t g = 0; g < bd.mesh_count; g++) {
+            const uint32_t gid = in.instance_custom_index + g;
+            if (gid >= d->geometry_count) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "instance_custom_index + geometry_index exceeds the geometry table");
+            if (d->geometries[gid].mesh != bd.meshes[g]) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "geometry table does not match the BLAS mesh list");
+            geoms[gid].z = blas_geom_offset[in.blas][g];
+        }
+    }
+
+    CU(ctx->nodes.upload(nodes.data(), nodes.size() * sizeof(Bvh8Node)));
+    CU(ctx->tris.upload(tris.data(), tris.size() * sizeof(float4)));
+    CU(ctx->tri_attr.upload(attrs.data(), attrs.size() * sizeof(uint4)));
+    CU(ctx->prim_to_tri.upload(prim_to_tri.data(), prim_to_tri.size() * 4));
+    CU(ctx->instances.upload(inst.data(), inst.size() * sizeof(InstanceRec)));
+    CU(ctx->tlas_prims.upload(tlas_prims.data(), tlas_prims.size() * 4));
+    CU(ctx->geometries.upload(geoms.data(), geoms.size() * sizeof(uint4)));
+    std::vector<float> ident(size_t(d->instance_count) * 16, 0.f);
+    for (uint32_t i = 0; i < d->instance_count; i++) ident[i * 16] = ident[i * 16 + 5] = ident[i * 16 + 10] = ident[i * 16 + 15] = 1.f;
+    CU(ctx->xform.upload(d->instance_transforms ? d->instance_transforms : ident.data(), size_t(d->instance_count) * 64));
+    CU(ctx->xform_it.upload(d->inverse_transposed_instance_transforms ? d->inverse_transposed_instance_transforms : ident.data(), size_t(d->instance_count) * 64));
+
+    SceneView& v = ctx->view;
+    v.accel.nodes = ctx->nodes.as<float4>();
+    v.accel.tris = ctx->tris.as<float4>();
+    v.accel.instances = ctx->instances.as<InstanceRec>();
+    v.accel.tlas_prims = ctx->tlas_prims.as<uint32_t>();
+    v.accel.root = root;
+    v.accel.two_level = identity_single ? 0u : 1u;
+    v.tri_attr = ctx->tri_attr.as<uint4>();
+    v.geometries = ctx->geometries.as<uint4>();
+    v.prim_to_tri = ctx->prim_to_tri.as<uint32_t>();
+    v.inst_xform = ctx->xform.as<float4>();
+    v.inst_xform_it = ctx->xform_it.as<float4>();
+
+    ctx->bvh_info.node_count = nodes.size();
+    ctx->bvh_info.triangle_count = tris.size() / 3;
+    ctx->bvh_info.node_bytes = nodes.size() * sizeof(Bvh8Node);
+    ctx->bvh_info.triangle_bytes = tris.size() * sizeof(float4);
+    ctx->bvh_info.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
+    ctx->scene_ready = true;
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_materials_upload(mpt_context* ctx, const void* entries, uint32_t entry_size, uint32_t material_count,
+                                        const mpt_material_type* types, uint32_t type_count) {
+    if (!ctx || (!entries && material_count) || !types) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (entry_size % 4 != 0 || entry_size < 20) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "material entry size must be a multiple of 4 and hold header + base colour");
+    CU(cudaSetDevice(ctx->device));
+    ctx->feature_union = 0;
+    std::vector<uint2> tt(type_count);
+    for (uint32_t i = 0; i < type_count; i++) {
+        if (types[i].model > MPT_MATERIAL_GLTF) return fail(ctx, MPT_ERR_UNSUPPORTED, "unknown material model");
+        tt[i] = make_uint2(types[i].model, types[i].features);
+        ctx->feature_union |= types[i].features;
+    }
+    for (uint32_t i = 0; i < material_count; i++) {
+        uint16_t tid;
+        std::memcpy(&tid, (const uint8_t*)entries + size_t(i) * entry_size, 2);
+        if (tid >= type_count) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "material_model_type_id out of range");
+        if (types[tid].model == MPT_MATERIAL_GLTF && entry_size < 60) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "glTF material entry smaller than its core payload");
+    }
+    CU(ctx->materials.upload(entries, size_t(entry_size) * material_count));
+    CU(ctx->material_types.upload(tt.data(), tt.size() * sizeof(uint2)));
+    ctx->view.materials = ctx->materials.as<uint32_t>();
+    ctx->view.material_stride_words = entry_size / 4;
+    ctx->view.material_types = ctx->material_types.as<uint2>();
+    ctx->materials_ready = true;
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_texture_upload(mpt_context* ctx, uint32_t texture_id, uint32_t width, uint32_t height, uint32_t format, uint32_t wrap_u,
+                                      uint32_t wrap_v, uint32_t filter, const void* pixels) {
+    if (!ctx || !pixels || width == 0 || height == 0) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "bad texture");
+    if (texture_id >= 0xFFFFu) return fail(ctx, MPT_ERR_LIMIT, "TextureID is 16 bit");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->textures.size() <= texture_id) ctx->textures.resize(texture_id + 1);
+    TextureSlot& slot = ctx->textures[texture_id];
+    if (slot.obj) { cudaDestroyTextureObject(slot.obj); slot.obj = 0; }
+    if (slot.array) { cudaFreeArray(slot.array); slot.array = nullptr; }
+    const bool f32 = format == MPT_TEX_RGBA32F;
+    const cudaChannelFormatDesc cd = f32 ? cudaCreateChannelDesc<float4>() : cudaCreateChannelDesc<uchar4>();
+    CU(cudaMallocArray(&slot.array, &cd, width, height));
+    const size_t pitch = size_t(width) * (f32 ? 16 : 4);
+    CU(cudaMemcpy2DToArray(slot.array, 0, 0, pixels, pitch, pitch, height, cudaMemcpyHostToDevice));
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = slot.array;
+    cudaTextureDesc td{};
+    auto am = [](uint32_t w) { return w == MPT_WRAP_CLAMP_TO_EDGE ? cudaAddressModeClamp : (w == MPT_WRAP_MIRRORED_REPEAT ? cudaAddressModeMirror : cudaAddressModeWrap); };
+    td.addressMode[0] = am(wrap_u);
+    td.addressMode[1] = am(wrap_v);
+    td.filterMode = filter == MPT_FILTER_NEAREST ? cudaFilterModePoint : cudaFilterModeLinear;
+    td.readMode = f32 ? cudaReadModeElementType : cudaReadModeNormalizedFloat;
+    td.sRGB = format == MPT_TEX_RGBA8_SRGB ? 1 : 0;
+    td.normalizedCoords = 1;
+    CU(cudaCreateTextureObject(&slot.obj, &rd, &td, nullptr));
+    std::vector<TextureRec> table(ctx->textures.size());
+    for (size_t i = 0; i < table.size(); i++) { table[i].obj = ctx->textures[i].obj; table[i].valid = ctx->textures[i].obj != 0; table[i].pad = 0; }
+    CU(ctx->texture_table.upload(table.data(), table.size() * sizeof(TextureRec)));
+    ctx->view.textures = ctx->texture_table.as<TextureRec>();
+    ctx->view.texture_count = uint32_t(table.size());
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_env_set(mpt_context* ctx, uint32_t type, const float* to_local, float intensity, uint32_t width, uint32_t height,
+                               const float* rgba32f) {
+    if (!ctx) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL context");
+    CU(cudaSetDevice(ctx->device));
+    if (type == MPT_ENV_EMPTY) { ctx->view.env_type = 0; return MPT_OK; }
+    if (type != MPT_ENV_LATLONG) return fail(ctx, MPT_ERR_UNSUPPORTED, "only Empty and LatLong environment maps are supported");
+    if (!to_local || !rgba32f || !width || !height) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "bad env map");
+    CU(ctx->env_pixels.upload(rgba32f, size_t(width) * height * 16));
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) ctx->view.env_m[r * 3 + c] = to_local[r * 4 + c];
+    ctx->view.env_intensity = intensity;
+    ctx->view.env_pixels = ctx->env_pixels.as<float4>();
+    ctx->view.env_w = width;
+    ctx->view.env_h = height;
+    ctx->view.env_type = 1;
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_primary_visibility(mpt_context* ctx, const mpt_camera* camera, uint32_t width, uint32_t height, uint32_t instance_mask,
+                                          void* d_tex1, void* stream) {
+    if (!ctx || !camera || !d_tex1 || !width || !height) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!ctx->scene_ready || !ctx->materials_ready) return fail(ctx, MPT_ERR_NOT_READY, "scene or materials not uploaded");
+    if (camera->aperture_radius > 0.f) return fail(ctx, MPT_ERR_UNSUPPORTED, "thin-lens camera is out of scope (pinhole only)");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!ctx->counters.p) { CU(ctx->counters.ensure(sizeof(Counters))); CU(cudaMemset(ctx->counters.p, 0, sizeof(Counters))); }
+    const uint32_t tiles = ((width + 7) / 8) * ((height + 3) / 4);
+    const uint32_t blocks = (tiles * 32 + kThreads - 1) / kThreads;
+    const CameraParams cam = to_device_camera(*camera);
+    if (ctx->profile_flags & 1u) k_primary<true><<<blocks, kThreads, 0, st>>>(ctx->view, cam, width, height, instance_mask, (PackedHitInfo*)d_tex1, ctx->counters.as<Counters>());
+    else k_primary<false><<<blocks, kThreads, 0, st>>>(ctx->view, cam, width, height, instance_mask, (PackedHitInfo*)d_tex1, ctx->counters.as<Counters>());
+    CU(cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    ctx->stats.rays_primary += uint64_t(width) * height;
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_trace(mpt_context* ctx, const void* d_rays, uint64_t n, uint32_t instance_mask, void* d_hits, void* stream) {
+    if (!ctx || (!d_rays && n) || (!d_hits && n)) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!ctx->scene_ready || !ctx->materials_ready) return fail(ctx, MPT_ERR_NOT_READY, "scene or materials not uploaded");
+    if (n == 0) return MPT_OK;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!ctx->counters.p) { CU(ctx->counters.ensure(sizeof(Counters))); CU(cudaMemset(ctx->counters.p, 0, sizeof(Counters))); }
+    const uint32_t blocks = uint32_t((n + kThreads - 1) / kThreads);
+    if (ctx->profile_flags & 1u) k_trace<true><<<blocks, kThreads, 0, st>>>(ctx->view, (const float4*)d_rays, n, instance_mask, (uint32_t*)d_hits, ctx->counters.as<Counters>());
+    else k_trace<false><<<blocks, kThreads, 0, st>>>(ctx->view, (const float4*)d_rays, n, instance_mask, (uint32_t*)d_hits, ctx->counters.as<Counters>());
+    CU(cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    ctx->stats.rays_continuation += n;
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_render(mpt_context* ctx, const mpt_camera* camera, const mpt_render_params* P, const void* d_tex1, const void* d_albedo,
+                              void* d_irradiance, void* stream) {
+    if (!ctx || !camera || !P || !d_irradiance) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!ctx->scene_ready || !ctx->materials_ready) return fail(ctx, MPT_ERR_NOT_READY, "scene or materials not uploaded");
+    if (!P->width || !P->height || P->spp < 0 || P->max_path_length < 1 || P->sample_stride == 0) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "bad render parameters");
+    if (camera->aperture_radius > 0.f) return fail(ctx, MPT_ERR_UNSUPPORTED, "thin-lens camera is out of scope (pinhole only)");
+    if (P->flags & MPT_RENDER_NEE) return fail(ctx, MPT_ERR_UNSUPPORTED, "MPT_RENDER_NEE is not implemented yet");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t npix = size_t(P->width) * P->height;
+    // K samples per pixel in flight: about 8M path slots, at least one sample per pixel
+    const size_t want = std::max<size_t>(npix, std::min<size_t>(npix * size_t(std::max(P->spp, 1)), size_t(8) << 20));
+    const size_t slots = (want / npix) * npix;
+    const mpt_status ps = ensure_pool(ctx, slots, (ctx->feature_union & MPT_GLTF_TRANSMISSION) != 0);
+    if (ps != MPT_OK) return ps;
+    const PackedHitInfo* tex1 = (const PackedHitInfo*)d_tex1;
+    if (!tex1) {
+        CU(ctx->tex1_internal.ensure(npix * sizeof(PackedHitInfo)));
+        const mpt_status s = mpt_primary_visibility(ctx, camera, P->width, P->height, P->instance_mask, ctx->tex1_internal.p, stream);
+        if (s != MPT_OK) return s;
+        tex1 = ctx->tex1_internal.as<PackedHitInfo>();
+    }
+    const CameraParams cam = to_device_camera(*camera);
+    if (P->spp == 0) { CU(cudaMemsetAsync(d_irradiance, 0, npix * 16, st)); return MPT_OK; }
+    if (ctx->feature_union == 0) return run_passes<0u>(ctx, cam, *P, tex1, (const float4*)d_albedo, (float4*)d_irradiance, st);
+    return run_passes<0x3Fu>(ctx, cam, *P, tex1, (const float4*)d_albedo, (float4*)d_irradiance, st);
+}
+
+MPT_API mpt_status mpt_render_host(mpt_context* ctx, const mpt_camera* camera, const mpt_render_params* P, const void* h_tex1, const void* h_albedo,
+                                   void* h_irradiance, void* stream) {
+    if (!ctx || !P || !h_irradiance) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t npix = size_t(P->width) * P->height;
+    CU(ctx->stage_out.ensure(npix * 16));
+    void* d_tex1 = nullptr;
+    void* d_albedo = nullptr;
+    if (h_tex1) {
+        CU(ctx->stage_tex1.ensure(npix * 16));
+        CU(cudaMemcpyAsync(ctx->stage_tex1.p, h_tex1, npix * 16, cudaMemcpyHostToDevice, st));
+        d_tex1 = ctx->stage_tex1.p;
+    }
+    if (h_albedo) {
+        CU(ctx->stage_albedo.ensure(npix * 16));
+        CU(cudaMemcpyAsync(ctx->stage_albedo.p, h_albedo, npix * 16, cudaMemcpyHostToDevice, st));
+        d_albedo = ctx->stage_albedo.p;
+    }
+    const mpt_status s = mpt_render(ctx, camera, P, d_tex1, d_albedo, ctx->stage_out.p, stream);
+    if (s != MPT_OK) return s;
+    CU(cudaMemcpyAsync(h_irradiance, ctx->stage_out.p, npix * 16, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_set_profiling(mpt_context* ctx, uint32_t profile_flags) {
+    if (!ctx) return MPT_ERR_INVALID_ARGUMENT;
+    ctx->profile_flags = profile_flags;
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_get_stats(mpt_context* ctx, mpt_stats* out) {
+    if (!ctx || !out) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    harvest_events(ctx);
+    *out = ctx->stats;
+    if (ctx->counters.p) {
+        Counters c;
+        CU(cudaMemcpy(&c, ctx->counters.p, sizeof(Counters), cudaMemcpyDeviceToHost));
+        out->rays_continuation += c.rays_continuation;
+        out->shaded_hits += c.shaded_hits;
+        out->nodes_visited += c.nodes_visited;
+        out->tris_tested += c.tris_tested;
+    }
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_reset_stats(mpt_context* ctx) {
+    if (!ctx) return MPT_ERR_INVALID_ARGUMENT;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    harvest_events(ctx);
+    ctx->stats = mpt_stats{};
+    if (ctx->counters.p) CU(cudaMemset(ctx->counters.p, 0, sizeof(Counters)));
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_bvh_get_info(mpt_context* ctx, mpt_bvh_info* out) {
+    if (!ctx || !out) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!ctx->scene_ready) return fail(ctx, MPT_ERR_NOT_READY, "scene not uploaded");
+    *out = ctx->bvh_info;
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_bsdf_check(mpt_context* ctx, const mpt_bsdf_check_params* p, float* out16) {
+    if (!ctx || !p || !out16) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (p->bsdf == 3 || p->bsdf == 6 || p->bsdf == 7 || p->bsdf > 8) return fail(ctx, MPT_ERR_UNSUPPORTED, "BSDF configuration is not a sub-tree of GltfBSDF");
+    CU(cudaSetDevice(ctx->device));
+    DevBuf o;
+    CU(o.ensure(64));
+    k_bsdf_check<<<1, 1>>>(*p, o.as<float>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(out16, o.p, 64, cudaMemcpyDeviceToHost));
+    return MPT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,417 @@
+// shading.cuh — device scene tables and the shading-point / material-sample evaluation.
+//
+// Replaces Scene::get_triangle_hit / get_surface / get_shading_point / _make_environment_map_shading_point
+// (include/merian-shaders/scene/scene.slang:312-382, 418-498), MaterialSystem::get_material_sample
+// (shading/materials/material-system.slang:51-72) with DiffuseMaterial (diffuse-material.slang:19-34) and
+// GltfMaterial (gltf-material.slang:153-308), LatLongMap::eval (scene/environment-map.slang:23-35),
+// ShadingPoint::make_ray (scene/hit.slang:134-147).
+//
+// Data layout in HBM (all 16-byte aligned, read with 128-bit loads):
+//   tris      3 x float4 per triangle record  v0|primitive_id, v1|geometry_index, v2|flags      (shared with traversal)
+//   tri_attr  3 x uint4  per triangle record  per corner: oct normal, half2 uv, oct tangent     (9 words + 3 pad)
+//   geometry  1 x uint4  per GeometryID       material_id|flags<<16, primitive_count, prim->tri offset, -
+// so a shaded hit costs two coalesced 48-byte records instead of the reference's index triple + 3 scattered
+// 24-byte PackedVertexData gathers (scene.slang:158-173,312-320).
+#pragma once
+
+#include "bsdf.cuh"
+#include "bvh8_traverse.cuh"
+
+namespace mpt {
+
+enum : uint32_t { // GeometryDataFlags, scene-data.slangh:15-42
+    G_PRETRANSFORMED = 0x1, G_FLIP_FACING = 0x8, G_FLAT_SHADING = 0x80, G_HAS_TANGENTS = 0x100, G_USE_ENV_MAP = 0x200, G_TWO_SIDED = 0x400
+};
+
+struct TextureRec {
+    cudaTextureObject_t obj;
+    uint32_t valid;
+    uint32_t pad;
+};
+
+struct SceneView {
+    AccelView accel;
+    const uint4* __restrict__ tri_attr;
+    const uint4* __restrict__ geometries;
+    const uint32_t* __restrict__ prim_to_tri;
+    const float4* __restrict__ inst_xform;    // 4 float4 per instance: rows of object->world
+    const float4* __restrict__ inst_xform_it; // rows of the inverse transpose
+    const uint32_t* __restrict__ materials;   // material buffer as words
+    uint32_t material_stride_words;
+    const uint2* __restrict__ material_types; // (model, features)
+    const TextureRec* __restrict__ textures;
+    uint32_t texture_count;
+    // environment
+    uint32_t env_type;
+    float env_m[9]; // (float3x3)to_local, row-major
+    float env_intensity;
+    const float4* __restrict__ env_pixels;
+    uint32_t env_w, env_h;
+};
+
+constexpr float kRayTMax = 1e7f;           // SCENE_RAY_TMAX, hit.slang:8
+constexpr float kEnvDistance = 1e7f;       // ENV_MAP_DISTANCE, environment-map.slang:11
+constexpr float kThroughputCut = 1e-5f;    // SCENE_THROUGHPUT_THRESHOLD, scene.slang:24
+constexpr float kMinRoughness = 0.0316f;   // merian_hint_min_roughness, material.slang:23
+constexpr float kAlphaThreshold = 0.5f;    // merian_alpha_test_threshold, material-system.slang:7
+constexpr uint32_t kNoTexture = 0xFFFFu;
+
+struct ShadingPoint { // hit.slang:105-147
+    f3 pos;
+    f3 face_normal_dec; // decode_normal(encode_normal(surface.face_normal)): what get_face_normal() returns
+    f3 emission;
+    Frame frame;
+    bool has_material;
+    Bsdf bsdf;
+    f3 absorption; // MaterialSample interior volume (gltf-material.slang:322-324)
+};
+
+// ---------------------------------------------------------------- textures
+MPT_DEV f4 sample_tex(const SceneView& S, uint32_t id, f2 uv) { // LOD0Sampler::sample, textures.slang:338-366
+    const float4 t = tex2D<float4>(S.textures[id].obj, uv.x, uv.y);
+    return mk4(t.x, t.y, t.z, t.w);
+}
+
+MPT_DEV int wrap_repeat(int i, int n) {
+    int m = i % n;
+    return m < 0 ? m + n : m;
+}
+// RGBA32F lat-long map, repeat addressing, bilinear with full fp32 weights (scene.cpp:786-789)
+MPT_DEV f3 env_eval(const SceneView& S, f3 dir) {
+    if (S.env_type != 1u) return mk3(0.f);
+    const f3 d = mk3(S.env_m[0] * dir.x + S.env_m[1] * dir.y + S.env_m[2] * dir.z, S.env_m[3] * dir.x + S.env_m[4] * dir.y + S.env_m[5] * dir.z,
+                     S.env_m[6] * dir.x + S.env_m[7] * dir.y + S.env_m[8] * dir.z);
+    const f2 uv = world_to_latlong(d);
+    const float fu = uv.x * float(S.env_w) - 0.5f, fv = uv.y * float(S.env_h) - 0.5f;
+    const float flu = floorf(fu), flv = floorf(fv);
+    const float a = fu - flu, b = fv - flv;
+    const int x0 = wrap_repeat(int(flu), int(S.env_w)), x1 = wrap_repeat(int(flu) + 1, int(S.env_w));
+    const int y0 = wrap_repeat(int(flv), int(S.env_h)), y1 = wrap_repeat(int(flv) + 1, int(S.env_h));
+    const float4 t00 = __ldg(S.env_pixels + size_t(y0) * S.env_w + x0), t10 = __ldg(S.env_pixels + size_t(y0) * S.env_w + x1);
+    const float4 t01 = __ldg(S.env_pixels + size_t(y1) * S.env_w + x0), t11 = __ldg(S.env_pixels + size_t(y1) * S.env_w + x1);
+    const float w00 = (1 - a) * (1 - b), w10 = a * (1 - b), w01 = (1 - a) * b, w11 = a * b;
+    return S.env_intensity * mk3(w00 * t00.x + w10 * t10.x + w01 * t01.x + w11 * t11.x, w00 * t00.y + w10 * t10.y + w01 * t01.y + w11 * t11.y,
+                                 w00 * t00.z + w10 * t10.z + w01 * t01.z + w11 * t11.z);
+}
+
+// ---------------------------------------------------------------- materials
+MPT_DEV float wordf(const uint32_t* p, int i) { return __uint_as_float(__ldg(p + i)); }
+MPT_DEV uint32_t lo16(uint32_t w) { return w & 0xFFFFu; }
+MPT_DEV uint32_t hi16(uint32_t w) { return w >> 16; }
+
+// keller_clamp_normal, utils/normal-map.slang:5-11
+MPT_DEV f3 keller_clamp(f3 ns, f3 ng, f3 wi) {
+    const f3 r = (-wi) - 2.0f * dot(ns, -wi) * ns;
+    if (dot(r, ng) < 0.f) return normalize(wi + normalize(r - ng * dot(ng, r)));
+    return ns;
+}
+
+struct ShadingData { // shading-data.slang:27-58 (only the members the supported models read)
+    f3 wi;
+    f2 uv;
+    Frame frame;
+    f3 face_normal;
+    float ior;
+    bool front_facing;
+};
+
+// Emission only: MaterialModel::get_emission (material.slang:40-47; gltf-material.slang:142-151; diffuse: 0).
+MPT_DEV f3 material_emission(const SceneView& S, uint32_t material_id, f2 uv) {
+    const uint32_t* e = S.materials + size_t(material_id) * S.material_stride_words;
+    const uint32_t hdr = __ldg(e);
+    const uint2 mt = __ldg(S.material_types + lo16(hdr));
+    if (mt.x == 0u) return mk3(0.f);
+    const uint32_t* p = e + 1;
+    f3 em = mk3(wordf(p, 4), wordf(p, 5), wordf(p, 6));
+    const uint32_t em_tex = hi16(__ldg(p + 13));
+    if (em_tex != kNoTexture) {
+        const f4 t = sample_tex(S, em_tex, uv);
+        em = em * mk3(t.x, t.y, t.z);
+    }
+    return em;
+}
+
+// Full material sample. FEAT as in bsdf.cuh.
+template <uint32_t FEAT>
+MPT_DEV void material_sample(const SceneView& S, uint32_t material_id, const ShadingData& sd, ShadingPoint& sp) {
+    const uint32_t* e = S.materials + size_t(material_id) * S.material_stride_words;
+    const uint32_t hdr = __ldg(e);
+    const uint2 mt = __ldg(S.material_types + lo16(hdr));
+    const uint32_t alpha_tex = hi16(hdr);
+    const uint32_t* p = e + 1;
+    Bsdf& b = sp.bsdf;
+    sp.absorption = mk3(0.f);
+    f4 base = mk4(wordf(p, 0), wordf(p, 1), wordf(p, 2), wordf(p, 3));
+    if (mt.x == 0u) { // DiffuseMaterial, diffuse-material.slang:19-34
+        sp.emission = mk3(0.f);
+        sp.frame = frame_apply_normal_map(sd.frame, mk3(0.f, 0.f, 1.f));
+        f3 albedo = mk3(base.x, base.y, base.z);
+        if (alpha_tex != kNoTexture) {
+            const f4 t = sample_tex(S, alpha_tex, sd.uv);
+            albedo = albedo * mk3(t.x, t.y, t.z);
+        }
+        b.gltf = 0u;
+        b.base = albedo;
+        return;
+    }
+    // ---- GltfMaterial::get_sample, gltf-material.slang:153-308; payload layout gltf_material.hpp:102-112
+    const uint32_t feat = mt.y & FEAT;
+    if (alpha_tex != kNoTexture) {
+        const f4 t = sample_tex(S, alpha_tex, sd.uv);
+        base = mk4(base.x * t.x, base.y * t.y, base.z * t.z, base.w * t.w);
+    }
+    f3 emission = mk3(wordf(p, 4), wordf(p, 5), wordf(p, 6));
+    float metallic = wordf(p, 7), roughness = wordf(p, 8);
+    const float normal_scale = wordf(p, 9);
+    const float ior = wordf(p, 11);
+    const uint32_t t01 = __ldg(p + 12), t23 = __ldg(p + 13);
+    const uint32_t mr_tex = lo16(t01), normal_tex = hi16(t01), em_tex = hi16(t23);
+    if (mr_tex != kNoTexture) {
+        const f4 mr = sample_tex(S, mr_tex, sd.uv);
+        roughness *= mr.y;
+        metallic *= mr.z;
+    }
+    Frame fr = sd.frame;
+    if (normal_tex != kNoTexture) {
+        const f4 raw = sample_tex(S, normal_tex, sd.uv);
+        const float nx = (raw.x * 2.0f - 1.0f) * normal_scale, ny = (raw.y * 2.0f - 1.0f) * normal_scale;
+        const float nz = sqrtf(fmaxf(0.0f, 1.0f - (nx * nx + ny * ny)));
+        const Frame mapped = frame_apply_normal_map(sd.frame, mk3(nx, ny, nz));
+        const f3 cn = keller_clamp(mapped.n, sd.face_normal, sd.wi); // merian_hint_clamp_normals = true
+        fr = frame_from_tangent(cn, mapped.t, 1.0f);
+    }
+    if (em_tex != kNoTexture) {
+        const f4 t = sample_tex(S, em_tex, sd.uv);
+        emission = emission * mk3(t.x, t.y, t.z);
+    }
+    const float alpha = sq(fmaxf(roughness, kMinRoughness));
+    b.gltf = 1u;
+    b.base = mk3(base.x, base.y, base.z);
+    b.ax = b.ay = b.alpha = alpha;
+    b.metallic = metallic;
+    const float ior_r = (ior - 1.0f) / (ior + 1.0f);
+    b.f0 = ior_r * ior_r;
+    b.eta = sd.ior / (sd.front_facing ? ior : 1.0f);
+    b.tw = 0.f;
+    b.coat_w = 0.f;
+    b.coat_alpha = sq(kMinRoughness);
+    b.sheen_col = mk3(0.f);
+    b.sheen_alpha = 0.f;
+    b.max_sheen = 0.f;
+    b.iri = 0.f;
+    b.iri_ior = 1.0f;
+    b.iri_thick = 0.f;
+    if (FEAT != 0u) {
+        // optional extension payloads follow the core fields in declaration order (gltf_material.hpp:114-145);
+        // byte offsets are multiples of 2, so read 16-bit granules.
+        const uint16_t* q16 = reinterpret_cast<const uint16_t*>(p) + 28;
+        auto rdf = [&](int byte_off) {
+            const uint32_t lo = q16[byte_off / 2], hi = q16[byte_off / 2 + 1];
+            return __uint_as_float(lo | (hi << 16));
+        };
+        auto rd16 = [&](int byte_off) { return uint32_t(q16[byte_off / 2]); };
+        int off = 0;
+        if (mt.y & F_TRANSMISSION) { if (feat & F_TRANSMISSION) b.tw = rdf(off); off += 4; }
+        if (mt.y & F_VOLUME) {
+            if ((feat & F_VOLUME) && sd.front_facing) sp.absorption = mk3(rdf(off), rdf(off + 4), rdf(off + 8));
+            off += 12;
+        }
+        if (mt.y & F_CLEARCOAT) {
+            if (feat & F_CLEARCOAT) {
+                b.coat_w = rdf(off);
+                float cr = rdf(off + 4);
+                const uint32_t ct = rd16(off + 8), crt = rd16(off + 10);
+                if (ct != kNoTexture) b.coat_w *= sample_tex(S, ct, sd.uv).x;
+                if (crt != kNoTexture) cr *= sample_tex(S, crt, sd.uv).y;
+                b.coat_alpha = sq(fmaxf(cr, kMinRoughness));
+            }
+            off += 12;
+        }
+        if (mt.y & F_SHEEN) {
+            if (feat & F_SHEEN) {
+                f3 col = mk3(rdf(off), rdf(off + 4), rdf(off + 8));
+                float sr = rdf(off + 12);
+                const uint32_t sct = rd16(off + 16), srt = rd16(off + 18);
+                if (sct != kNoTexture) { const f4 t = sample_tex(S, sct, sd.uv); col = col * mk3(t.x, t.y, t.z); }
+                if (srt != kNoTexture) sr *= sample_tex(S, srt, sd.uv).w;
+                b.sheen_col = col;
+                b.sheen_alpha = sq(sr);
+                b.max_sheen = max3(col);
+            }
+            off += 20;
+        }
+        if (mt.y & F_IRIDESCENCE) {
+            if (feat & F_IRIDESCENCE) {
+                b.iri = rdf(off);
+                b.iri_ior = rdf(off + 4);
+                const float tmin = rdf(off + 8), tmax = rdf(off + 12);
+                const uint32_t it = rd16(off + 16), itt = rd16(off + 18);
+                if (it != kNoTexture) b.iri *= sample_tex(S, it, sd.uv).x;
+                float t = 1.0f;
+                if (itt != kNoTexture) t = sample_tex(S, itt, sd.uv).y;
+                b.iri_thick = mix(tmin, tmax, t);
+            }
+            off += 20;
+        }
+        if (mt.y & F_ANISOTROPY) {
+            if (feat & F_ANISOTROPY) {
+                float strength = rdf(off);
+                const float rot = rdf(off + 4);
+                const uint32_t at = rd16(off + 8);
+                float dx = cosf(rot), dy = sinf(rot);
+                if (at != kNoTexture) {
+                    const f4 a = sample_tex(S, at, sd.uv);
+                    float ex = a.x * 2.0f - 1.0f, ey = a.y * 2.0f - 1.0f;
+                    const float l = sqrtf(ex * ex + ey * ey);
+                    ex /= l;
+                    ey /= l;
+                    const float ndx = dx * ex - dy * ey, ndy = dx * ey + dy * ex;
+                    dx = ndx;
+                    dy = ndy;
+                    strength *= a.z;
+                }
+                if (strength > 0.0f) {
+                    b.ax = mix(alpha, 1.0f, strength * strength);
+                    const f3 t = dx * fr.t + dy * fr.b;
+                    fr = frame_from_tangent(fr.n, t, 1.0f);
+                }
+            }
+            off += 10;
+        }
+    }
+    sp.frame = fr;
+    sp.emission = emission;
+}
+
+// ---------------------------------------------------------------- shading point
+MPT_DEV f3 xf_point(const float4* m, f3 p) {
+    const float4 r0 = __ldg(m), r1 = __ldg(m + 1), r2 = __ldg(m + 2);
+    return mk3(r0.x * p.x + r0.y * p.y + r0.z * p.z + r0.w, r1.x * p.x + r1.y * p.y + r1.z * p.z + r1.w, r2.x * p.x + r2.y * p.y + r2.z * p.z + r2.w);
+}
+MPT_DEV f3 xf_vec(const float4* m, f3 v) {
+    const float4 r0 = __ldg(m), r1 = __ldg(m + 1), r2 = __ldg(m + 2);
+    return mk3(r0.x * v.x + r0.y * v.y + r0.z * v.z, r1.x * v.x + r1.y * v.y + r1.z * v.z, r2.x * v.x + r2.y * v.y + r2.z * v.z);
+}
+
+// scene.slang:482-498
+MPT_DEV void env_shading_point(const SceneView& S, f3 ray_o, f3 ray_d, ShadingPoint& sp) {
+    sp.pos = ray_o + ray_d * kEnvDistance;
+    sp.face_normal_dec = -ray_d; // never read: has_material is false
+    sp.emission = env_eval(S, ray_d);
+    sp.has_material = false;
+}
+
+// scene.slang:418-469 with get_surface (:322-382) inlined. `hit.tri` must be valid.
+template <uint32_t FEAT>
+MPT_DEV void surface_shading_point(const SceneView& S, f3 ray_o, f3 ray_d, const HitRec& hit, float ctx_ior, bool with_material, ShadingPoint& sp) {
+    const float4* tp = S.accel.tris + size_t(hit.tri) * 3;
+    const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
+    const uint32_t geometry_index = __float_as_uint(tb.w);
+    const uint32_t instance_id = S.accel.instances[hit.instance].custom_index;
+    const uint4 gd = __ldg(S.geometries + instance_id + geometry_index);
+    const uint32_t gflags = gd.x >> 16, material_id = gd.x & 0xFFFFu;
+    if (gflags & G_USE_ENV_MAP) { env_shading_point(S, ray_o, ray_d, sp); return; }
+
+    const uint4* ap = S.tri_attr + size_t(hit.tri) * 3;
+    const uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1), a2 = __ldg(ap + 2);
+    const f3 v0 = xyz(ta), v1 = xyz(tb), v2 = xyz(tc);
+    const float bx = 1.0f - hit.u - hit.v, by = hit.u, bz = hit.v; // Hit::get_barycentrics3, hit.slang:58-60
+
+    const bool pre = gflags & G_PRETRANSFORMED;
+    const float4* M = S.inst_xform + size_t(hit.instance) * 4;
+    const f3 p_obj = bx * v0 + by * v1 + bz * v2;
+    const f3 pos = pre ? p_obj : xf_point(M, p_obj);
+    const f3 e01 = pre ? (v1 - v0) : xf_vec(M, v1 - v0);
+    const f3 e02 = pre ? (v2 - v0) : xf_vec(M, v2 - v0);
+    f3 face_normal = normalize(cross(e01, e02));
+    if (gflags & G_FLIP_FACING) face_normal = -face_normal;
+
+    f3 vertex_normal;
+    if (gflags & G_FLAT_SHADING) {
+        vertex_normal = face_normal;
+    } else {
+        const f3 n_obj = normalize(bx * decode_normal(a0.x) + by * decode_normal(a0.w) + bz * decode_normal(a1.z));
+        vertex_normal = pre ? n_obj : normalize(xf_vec(S.inst_xform_it + size_t(hit.instance) * 4, n_obj));
+    }
+    const f2 uv0 = half2_bits_to_f2(a0.y), uv1 = half2_bits_to_f2(a1.x), uv2 = half2_bits_to_f2(a1.w);
+    Frame frame;
+    if (gflags & G_HAS_TANGENTS) {
+        const f4 t0 = decode_tangent(a0.z), t1 = decode_tangent(a1.y), t2 = decode_tangent(a2.x);
+        const f3 t = mk3(bx * t0.x + by * t1.x + bz * t2.x, bx * t0.y + by * t1.y + bz * t2.y, bx * t0.z + by * t1.z + bz * t2.z);
+        const float tw = bx * t0.w + by * t1.w + bz * t2.w;
+        const f3 tn = normalize(t);
+        frame = frame_from_tangent(vertex_normal, pre ? tn : xf_vec(M, tn), sgn(tw));
+    } else {
+        const f2 duv1 = uv1 - uv0, duv2 = uv2 - uv0;
+        const float det = duv1.x * duv2.y - duv2.x * duv1.y;
+        if (fabsf(det) > 1e-8f) {
+            const float winding = (gflags & G_FLIP_FACING) ? 1.f : -1.f;
+            const f3 tangent = (duv2.y * e01 - duv1.y * e02) / det;
+            frame = frame_from_tangent(vertex_normal, tangent, sgn(det) * winding);
+        } else {
+            frame = frame_from_normal(vertex_normal);
+        }
+    }
+    const f2 uv = bx * uv0 + by * uv1 + bz * uv2;
+
+    f3 fn = face_normal;
+    bool front_facing = true;
+    if (gflags & G_TWO_SIDED) {
+        front_facing = dot(-ray_d, face_normal) >= 0.f;
+        if (!front_facing) {
+            frame.n = -frame.n; // OrthonormalFrame::flip_normal, frame.slang:122-125
+            fn = -fn;
+        }
+    }
+    sp.pos = pos;
+    sp.face_normal_dec = decode_normal(encode_normal(face_normal)); // sp.enc_face_normal round trip, scene.slang:443
+    sp.has_material = with_material;
+    if (with_material) {
+        ShadingData sd;
+        sd.wi = -ray_d;
+        sd.uv = uv;
+        sd.frame = frame;
+        sd.face_normal = fn;
+        sd.ior = ctx_ior;
+        sd.front_facing = front_facing;
+        material_sample<FEAT>(S, material_id, sd, sp);
+    } else {
+        sp.emission = material_emission(S, material_id, uv);
+        sp.frame = frame;
+    }
+}
+
+// Alpha test for non-opaque candidates (scene.slang:503-516, material-system.slang:28-38).
+struct MaterialAlphaTest {
+    const SceneView* S;
+    MPT_DEV bool operator()(uint32_t tri, uint32_t instance, float u, float v) const {
+        const float4 tb = __ldg(S->accel.tris + size_t(tri) * 3 + 1);
+        const uint32_t gid = S->accel.instances[instance].custom_index + __float_as_uint(tb.w);
+        const uint32_t material_id = __ldg(S->geometries + gid).x & 0xFFFFu;
+        const uint32_t hdr = __ldg(S->materials + size_t(material_id) * S->material_stride_words);
+        const uint32_t alpha_tex = hi16(hdr);
+        if (alpha_tex == kNoTexture) return false;
+        const uint4* ap = S->tri_attr + size_t(tri) * 3;
+        const uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
+        const f2 uv = (1.0f - u - v) * half2_bits_to_f2(a0.y) + u * half2_bits_to_f2(a1.x) + v * half2_bits_to_f2(a1.w);
+        return sample_tex(*S, alpha_tex, uv).w < kAlphaThreshold;
+    }
+};
+
+// camera.slang:29-56 (pinhole)
+struct CameraParams {
+    f3 position, U, V, W;
+    float near_plane, far_plane;
+    float jitter_x, jitter_y;
+};
+MPT_DEV void camera_ray(const CameraParams& c, uint32_t px, uint32_t py, uint32_t w, uint32_t h, f3& o, f3& d, float& tmin, float& tmax) {
+    const float pxn = (float(px) + 0.5f + c.jitter_x) / float(w), pyn = (float(py) + 0.5f + c.jitter_y) / float(h);
+    const float nx = 2.f * pxn + -1.f, ny = -2.f * pyn + 1.f;
+    o = c.position;
+    d = normalize(nx * c.U + ny * c.V + c.W);
+    const float inv_cos = 1.f / dot(normalize(c.W), d);
+    tmin = c.near_plane * inv_cos;
+    tmax = c.far_plane * inv_cos;
+}
+
+} // namespace mpt
