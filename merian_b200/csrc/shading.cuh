@@ -404,14 +404,24 @@ struct CameraParams {
     float near_plane, far_plane;
     float jitter_x, jitter_y;
 };
+// Every operation is individually rounded (no FMA contraction) so that the primary rays are bit-identical to a plain
+// IEEE evaluation of camera.slang:29-56 on the host; primary-visibility parity is then exact up to true ties.
+MPT_DEV f3 normalize_rn(f3 v) {
+    const float l = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fmul_rn(v.z, v.z)));
+    return mk3(__fdiv_rn(v.x, l), __fdiv_rn(v.y, l), __fdiv_rn(v.z, l));
+}
 MPT_DEV void camera_ray(const CameraParams& c, uint32_t px, uint32_t py, uint32_t w, uint32_t h, f3& o, f3& d, float& tmin, float& tmax) {
-    const float pxn = (float(px) + 0.5f + c.jitter_x) / float(w), pyn = (float(py) + 0.5f + c.jitter_y) / float(h);
-    const float nx = 2.f * pxn + -1.f, ny = -2.f * pyn + 1.f;
+    const float pxn = __fdiv_rn(__fadd_rn(__fadd_rn(float(px), 0.5f), c.jitter_x), float(w));
+    const float pyn = __fdiv_rn(__fadd_rn(__fadd_rn(float(py), 0.5f), c.jitter_y), float(h));
+    const float nx = __fadd_rn(__fmul_rn(2.f, pxn), -1.f), ny = __fadd_rn(__fmul_rn(-2.f, pyn), 1.f);
     o = c.position;
-    d = normalize(nx * c.U + ny * c.V + c.W);
-    const float inv_cos = 1.f / dot(normalize(c.W), d);
-    tmin = c.near_plane * inv_cos;
-    tmax = c.far_plane * inv_cos;
+    d = normalize_rn(mk3(__fadd_rn(__fadd_rn(__fmul_rn(nx, c.U.x), __fmul_rn(ny, c.V.x)), c.W.x),
+                         __fadd_rn(__fadd_rn(__fmul_rn(nx, c.U.y), __fmul_rn(ny, c.V.y)), c.W.y),
+                         __fadd_rn(__fadd_rn(__fmul_rn(nx, c.U.z), __fmul_rn(ny, c.V.z)), c.W.z)));
+    const f3 wn = normalize_rn(c.W);
+    const float inv_cos = __fdiv_rn(1.f, __fadd_rn(__fadd_rn(__fmul_rn(wn.x, d.x), __fmul_rn(wn.y, d.y)), __fmul_rn(wn.z, d.z)));
+    tmin = __fmul_rn(c.near_plane, inv_cos);
+    tmax = __fmul_rn(c.far_plane, inv_cos);
 }
 
 } // namespace mpt

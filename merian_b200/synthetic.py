@@ -116,7 +116,8 @@ def cornell(seed: int = 0) -> SceneDescription:
         _mesh_from_parts([tall], 0),
     ]
     nodes = [Node(meshes=[i]) for i in range(len(meshes))]
-    cam = CameraDesc(position=(0.5, 0.5, 2.4), target=(0.5, 0.5, 0.0), yfov_deg=39.3, aspect=1.0, near=0.01, far=100.0)
+    # slightly off-axis so that the quads' shared diagonals do not run exactly through pixel centres
+    cam = CameraDesc(position=(0.5, 0.5, 2.4), target=(0.493, 0.508, 0.0), yfov_deg=39.3, aspect=1.0, near=0.01, far=100.0)
     return SceneDescription(meshes=meshes, nodes=nodes, materials=[white, red, green, light], camera=cam, name="cornell",
                             seed=seed)
 

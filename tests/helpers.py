@@ -39,6 +39,18 @@ def compare_hits(a, b):
     return 1.0 - same.mean(), float(d[same].max()) if same.any() else 0.0, same
 
 
+def edge_ties(a, b, same, eps=2e-3):
+    """Enumerate mismatching pixels and classify them: a shared-edge tie has BOTH hits on a triangle edge
+    (min barycentric weight ~ 0). Returns (n_mismatch, n_ties)."""
+    def on_edge(h):
+        bb = h["barycentrics"].astype(np.float32)
+        w = np.stack([bb[..., 0], bb[..., 1], 1.0 - bb[..., 0] - bb[..., 1]], -1)
+        return (np.abs(w).min(axis=-1) <= eps) & (h["instance_id"] != 0xFFFFFFFF)
+    mis = ~same
+    ties = mis & on_edge(a) & on_edge(b)
+    return int(mis.sum()), int(ties.sum())
+
+
 def rel_mse(img, ref, eps=1e-2):
     l, r = luminance(img), luminance(ref)
     return float(np.mean((l - r) ** 2 / (r ** 2 + eps)))
