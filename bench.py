@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the `pt` hot path (BASELINE.json: Msamples/s, 1080p pt, path length 5).
+
+Workload (config C3, BASELINE.json configs[2]): procedural 1M-triangle terrain (seed 1) + 4096x2048 lat-long HDR
+environment, 1920x1080, 64 spp, max path length 5, one grey glTF material (roughness 0.5, metallic 0).
+A "step" = one frame = width*height*spp paths through mpt_render (primary hits from the GBuffer hit texture).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (libmpt.so on B200)
+  python bench.py --impl reference ...                          the reference arm: the CPU restatement of the
+                                                                reference's algorithm (oracle/) on the host cores
+Multi-GPU: one process per GPU (torchrun); the scene is replicated, rank r renders sample indices r, r+N, ...
+(weak scaling: 64 spp per GPU, 64*N spp per frame) into a private sum buffer; one NCCL reduce to rank 0 per frame.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT, SPP, MAX_PATH_LENGTH = 1920, 1080, 64, 5
+METRIC = "Msamples/s (1080p pt, path len 5)"
+
+
+def load_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic():
+    """ncu `dram__bytes_read.sum + dram__bytes_write.sum` per extend launch from the committed capture, or None."""
+    p = os.path.join(ROOT, "profiles", "extend_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get("dram_bytes_per_launch")
+    return None
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks and throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def build_scene(small=False):
+    from merian_b200 import synthetic
+    from merian_b200.scene import SceneTables
+    if small:  # CI-sized variant for CPU tests of the harness
+        return SceneTables(synthetic.terrain(nx=100, ny=50, env_size=(256, 128)))
+    return SceneTables(synthetic.terrain(nx=1000, ny=500, seed=1, env_size=(4096, 2048)))
+
+
+def cpu_baseline(tables, width, height, spp, seconds_hint=15.0):
+    """The oracle (kind 'port': a CPU restatement of the reference's algorithm, not the reference) on a bounded
+    sample of the same workload: same scene, camera and path length, reduced resolution."""
+    from merian_b200 import abi
+    from merian_b200.scene import upload_scene
+    from oracle.oracle_py import OracleContext
+    o = OracleContext()
+    upload_scene(o, tables)
+    cam = tables.desc.camera.to_abi(0)
+    w, h, s = width // 4, height // 4, 8
+    P = abi.RenderParams(w, h, 0, s, MAX_PATH_LENGTH, 0xFF, abi.RENDER_EMISSION_ON_PRIMARY, 0, 1, 0.0)
+    o.render(cam, abi.RenderParams(w // 4, h // 4, 0, 1, MAX_PATH_LENGTH, 0xFF, abi.RENDER_EMISSION_ON_PRIMARY, 0, 1, 0.0))  # warm
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        P.frame = n
+        o.render(cam, P)
+        n += 1
+        if time.perf_counter() - t0 > seconds_hint or n >= 64:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": w * h * s * n / dt / 1e6, "unit": "Msamples/s", "cores": o.num_threads(), "kind": "port",
+            "sample": f"{n} frames of {w}x{h} x {s} spp, max path length {MAX_PATH_LENGTH}, same scene/camera ({dt:.1f} s)"}, o, cam
+
+
+def run_reference(args):
+    """--impl reference: the reference's Vulkan/Slang `pt` cannot be built in this image, so this arm
+    times the CPU restatement of its algorithm (oracle/) with all host threads on a bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from merian_b200 import abi
+    tables = build_scene(args.small)
+    base, o, cam = cpu_baseline(tables, args.width, args.height, args.spp, seconds_hint=1.0)
+    w, h, s = args.width // 4, args.height // 4, 8
+    P = abi.RenderParams(w, h, 0, s, MAX_PATH_LENGTH, 0xFF, abi.RENDER_EMISSION_ON_PRIMARY, 0, 1, 0.0)
+    for i in range(args.warmup):
+        P.frame = i
+        o.render(cam, P)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        P.frame = args.warmup + i
+        o.render(cam, P)
+    dt = time.perf_counter() - t0
+    value = w * h * s * args.steps / dt / 1e6
+    sample = f"each step = {w}x{h} x {s} spp of the workload (1/128 of a frame), oracle port, {o.num_threads()} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "width": args.width, "height": args.height, "spp": args.spp, "max_path_length": MAX_PATH_LENGTH,
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Msamples/s", "cores": o.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_name(args):
+    return (f"C3: pt on synthetic 1M-triangle terrain (seed 1) + 4096x2048 lat-long HDR env, {args.width}x{args.height}, {args.spp} spp, "
+            f"max path length {MAX_PATH_LENGTH}" if not args.small else "C3-small (harness test)")
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from merian_b200 import abi
+    from merian_b200.context import Context
+    from merian_b200.scene import upload_scene
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    tables = build_scene(args.small)
+    ctx = Context(local_rank)
+    upload_scene(ctx, tables)
+    bvh = ctx.bvh_info()
+    desc = tables.desc
+    W, H, spp = args.width, args.height, args.spp
+    npix = W * H
+
+    def params(frame, flags=abi.RENDER_EMISSION_ON_PRIMARY):
+        if world > 1:
+            return abi.RenderParams(W, H, frame, spp, MAX_PATH_LENGTH, 0xFF, flags | abi.RENDER_OUTPUT_SUM, rank, world, 0.0)
+        return abi.RenderParams(W, H, frame, spp, MAX_PATH_LENGTH, 0xFF, flags, 0, 1, 0.0)
+
+    cam = desc.camera.to_abi(0)
+    tex1 = ctx.primary_visibility_device(cam, W, H)  # the GBuffer node's product (gbuffer_rt.slang), resident in HBM
+    out = torch.empty((H, W, 4), dtype=torch.float32, device=dev)
+
+    def step(frame):
+        ctx.render_device(cam, params(frame), tex1=tex1, out=out)
+        if world > 1:
+            dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)  # NCCL over NVLink: accumulation buffers -> rank 0
+            if rank == 0:
+                out.mul_(1.0 / (spp * world))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- algorithmic work per ray: one instrumented (counting) frame outside the timed region
+    ctx.set_profiling(1)
+    ctx.reset_stats()
+    ctx.render_device(cam, params(10_000), tex1=tex1, out=out)
+    cs = ctx.stats()
+    rays_c = max(cs.rays_continuation, 1)
+    nodes_per_ray, tris_per_ray = cs.nodes_visited / rays_c, cs.tris_tested / rays_c
+    bytes_per_ray = 80.0 * nodes_per_ray + 48.0 * tris_per_ray + 48.0  # node + triangle records + ray read (32) + hit write (16)
+    ctx.set_profiling(0)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    ctx.set_profiling(2)  # CUDA-event timing of every extend / shade launch inside the timed region
+    ctx.reset_stats()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    st = ctx.stats()
+    ctx.set_profiling(0)
+
+    rays = torch.tensor([float(st.rays_continuation), float(st.shaded_hits), float(st.kernel_launches)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(rays, op=dist.ReduceOp.SUM)
+    total_samples = npix * spp * world * args.steps
+    value = total_samples / (ms * 1e-3) / 1e6
+    mrays = float(rays[0].item()) / (ms * 1e-3) / 1e6
+
+    # ---- end to end through the C-ABI with HOST buffers: H2D GBuffer hits, render, D2H irradiance
+    h_tex1 = tex1.cpu().pin_memory()
+    h_out = torch.empty((H, W, 4), dtype=torch.float32).pin_memory()
+    e2e_steps = max(1, min(args.steps, 3))
+    ctx.render_host(cam, params(0), h_tex1=h_tex1, h_out=h_out)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        ctx.render_host(cam, params(args.warmup + i), h_tex1=h_tex1, h_out=h_out)
+        if world > 1:
+            pass  # per-rank partial sums stay on the host; the reduce is part of `value`, not of the host round trip
+    torch.cuda.synchronize()
+    e2e_dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
+    e2e_value = npix * spp * world * e2e_steps / float(e2e_dt.item()) / 1e6
+
+    if rank == 0:
+        peak, peak_src = load_peak()
+        extend_ms = st.extend_ms / max(st.extend_launches, 1)
+        rays_per_launch = st.rays_continuation / max(st.extend_launches, 1)
+        achieved = bytes_per_ray * rays_per_launch / (extend_ms * 1e-3) / 1e9 if extend_ms > 0 else 0.0
+        base = None
+        if world == 1 and not args.no_cpu_baseline:
+            base, _, _ = cpu_baseline(tables, W, H, spp)
+        line = {
+            "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args), "width": W, "height": H, "spp_per_gpu": spp, "spp_total": spp * world,
+                       "max_path_length": MAX_PATH_LENGTH, "triangles": tables.triangle_count, "seed": desc.seed,
+                       "parallelism": f"sample-sharded x{world}, NCCL reduce of the sum buffers" if world > 1 else "single GPU",
+                       "l2": "inputs larger than L2: BVH8 %.0f MB + triangle/attribute records %.0f MB + env 134 MB + >1 GB of path state per pass"
+                             % (bvh.node_bytes / 1e6, 2 * bvh.triangle_bytes / 1e6)},
+            "mrays_per_s": mrays,  # continuation rays (primary hits come from the GBuffer texture)
+            "rays_per_sample": float(rays[0].item()) / total_samples,
+            "roofline": {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": load_traffic(), "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
+                         "tris_per_ray": tris_per_ray, "rays_per_launch": rays_per_launch, "avg_launch_ms": extend_ms,
+                         "extend_share_of_step": st.extend_ms / ms if ms > 0 else None, "shade_share_of_step": st.shade_ms / ms if ms > 0 else None},
+            "cpu_baseline": base,
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": npix * 16, "d2h_bytes_per_step": npix * 16},
+            "gpu_launches": int(rays[2].item()),
+            "clocks": clocks,
+            "bvh": {"nodes": bvh.node_count, "node_mb": bvh.node_bytes / 1e6, "triangle_mb": bvh.triangle_bytes / 1e6, "build_ms": bvh.build_ms},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=WIDTH)
+    ap.add_argument("--height", type=int, default=HEIGHT)
+    ap.add_argument("--spp", type=int, default=SPP)
+    ap.add_argument("--small", action="store_true", help="tiny scene (harness test only; not a bench value)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours" and not args.small:
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
