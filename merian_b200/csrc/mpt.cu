@@ -226,27 +226,52 @@ __global__ void __launch_bounds__(kThreads) k_shade_primary(const __grid_constan
 }
 
 // --------------------------------------------------------------------------------------- wavefront: extend
+// Persistent warps with per-lane dynamic fetch: a lane whose ray has finished does not wait for the slowest ray of
+// its batch; when fewer than kRefillThreshold lanes of the warp are still traversing, the warp re-converges, all idle
+// lanes claim new rays with ONE atomicAdd (ballot + prefix popcount), and traversal resumes.
+constexpr int kRefillThreshold = 24;
 template <bool COUNT>
-__global__ void __launch_bounds__(kThreads) k_extend(const __grid_constant__ SceneView S, const float4* __restrict__ q_o, const float4* __restrict__ q_d, HitRec* __restrict__ hits,
-                                                     uint32_t bounce, uint32_t mask, Counters* ctr) {
+__global__ void __launch_bounds__(kThreads) k_extend(const __grid_constant__ SceneView S, const float4* __restrict__ q_o, const float4* __restrict__ q_d,
+                                                     HitRec* __restrict__ hits, uint32_t bounce, uint32_t mask, Counters* ctr) {
     const uint32_t n = ctr->qcount[bounce];
-    uint32_t nn = 0, nt = 0;
     MaterialAlphaTest at{&S};
+    uint2 stack_mem[kStackSize];
+    Traversal<COUNT, MaterialAlphaTest> T(S.accel, at, stack_mem);
+    bool active = false, exhausted = false;
+    uint32_t j = 0;
     while (true) {
-        uint32_t base = 0;
-        if (lane_id() == 0) base = atomicAdd(&ctr->fetch[bounce], 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= n) break;
-        const uint32_t j = base + lane_id();
-        if (j < n) {
-            const float4 ro = __ldg(q_o + j), rd = __ldg(q_d + j);
-            const HitRec hr = trace_closest<COUNT>(S.accel, xyz(ro), xyz(rd), 0.f /* SCENE_RAY_TMIN */, rd.w, mask, at, nn, nt);
-            *reinterpret_cast<uint4*>(hits + j) = make_uint4(hr.tri, hr.instance, __float_as_uint(hr.u), __float_as_uint(hr.v));
+        const uint32_t need = __ballot_sync(0xFFFFFFFFu, !active && !exhausted);
+        if (need) {
+            const int leader = __ffs(need) - 1;
+            uint32_t base = 0;
+            if (int(lane_id()) == leader) base = atomicAdd(&ctr->fetch[bounce], uint32_t(__popc(need)));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (!active && !exhausted) {
+                j = base + __popc(need & ((1u << lane_id()) - 1u));
+                if (j < n) {
+                    const float4 ro = __ldg(q_o + j), rd = __ldg(q_d + j);
+                    active = T.init(xyz(ro), xyz(rd), 0.f /* SCENE_RAY_TMIN */, rd.w, mask);
+                    if (!active) *reinterpret_cast<uint4*>(hits + j) = make_uint4(kMiss, kMiss, 0u, 0u);
+                } else {
+                    exhausted = true;
+                }
+            }
         }
+        const bool queue_empty = __any_sync(0xFFFFFFFFu, exhausted);
+        if (!__any_sync(0xFFFFFFFFu, active)) break;
+        while (active) {
+            if (T.step()) {
+                *reinterpret_cast<uint4*>(hits + j) = make_uint4(T.hit.tri, T.hit.instance, __float_as_uint(T.hit.u), __float_as_uint(T.hit.v));
+                active = false;
+                break;
+            }
+            if (!queue_empty && __popc(__activemask()) < kRefillThreshold) break;
+        }
+        __syncwarp();
     }
     if (COUNT) {
-        atomicAdd(&ctr->nodes_visited, (unsigned long long)nn);
-        atomicAdd(&ctr->tris_tested, (unsigned long long)nt);
+        atomicAdd(&ctr->nodes_visited, (unsigned long long)T.n_nodes);
+        atomicAdd(&ctr->tris_tested, (unsigned long long)T.n_tris);
     }
 }
 
@@ -476,6 +501,7 @@ struct TextureSlot {
 struct mpt_context {
     int device = 0;
     int sm_count = 148;
+    uint32_t extend_blocks_per_sm = 8;
     std::string error;
     // scene
     DevBuf nodes, tris, tri_attr, geometries, prim_to_tri, instances, tlas_prims, xform, xform_it;
@@ -600,7 +626,7 @@ mpt_status run_passes(mpt_context* ctx, const CameraParams& cam, const mpt_rende
     Counters* ctr = ctx->counters.as<Counters>();
     const bool count = ctx->profile_flags & 1u;
     const int L = std::min(P.max_path_length, kMaxBounces);
-    const uint32_t persistent_blocks = uint32_t(ctx->sm_count) * 8u;
+    const uint32_t persistent_blocks = uint32_t(ctx->sm_count) * ctx->extend_blocks_per_sm;
     const uint32_t pix_blocks = (npix + kThreads - 1) / kThreads;
 
     RenderConst rc{};
@@ -665,6 +691,8 @@ MPT_API mpt_status mpt_create(int device, mpt_context** out_ctx) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->view.env_type = 0;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false>, kThreads, 0) == cudaSuccess && occ > 0) ctx->extend_blocks_per_sm = uint32_t(occ);
     *out_ctx = ctx;
     return MPT_OK;
 }
