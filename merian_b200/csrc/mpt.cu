@@ -4,9 +4,11 @@
 //   k_shade_primary   one thread per pixel: primary shading point from the GBuffer hit (render_pt.slang:99-103),
 //                     then for each of the K samples: seed RNG, BSDF sample, continuation ray -> queue
 //   for bounce = 1 .. L-1:
-//     k_extend        persistent warps fetch batches of 32 rays from the queue (atomic counter), BVH8 closest hit
-//     k_shade_bounce  shading point, Beer-Lambert, emission accumulate, next BSDF sample; survivors are compacted
-//                     into the next queue with warp ballot + prefix popcount + one atomicAdd per warp
+//     k_extend        persistent warps, per-lane dynamic fetch from the ray queue (atomic counter), BVH8 closest hit;
+//                     misses are shaded in place (environment lookup, path ends), hits are compacted into the hit
+//                     queue with warp ballot + prefix popcount + one atomicAdd per warp
+//     k_shade_bounce  hit queue only: shading point, Beer-Lambert, emission accumulate, next BSDF sample; survivors
+//                     are compacted into the next ray queue the same way
 //   k_resolve         per pixel: NaN/Inf rejection, sum of the K sample radiances and luminance^2 (render_pt.slang:116-129)
 // Queues are double-buffered SoA (origin|slot, direction|tmax); per-path state lives in fixed slots.
 #include "../../include/mpt.h"
@@ -30,6 +32,7 @@ constexpr int kThreads = 128;
 
 struct Counters {
     uint32_t qcount[kMaxBounces + 2]; // qcount[b] = rays queued for the extend of bounce b
+    uint32_t hcount[kMaxBounces + 2]; // hcount[b] = surface hits found by the extend of bounce b
     uint32_t fetch[kMaxBounces + 2];  // persistent-thread fetch cursors
     unsigned long long rays_continuation, rays_primary, shaded_hits, nodes_visited, tris_tested;
 };
@@ -44,7 +47,9 @@ static_assert(sizeof(PackedHitInfo) == 16, "PackedHitInfo is one uint4 texel");
 struct PathBuffers {
     float4* q_o[2];   // origin.xyz | slot (bits)
     float4* q_d[2];   // direction.xyz | tmax
-    HitRec* hits;
+    uint4* hq_hit;    // hit queue: tri | instance | u | v
+    float4* hq_dir;   // hit queue: ray direction.xyz | slot (bits)
+    float4* hq_org;   // hit queue: ray origin.xyz | -   (only written when the scene has transmissive materials)
     float4* thr;      // throughput.rgb | current_ior
     float4* rad;      // radiance.rgb | rng state (bits)
     float4* med;      // medium mu_t.rgb | -   (only touched when the scene has transmissive materials)
@@ -230,16 +235,48 @@ __global__ void __launch_bounds__(kThreads) k_shade_primary(const __grid_constan
 // its batch; when fewer than kRefillThreshold lanes of the warp are still traversing, the warp re-converges, all idle
 // lanes claim new rays with ONE atomicAdd (ballot + prefix popcount), and traversal resumes.
 constexpr int kRefillThreshold = 24;
-template <bool COUNT>
+template <bool COUNT, bool MEDIUM>
 __global__ void __launch_bounds__(kThreads) k_extend(const __grid_constant__ SceneView S, const float4* __restrict__ q_o, const float4* __restrict__ q_d,
-                                                     HitRec* __restrict__ hits, uint32_t bounce, uint32_t mask, Counters* ctr) {
+                                                     PathBuffers pb, uint32_t bounce, uint32_t mask, Counters* ctr) {
     const uint32_t n = ctr->qcount[bounce];
     MaterialAlphaTest at{&S};
     uint2 stack_mem[kStackSize];
     Traversal<COUNT, MaterialAlphaTest> T(S.accel, at, stack_mem);
-    bool active = false, exhausted = false;
-    uint32_t j = 0;
+    bool active = false, exhausted = false, finished = false;
+    uint32_t slot = 0;
     while (true) {
+        // ---- retire finished rays (the warp is converged here)
+        const bool is_hit = finished && T.hit.tri != kMiss;
+        const uint32_t hm = __ballot_sync(0xFFFFFFFFu, is_hit);
+        if (hm) {
+            const int leader = __ffs(hm) - 1;
+            uint32_t base = 0;
+            if (int(lane_id()) == leader) base = atomicAdd(&ctr->hcount[bounce], uint32_t(__popc(hm)));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (is_hit) {
+                const uint32_t hi = base + __popc(hm & ((1u << lane_id()) - 1u));
+                pb.hq_hit[hi] = make_uint4(T.hit.tri, T.hit.instance, __float_as_uint(T.hit.u), __float_as_uint(T.hit.v));
+                pb.hq_dir[hi] = make_float4(T.dir.x, T.dir.y, T.dir.z, __uint_as_float(slot));
+                if (MEDIUM) pb.hq_org[hi] = make_float4(T.org.x, T.org.y, T.org.z, 0.f);
+            }
+        }
+        if (finished && !is_hit && S.env_type != 0u) {
+            // miss: _make_environment_map_shading_point (scene.slang:482-498) + render_pt.slang:84-86; the path ends
+            const float4 th = pb.thr[slot];
+            f3 throughput = mk3(th.x, th.y, th.z);
+            if (MEDIUM) {
+                const float4 m = pb.med[slot];
+                if (m.x != 0.f || m.y != 0.f || m.z != 0.f) throughput *= vexp(-(kEnvDistance * length(T.dir)) * mk3(m.x, m.y, m.z));
+            }
+            const f3 e = throughput * env_eval(S, T.dir);
+            float4 ra = pb.rad[slot];
+            ra.x += e.x;
+            ra.y += e.y;
+            ra.z += e.z;
+            pb.rad[slot] = ra;
+        }
+        finished = false;
+        // ---- refill idle lanes
         const uint32_t need = __ballot_sync(0xFFFFFFFFu, !active && !exhausted);
         if (need) {
             const int leader = __ffs(need) - 1;
@@ -247,22 +284,23 @@ __global__ void __launch_bounds__(kThreads) k_extend(const __grid_constant__ Sce
             if (int(lane_id()) == leader) base = atomicAdd(&ctr->fetch[bounce], uint32_t(__popc(need)));
             base = __shfl_sync(0xFFFFFFFFu, base, leader);
             if (!active && !exhausted) {
-                j = base + __popc(need & ((1u << lane_id()) - 1u));
+                const uint32_t j = base + __popc(need & ((1u << lane_id()) - 1u));
                 if (j < n) {
                     const float4 ro = __ldg(q_o + j), rd = __ldg(q_d + j);
+                    slot = __float_as_uint(ro.w);
                     active = T.init(xyz(ro), xyz(rd), 0.f /* SCENE_RAY_TMIN */, rd.w, mask);
-                    if (!active) *reinterpret_cast<uint4*>(hits + j) = make_uint4(kMiss, kMiss, 0u, 0u);
+                    finished = !active; // masked out: a miss
                 } else {
                     exhausted = true;
                 }
             }
         }
         const bool queue_empty = __any_sync(0xFFFFFFFFu, exhausted);
-        if (!__any_sync(0xFFFFFFFFu, active)) break;
+        if (!__any_sync(0xFFFFFFFFu, active || finished)) break;
         while (active) {
             if (T.step()) {
-                *reinterpret_cast<uint4*>(hits + j) = make_uint4(T.hit.tri, T.hit.instance, __float_as_uint(T.hit.u), __float_as_uint(T.hit.v));
                 active = false;
+                finished = true;
                 break;
             }
             if (!queue_empty && __popc(__activemask()) < kRefillThreshold) break;
@@ -278,12 +316,11 @@ __global__ void __launch_bounds__(kThreads) k_extend(const __grid_constant__ Sce
 // --------------------------------------------------------------------------------------- wavefront: shade after extend
 template <uint32_t FEAT>
 __global__ void __launch_bounds__(kThreads) k_shade_bounce(const __grid_constant__ SceneView S, RenderConst rc, PathBuffers pb, uint32_t bounce, Counters* ctr) {
-    const uint32_t n = ctr->qcount[bounce];
-    const uint32_t in = (bounce - 1) & 1u, out = bounce & 1u;
+    const uint32_t n = ctr->hcount[bounce];
+    const uint32_t out = bounce & 1u;
     const bool more = int32_t(bounce) + 1 < rc.max_path_length; // with_material, render_pt.slang:80
     const uint32_t warps_total = (gridDim.x * blockDim.x) >> 5;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t n_shaded = 0;
     for (uint32_t base = warp * 32u; base < n; base += warps_total * 32u) {
         const uint32_t j = base + lane_id();
         const bool valid = j < n;
@@ -292,32 +329,33 @@ __global__ void __launch_bounds__(kThreads) k_shade_bounce(const __grid_constant
         float ior = 1.f;
         uint32_t slot = 0;
         if (valid) {
-            const float4 ro = __ldg(pb.q_o[in] + j), rd = __ldg(pb.q_d[in] + j);
-            const uint4 hw = *reinterpret_cast<const uint4*>(pb.hits + j);
+            const uint4 hw = __ldg(pb.hq_hit + j);
+            const float4 rd = __ldg(pb.hq_dir + j);
             HitRec hr;
             hr.tri = hw.x;
             hr.instance = hw.y;
             hr.u = __uint_as_float(hw.z);
             hr.v = __uint_as_float(hw.w);
-            slot = __float_as_uint(ro.w);
+            slot = __float_as_uint(rd.w);
             const float4 th = pb.thr[slot];
-            float4 ra = pb.rad[slot];
+            const float4 ra = pb.rad[slot];
             throughput = mk3(th.x, th.y, th.z);
             ior = th.w;
-            if (FEAT & F_TRANSMISSION) { const float4 m = pb.med[slot]; medium = mk3(m.x, m.y, m.z); }
-            const f3 o = xyz(ro), d = xyz(rd);
-            ShadingPoint sp;
-            if (hr.tri != kMiss) {
-                surface_shading_point<FEAT>(S, o, d, hr, ior, more, sp);
-                n_shaded++;
-            } else {
-                env_shading_point(S, o, d, sp);
+            const f3 d = xyz(rd);
+            f3 o = mk3(0.f);
+            if (FEAT & F_TRANSMISSION) {
+                const float4 m = pb.med[slot];
+                medium = mk3(m.x, m.y, m.z);
+                o = xyz(__ldg(pb.hq_org + j));
             }
+            ShadingPoint sp;
+            surface_shading_point<FEAT>(S, o, d, hr, ior, more, sp);
+            if (!sp.has_material && !more) {} // emission-only vertex
             // Beer-Lambert over the segment just travelled, render_pt.slang:84 (Vacuum: mu_t = 0 -> exactly 1)
             if (FEAT & F_TRANSMISSION) {
                 if (medium.x != 0.f || medium.y != 0.f || medium.z != 0.f) throughput *= vexp(-length(o - sp.pos) * medium);
             }
-            f3 radiance = mk3(ra.x, ra.y, ra.z) + throughput * sp.emission; // :86
+            const f3 radiance = mk3(ra.x, ra.y, ra.z) + throughput * sp.emission; // :86
             Rng rng = make_pcg(__float_as_uint(ra.w));
             if (more) alive = scatter<FEAT>(sp, d, rng, throughput, ior, medium, no, nd);
             pb.rad[slot] = make_float4(radiance.x, radiance.y, radiance.z, __uint_as_float(rng.state));
@@ -332,18 +370,16 @@ __global__ void __launch_bounds__(kThreads) k_shade_bounce(const __grid_constant
             pb.q_d[out][qi] = make_float4(nd.x, nd.y, nd.z, kRayTMax);
         }
     }
-    // one atomic per warp for the statistics
-    for (int off = 16; off > 0; off >>= 1) n_shaded += __shfl_down_sync(0xFFFFFFFFu, n_shaded, off);
-    if (lane_id() == 0 && n_shaded) atomicAdd(&ctr->shaded_hits, (unsigned long long)n_shaded);
 }
 
 // --------------------------------------------------------------------------------------- resolve
 __global__ void __launch_bounds__(kThreads) k_resolve(RenderConst rc, PathBuffers pb, const float4* albedo, float4* out, Counters* ctr) {
     const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix == 0) {
-        unsigned long long rays = 0;
-        for (int b = 1; b < rc.max_path_length && b < kMaxBounces; b++) rays += ctr->qcount[b];
+        unsigned long long rays = 0, shaded = 0;
+        for (int b = 1; b < rc.max_path_length && b < kMaxBounces; b++) { rays += ctr->qcount[b]; shaded += ctr->hcount[b]; }
         atomicAdd(&ctr->rays_continuation, rays);
+        atomicAdd(&ctr->shaded_hits, shaded);
     }
     if (pix >= rc.npix) return;
     f3 demod = mk3(1.f);
@@ -512,7 +548,7 @@ struct mpt_context {
     bool scene_ready = false, materials_ready = false;
     mpt_bvh_info bvh_info{};
     // wavefront pool
-    DevBuf q_o[2], q_d[2], hits, thr, rad, med, counters, tex1_internal, stage_tex1, stage_albedo, stage_out;
+    DevBuf q_o[2], q_d[2], hq_hit, hq_dir, hq_org, thr, rad, med, counters, tex1_internal, stage_tex1, stage_albedo, stage_out;
     size_t pool_slots = 0;
     // stats / profiling
     uint32_t profile_flags = 0;
@@ -599,12 +635,16 @@ mpt_status ensure_pool(mpt_context* ctx, size_t slots, bool need_medium) {
             CU(ctx->q_o[i].ensure(slots * sizeof(float4)));
             CU(ctx->q_d[i].ensure(slots * sizeof(float4)));
         }
-        CU(ctx->hits.ensure(slots * sizeof(HitRec)));
+        CU(ctx->hq_hit.ensure(slots * sizeof(uint4)));
+        CU(ctx->hq_dir.ensure(slots * sizeof(float4)));
         CU(ctx->thr.ensure(slots * sizeof(float4)));
         CU(ctx->rad.ensure(slots * sizeof(float4)));
         ctx->pool_slots = slots;
     }
-    if (need_medium) CU(ctx->med.ensure(ctx->pool_slots * sizeof(float4)));
+    if (need_medium) {
+        CU(ctx->med.ensure(ctx->pool_slots * sizeof(float4)));
+        CU(ctx->hq_org.ensure(ctx->pool_slots * sizeof(float4)));
+    }
     if (!ctx->counters.p) {
         CU(ctx->counters.ensure(sizeof(Counters)));
         CU(cudaMemset(ctx->counters.p, 0, sizeof(Counters)));
@@ -619,7 +659,9 @@ mpt_status run_passes(mpt_context* ctx, const CameraParams& cam, const mpt_rende
     const uint32_t K = uint32_t(std::max<size_t>(1, std::min<size_t>(size_t(std::max(P.spp, 1)), ctx->pool_slots / npix)));
     PathBuffers pb;
     for (int i = 0; i < 2; i++) { pb.q_o[i] = ctx->q_o[i].as<float4>(); pb.q_d[i] = ctx->q_d[i].as<float4>(); }
-    pb.hits = ctx->hits.as<HitRec>();
+    pb.hq_hit = ctx->hq_hit.as<uint4>();
+    pb.hq_dir = ctx->hq_dir.as<float4>();
+    pb.hq_org = ctx->hq_org.as<float4>();
     pb.thr = ctx->thr.as<float4>();
     pb.rad = ctx->rad.as<float4>();
     pb.med = ctx->med.as<float4>();
@@ -649,8 +691,9 @@ mpt_status run_passes(mpt_context* ctx, const CameraParams& cam, const mpt_rende
         for (int b = 1; b < L; b++) {
             const uint32_t in = uint32_t(b - 1) & 1u;
             time_launch(ctx, true, st, [&] {
-                if (count) k_extend<true><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, pb.q_o[in], pb.q_d[in], pb.hits, uint32_t(b), P.instance_mask, ctr);
-                else k_extend<false><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, pb.q_o[in], pb.q_d[in], pb.hits, uint32_t(b), P.instance_mask, ctr);
+                constexpr bool MED = (FEAT & F_TRANSMISSION) != 0;
+                if (count) k_extend<true, MED><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, pb.q_o[in], pb.q_d[in], pb, uint32_t(b), P.instance_mask, ctr);
+                else k_extend<false, MED><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, pb.q_o[in], pb.q_d[in], pb, uint32_t(b), P.instance_mask, ctr);
             });
             time_launch(ctx, false, st, [&] { k_shade_bounce<FEAT><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, rc, pb, uint32_t(b), ctr); });
             ctx->stats.kernel_launches += 2;
@@ -692,7 +735,7 @@ MPT_API mpt_status mpt_create(int device, mpt_context** out_ctx) {
     ctx->sm_count = prop.multiProcessorCount;
     ctx->view.env_type = 0;
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false>, kThreads, 0) == cudaSuccess && occ > 0) ctx->extend_blocks_per_sm = uint32_t(occ);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false, false>, kThreads, 0) == cudaSuccess && occ > 0) ctx->extend_blocks_per_sm = uint32_t(occ);
     *out_ctx = ctx;
     return MPT_OK;
 }
