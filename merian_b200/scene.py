@@ -360,7 +360,8 @@ class SceneTables:
             g["mask"] = mesh.instance_mask
             g["all_opaque"] = g["all_opaque"] and bool(mesh.flags & MESH_IS_OPAQUE)
             g["meshes"].append(mesh_id)  # SmallSet<MeshID>: ascending because mesh_id ascends
-            g["instances"] = inst
+            if len(g["meshes"]) == 1:
+                g["instances"] = inst  # MeshGroup::get_instances = instances of the FIRST mesh (scene.hpp:380-383)
         self.groups = groups
 
         # ---- device vertex/index data per mesh (A13). Pretransformed groups bake the node transform.
@@ -370,7 +371,8 @@ class SceneTables:
         for g in groups:
             for mesh_id in g["meshes"]:
                 mesh = d.meshes[mesh_id]
-                M = None if g["instanced"] else d.nodes[g["instances"][0]].transform
+                # scene.cpp:1498-1501: a pretransformed mesh bakes the transform of ITS OWN (single) node
+                M = None if g["instanced"] else d.nodes[instances_of[mesh_id][0]].transform
                 self.mesh_vertices[mesh_id] = pack_vertices(mesh.positions, mesh.normals, mesh.uvs, mesh.tangents, M)
                 if mesh.indices is not None:
                     idx = np.ascontiguousarray(mesh.indices)

@@ -1088,6 +1088,25 @@ int oracle_intersect_triangle(const float* o, const float* d, const float* v0, c
                ? 1 : 0;
 }
 
+// tests/material_system/read_material.slang + sample_material.slang restated (tests/test_material_system.cpp:107-215):
+// header words, first four payload floats, and MaterialSample::eval(wi, wo) in the frame N=(0,0,1), T=(1,0,0).
+void oracle_material_read(oracle_context* c, uint32_t material_id, uint32_t* out7) {
+    const uint8_t* e = c->scene.entry(material_id);
+    out7[0] = Scene::rd16(e);
+    out7[1] = Scene::rd16(e + 2);
+    for (int i = 0; i < 4; i++) std::memcpy(&out7[2 + i], e + 4 + 4 * i, 4);
+    out7[6] = c->scene.material_count;
+}
+void oracle_material_eval(oracle_context* c, uint32_t material_id, const float* wi, const float* wo, const float* uv, float* out3) {
+    ShadingData sd{float3(wi[0], wi[1], wi[2]), float3(0.f), float2(uv[0], uv[1]), Frame(float3(0, 0, 1), float3(1, 0, 0)), float3(0, 0, 1), 0, 1.0f, true};
+    float3 emission;
+    Frame fr;
+    const MaterialSample ms = c->scene.get_material_sample(material_id, sd, emission, fr);
+    Rng rng = Rng::pcg(1u);
+    const float3 f = ms.eval(fr.to_local(sd.wi), fr.to_local(float3(wo[0], wo[1], wo[2])), rng);
+    out3[0] = f.x; out3[1] = f.y; out3[2] = f.z;
+}
+
 // BSDF ids as in mpt_bsdf_check_params; configs as in tests/test_bsdf.cpp:62-160.
 int oracle_bsdf_check(const mpt_bsdf_check_params* p, float* out16) {
     const float3 wi(p->wi[0], p->wi[1], p->wi[2]);

@@ -1,8 +1,10 @@
 #!/bin/bash
-# Round-1 GPU session: tests, smoke, bench, ncu launch list + one full capture of k_extend.
+# Round-1 GPU session: tests, smoke, bench, ncu launch list + one full capture of k_extend / k_shade_bounce.
 set -x
 mkdir -p gpurun_out
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+nvidia-smi -L > gpurun_out/gpu.txt; nproc >> gpurun_out/gpu.txt
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; tail -15 gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -3 gpurun_out/smoke.log
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
 tail -c 3000 gpurun_out/bench.json
 tail -5 gpurun_out/bench.err
