@@ -6,7 +6,9 @@ import os
 from . import abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmpt.so")
+# MPT_LIB_VARIANT=name loads csrc/libmpt_name.so (A/B builds for profiling sessions, see csrc/Makefile `variant`)
+_VARIANT = os.environ.get("MPT_LIB_VARIANT", "")
+LIB_PATH = os.path.join(_HERE, "csrc", f"libmpt_{_VARIANT}.so" if _VARIANT else "libmpt.so")
 _lib = None
 
 EXPORTS = ["mpt_abi_version", "mpt_create", "mpt_destroy", "mpt_last_error", "mpt_scene_upload", "mpt_materials_upload",

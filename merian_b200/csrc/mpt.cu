@@ -18,6 +18,7 @@
 #include <chrono>
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -106,7 +107,7 @@ MPT_DEV bool scatter(const ShadingPoint& sp, f3 ray_d, Rng& rng, f3& throughput,
 }
 
 // --------------------------------------------------------------------------------------- primary visibility
-template <bool COUNT>
+template <bool COUNT, bool TWO_LEVEL>
 __global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ SceneView S, CameraParams cam, uint32_t w, uint32_t h, uint32_t mask, PackedHitInfo* out,
                                                       Counters* ctr) {
     // 8x4 pixel tiles per warp keep primary rays of a warp spatially coherent
@@ -120,7 +121,7 @@ __global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ Sc
     camera_ray(cam, x, y, w, h, o, d, tmin, tmax);
     uint32_t nn = 0, nt = 0;
     MaterialAlphaTest at{&S};
-    const HitRec hr = trace_closest<COUNT>(S.accel, o, d, tmin, tmax, mask, at, nn, nt);
+    const HitRec hr = trace_closest<COUNT, TWO_LEVEL>(S.accel, o, d, tmin, tmax, mask, at, nn, nt);
     PackedHitInfo p;
     if (hr.tri == kMiss) {
         p.instance_id = kMiss;
@@ -144,14 +145,14 @@ __global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ Sc
 }
 
 // --------------------------------------------------------------------------------------- arbitrary rays
-template <bool COUNT>
+template <bool COUNT, bool TWO_LEVEL>
 __global__ void __launch_bounds__(kThreads) k_trace(const __grid_constant__ SceneView S, const float4* rays, uint64_t n, uint32_t mask, uint32_t* hits6, Counters* ctr) {
     const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 ro = __ldg(rays + 2 * i), rd = __ldg(rays + 2 * i + 1);
     uint32_t nn = 0, nt = 0;
     MaterialAlphaTest at{&S};
-    const HitRec hr = trace_closest<COUNT>(S.accel, xyz(ro), xyz(rd), ro.w, rd.w, mask, at, nn, nt);
+    const HitRec hr = trace_closest<COUNT, TWO_LEVEL>(S.accel, xyz(ro), xyz(rd), ro.w, rd.w, mask, at, nn, nt);
     uint32_t* o = hits6 + 6 * i;
     if (hr.tri == kMiss) {
         o[0] = o[1] = o[2] = o[3] = kMiss;
@@ -234,14 +235,23 @@ __global__ void __launch_bounds__(kThreads) k_shade_primary(const __grid_constan
 // Persistent warps with per-lane dynamic fetch: a lane whose ray has finished does not wait for the slowest ray of
 // its batch; when fewer than kRefillThreshold lanes of the warp are still traversing, the warp re-converges, all idle
 // lanes claim new rays with ONE atomicAdd (ballot + prefix popcount), and traversal resumes.
-constexpr int kRefillThreshold = 24;
-template <bool COUNT, bool MEDIUM>
-__global__ void __launch_bounds__(kThreads) k_extend(const __grid_constant__ SceneView S, const float4* __restrict__ q_o, const float4* __restrict__ q_d,
-                                                     PathBuffers pb, uint32_t bounce, uint32_t mask, Counters* ctr) {
+struct ExtendTune {
+    uint32_t refill;   // re-converge and refill when fewer than this many lanes are still traversing
+    uint32_t postpone; // Traversal::postpone
+};
+// 7 resident blocks of 128 threads per SM (<= 72 registers, no spills): measured optimum on B200 (6 blocks/80 regs: -5 %,
+// 8 blocks/64 regs with spills: -2 %, DESIGN.md "extend: occupancy").
+#ifndef MPT_EXTEND_MIN_BLOCKS
+#define MPT_EXTEND_MIN_BLOCKS 7
+#endif
+template <bool COUNT, bool MEDIUM, bool TWO_LEVEL>
+__global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_extend(const __grid_constant__ SceneView S, const float4* __restrict__ q_o, const float4* __restrict__ q_d,
+                                                     PathBuffers pb, uint32_t bounce, uint32_t mask, ExtendTune tune, Counters* ctr) {
     const uint32_t n = ctr->qcount[bounce];
     MaterialAlphaTest at{&S};
     uint2 stack_mem[kStackSize];
-    Traversal<COUNT, MaterialAlphaTest> T(S.accel, at, stack_mem);
+    Traversal<COUNT, TWO_LEVEL, MaterialAlphaTest> T(S.accel, at, stack_mem);
+
     bool active = false, exhausted = false, finished = false;
     uint32_t slot = 0;
     while (true) {
@@ -256,8 +266,9 @@ __global__ void __launch_bounds__(kThreads) k_extend(const __grid_constant__ Sce
             if (is_hit) {
                 const uint32_t hi = base + __popc(hm & ((1u << lane_id()) - 1u));
                 pb.hq_hit[hi] = make_uint4(T.hit.tri, T.hit.instance, __float_as_uint(T.hit.u), __float_as_uint(T.hit.v));
-                pb.hq_dir[hi] = make_float4(T.dir.x, T.dir.y, T.dir.z, __uint_as_float(slot));
-                if (MEDIUM) pb.hq_org[hi] = make_float4(T.org.x, T.org.y, T.org.z, 0.f);
+                const f3 rd = T.dir();
+                pb.hq_dir[hi] = make_float4(rd.x, rd.y, rd.z, __uint_as_float(slot));
+                if (MEDIUM) { const f3 ro = T.org(); pb.hq_org[hi] = make_float4(ro.x, ro.y, ro.z, 0.f); }
             }
         }
         if (finished && !is_hit && S.env_type != 0u) {
@@ -266,9 +277,9 @@ __global__ void __launch_bounds__(kThreads) k_extend(const __grid_constant__ Sce
             f3 throughput = mk3(th.x, th.y, th.z);
             if (MEDIUM) {
                 const float4 m = pb.med[slot];
-                if (m.x != 0.f || m.y != 0.f || m.z != 0.f) throughput *= vexp(-(kEnvDistance * length(T.dir)) * mk3(m.x, m.y, m.z));
+                if (m.x != 0.f || m.y != 0.f || m.z != 0.f) throughput *= vexp(-(kEnvDistance * length(T.dir())) * mk3(m.x, m.y, m.z));
             }
-            const f3 e = throughput * env_eval(S, T.dir);
+            const f3 e = throughput * env_eval(S, T.dir());
             float4 ra = pb.rad[slot];
             ra.x += e.x;
             ra.y += e.y;
@@ -303,7 +314,7 @@ __global__ void __launch_bounds__(kThreads) k_extend(const __grid_constant__ Sce
                 finished = true;
                 break;
             }
-            if (!queue_empty && __popc(__activemask()) < kRefillThreshold) break;
+            if (!queue_empty && uint32_t(__popc(__activemask())) < tune.refill) break;
         }
         __syncwarp();
     }
@@ -538,6 +549,7 @@ struct mpt_context {
     int device = 0;
     int sm_count = 148;
     uint32_t extend_blocks_per_sm = 8;
+    ExtendTune tune{16u, 0u};
     std::string error;
     // scene
     DevBuf nodes, tris, tri_attr, geometries, prim_to_tri, instances, tlas_prims, xform, xform_it;
@@ -692,8 +704,11 @@ mpt_status run_passes(mpt_context* ctx, const CameraParams& cam, const mpt_rende
             const uint32_t in = uint32_t(b - 1) & 1u;
             time_launch(ctx, true, st, [&] {
                 constexpr bool MED = (FEAT & F_TRANSMISSION) != 0;
-                if (count) k_extend<true, MED><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, pb.q_o[in], pb.q_d[in], pb, uint32_t(b), P.instance_mask, ctr);
-                else k_extend<false, MED><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, pb.q_o[in], pb.q_d[in], pb, uint32_t(b), P.instance_mask, ctr);
+                const bool tl = ctx->view.accel.two_level != 0;
+#define MPT_LAUNCH_EXTEND(C, TL) k_extend<C, MED, TL><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, pb.q_o[in], pb.q_d[in], pb, uint32_t(b), P.instance_mask, ctx->tune, ctr)
+                if (count) { if (tl) MPT_LAUNCH_EXTEND(true, true); else MPT_LAUNCH_EXTEND(true, false); }
+                else { if (tl) MPT_LAUNCH_EXTEND(false, true); else MPT_LAUNCH_EXTEND(false, false); }
+#undef MPT_LAUNCH_EXTEND
             });
             time_launch(ctx, false, st, [&] { k_shade_bounce<FEAT><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, rc, pb, uint32_t(b), ctr); });
             ctx->stats.kernel_launches += 2;
@@ -735,7 +750,12 @@ MPT_API mpt_status mpt_create(int device, mpt_context** out_ctx) {
     ctx->sm_count = prop.multiProcessorCount;
     ctx->view.env_type = 0;
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false, false>, kThreads, 0) == cudaSuccess && occ > 0) ctx->extend_blocks_per_sm = uint32_t(occ);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false, false, false>, kThreads, 0) == cudaSuccess && occ > 0) ctx->extend_blocks_per_sm = uint32_t(occ);
+    // tuning knobs for profiling sessions (defaults are the measured optimum on B200)
+    auto env_u32 = [](const char* name, uint32_t def) { const char* v = getenv(name); return v ? uint32_t(strtoul(v, nullptr, 10)) : def; };
+    ctx->tune.refill = env_u32("MPT_REFILL_THRESHOLD", ctx->tune.refill);
+    ctx->tune.postpone = env_u32("MPT_POSTPONE_THRESHOLD", ctx->tune.postpone);
+    ctx->extend_blocks_per_sm = std::min(ctx->extend_blocks_per_sm, env_u32("MPT_EXTEND_BLOCKS_PER_SM", ctx->extend_blocks_per_sm));
     *out_ctx = ctx;
     return MPT_OK;
 }
@@ -919,6 +939,7 @@ MPT_API mpt_status mpt_scene_upload(mpt_context* ctx, const mpt_scene_desc* d) {
     v.accel.tlas_prims = ctx->tlas_prims.as<uint32_t>();
     v.accel.root = root;
     v.accel.two_level = identity_single ? 0u : 1u;
+    v.accel.prmt_bias = 0x47000000u;
     v.tri_attr = ctx->tri_attr.as<uint4>();
     v.geometries = ctx->geometries.as<uint4>();
     v.prim_to_tri = ctx->prim_to_tri.as<uint32_t>();
@@ -1024,8 +1045,11 @@ MPT_API mpt_status mpt_primary_visibility(mpt_context* ctx, const mpt_camera* ca
     const uint32_t tiles = ((width + 7) / 8) * ((height + 3) / 4);
     const uint32_t blocks = (tiles * 32 + kThreads - 1) / kThreads;
     const CameraParams cam = to_device_camera(*camera);
-    if (ctx->profile_flags & 1u) k_primary<true><<<blocks, kThreads, 0, st>>>(ctx->view, cam, width, height, instance_mask, (PackedHitInfo*)d_tex1, ctx->counters.as<Counters>());
-    else k_primary<false><<<blocks, kThreads, 0, st>>>(ctx->view, cam, width, height, instance_mask, (PackedHitInfo*)d_tex1, ctx->counters.as<Counters>());
+    const bool cnt = ctx->profile_flags & 1u, tl = ctx->view.accel.two_level != 0;
+#define MPT_LAUNCH_PRIMARY(C, TL) k_primary<C, TL><<<blocks, kThreads, 0, st>>>(ctx->view, cam, width, height, instance_mask, (PackedHitInfo*)d_tex1, ctx->counters.as<Counters>())
+    if (cnt) { if (tl) MPT_LAUNCH_PRIMARY(true, true); else MPT_LAUNCH_PRIMARY(true, false); }
+    else { if (tl) MPT_LAUNCH_PRIMARY(false, true); else MPT_LAUNCH_PRIMARY(false, false); }
+#undef MPT_LAUNCH_PRIMARY
     CU(cudaGetLastError());
     ctx->stats.kernel_launches++;
     ctx->stats.rays_primary += uint64_t(width) * height;
@@ -1040,8 +1064,11 @@ MPT_API mpt_status mpt_trace(mpt_context* ctx, const void* d_rays, uint64_t n, u
     cudaStream_t st = (cudaStream_t)stream;
     if (!ctx->counters.p) { CU(ctx->counters.ensure(sizeof(Counters))); CU(cudaMemset(ctx->counters.p, 0, sizeof(Counters))); }
     const uint32_t blocks = uint32_t((n + kThreads - 1) / kThreads);
-    if (ctx->profile_flags & 1u) k_trace<true><<<blocks, kThreads, 0, st>>>(ctx->view, (const float4*)d_rays, n, instance_mask, (uint32_t*)d_hits, ctx->counters.as<Counters>());
-    else k_trace<false><<<blocks, kThreads, 0, st>>>(ctx->view, (const float4*)d_rays, n, instance_mask, (uint32_t*)d_hits, ctx->counters.as<Counters>());
+    const bool cnt = ctx->profile_flags & 1u, tl = ctx->view.accel.two_level != 0;
+#define MPT_LAUNCH_TRACE(C, TL) k_trace<C, TL><<<blocks, kThreads, 0, st>>>(ctx->view, (const float4*)d_rays, n, instance_mask, (uint32_t*)d_hits, ctx->counters.as<Counters>())
+    if (cnt) { if (tl) MPT_LAUNCH_TRACE(true, true); else MPT_LAUNCH_TRACE(true, false); }
+    else { if (tl) MPT_LAUNCH_TRACE(false, true); else MPT_LAUNCH_TRACE(false, false); }
+#undef MPT_LAUNCH_TRACE
     CU(cudaGetLastError());
     ctx->stats.kernel_launches++;
     ctx->stats.rays_continuation += n;
@@ -1061,7 +1088,7 @@ MPT_API mpt_status mpt_render(mpt_context* ctx, const mpt_camera* camera, const 
     // K samples per pixel in flight: about 8M path slots, at least one sample per pixel
     const size_t want = std::max<size_t>(npix, std::min<size_t>(npix * size_t(std::max(P->spp, 1)), size_t(8) << 20));
     const size_t slots = (want / npix) * npix;
-    const mpt_status ps = ensure_pool(ctx, slots, (ctx->feature_union & MPT_GLTF_TRANSMISSION) != 0);
+    const mpt_status ps = ensure_pool(ctx, slots, (ctx->feature_union & (MPT_GLTF_TRANSMISSION | MPT_GLTF_VOLUME)) != 0);
     if (ps != MPT_OK) return ps;
     const PackedHitInfo* tex1 = (const PackedHitInfo*)d_tex1;
     if (!tex1) {
@@ -1072,7 +1099,11 @@ MPT_API mpt_status mpt_render(mpt_context* ctx, const mpt_camera* camera, const 
     }
     const CameraParams cam = to_device_camera(*camera);
     if (P->spp == 0) { CU(cudaMemsetAsync(d_irradiance, 0, npix * 16, st)); return MPT_OK; }
+    // three specialisations of the shading kernels (SURVEY.md §7 "hard parts": Slang drops disabled extensions at compile time):
+    // core glTF only / surface extensions / everything incl. transmission + volume (the only one that carries medium state)
     if (ctx->feature_union == 0) return run_passes<0u>(ctx, cam, *P, tex1, (const float4*)d_albedo, (float4*)d_irradiance, st);
+    if (!(ctx->feature_union & (MPT_GLTF_TRANSMISSION | MPT_GLTF_VOLUME)))
+        return run_passes<0x3Cu>(ctx, cam, *P, tex1, (const float4*)d_albedo, (float4*)d_irradiance, st);
     return run_passes<0x3Fu>(ctx, cam, *P, tex1, (const float4*)d_albedo, (float4*)d_irradiance, st);
 }
 
