@@ -237,6 +237,12 @@ MPT_API mpt_status mpt_materials_upload(mpt_context* ctx, const void* entries, u
                                         uint32_t material_count, const mpt_material_type* types,
                                         uint32_t type_count);
 
+/* MaterialSystem hints, compile-time constants of the reference's composition (material_system.hpp:83-97,
+ * material.slang:20-23, material-system.slang:7): alpha-test threshold (default 0.5), minimum roughness (0.0316) and
+ * whether normal-mapped shading normals are clamped (Keller) to the visible hemisphere (true). */
+MPT_API mpt_status mpt_materials_set_hints(mpt_context* ctx, float alpha_test_threshold, float min_roughness,
+                                           uint32_t clamp_normals);
+
 /* Replaces TextureManager texture creation (texture_manager.cpp:207-243). */
 MPT_API mpt_status mpt_texture_upload(mpt_context* ctx, uint32_t texture_id, uint32_t width,
                                       uint32_t height, uint32_t format, uint32_t wrap_u,

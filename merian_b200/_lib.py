@@ -12,8 +12,11 @@ LIB_PATH = os.path.join(_HERE, "csrc", f"libmpt_{_VARIANT}.so" if _VARIANT else 
 _lib = None
 
 EXPORTS = ["mpt_abi_version", "mpt_create", "mpt_destroy", "mpt_last_error", "mpt_scene_upload", "mpt_materials_upload",
-           "mpt_texture_upload", "mpt_env_set", "mpt_primary_visibility", "mpt_trace", "mpt_render", "mpt_render_host",
-           "mpt_set_profiling", "mpt_get_stats", "mpt_reset_stats", "mpt_bvh_get_info", "mpt_bsdf_check"]
+           "mpt_materials_set_hints", "mpt_texture_upload", "mpt_env_set", "mpt_primary_visibility", "mpt_trace", "mpt_render", "mpt_render_host",
+           "mpt_set_profiling", "mpt_get_stats", "mpt_reset_stats", "mpt_bvh_get_info", "mpt_bsdf_check",
+           # include/mpt_node.h
+           "mptn_create", "mptn_destroy", "mptn_last_error", "mptn_load_config", "mptn_dump_config", "mptn_describe_outputs",
+           "mptn_set_shard", "mptn_process"]
 
 
 class MptError(RuntimeError):
@@ -37,6 +40,7 @@ def lib():
         l.mpt_destroy.restype = None
         l.mpt_scene_upload.argtypes = [C.c_void_p, C.POINTER(abi.SceneDesc)]
         l.mpt_materials_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
+        l.mpt_materials_set_hints.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_uint32]
         l.mpt_texture_upload.argtypes = [C.c_void_p] + [C.c_uint32] * 7 + [C.c_void_p]
         l.mpt_env_set.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_float, C.c_uint32, C.c_uint32, C.c_void_p]
         l.mpt_primary_visibility.argtypes = [C.c_void_p, C.POINTER(abi.Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
@@ -48,6 +52,16 @@ def lib():
         l.mpt_reset_stats.argtypes = [C.c_void_p]
         l.mpt_bvh_get_info.argtypes = [C.c_void_p, C.POINTER(abi.BvhInfo)]
         l.mpt_bsdf_check.argtypes = [C.c_void_p, C.POINTER(abi.BsdfCheckParams), C.c_void_p]
+        l.mptn_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        l.mptn_destroy.argtypes = [C.c_void_p]
+        l.mptn_destroy.restype = None
+        l.mptn_last_error.restype = C.c_char_p
+        l.mptn_last_error.argtypes = [C.c_void_p]
+        l.mptn_load_config.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint32)]
+        l.mptn_dump_config.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        l.mptn_describe_outputs.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32] + [C.POINTER(C.c_uint32)] * 3
+        l.mptn_set_shard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        l.mptn_process.argtypes = [C.c_void_p, C.POINTER(abi.Camera), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
         if l.mpt_abi_version() != abi.MPT_ABI_VERSION:
             raise RuntimeError("libmpt.so ABI version mismatch")
         _lib = l

@@ -52,6 +52,9 @@ class Context:
     def materials_upload(self, entries, entry_size, count, types, type_count):
         self._check(self.l.mpt_materials_upload(self.h, entries, entry_size, count, C.cast(types, C.c_void_p), type_count))
 
+    def materials_set_hints(self, alpha_test_threshold=0.5, min_roughness=0.0316, clamp_normals=True):
+        self._check(self.l.mpt_materials_set_hints(self.h, alpha_test_threshold, min_roughness, 1 if clamp_normals else 0))
+
     def texture_upload(self, tid, w, h, fmt, wrap_u, wrap_v, filt, pixels):
         self._check(self.l.mpt_texture_upload(self.h, tid, w, h, fmt, wrap_u, wrap_v, filt, _hp(pixels)))
 

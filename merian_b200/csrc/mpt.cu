@@ -749,6 +749,9 @@ MPT_API mpt_status mpt_create(int device, mpt_context** out_ctx) {
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
     ctx->view.env_type = 0;
+    ctx->view.alpha_threshold = kAlphaThreshold;
+    ctx->view.min_roughness = kMinRoughness;
+    ctx->view.clamp_normals = 1u;
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false, false, false>, kThreads, 0) == cudaSuccess && occ > 0) ctx->extend_blocks_per_sm = uint32_t(occ);
     // tuning knobs for profiling sessions (defaults are the measured optimum on B200)
@@ -979,6 +982,16 @@ MPT_API mpt_status mpt_materials_upload(mpt_context* ctx, const void* entries, u
     ctx->view.material_stride_words = entry_size / 4;
     ctx->view.material_types = ctx->material_types.as<uint2>();
     ctx->materials_ready = true;
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_materials_set_hints(mpt_context* ctx, float alpha_test_threshold, float min_roughness, uint32_t clamp_normals) {
+    if (!ctx) return MPT_ERR_INVALID_ARGUMENT;
+    if (!(alpha_test_threshold >= 0.f && alpha_test_threshold <= 1.f) || !(min_roughness >= 0.f && min_roughness <= 1.f))
+        return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "hints out of range");
+    ctx->view.alpha_threshold = alpha_test_threshold;
+    ctx->view.min_roughness = min_roughness;
+    ctx->view.clamp_normals = clamp_normals ? 1u : 0u;
     return MPT_OK;
 }
 

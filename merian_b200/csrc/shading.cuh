@@ -47,6 +47,9 @@ struct SceneView {
     float env_intensity;
     const float4* __restrict__ env_pixels;
     uint32_t env_w, env_h;
+    // MaterialSystem hints (material_system.hpp:83-97)
+    float alpha_threshold, min_roughness;
+    uint32_t clamp_normals;
 };
 
 constexpr float kRayTMax = 1e7f;           // SCENE_RAY_TMAX, hit.slang:8
@@ -177,14 +180,14 @@ MPT_DEV void material_sample(const SceneView& S, uint32_t material_id, const Sha
         const float nx = (raw.x * 2.0f - 1.0f) * normal_scale, ny = (raw.y * 2.0f - 1.0f) * normal_scale;
         const float nz = sqrtf(fmaxf(0.0f, 1.0f - (nx * nx + ny * ny)));
         const Frame mapped = frame_apply_normal_map(sd.frame, mk3(nx, ny, nz));
-        const f3 cn = keller_clamp(mapped.n, sd.face_normal, sd.wi); // merian_hint_clamp_normals = true
+        const f3 cn = S.clamp_normals ? keller_clamp(mapped.n, sd.face_normal, sd.wi) : mapped.n; // merian_hint_clamp_normals
         fr = frame_from_tangent(cn, mapped.t, 1.0f);
     }
     if (em_tex != kNoTexture) {
         const f4 t = sample_tex(S, em_tex, sd.uv);
         emission = emission * mk3(t.x, t.y, t.z);
     }
-    const float alpha = sq(fmaxf(roughness, kMinRoughness));
+    const float alpha = sq(fmaxf(roughness, S.min_roughness));
     b.gltf = 1u;
     b.base = mk3(base.x, base.y, base.z);
     b.ax = b.ay = b.alpha = alpha;
@@ -194,7 +197,7 @@ MPT_DEV void material_sample(const SceneView& S, uint32_t material_id, const Sha
     b.eta = sd.ior / (sd.front_facing ? ior : 1.0f);
     b.tw = 0.f;
     b.coat_w = 0.f;
-    b.coat_alpha = sq(kMinRoughness);
+    b.coat_alpha = sq(S.min_roughness);
     b.sheen_col = mk3(0.f);
     b.sheen_alpha = 0.f;
     b.max_sheen = 0.f;
@@ -223,7 +226,7 @@ MPT_DEV void material_sample(const SceneView& S, uint32_t material_id, const Sha
                 const uint32_t ct = rd16(off + 8), crt = rd16(off + 10);
                 if (ct != kNoTexture) b.coat_w *= sample_tex(S, ct, sd.uv).x;
                 if (crt != kNoTexture) cr *= sample_tex(S, crt, sd.uv).y;
-                b.coat_alpha = sq(fmaxf(cr, kMinRoughness));
+                b.coat_alpha = sq(fmaxf(cr, S.min_roughness));
             }
             off += 12;
         }
@@ -394,7 +397,7 @@ struct MaterialAlphaTest {
         const uint4* ap = S->tri_attr + size_t(tri) * 3;
         const uint4 a0 = __ldg(ap), a1 = __ldg(ap + 1);
         const f2 uv = (1.0f - u - v) * half2_bits_to_f2(a0.y) + u * half2_bits_to_f2(a1.x) + v * half2_bits_to_f2(a1.w);
-        return sample_tex(*S, alpha_tex, uv).w < kAlphaThreshold;
+        return sample_tex(*S, alpha_tex, uv).w < S->alpha_threshold;
     }
 };
 

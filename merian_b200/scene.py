@@ -229,7 +229,7 @@ class Mesh:
     indices: Optional[np.ndarray] = None  # (P,3) uint8/uint16/uint32, or None (IndexType::None)
     material_id: int = 0
     flags: int = MESH_IS_OPAQUE
-    instance_mask: int = 0xFF
+    instance_mask: int = 0x01  # Scene::Mesh default (scene.hpp:193)
 
 
 @dataclass

@@ -305,8 +305,8 @@ inline float3 offset_ray_origin(float3 pos, float3 n) {
 constexpr float SCENE_RAY_TMIN = 0.f, SCENE_RAY_TMAX = 1e7f; // hit.slang:7-8
 constexpr float ENV_MAP_DISTANCE = 1e7f;                      // environment-map.slang:11
 constexpr float SCENE_THROUGHPUT_THRESHOLD = 1e-5f;           // scene.slang:24
-constexpr float MIN_ROUGHNESS = 0.0316f;                      // material.slang:23
-constexpr float ALPHA_TEST_THRESHOLD = 0.5f;                  // material-system.slang:7
+constexpr float DEFAULT_MIN_ROUGHNESS = 0.0316f;              // material.slang:23
+constexpr float DEFAULT_ALPHA_TEST_THRESHOLD = 0.5f;          // material-system.slang:7
 
 struct Scene {
     std::vector<Mesh> meshes;
@@ -322,6 +322,9 @@ struct Scene {
     uint32_t material_entry_size = 0, material_count = 0;
     std::vector<mpt_material_type> material_types;
     std::vector<Texture> textures;
+    // MaterialSystem hints (material_system.hpp:83-97): compile-time constants of the reference's composition
+    float MIN_ROUGHNESS = DEFAULT_MIN_ROUGHNESS, ALPHA_TEST_THRESHOLD = DEFAULT_ALPHA_TEST_THRESHOLD;
+    bool clamp_normals = true;
 
     uint32_t env_type = MPT_ENV_EMPTY;
     float env_to_local[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
@@ -406,7 +409,7 @@ struct Scene {
             const float nz = std::sqrt(std::max(0.0f, 1.0f - dot(nxy, nxy)));
             const Frame mapped = sd.frame.apply_normal_map(float3(nxy.x, nxy.y, nz));
             // merian_hint_clamp_normals = true (material.slang:20)
-            const float3 clamped_n = keller_clamp_normal(mapped.n, sd.face_normal, sd.wi);
+            const float3 clamped_n = clamp_normals ? keller_clamp_normal(mapped.n, sd.face_normal, sd.wi) : mapped.n;
             shading_frame = Frame(clamped_n, mapped.t);
         }
         const float alpha = pow2(std::max(roughness, MIN_ROUGHNESS));
@@ -940,6 +943,13 @@ int oracle_materials_upload(oracle_context* c, const void* entries, uint32_t ent
     s.material_entry_size = entry_size;
     s.material_count = count;
     s.material_types.assign(types, types + type_count);
+    return 0;
+}
+
+int oracle_materials_set_hints(oracle_context* c, float alpha_test_threshold, float min_roughness, uint32_t clamp_normals) {
+    c->scene.ALPHA_TEST_THRESHOLD = alpha_test_threshold;
+    c->scene.MIN_ROUGHNESS = min_roughness;
+    c->scene.clamp_normals = clamp_normals != 0;
     return 0;
 }
 

@@ -71,6 +71,9 @@ class OracleContext:
     def materials_upload(self, entries, entry_size, count, types, type_count):
         assert self.l.oracle_materials_upload(self.h, entries, C.c_uint32(entry_size), C.c_uint32(count), types, C.c_uint32(type_count)) == 0
 
+    def materials_set_hints(self, alpha_test_threshold=0.5, min_roughness=0.0316, clamp_normals=True):
+        assert self.l.oracle_materials_set_hints(self.h, C.c_float(alpha_test_threshold), C.c_float(min_roughness), C.c_uint32(1 if clamp_normals else 0)) == 0
+
     def texture_upload(self, tid, w, h, fmt, wrap_u, wrap_v, filt, pixels):
         assert self.l.oracle_texture_upload(self.h, C.c_uint32(tid), C.c_uint32(w), C.c_uint32(h), C.c_uint32(fmt), C.c_uint32(wrap_u),
                                             C.c_uint32(wrap_v), C.c_uint32(filt), _p(pixels)) == 0

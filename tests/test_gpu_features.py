@@ -288,3 +288,31 @@ def test_error_behaviour(gpu_ctx):
     one = fresh.render(cam, render_params(8, 8, 3, L=1))  # max path length 1: emission at the primary vertex only
     assert np.isfinite(one).all()
     fresh.close()
+
+
+def test_material_system_hints(gpu_ctx):
+    """alpha-test threshold / min roughness / normal clamping are MaterialSystem settings (material_system.hpp:83-97)."""
+    rng = np.random.default_rng(11)
+    a = np.zeros((16, 16, 4), np.uint8)
+    a[..., :3] = 220
+    a[..., 3] = rng.integers(0, 256, (16, 16))
+    nm = np.zeros((16, 16, 4), np.uint8)
+    nm[..., 0] = rng.integers(60, 200, (16, 16))
+    nm[..., 1] = rng.integers(60, 200, (16, 16))
+    nm[..., 2:] = 255
+    texs = [Texture(a, srgb=False, filter=abi.FILTER_NEAREST), Texture(nm, srgb=False, filter=abi.FILTER_NEAREST)]
+    mats = [GltfMaterial(base_color_factor=(0.8, 0.8, 0.8, 1), base_color_texture=0, normal_texture=1, metallic_factor=1.0, roughness_factor=0.0),
+            GltfMaterial(base_color_factor=(0.2, 0.6, 0.2, 1), metallic_factor=0, roughness_factor=1.0)]
+    t = SceneTables(_layer_scene(mats, [_quad_mesh(0.5, 1.0, 0, flags=0), _quad_mesh(-0.5, 2.0, 1)], texs))
+    o = _both(gpu_ctx, t)
+    cam = t.desc.camera.to_abi(0)
+    base = gpu_ctx.primary_visibility(cam, 96, 96)
+    try:
+        for hints in ((0.8, 0.2, False), (0.2, 0.0316, True)):
+            gpu_ctx.materials_set_hints(*hints)
+            o.materials_set_hints(*hints)
+            ref = _check_vis(gpu_ctx, o, cam, 96, 96)
+            _check_render(gpu_ctx, o, cam, render_params(64, 64, 16), tol_frac=0.10)
+        assert (ref["instance_id"] + ref["geometry_index"] != base["instance_id"] + base["geometry_index"]).any()  # threshold moved the holes
+    finally:
+        gpu_ctx.materials_set_hints()
