@@ -237,7 +237,6 @@ __global__ void __launch_bounds__(kThreads) k_shade_primary(const __grid_constan
 // lanes claim new rays with ONE atomicAdd (ballot + prefix popcount), and traversal resumes.
 struct ExtendTune {
     uint32_t refill;   // re-converge and refill when fewer than this many lanes are still traversing
-    uint32_t postpone; // Traversal::postpone
 };
 // 7 resident blocks of 128 threads per SM (<= 72 registers, no spills): measured optimum on B200 (6 blocks/80 regs: -5 %,
 // 8 blocks/64 regs with spills: -2 %, DESIGN.md "extend: occupancy").
@@ -549,7 +548,11 @@ struct mpt_context {
     int device = 0;
     int sm_count = 148;
     uint32_t extend_blocks_per_sm = 8;
-    ExtendTune tune{16u, 0u};
+    ExtendTune tune{16u};
+    // Path slots in flight, in Mi (128 B of queues + state each, 160 B with a medium). Launches of a few hundred thousand rays
+    // are latency-bound (one batch per warp, time = the slowest ray), so bigger passes amortise the tails of the late
+    // bounces: 8 / 16 / 32 / 64 Mi slots -> 2379 / 2632 / 2780 / 2859 Msamples/s on C3. 64 Mi slots = 8.6 GB of 180 GB.
+    uint32_t pool_mslots = 64;
     std::string error;
     // scene
     DevBuf nodes, tris, tri_attr, geometries, prim_to_tri, instances, tlas_prims, xform, xform_it;
@@ -757,7 +760,7 @@ MPT_API mpt_status mpt_create(int device, mpt_context** out_ctx) {
     // tuning knobs for profiling sessions (defaults are the measured optimum on B200)
     auto env_u32 = [](const char* name, uint32_t def) { const char* v = getenv(name); return v ? uint32_t(strtoul(v, nullptr, 10)) : def; };
     ctx->tune.refill = env_u32("MPT_REFILL_THRESHOLD", ctx->tune.refill);
-    ctx->tune.postpone = env_u32("MPT_POSTPONE_THRESHOLD", ctx->tune.postpone);
+    ctx->pool_mslots = std::max(1u, env_u32("MPT_POOL_MSLOTS", ctx->pool_mslots));
     ctx->extend_blocks_per_sm = std::min(ctx->extend_blocks_per_sm, env_u32("MPT_EXTEND_BLOCKS_PER_SM", ctx->extend_blocks_per_sm));
     *out_ctx = ctx;
     return MPT_OK;
@@ -1099,7 +1102,12 @@ MPT_API mpt_status mpt_render(mpt_context* ctx, const mpt_camera* camera, const 
     cudaStream_t st = (cudaStream_t)stream;
     const size_t npix = size_t(P->width) * P->height;
     // K samples per pixel in flight: about 8M path slots, at least one sample per pixel
-    const size_t want = std::max<size_t>(npix, std::min<size_t>(npix * size_t(std::max(P->spp, 1)), size_t(8) << 20));
+    size_t budget = size_t(ctx->pool_mslots) << 20;
+    if (budget > ctx->pool_slots) { // growing: never take more than a quarter of what is free right now
+        size_t free_b = 0, total_b = 0;
+        if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess) budget = std::max(ctx->pool_slots, std::min(budget, free_b / 4 / 160));
+    }
+    const size_t want = std::max<size_t>(npix, std::min<size_t>(npix * size_t(std::max(P->spp, 1)), budget));
     const size_t slots = (want / npix) * npix;
     const mpt_status ps = ensure_pool(ctx, slots, (ctx->feature_union & (MPT_GLTF_TRANSMISSION | MPT_GLTF_VOLUME)) != 0);
     if (ps != MPT_OK) return ps;

@@ -241,7 +241,7 @@ class Node:
 
 @dataclass
 class Texture:
-    pixels: np.ndarray  # (H,W,4) uint8 or float32
+    pixels: object  # (H,W,4) uint8 or float32 array, or a callable returning one (generated at upload time)
     srgb: bool = False
     wrap_u: int = abi.WRAP_REPEAT
     wrap_v: int = abi.WRAP_REPEAT
@@ -482,7 +482,7 @@ def upload_scene(backend, tables: SceneTables):
     (merian_b200.Context for the product; oracle_py.OracleContext in tests)."""
     d = tables.desc
     for tid, t in enumerate(d.textures):
-        px = np.ascontiguousarray(t.pixels)
+        px = np.ascontiguousarray(t.pixels() if callable(t.pixels) else t.pixels)  # callables defer large synthetic textures
         if px.dtype == np.uint8:
             fmt = abi.TEX_RGBA8_SRGB if t.srgb else abi.TEX_RGBA8_UNORM
         else:

@@ -159,9 +159,37 @@ def _noise_texture(size, seed, channels="rgb"):
     return px
 
 
+class _TileTextures:
+    """C4's 4 x 64 textures at full size without minutes of noise synthesis or 17 GB of host memory: four seeded base
+    tiles per kind, and texture k = base tile (k mod 4) rolled by a seeded offset (tiling noise stays tiling) — made when
+    the texture is uploaded, not when the scene is described."""
+
+    def __init__(self, size, seed):
+        self.size, self.seed, self._base = size, seed, {}
+
+    def base(self, kind, i):
+        if (kind, i) not in self._base:
+            px = _noise_texture(self.size, self.seed * 7919 + 16 * kind + i)
+            if kind == 2:  # normal map: small tilt around +z
+                px[..., 0] = 128 + (px[..., 0].astype(np.int32) - 128) // 4
+                px[..., 1] = 128 + (px[..., 1].astype(np.int32) - 128) // 4
+                px[..., 2] = 255
+            elif kind == 3:  # emissive: sparse bright spots
+                px[..., :3] = np.where(px[..., :3] > 200, px[..., :3], 0)
+            self._base[(kind, i)] = px
+        return self._base[(kind, i)]
+
+    def make(self, kind, mat_id):
+        def gen():
+            r = np.random.default_rng(self.seed * 104729 + 4 * mat_id + kind)
+            dy, dx = (int(v) for v in r.integers(0, self.size, 2))
+            return np.ascontiguousarray(np.roll(self.base(kind, mat_id % 4), (dy, dx), axis=(0, 1)))
+        return gen
+
+
 def terrain(nx: int = 1000, ny: int = 500, size: float = 100.0, height: float = 12.0, seed: int = 1, patches=(1, 1),
             textured: bool = False, texture_size: int = 4096, env: bool = True, env_size=(4096, 2048), width: int = 1920,
-            height_px: int = 1080) -> SceneDescription:
+            height_px: int = 1080, tiled_textures: bool = False) -> SceneDescription:
     """Displaced grid of nx*ny*2 triangles over a size x size square (y up), fBm height.
     patches=(px,py) splits it into px*py meshes, one glTF material each (C4: 8x8 = 64 textured materials)."""
     H = fbm((ny + 1, nx + 1), seed, octaves=7) * height
@@ -178,6 +206,7 @@ def terrain(nx: int = 1000, ny: int = 500, size: float = 100.0, height: float = 
 
     px_n, py_n = patches
     rng = np.random.default_rng(seed + 1000)
+    tiles = _TileTextures(texture_size, seed) if (textured and tiled_textures) else None
     meshes, materials, textures = [], [], []
     for pj in range(py_n):
         for pi in range(px_n):
@@ -194,7 +223,16 @@ def terrain(nx: int = 1000, ny: int = 500, size: float = 100.0, height: float = 
             # CCW seen from +y: (v00, v01, v11), (v00, v11, v10)
             idx = np.stack([np.stack([v00, v01, v11], 1), np.stack([v00, v11, v10], 1)], 1).reshape(-1, 3).astype(np.uint32)
             mat_id = len(materials)
-            if textured:
+            if textured and tiles is not None:
+                tbase = len(textures)
+                for kind, srgb in ((0, True), (1, False), (2, False), (3, True)):
+                    textures.append(Texture(tiles.make(kind, mat_id), srgb=srgb))
+                materials.append(GltfMaterial(base_color_factor=(1, 1, 1, 1), emissive_factor=(0.2, 0.2, 0.2),
+                                              roughness_factor=float(rng.uniform(0.05, 1.0)),
+                                              metallic_factor=float(rng.integers(0, 2)), base_color_texture=tbase,
+                                              metallic_roughness_texture=tbase + 1, normal_texture=tbase + 2,
+                                              emissive_texture=tbase + 3))
+            elif textured:
                 tbase = len(textures)
                 textures.append(Texture(_noise_texture(texture_size, seed * 7919 + 4 * mat_id + 0), srgb=True))
                 textures.append(Texture(_noise_texture(texture_size, seed * 7919 + 4 * mat_id + 1), srgb=False))

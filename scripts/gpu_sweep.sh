@@ -14,6 +14,6 @@ for l in open('gpurun_out/sweep.jsonl'):
     if l.startswith('=='): print(l.strip(), end='  ')
     else:
         try:
-            d=json.loads(l); r=d['roofline']; print(f"{d['value']:.0f} Ms/s  extend {r['avg_launch_ms']:.3f} ms  share {r['extend_share_of_step']:.2f} shade {r['shade_share_of_step']:.2f} frac {r['frac']:.3f}")
+            d=json.loads(l); r=d['roofline']; print(f"{d['value']:.0f} Ms/s  extend {r['avg_launch_ms']:.3f} ms  share {r['extend_share_of_step']:.2f} shade {r['shade_share_of_step']:.2f} frac {r['frac']:.3f} clk {d['clocks']['sm_mhz']} {d['clocks']['reasons']}")
         except Exception as e: print('ERR', l[:200])
 PY
