@@ -36,12 +36,14 @@ def load_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def load_traffic():
-    """ncu `dram__bytes_read.sum + dram__bytes_write.sum` per extend launch from the committed capture, or None."""
+def load_traffic(rays_per_launch):
+    """ncu `dram__bytes_read.sum + dram__bytes_write.sum` of k_extend from the committed `--set full` capture
+    (profiles/extend_traffic.json holds it per ray), scaled to the rays of this run's average launch; or None."""
     p = os.path.join(ROOT, "profiles", "extend_traffic.json")
     if os.path.exists(p):
         with open(p) as f:
-            return json.load(f).get("dram_bytes_per_launch")
+            per_ray = json.load(f).get("dram_bytes_per_ray")
+        return per_ray * rays_per_launch if per_ray else None
     return None
 
 
@@ -278,7 +280,7 @@ def run_ours(args):
             "mrays_per_s": mrays,  # continuation rays (primary hits come from the GBuffer texture)
             "rays_per_sample": float(rays[0].item()) / total_samples,
             "roofline": {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": load_traffic(), "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
+                         "traffic": load_traffic(rays_per_launch), "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
                          "tris_per_ray": tris_per_ray, "rays_per_launch": rays_per_launch, "avg_launch_ms": extend_ms,
                          "extend_share_of_step": st.extend_ms / ms if ms > 0 else None, "shade_share_of_step": st.shade_ms / ms if ms > 0 else None},
             "cpu_baseline": base,
