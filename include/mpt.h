@@ -279,6 +279,46 @@ MPT_API mpt_status mpt_render_host(mpt_context* ctx, const mpt_camera* camera,
                                    const mpt_render_params* params, const void* h_tex1,
                                    const void* h_albedo, void* h_irradiance, void* stream);
 
+/* ---- Accumulate, plain mode ----------------------------------------------
+ * Replaces the accumulate pass of the `Accumulate` node (include/merian-graph/nodes/accumulate/accumulate.slang:103-255,
+ * src/merian-graph/nodes/accumulate/accumulate.cpp:153-167) for a signal that is reused at the SAME pixel
+ * ("use motion vectors" off), firefly filter and adaptive alpha off:
+ *   src: NaN/Inf -> 0, luminance clamped to `hard_clamp`;  clear or alpha == 0: out = src, history = 1;
+ *   else history' = min(history + 1, max_history), out = lerp(prev_out, src, max(1 - alpha, 1 / history')).
+ * History texels are the reference's (uint2: .x = GBuffer enc_normal, .y = f16 linear_z | f16 length << 16), so the f16
+ * counter saturates at 2048 exactly like the reference; MPT_ACC_HISTORY_F32 stores the length as f32 bits in .y
+ * instead (no depth, no cap). MPT_ACC_GBUFFER_CHECK = "gbuffer check: always" for the same pixel
+ * (reprojection_valid, reprojection.slang:56-71) without the stochastic neighbourhood search; without the flag the
+ * check mode is "never". prev and out may alias (in-place accumulation). */
+enum { MPT_ACC_GBUFFER_CHECK = 0x1, MPT_ACC_HISTORY_F32 = 0x2 };
+typedef struct mpt_accumulate_params {
+    uint32_t width, height;
+    float alpha;             /* "alpha", pc.accum_alpha (accumulate.cpp:175) */
+    float max_history;       /* "max history"; INFINITY = "inf history" (accumulate.cpp:178-183) */
+    float hard_clamp;        /* "hard clamp", pc.firefly_hard_clamp; INFINITY = off (accumulate.cpp:229-233) */
+    float normal_reject_cos; /* pc.normal_reject_cos  (only with MPT_ACC_GBUFFER_CHECK) */
+    float z_reject_percent;  /* pc.z_reject_percent   (only with MPT_ACC_GBUFFER_CHECK) */
+    uint32_t clear;          /* pc.clear: first iteration or a clear request (accumulate.cpp:154-160) */
+    uint32_t flags;          /* MPT_ACC_* */
+} mpt_accumulate_params;
+typedef struct mpt_accumulate_buffers {
+    const void* d_prev_out;     /* float4 per pixel (in_prev_out);  may be NULL when clear */
+    const void* d_prev_history; /* uint2 per pixel  (in_prev_history); may be NULL when clear */
+    void* d_out;                /* float4 per pixel (out_out) */
+    void* d_history;            /* uint2 per pixel  (out_history) */
+    const void* d_gbuf_tex0;    /* GBuffer tex0, uint2 per pixel, or NULL (history normal = 0) */
+    const void* d_gbuf_tex2;    /* GBuffer tex2, float4 per pixel, or NULL (history depth = 0) */
+} mpt_accumulate_buffers;
+/* d_src: float4 per pixel (rgb + second moment in a), e.g. the irradiance image of mpt_render. */
+MPT_API mpt_status mpt_accumulate(mpt_context* ctx, const mpt_accumulate_params* params, const void* d_src,
+                                  const mpt_accumulate_buffers* buffers, void* stream);
+/* mpt_render with the accumulate step fused into the resolve kernel: the frame's irradiance image is never written
+ * to or re-read from HBM (saves 2 x 16 B per pixel per iteration). Same arguments as mpt_render + mpt_accumulate. */
+MPT_API mpt_status mpt_render_accumulate(mpt_context* ctx, const mpt_camera* camera, const mpt_render_params* params,
+                                         const void* d_tex1, const void* d_albedo,
+                                         const mpt_accumulate_params* acc_params,
+                                         const mpt_accumulate_buffers* buffers, void* stream);
+
 /* Counters. profile_flags: bit0 = count BVH nodes/triangles per ray (slower kernels), bit1 = CUDA-event
  * timing of every extend/shade launch. */
 MPT_API mpt_status mpt_set_profiling(mpt_context* ctx, uint32_t profile_flags);

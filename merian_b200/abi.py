@@ -92,6 +92,20 @@ class RenderParams(C.Structure):
                 ("sample_offset", C.c_uint32), ("sample_stride", C.c_uint32), ("scene_time", C.c_float)]
 
 
+ACC_GBUFFER_CHECK, ACC_HISTORY_F32 = 0x1, 0x2
+
+
+class AccumulateParams(C.Structure):  # push constants of accumulate.slang:80-97 that the plain path reads
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("alpha", C.c_float), ("max_history", C.c_float),
+                ("hard_clamp", C.c_float), ("normal_reject_cos", C.c_float), ("z_reject_percent", C.c_float),
+                ("clear", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class AccumulateBuffers(C.Structure):
+    _fields_ = [("d_prev_out", C.c_void_p), ("d_prev_history", C.c_void_p), ("d_out", C.c_void_p), ("d_history", C.c_void_p),
+                ("d_gbuf_tex0", C.c_void_p), ("d_gbuf_tex2", C.c_void_p)]
+
+
 class Ray(C.Structure):
     _fields_ = [("origin", C.c_float * 3), ("tmin", C.c_float), ("direction", C.c_float * 3), ("tmax", C.c_float)]
 

@@ -105,6 +105,25 @@ class Context:
                                            self._stream()))
         return h_out
 
+    # ------------------------------------------------------------------ Accumulate node, plain mode (include/mpt.h)
+    @staticmethod
+    def _acc_buffers(prev_out, prev_history, out, history, tex0, tex2):
+        p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        return abi.AccumulateBuffers(p(prev_out), p(prev_history), p(out), p(history), p(tex0), p(tex2))
+
+    def accumulate_device(self, acc_params, src, prev_out, prev_history, out, history, tex0=None, tex2=None):
+        """src/prev_out/out: float32 (H, W, 4); prev_history/history: int32 (H, W, 2) holding the uint2 texels."""
+        b = self._acc_buffers(prev_out, prev_history, out, history, tex0, tex2)
+        self._check(self.l.mpt_accumulate(self.h, C.byref(acc_params), C.c_void_p(src.data_ptr()), C.byref(b), self._stream()))
+        return out, history
+
+    def render_accumulate_device(self, cam, params, acc_params, prev_out, prev_history, out, history, tex1=None, albedo=None, tex0=None, tex2=None):
+        b = self._acc_buffers(prev_out, prev_history, out, history, tex0, tex2)
+        self._check(self.l.mpt_render_accumulate(self.h, C.byref(cam), C.byref(params), C.c_void_p(tex1.data_ptr()) if tex1 is not None else None,
+                                                 C.c_void_p(albedo.data_ptr()) if albedo is not None else None, C.byref(acc_params), C.byref(b),
+                                                 self._stream()))
+        return out, history
+
     # ------------------------------------------------------------------ counters
     def set_profiling(self, flags):
         self._check(self.l.mpt_set_profiling(self.h, flags))

@@ -382,8 +382,79 @@ __global__ void __launch_bounds__(kThreads) k_shade_bounce(const __grid_constant
     }
 }
 
+// --------------------------------------------------------------------------------------- accumulate
+// The plain path of the Accumulate node (include/merian-graph/nodes/accumulate/accumulate.slang:103-255 with
+// USE_MOTION_VECTORS = false, firefly filter and adaptive alpha off): same pixel of the previous frame, optional GBuffer
+// validation of that pixel (GBUFFER_CHECK_ALWAYS without the stochastic neighbourhood search), history length counter,
+// result = lerp(prev, src, max(1 - alpha, 1 / history)). Every product and sum is rounded separately so the image
+// is bit-identical to the oracle's.
+struct AccumArgs {
+    const float4* prev_out;
+    const uint2* prev_history; // .x = enc_normal, .y = f16 linear_z | f16 length << 16 (accumulate.slang:49-52)
+    float4* out;
+    uint2* history;
+    const uint2* gbuf_tex0;    // .x = enc_normal (gbuffer.slang:79), or NULL
+    const float4* gbuf_tex2;   // .z = linear_z, .w = delta_z (gbuffer.slang:81), or NULL
+    float alpha, max_history, hard_clamp, normal_reject_cos, z_reject_percent;
+    uint32_t clear, flags, enabled;
+};
+MPT_DEV float lerp_rn(float a, float b, float s) { return __fadd_rn(__fmul_rn(a, __fsub_rn(1.0f, s)), __fmul_rn(b, s)); }
+MPT_DEV float luminance_rn(float r, float g, float b) { return __fadd_rn(__fadd_rn(__fmul_rn(r, 0.299f), __fmul_rn(g, 0.587f)), __fmul_rn(b, 0.114f)); }
+MPT_DEV void accumulate_pixel(const AccumArgs& a, uint32_t pix, float4 src) {
+    uint32_t enc_normal = 0u;
+    float linear_z = 0.f, delta_z = 0.f;
+    if (a.gbuf_tex0) enc_normal = a.gbuf_tex0[pix].x;
+    if (a.gbuf_tex2) { const float4 m = a.gbuf_tex2[pix]; linear_z = fminf(m.z, 65504.0f); delta_z = m.w; } // MAX_HISTORY_Z, :45,110
+    // firefly hard clamp, :120-138 (filter off: max_l = pc.firefly_hard_clamp)
+    if (!(isfinite(src.x) && isfinite(src.y) && isfinite(src.z) && isfinite(src.w))) {
+        src = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+        const float l = luminance_rn(src.x, src.y, src.z);
+        if (l > a.hard_clamp) {
+            const float factor = __fdiv_rn(a.hard_clamp, l);
+            src.x = __fmul_rn(src.x, factor); src.y = __fmul_rn(src.y, factor); src.z = __fmul_rn(src.z, factor);
+            src.w = __fmul_rn(src.w, __fmul_rn(factor, factor));
+        }
+    }
+    const bool f32_history = (a.flags & MPT_ACC_HISTORY_F32) != 0u;
+    auto encode_history = [&](float length) {
+        if (f32_history) return make_uint2(enc_normal, __float_as_uint(length));
+        return make_uint2(enc_normal, uint32_t(__half_as_ushort(__float2half_rn(linear_z))) | (uint32_t(__half_as_ushort(__float2half_rn(length))) << 16));
+    };
+    if (a.clear || a.alpha == 0.f) { // :141-146
+        a.out[pix] = src;
+        a.history[pix] = encode_history(1.0f);
+        return;
+    }
+    const uint2 ph = a.prev_history[pix];
+    const float prev_length = f32_history ? __uint_as_float(ph.y) : __half2float(__ushort_as_half((unsigned short)(ph.y >> 16)));
+    bool found = true;
+    if (a.flags & MPT_ACC_GBUFFER_CHECK) { // reprojection_valid, reprojection.slang:56-71
+        const f3 n = decode_normal(enc_normal), pn = decode_normal(ph.x);
+        const float prev_z = __half2float(__ushort_as_half((unsigned short)(ph.y & 0xFFFFu)));
+        const float d = __fadd_rn(__fadd_rn(__fmul_rn(n.x, pn.x), __fmul_rn(n.y, pn.y)), __fmul_rn(n.z, pn.z));
+        found = a.normal_reject_cos <= d && fabsf(__fadd_rn(__fsub_rn(linear_z, prev_z), delta_z)) <= __fmul_rn(a.z_reject_percent, fmaxf(linear_z, prev_z));
+    }
+    const float4 po = found ? a.prev_out[pix] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (found && isfinite(po.x) && isfinite(po.y) && isfinite(po.z) && isfinite(po.w)) { // :228-251
+        const float new_history = fminf(__fadd_rn(prev_length, 1.0f), a.max_history);
+        const float alpha = fmaxf(__fsub_rn(1.0f, a.alpha), __fdiv_rn(1.0f, new_history));
+        a.out[pix] = make_float4(lerp_rn(po.x, src.x, alpha), lerp_rn(po.y, src.y, alpha), lerp_rn(po.z, src.z, alpha), lerp_rn(po.w, src.w, alpha));
+        a.history[pix] = encode_history(new_history);
+    } else {
+        a.out[pix] = src;
+        a.history[pix] = encode_history(1.0f);
+    }
+}
+__global__ void __launch_bounds__(kThreads) k_accumulate(AccumArgs a, const float4* src, uint32_t npix) {
+    const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix < npix) accumulate_pixel(a, pix, src[pix]);
+}
+
 // --------------------------------------------------------------------------------------- resolve
-__global__ void __launch_bounds__(kThreads) k_resolve(RenderConst rc, PathBuffers pb, const float4* albedo, float4* out, Counters* ctr) {
+// `sum` carries the running sums between the passes of one call; on the last pass the result goes to `out`, or through
+// accumulate_pixel into the accumulation buffers when `acc.enabled` (fused Accumulate: no irradiance image round trip).
+__global__ void __launch_bounds__(kThreads) k_resolve(RenderConst rc, PathBuffers pb, const float4* albedo, float4* out, AccumArgs acc, Counters* ctr) {
     const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix == 0) {
         unsigned long long rays = 0, shaded = 0;
@@ -417,7 +488,8 @@ __global__ void __launch_bounds__(kThreads) k_resolve(RenderConst rc, PathBuffer
         irr = irr / float(rc.spp);
         m2 /= float(rc.spp);
     }
-    out[pix] = make_float4(irr.x, irr.y, irr.z, m2);
+    if (rc.last_pass && acc.enabled) accumulate_pixel(acc, pix, make_float4(irr.x, irr.y, irr.z, m2));
+    else out[pix] = make_float4(irr.x, irr.y, irr.z, m2);
 }
 
 // --------------------------------------------------------------------------------------- BSDF property suite on the device
@@ -669,7 +741,7 @@ mpt_status ensure_pool(mpt_context* ctx, size_t slots, bool need_medium) {
 
 template <uint32_t FEAT>
 mpt_status run_passes(mpt_context* ctx, const CameraParams& cam, const mpt_render_params& P, const PackedHitInfo* tex1, const float4* albedo,
-                      float4* out, cudaStream_t st) {
+                      float4* out, const AccumArgs& acc, cudaStream_t st) {
     const uint32_t npix = P.width * P.height;
     const uint32_t K = uint32_t(std::max<size_t>(1, std::min<size_t>(size_t(std::max(P.spp, 1)), ctx->pool_slots / npix)));
     PathBuffers pb;
@@ -716,7 +788,7 @@ mpt_status run_passes(mpt_context* ctx, const CameraParams& cam, const mpt_rende
             time_launch(ctx, false, st, [&] { k_shade_bounce<FEAT><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, rc, pb, uint32_t(b), ctr); });
             ctx->stats.kernel_launches += 2;
         }
-        k_resolve<<<pix_blocks, kThreads, 0, st>>>(rc, pb, albedo, out, ctr);
+        k_resolve<<<pix_blocks, kThreads, 0, st>>>(rc, pb, albedo, out, acc, ctr);
         ctx->stats.kernel_launches++;
         done += k;
         first = false;
@@ -1091,8 +1163,10 @@ MPT_API mpt_status mpt_trace(mpt_context* ctx, const void* d_rays, uint64_t n, u
     return MPT_OK;
 }
 
-MPT_API mpt_status mpt_render(mpt_context* ctx, const mpt_camera* camera, const mpt_render_params* P, const void* d_tex1, const void* d_albedo,
-                              void* d_irradiance, void* stream) {
+} // extern "C"
+namespace {
+mpt_status render_impl(mpt_context* ctx, const mpt_camera* camera, const mpt_render_params* P, const void* d_tex1, const void* d_albedo,
+                       void* d_irradiance, const AccumArgs& acc, void* stream) {
     if (!ctx || !camera || !P || !d_irradiance) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!ctx->scene_ready || !ctx->materials_ready) return fail(ctx, MPT_ERR_NOT_READY, "scene or materials not uploaded");
     if (!P->width || !P->height || P->spp < 0 || P->max_path_length < 1 || P->sample_stride == 0) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "bad render parameters");
@@ -1119,13 +1193,73 @@ MPT_API mpt_status mpt_render(mpt_context* ctx, const mpt_camera* camera, const 
         tex1 = ctx->tex1_internal.as<PackedHitInfo>();
     }
     const CameraParams cam = to_device_camera(*camera);
-    if (P->spp == 0) { CU(cudaMemsetAsync(d_irradiance, 0, npix * 16, st)); return MPT_OK; }
+    if (P->spp == 0) {
+        CU(cudaMemsetAsync(d_irradiance, 0, npix * 16, st));
+        if (acc.enabled) k_accumulate<<<uint32_t((npix + kThreads - 1) / kThreads), kThreads, 0, st>>>(acc, (const float4*)d_irradiance, uint32_t(npix));
+        return MPT_OK;
+    }
     // three specialisations of the shading kernels (SURVEY.md §7 "hard parts": Slang drops disabled extensions at compile time):
     // core glTF only / surface extensions / everything incl. transmission + volume (the only one that carries medium state)
-    if (ctx->feature_union == 0) return run_passes<0u>(ctx, cam, *P, tex1, (const float4*)d_albedo, (float4*)d_irradiance, st);
+    if (ctx->feature_union == 0) return run_passes<0u>(ctx, cam, *P, tex1, (const float4*)d_albedo, (float4*)d_irradiance, acc, st);
     if (!(ctx->feature_union & (MPT_GLTF_TRANSMISSION | MPT_GLTF_VOLUME)))
-        return run_passes<0x3Cu>(ctx, cam, *P, tex1, (const float4*)d_albedo, (float4*)d_irradiance, st);
-    return run_passes<0x3Fu>(ctx, cam, *P, tex1, (const float4*)d_albedo, (float4*)d_irradiance, st);
+        return run_passes<0x3Cu>(ctx, cam, *P, tex1, (const float4*)d_albedo, (float4*)d_irradiance, acc, st);
+    return run_passes<0x3Fu>(ctx, cam, *P, tex1, (const float4*)d_albedo, (float4*)d_irradiance, acc, st);
+}
+
+mpt_status make_accum_args(mpt_context* ctx, const mpt_accumulate_params* A, const mpt_accumulate_buffers* B, AccumArgs& a) {
+    if (!A || !B || !B->d_out || !B->d_history) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL accumulate argument");
+    const bool blends = !(A->clear || A->alpha == 0.f);
+    if (blends && (!B->d_prev_out || !B->d_prev_history)) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "accumulation without clear needs the previous out / history");
+    if (!(A->alpha >= 0.f && A->alpha <= 1.f)) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "accumulate alpha must be in [0, 1]");
+    if ((A->flags & MPT_ACC_GBUFFER_CHECK) && (A->flags & MPT_ACC_HISTORY_F32))
+        return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "MPT_ACC_HISTORY_F32 stores no depth: it cannot be combined with MPT_ACC_GBUFFER_CHECK");
+    if ((A->flags & MPT_ACC_GBUFFER_CHECK) && (!B->d_gbuf_tex0 || !B->d_gbuf_tex2)) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "MPT_ACC_GBUFFER_CHECK needs GBuffer tex0 and tex2");
+    a.prev_out = (const float4*)B->d_prev_out;
+    a.prev_history = (const uint2*)B->d_prev_history;
+    a.out = (float4*)B->d_out;
+    a.history = (uint2*)B->d_history;
+    a.gbuf_tex0 = (const uint2*)B->d_gbuf_tex0;
+    a.gbuf_tex2 = (const float4*)B->d_gbuf_tex2;
+    a.alpha = A->alpha; a.max_history = A->max_history; a.hard_clamp = A->hard_clamp;
+    a.normal_reject_cos = A->normal_reject_cos; a.z_reject_percent = A->z_reject_percent;
+    a.clear = A->clear; a.flags = A->flags; a.enabled = 1u;
+    return MPT_OK;
+}
+} // namespace
+extern "C" {
+
+MPT_API mpt_status mpt_render(mpt_context* ctx, const mpt_camera* camera, const mpt_render_params* P, const void* d_tex1, const void* d_albedo,
+                              void* d_irradiance, void* stream) {
+    if (!d_irradiance) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    return render_impl(ctx, camera, P, d_tex1, d_albedo, d_irradiance, AccumArgs{}, stream);
+}
+
+MPT_API mpt_status mpt_accumulate(mpt_context* ctx, const mpt_accumulate_params* A, const void* d_src, const mpt_accumulate_buffers* B, void* stream) {
+    if (!ctx || !d_src) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    AccumArgs a{};
+    const mpt_status s = make_accum_args(ctx, A, B, a);
+    if (s != MPT_OK) return s;
+    if (!A->width || !A->height) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "empty image");
+    CU(cudaSetDevice(ctx->device));
+    const uint32_t npix = A->width * A->height;
+    k_accumulate<<<(npix + kThreads - 1) / kThreads, kThreads, 0, (cudaStream_t)stream>>>(a, (const float4*)d_src, npix);
+    CU(cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_render_accumulate(mpt_context* ctx, const mpt_camera* camera, const mpt_render_params* P, const void* d_tex1,
+                                         const void* d_albedo, const mpt_accumulate_params* A, const mpt_accumulate_buffers* B, void* stream) {
+    if (!ctx || !P) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    AccumArgs a{};
+    const mpt_status s = make_accum_args(ctx, A, B, a);
+    if (s != MPT_OK) return s;
+    if (A->width != P->width || A->height != P->height) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "accumulate and render extents differ");
+    if (P->flags & MPT_RENDER_OUTPUT_SUM) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "MPT_RENDER_OUTPUT_SUM (partial sums of one shard) cannot be accumulated: reduce first, then mpt_accumulate");
+    CU(cudaSetDevice(ctx->device));
+    // the running sums of a multi-pass call (and the spp = 0 image) live in a scratch image; with one pass it is never touched
+    CU(ctx->stage_out.ensure(size_t(P->width) * P->height * 16));
+    return render_impl(ctx, camera, P, d_tex1, d_albedo, ctx->stage_out.p, a, stream);
 }
 
 MPT_API mpt_status mpt_render_host(mpt_context* ctx, const mpt_camera* camera, const mpt_render_params* P, const void* h_tex1, const void* h_albedo,

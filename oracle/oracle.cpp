@@ -1054,6 +1054,72 @@ int oracle_render(oracle_context* c, const mpt_camera* cam, const mpt_render_par
     return 0;
 }
 
+// Accumulate node, plain path (accumulate.slang:103-255 with USE_MOTION_VECTORS = false, firefly filter and adaptive alpha
+// off, GBUFFER_CHECK_NEVER or GBUFFER_CHECK_ALWAYS without EXTENDED_SEARCH). Texel formats: accumulate.slang:47-61.
+int oracle_accumulate(const mpt_accumulate_params* A, const float* src_img, const float* prev_out_img, const uint32_t* prev_history,
+                      float* out_img, uint32_t* history, const uint32_t* tex0, const float* tex2) {
+    const size_t npix = size_t(A->width) * A->height;
+    const bool f32_history = (A->flags & MPT_ACC_HISTORY_F32) != 0;
+    for (size_t i = 0; i < npix; i++) {
+        float4 src(src_img[4 * i], src_img[4 * i + 1], src_img[4 * i + 2], src_img[4 * i + 3]);
+        const uint32_t enc_normal = tex0 ? tex0[2 * i] : 0u;                                  // in_gbuffer.get_encoded_normal, :109
+        const float linear_z = std::min(tex2 ? tex2[4 * i + 2] : 0.f, 65504.0f);              // min(gbuf.linear_z, MAX_HISTORY_Z), :111
+        const float delta_z = tex2 ? tex2[4 * i + 3] : 0.f;
+        auto encode_history = [&](float length, uint32_t* o) {                                // :49-52
+            o[0] = enc_normal;
+            o[1] = f32_history ? as_uint(length) : (uint32_t(float_to_half(linear_z)) | (uint32_t(float_to_half(length)) << 16));
+        };
+        // firefly clamping, :120-138 (filter disabled: max_l = pc.firefly_hard_clamp)
+        const float max_l = A->hard_clamp;
+        const bool bad = std::isnan(src.x) || std::isnan(src.y) || std::isnan(src.z) || std::isnan(src.w) || std::isinf(src.x) || std::isinf(src.y) ||
+                         std::isinf(src.z) || std::isinf(src.w);
+        if (bad) {
+            src = float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            const float l = yuv_luminance(float3(src.x, src.y, src.z));
+            if (l > max_l) {
+                const float factor = max_l / l;
+                src.x *= factor; src.y *= factor; src.z *= factor;
+                src.w *= factor * factor;
+            }
+        }
+        float* o = out_img + 4 * i;
+        if (A->clear == 1 || A->alpha == 0.f) {                                               // :141-146
+            o[0] = src.x; o[1] = src.y; o[2] = src.z; o[3] = src.w;
+            encode_history(1.0f, history + 2 * i);
+            continue;
+        }
+        // no motion vectors: prev_ipos = ipos, is_static = true, :176-180
+        const uint32_t ph0 = prev_history[2 * i], ph1 = prev_history[2 * i + 1];
+        const float hist_length = f32_history ? as_float(ph1) : half_to_float(uint16_t(ph1 >> 16));
+        bool found = true;                                                                    // skip_gbuffer_check, :186-187
+        if (A->flags & MPT_ACC_GBUFFER_CHECK) {                                               // reprojection_valid, reprojection.slang:56-71
+            const float3 n = decode_normal(enc_normal), pn = decode_normal(ph0);
+            const float prev_z = half_to_float(uint16_t(ph1 & 0xFFFFu));
+            found = (A->normal_reject_cos <= dot(n, pn)) && (std::fabs((linear_z - prev_z) + delta_z) <= A->z_reject_percent * std::max(linear_z, prev_z));
+        }
+        float4 prev_out(0.f, 0.f, 0.f, 0.f);
+        float prev_history_len = 0.f;
+        if (found) {
+            prev_history_len = hist_length;
+            prev_out = float4(prev_out_img[4 * i], prev_out_img[4 * i + 1], prev_out_img[4 * i + 2], prev_out_img[4 * i + 3]);
+        }
+        const bool prev_bad = std::isnan(prev_out.x) || std::isnan(prev_out.y) || std::isnan(prev_out.z) || std::isnan(prev_out.w) ||
+                              std::isinf(prev_out.x) || std::isinf(prev_out.y) || std::isinf(prev_out.z) || std::isinf(prev_out.w);
+        if (found && !prev_bad) {                                                             // :228-251
+            const float new_history = std::min(prev_history_len + 1.0f, A->max_history);
+            const float alpha = std::max(1.0f - A->alpha, 1.0f / new_history);
+            o[0] = lerp(prev_out.x, src.x, alpha); o[1] = lerp(prev_out.y, src.y, alpha);
+            o[2] = lerp(prev_out.z, src.z, alpha); o[3] = lerp(prev_out.w, src.w, alpha);
+            encode_history(new_history, history + 2 * i);
+        } else {
+            o[0] = src.x; o[1] = src.y; o[2] = src.z; o[3] = src.w;
+            encode_history(1.0f, history + 2 * i);
+        }
+    }
+    return 0;
+}
+
 int oracle_num_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -104,6 +104,17 @@ class OracleContext:
         return self.l.oracle_num_threads()
 
 
+def accumulate(acc_params, src, prev_out=None, prev_history=None, tex0=None, tex2=None):
+    """Accumulate node, plain path (accumulate.slang). Returns (out float32 (H, W, 4), history uint32 (H, W, 2))."""
+    h, w = acc_params.height, acc_params.width
+    out = np.zeros((h, w, 4), np.float32)
+    hist = np.zeros((h, w, 2), np.uint32)
+    c = lambda a, dt: None if a is None else np.ascontiguousarray(a, dtype=dt)
+    src, prev_out, prev_history, tex0, tex2 = c(src, np.float32), c(prev_out, np.float32), c(prev_history, np.uint32), c(tex0, np.uint32), c(tex2, np.float32)
+    assert lib().oracle_accumulate(C.byref(acc_params), _p(src), _p(prev_out), _p(prev_history), _p(out), _p(hist), _p(tex0), _p(tex2)) == 0
+    return out, hist
+
+
 def bsdf_check(**kw):
     p = abi.BsdfCheckParams()
     p.bsdf = kw["bsdf"]
