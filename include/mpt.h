@@ -34,7 +34,8 @@ typedef enum mpt_status {
     MPT_ERR_CUDA = 2,
     MPT_ERR_NOT_READY = 3, /* scene / materials not uploaded yet (render_pt.cpp:98: !scene->is_ready()) */
     MPT_ERR_UNSUPPORTED = 4,
-    MPT_ERR_LIMIT = 5
+    MPT_ERR_LIMIT = 5,
+    MPT_ERR_IO = 6 /* file missing / malformed / short (image_io.cpp throws std::runtime_error for these) */
 } mpt_status;
 
 typedef struct mpt_context mpt_context;
@@ -318,6 +319,23 @@ MPT_API mpt_status mpt_render_accumulate(mpt_context* ctx, const mpt_camera* cam
                                          const void* d_tex1, const void* d_albedo,
                                          const mpt_accumulate_params* acc_params,
                                          const mpt_accumulate_buffers* buffers, void* stream);
+
+/* ---- PFM in / out -------------------------------------------------------
+ * The float wire format at both ends of the path: lat-long env maps come in through image_load_f32
+ * (src/merian-shaders/scene/scene.cpp:780-795) and the `Image Write` node's PFM leg goes out through image_save_f32
+ * (src/merian-graph/nodes/image_write/image_write.cpp:23-30). Format per src/merian/io/image_io.cpp:53-168: "PF" (rgb) or
+ * "Pf" (grey), "width height", scale (negative = little endian), ONE whitespace byte, bottom-up rows of f32. Images in
+ * memory are top-down. Host-only calls take no context; their errors are read with mpt_last_error(NULL). */
+MPT_API mpt_status mpt_pfm_info(const char* path, uint32_t* width, uint32_t* height, uint32_t* channels);
+/* desired_channels 0 = as in the file, else 1..4 (grey replicated, alpha = 1); out holds width*height*channels floats. */
+MPT_API mpt_status mpt_pfm_load(const char* path, uint32_t desired_channels, float* out, uint64_t capacity_floats);
+/* channels 1, 3 or 4; RGBA is written as RGB (PFM has no alpha); little endian, scale -1. */
+MPT_API mpt_status mpt_pfm_save(const char* path, const float* data, uint32_t width, uint32_t height, uint32_t channels);
+/* Scene::process_pending_env_load for a lat-long .pfm (scene.cpp:775-800): load as RGBA32F and mpt_env_set. */
+MPT_API mpt_status mpt_env_load(mpt_context* ctx, const char* path, const float* to_local, float intensity);
+/* The PFM leg of the `Image Write` node for a float4 device image (e.g. the accumulate output): D2H + mpt_pfm_save. */
+MPT_API mpt_status mpt_image_write(mpt_context* ctx, const char* path, const void* d_rgba32f, uint32_t width,
+                                   uint32_t height, void* stream);
 
 /* Counters. profile_flags: bit0 = count BVH nodes/triangles per ray (slower kernels), bit1 = CUDA-event
  * timing of every extend/shade launch. */

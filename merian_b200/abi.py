@@ -8,7 +8,7 @@ import ctypes as C
 MPT_ABI_VERSION = 1
 
 # mpt_status
-MPT_OK, MPT_ERR_INVALID_ARGUMENT, MPT_ERR_CUDA, MPT_ERR_NOT_READY, MPT_ERR_UNSUPPORTED, MPT_ERR_LIMIT = range(6)
+MPT_OK, MPT_ERR_INVALID_ARGUMENT, MPT_ERR_CUDA, MPT_ERR_NOT_READY, MPT_ERR_UNSUPPORTED, MPT_ERR_LIMIT, MPT_ERR_IO = range(7)
 
 # GeometryDataFlags, include/merian-shaders/scene/scene-data.slangh:15-42
 GEOM_PRETRANSFORMED = 0x1

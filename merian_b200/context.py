@@ -61,6 +61,17 @@ class Context:
     def env_set(self, typ, to_local, intensity, w, h, pixels):
         self._check(self.l.mpt_env_set(self.h, typ, _hp(to_local), intensity, w, h, _hp(pixels)))
 
+    def env_load(self, path, to_local, intensity=1.0):
+        """Lat-long .pfm straight from disk (Scene::process_pending_env_load)."""
+        import os
+        self._check(self.l.mpt_env_load(self.h, os.fsencode(path), _hp(np.ascontiguousarray(to_local, np.float32)), intensity))
+
+    def image_write(self, path, image):
+        """PFM leg of the Image Write node for a float32 (H, W, 4) device tensor."""
+        import os
+        h, w = image.shape[:2]
+        self._check(self.l.mpt_image_write(self.h, os.fsencode(path), C.c_void_p(image.data_ptr()), w, h, self._stream()))
+
     # ------------------------------------------------------------------ device entry points (torch tensors)
     def primary_visibility_device(self, cam, w, h, mask=0xFF, out=None):
         if out is None:

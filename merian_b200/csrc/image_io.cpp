@@ -1,0 +1,95 @@
+// image_io.cpp — see image_io.h.
+#include "image_io.h"
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+
+namespace mpt {
+namespace {
+
+struct FileCloser {
+    void operator()(FILE* f) const { if (f) fclose(f); }
+};
+using File = std::unique_ptr<FILE, FileCloser>;
+
+// magic, width, height, scale separated by whitespace, then exactly ONE whitespace byte before the pixels
+std::string parse_header(FILE* f, const char* path, PfmInfo& info) {
+    char magic[3] = {0, 0, 0};
+    float scale = 0.f;
+    if (fscanf(f, "%2s", magic) != 1) return std::string("image_io: bad PFM magic in ") + path;
+    if (std::strcmp(magic, "PF") == 0) info.channels = 3;
+    else if (std::strcmp(magic, "Pf") == 0) info.channels = 1;
+    else return std::string("image_io: bad PFM magic in ") + path;
+    if (fscanf(f, "%d %d %f", &info.width, &info.height, &scale) != 3 || info.width <= 0 || info.height <= 0)
+        return std::string("image_io: malformed PFM header in ") + path;
+    if (fgetc(f) == EOF) return std::string("image_io: malformed PFM header in ") + path;
+    info.little_endian = scale < 0.f;
+    return {};
+}
+
+} // namespace
+
+std::string pfm_read_info(const char* path, PfmInfo& info) {
+    File f(fopen(path, "rb"));
+    if (!f) return std::string("image_io: cannot open ") + path;
+    return parse_header(f.get(), path, info);
+}
+
+std::string pfm_load(const char* path, int desired_channels, PfmInfo& info, std::vector<float>& out) {
+    File f(fopen(path, "rb"));
+    if (!f) return std::string("image_io: cannot open ") + path;
+    std::string err = parse_header(f.get(), path, info);
+    if (!err.empty()) return err;
+    if (desired_channels < 0 || desired_channels > 4) return "image_io: desired_channels must be 0..4";
+    const int sc = info.channels, oc = desired_channels == 0 ? sc : desired_channels;
+    const size_t w = size_t(info.width), h = size_t(info.height);
+    out.assign(w * h * size_t(oc), 0.f);
+    std::vector<float> row(w * size_t(sc));
+    for (size_t y_file = 0; y_file < h; y_file++) { // the file is bottom-up
+        if (fread(row.data(), sizeof(float), row.size(), f.get()) != row.size()) return std::string("image_io: truncated PFM in ") + path;
+        if (!info.little_endian) {
+            for (float& v : row) {
+                uint32_t b;
+                std::memcpy(&b, &v, 4);
+                b = (b << 24) | ((b & 0xFF00u) << 8) | ((b >> 8) & 0xFF00u) | (b >> 24);
+                std::memcpy(&v, &b, 4);
+            }
+        }
+        float* dst = out.data() + (h - 1 - y_file) * w * size_t(oc);
+        if (oc == sc) {
+            std::memcpy(dst, row.data(), row.size() * sizeof(float));
+            continue;
+        }
+        for (size_t x = 0; x < w; x++) {
+            const float r = row[x * sc], g = sc >= 2 ? row[x * sc + 1] : r, b = sc >= 3 ? row[x * sc + 2] : r;
+            const float px[4] = {r, g, b, 1.f};
+            for (int c = 0; c < oc; c++) dst[x * oc + c] = px[c];
+        }
+    }
+    return {};
+}
+
+std::string pfm_save(const char* path, const float* data, int width, int height, int channels) {
+    if (channels != 1 && channels != 3 && channels != 4) return "image_io: PFM supports only 1, 3 or 4 channels";
+    if (width <= 0 || height <= 0 || !data) return "image_io: empty image";
+    File f(fopen(path, "wb"));
+    if (!f) return std::string("image_io: cannot open ") + path + " for write";
+    const int oc = channels == 1 ? 1 : 3;
+    fprintf(f.get(), "%s\n%d %d\n-1\n", oc == 3 ? "PF" : "Pf", width, height);
+    std::vector<float> row(size_t(width) * oc);
+    for (int y = height - 1; y >= 0; --y) {
+        const float* src = data + size_t(y) * width * channels;
+        const float* wr = src;
+        if (channels != oc) {
+            for (int x = 0; x < width; x++)
+                for (int c = 0; c < oc; c++) row[size_t(x) * oc + c] = src[size_t(x) * channels + c];
+            wr = row.data();
+        }
+        if (fwrite(wr, sizeof(float), row.size(), f.get()) != row.size()) return std::string("image_io: short write to ") + path;
+    }
+    return {};
+}
+
+} // namespace mpt

@@ -13,6 +13,7 @@
 // Queues are double-buffered SoA (origin|slot, direction|tmax); per-path state lives in fixed slots.
 #include "../../include/mpt.h"
 #include "bvh8.h"
+#include "image_io.h"
 #include "shading.cuh"
 
 #include <chrono>
@@ -1285,6 +1286,60 @@ MPT_API mpt_status mpt_render_host(mpt_context* ctx, const mpt_camera* camera, c
     if (s != MPT_OK) return s;
     CU(cudaMemcpyAsync(h_irradiance, ctx->stage_out.p, npix * 16, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    return MPT_OK;
+}
+
+// ---- wire formats at either end of the path
+MPT_API mpt_status mpt_pfm_info(const char* path, uint32_t* width, uint32_t* height, uint32_t* channels) {
+    mpt_context* ctx = nullptr;
+    if (!path || !width || !height || !channels) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    PfmInfo info;
+    const std::string err = pfm_read_info(path, info);
+    if (!err.empty()) return fail(ctx, MPT_ERR_IO, err);
+    *width = uint32_t(info.width); *height = uint32_t(info.height); *channels = uint32_t(info.channels);
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_pfm_load(const char* path, uint32_t desired_channels, float* out, uint64_t capacity_floats) {
+    mpt_context* ctx = nullptr;
+    if (!path || !out) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    PfmInfo info;
+    std::vector<float> px;
+    const std::string err = pfm_load(path, int(desired_channels), info, px);
+    if (!err.empty()) return fail(ctx, MPT_ERR_IO, err);
+    if (px.size() > capacity_floats) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "output buffer too small for the image");
+    std::memcpy(out, px.data(), px.size() * sizeof(float));
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_pfm_save(const char* path, const float* data, uint32_t width, uint32_t height, uint32_t channels) {
+    mpt_context* ctx = nullptr;
+    if (!path || !data) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    const std::string err = pfm_save(path, data, int(width), int(height), int(channels));
+    if (!err.empty()) return fail(ctx, err.find("supports only") != std::string::npos || err.find("empty") != std::string::npos ? MPT_ERR_INVALID_ARGUMENT : MPT_ERR_IO, err);
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_env_load(mpt_context* ctx, const char* path, const float* to_local, float intensity) {
+    if (!ctx || !path || !to_local) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    const size_t n = std::strlen(path);
+    if (n < 4 || (std::strcmp(path + n - 4, ".pfm") != 0 && std::strcmp(path + n - 4, ".PFM") != 0))
+        return fail(ctx, MPT_ERR_UNSUPPORTED, "mpt_env_load reads .pfm lat-long maps only (decode other formats on the host and call mpt_env_set)");
+    PfmInfo info;
+    std::vector<float> px;
+    const std::string err = pfm_load(path, 4, info, px); // image_load_f32 -> create_texture_from_rgba32f, scene.cpp:785-789
+    if (!err.empty()) return fail(ctx, MPT_ERR_IO, err);
+    return mpt_env_set(ctx, MPT_ENV_LATLONG, to_local, intensity, uint32_t(info.width), uint32_t(info.height), px.data());
+}
+
+MPT_API mpt_status mpt_image_write(mpt_context* ctx, const char* path, const void* d_rgba32f, uint32_t width, uint32_t height, void* stream) {
+    if (!ctx || !path || !d_rgba32f || !width || !height) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<float> host(size_t(width) * height * 4);
+    CU(cudaMemcpyAsync(host.data(), d_rgba32f, host.size() * sizeof(float), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU(cudaStreamSynchronize((cudaStream_t)stream));
+    const std::string err = pfm_save(path, host.data(), int(width), int(height), 4);
+    if (!err.empty()) return fail(ctx, MPT_ERR_IO, err);
     return MPT_OK;
 }
 
