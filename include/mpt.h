@@ -262,6 +262,21 @@ MPT_API mpt_status mpt_primary_visibility(mpt_context* ctx, const mpt_camera* ca
                                           uint32_t height, uint32_t instance_mask, void* d_tex1,
                                           void* stream);
 
+/* The whole `GBuffer (Raytraced)` node: replaces the gbuffer_rt raygen
+ * (include/merian-graph/nodes/gbuffer_rt/gbuffer_rt.slang:18-94) with the texel layouts of include/merian-shaders/gbuffer.slang:63-82,152-172.
+ * Any image may be NULL (not written). prev_camera NULL = camera (static view: motion vector = -jitter, delta_z = 0).
+ * Static scenes only (prev_pos = pos); material textures are read at LOD 0 (no mip chains in libmpt). */
+typedef struct mpt_gbuffer_images {
+    void* d_tex0;     /* uint2:  .x = encode_normal(material shading normal), .y = half2 grad_z          */
+    void* d_tex1;     /* uint4:  PackedHitInfo (same as mpt_primary_visibility)                           */
+    void* d_tex2;     /* float4: .xy = pixel-space motion vector, .z = min(linear_z, 65504), .w = delta_z */
+    void* d_tex3;     /* float4: .rgb = BSDF::get_albedo(wi) (miss: environment radiance), .a = 1         */
+    void* d_emission; /* float4: .rgb = emission of the primary vertex (the node's `emission` output)     */
+} mpt_gbuffer_images;
+MPT_API mpt_status mpt_gbuffer(mpt_context* ctx, const mpt_camera* camera, const mpt_camera* prev_camera,
+                               uint32_t width, uint32_t height, uint32_t instance_mask,
+                               const mpt_gbuffer_images* images, void* stream);
+
 /* Closest-hit queries for arbitrary rays (Scene::trace_ray, scene.slang:62-76) with
  * RAY_FLAG_CULL_BACK_FACING_TRIANGLES (acceleration-structure.slang:64). d_rays: mpt_ray[n], d_hits: mpt_hit[n]. */
 MPT_API mpt_status mpt_trace(mpt_context* ctx, const void* d_rays, uint64_t n, uint32_t instance_mask,

@@ -106,6 +106,10 @@ class AccumulateBuffers(C.Structure):
                 ("d_gbuf_tex0", C.c_void_p), ("d_gbuf_tex2", C.c_void_p)]
 
 
+class GBufferImages(C.Structure):  # gbuffer.slang:63-82
+    _fields_ = [("d_tex0", C.c_void_p), ("d_tex1", C.c_void_p), ("d_tex2", C.c_void_p), ("d_tex3", C.c_void_p), ("d_emission", C.c_void_p)]
+
+
 class Ray(C.Structure):
     _fields_ = [("origin", C.c_float * 3), ("tmin", C.c_float), ("direction", C.c_float * 3), ("tmax", C.c_float)]
 

@@ -83,6 +83,22 @@ class Context:
         t = self.primary_visibility_device(cam, w, h, mask)
         return t.cpu().numpy().view(abi.PACKED_HIT_DTYPE).reshape(h, w)
 
+    def gbuffer_device(self, cam, w, h, prev_cam=None, mask=0xFF):
+        """The GBuffer (Raytraced) node: dict of device tensors tex0 (H,W,2 i32), tex1 (H,W,4 i32), tex2, tex3, emission (H,W,4 f32)."""
+        dev = self.torch_device
+        g = {"tex0": torch.empty((h, w, 2), dtype=torch.int32, device=dev), "tex1": torch.empty((h, w, 4), dtype=torch.int32, device=dev),
+             "tex2": torch.empty((h, w, 4), dtype=torch.float32, device=dev), "tex3": torch.empty((h, w, 4), dtype=torch.float32, device=dev),
+             "emission": torch.empty((h, w, 4), dtype=torch.float32, device=dev)}
+        imgs = abi.GBufferImages(*[C.c_void_p(g[k].data_ptr()) for k in ("tex0", "tex1", "tex2", "tex3", "emission")])
+        self._check(self.l.mpt_gbuffer(self.h, C.byref(cam), C.byref(prev_cam) if prev_cam is not None else None, w, h, mask, C.byref(imgs), self._stream()))
+        return g
+
+    def gbuffer(self, cam, w, h, prev_cam=None, mask=0xFF):
+        g = {k: v.cpu().numpy() for k, v in self.gbuffer_device(cam, w, h, prev_cam, mask).items()}
+        g["tex0"] = g["tex0"].view(np.uint32)
+        g["tex1"] = g["tex1"].view(abi.PACKED_HIT_DTYPE).reshape(h, w)
+        return g
+
     def trace_device(self, rays, mask=0xFF, hits=None):
         n = rays.shape[0]
         if hits is None:

@@ -282,6 +282,60 @@ template <uint32_t FEAT> MPT_DEV void bsdf_eval_pdf(const Bsdf& b, f3 wi, f3 wo,
     }
 }
 
+// ---------------------------------------------------------------- directional albedo (BSDF::get_albedo, bsdf.slang:19)
+// A denoiser guide, not part of the pt estimate: it feeds GBuffer tex3 (gbuffer_rt.slang:71-72) and through it
+// merian_render_demodulate_albedo. ggx_integral_approx_correlated: brdf-ggx.slang:285-318 (RT Gems ch. 32 fit).
+MPT_DEV f3 ggx_preintegrated(f3 F0, float alpha, float cos_theta) {
+    const float c = fabsf(cos_theta), c2 = c * c, c3 = c2 * c, a = alpha, a3 = alpha * alpha * alpha;
+    const float m1x = 0.995367f + -1.38839f * c, m1y = -0.24751f + 1.97442f * c;
+    const float m2x = 1.0f + 2.68132f * c + 52.366f * c3, m2y = 16.0932f + -3.98452f * c + 59.3013f * c3, m2z = -5.18731f + 255.259f * c + 2544.07f * c3;
+    float bias = (m1x + m1y * a) / (m2x + m2y * a + m2z * a3);
+    const float m3x = -0.0564526f + 3.82901f * c, m3y = 16.91f + -11.0303f * c;
+    const float m4x = 1.0f + 4.11118f * c2 + -1.37886f * c3, m4y = 19.3254f + -28.9947f * c2 + 16.9514f * c3, m4z = 0.545386f + 96.0994f * c2 + -79.4492f * c3;
+    const float scale = (m3x + m3y * a) / (m4x + m4y * a + m4z * a3);
+    bias *= clampf((F0.x + F0.y + F0.z) * (1.0f / 3.0f) * 50.0f, 0.f, 1.f);
+    return F0 * fmaxf(0.0f, scale) + fmaxf(0.0f, bias);
+}
+template <uint32_t FEAT> MPT_DEV f3 bsdf_albedo(const Bsdf& b, f3 wi) {
+    if (!b.gltf) return b.base; // LambertDiffuseBRDF::get_albedo
+    const float spec_alpha = sqrtf(b.ax * b.ay);
+    const bool iri = (FEAT & F_IRIDESCENCE) && b.iri > 0.0f;
+    // Reflective = Mix(Dielectric, Conductor, metallic) (bsdf-mix.slang:51-54: a plain lerp, both branches evaluated)
+    // opaque dielectric: IridescentFresnelMix<GGX, Lambert>::get_albedo, bsdf-iridescence.slang:160-170
+    f3 spec = ggx_preintegrated(mk3(b.f0), spec_alpha, wi.z);
+    if (iri) {
+        const f3 irf = fresnel_iridescent(1.0f, b.iri_ior, mk3(b.f0), b.iri_thick, wi.z);
+        const float die = fresnel_dielectric(wi.z, b.eta);
+        spec = vclamp(spec * mix(mk3(1.0f), irf / fmaxf(die, 1e-4f), b.iri), 0.0f, 1.0f);
+    }
+    f3 dielectric = spec + (mk3(1.0f) - spec) * b.base;
+    {   // Mix(opaque, IridescentRoughDielectric, transmission weight); rough dielectric albedo: bsdf-iridescence.slang:305-315
+        const f3 f0 = mk3(sq((1.0f - b.eta) / (1.0f + b.eta)));
+        f3 rs = ggx_preintegrated(f0, b.alpha, wi.z);
+        if (iri) rs = vclamp(rs * rd_reflectance<FEAT>(b, wi.z) / fmaxf(fresnel_dielectric(wi.z, b.eta), 1e-4f), 0.0f, 1.0f);
+        const f3 rough = rs + (mk3(1.0f) - rs) * sq(b.eta) * b.base;
+        dielectric = mix(dielectric, rough, (FEAT & F_TRANSMISSION) ? b.tw : 0.f);
+    }
+    // IridescentConductor<GGX>::get_albedo, bsdf-iridescence.slang:59-65
+    f3 conductor = ggx_preintegrated(b.base, spec_alpha, wi.z);
+    if (iri) {
+        const f3 F = mix(schlick3(wi.z, b.base), fresnel_iridescent(1.0f, b.iri_ior, b.base, b.iri_thick, wi.z), b.iri);
+        const f3 sch = schlick3(wi.z, b.base);
+        conductor = conductor * F / mk3(fmaxf(sch.x, 1e-4f), fmaxf(sch.y, 1e-4f), fmaxf(sch.z, 1e-4f));
+    }
+    const f3 reflective = mix(dielectric, conductor, b.metallic);
+    // SheenLayer::get_albedo, bsdf-sheen-layer.slang:69-71 (sheen colour 0 => sheen term 0, scaling 1)
+    f3 sheened = reflective;
+    if (FEAT & F_SHEEN) {
+        // SheenBRDF clamps its own alpha to 1e-6 (brdf-sheen.slang:15), the layer's albedo scaling does not
+        sheened = b.sheen_col * sheen_albedo(wi.z, fmaxf(b.sheen_alpha, 1e-6f)) + (1.f - b.max_sheen * sheen_albedo(wi.z, b.sheen_alpha)) * reflective;
+    }
+    // GltfBSDF = Mix(Sheened, FresnelMix<GGX coat, Sheened>(0.04), coat weight), bsdf-fresnel-mix.slang:50-53
+    const f3 cs = ggx_preintegrated(mk3(0.04f), b.coat_alpha, wi.z);
+    const f3 coated = cs + (mk3(1.0f) - cs) * sheened;
+    return mix(sheened, coated, (FEAT & F_CLEARCOAT) ? b.coat_w : 0.f);
+}
+
 // ---------------------------------------------------------------- direction sampling: same RNG draws, same order as the nest
 MPT_DEV bool sample_cos_dir(f3 wi, Rng& rng, f3& wo) { // sampling.slang:24-29 + Lambert/Sheen guards
     const float x0 = rng.next_float(), x1 = rng.next_float();

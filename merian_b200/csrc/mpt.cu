@@ -145,6 +145,76 @@ __global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ Sc
     }
 }
 
+// --------------------------------------------------------------------------------------- GBuffer (Raytraced) node
+// gbuffer_rt.slang:18-94 with the stores of gbuffer.slang:152-172: primary hit, material shading normal, linear depth and its
+// screen-space gradient, depth change and motion vector against the previous camera, directional albedo, emission.
+// Static scene (prev_pos = pos); material textures are read at LOD 0 (libmpt holds no mip chains), so the ray-differential
+// UV gradients of gbuffer_rt.slang:41-50 have no consumer here.
+struct GBufferOut {
+    uint2* tex0;           // enc_normal | half2 grad_z
+    PackedHitInfo* tex1;
+    float4* tex2;          // motion vector.xy | linear_z | delta_z
+    float4* tex3;          // albedo.rgb | 1
+    float4* emission;
+};
+template <uint32_t FEAT, bool TWO_LEVEL>
+__global__ void __launch_bounds__(kThreads) k_gbuffer(const __grid_constant__ SceneView S, CameraParams cam, CameraParams prev_cam, uint32_t w, uint32_t h, uint32_t mask,
+                                                      GBufferOut out) {
+    const uint32_t tiles_x = (w + 7) / 8;
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t tx = warp % tiles_x, ty = warp / tiles_x;
+    const uint32_t x = tx * 8 + (lane_id() & 7u), y = ty * 4 + (lane_id() >> 3);
+    if (x >= w || y >= h) return;
+    f3 o, d;
+    float tmin, tmax;
+    camera_ray(cam, x, y, w, h, o, d, tmin, tmax);
+    uint32_t nn = 0, nt = 0;
+    MaterialAlphaTest at{&S};
+    const HitRec hr = trace_closest<false, TWO_LEVEL>(S.accel, o, d, tmin, tmax, mask, at, nn, nt);
+    const size_t pix = size_t(y) * w + x;
+    PackedHitInfo p;
+    ShadingPoint sp;
+    bool surface = false;
+    if (hr.tri == kMiss) {
+        p.instance_id = kMiss; p.primitive_id = kMiss; p.geometry_index = 0xFFFF; p.instance_index = 0xFFFF;
+        p.bary = __floats2half2_rn(0.f, 0.f);
+    } else {
+        const float4* tp = S.accel.tris + size_t(hr.tri) * 3;
+        p.instance_id = S.accel.instances[hr.instance].custom_index;
+        p.primitive_id = __float_as_uint(__ldg(tp).w);
+        p.geometry_index = uint16_t(__float_as_uint(__ldg(tp + 1).w));
+        p.instance_index = uint16_t(hr.instance);
+        p.bary = __floats2half2_rn(hr.u, hr.v);
+        surface_shading_point<FEAT>(S, o, d, hr, 1.0f, true, sp); // falls back to the environment for UseEnvMap geometry
+        surface = sp.has_material;
+    }
+    if (!surface) env_shading_point(S, o, d, sp);
+    if (out.tex1) out.tex1[pix] = p;
+    const float linear_z = length(sp.pos - o);
+    f2 grad_z = mk2(0.f, 0.f);
+    float delta_z = 0.f;
+    f3 albedo = sp.emission; // miss: store_albedo(Albedo(sp.emission)), gbuffer_rt.slang:90
+    if (surface) {
+        f3 ox, rx, oy, ry;
+        float t0, t1;
+        camera_ray(cam, x + 1, y, w, h, ox, rx, t0, t1);
+        camera_ray(cam, x, y + 1, w, h, oy, ry, t0, t1);
+        const float n_dot_oo = dot(sp.geo_normal, sp.pos - o); // Surface::compute_grad_z, hit.slang:99-103
+        grad_z = mk2(n_dot_oo / dot(sp.geo_normal, rx) - linear_z, n_dot_oo / dot(sp.geo_normal, ry) - linear_z);
+        delta_z = length(sp.pos - prev_cam.position) - linear_z;
+        albedo = bsdf_albedo<FEAT>(sp.bsdf, sp.frame.to_local(-d));
+    }
+    const f2 pp = project_pinhole(prev_cam, sp.pos, w, h); // Scene::compute_motion_vector, scene.slang:404-414
+    const f2 mv = mk2(pp.x - float(x) - cam.jitter_x, pp.y - float(y) - cam.jitter_y);
+    if (out.tex0) {
+        const __half2 g = __floats2half2_rn(grad_z.x, grad_z.y);
+        out.tex0[pix] = make_uint2(encode_normal(sp.frame.n), *reinterpret_cast<const uint32_t*>(&g));
+    }
+    if (out.tex2) out.tex2[pix] = make_float4(mv.x, mv.y, fminf(linear_z, 65504.0f), delta_z);
+    if (out.tex3) out.tex3[pix] = make_float4(albedo.x, albedo.y, albedo.z, 1.f);
+    if (out.emission) out.emission[pix] = make_float4(sp.emission.x, sp.emission.y, sp.emission.z, 0.f); // x transmittance of Vacuum = 1
+}
+
 // --------------------------------------------------------------------------------------- arbitrary rays
 template <bool COUNT, bool TWO_LEVEL>
 __global__ void __launch_bounds__(kThreads) k_trace(const __grid_constant__ SceneView S, const float4* rays, uint64_t n, uint32_t mask, uint32_t* hits6, Counters* ctr) {
@@ -1139,6 +1209,30 @@ MPT_API mpt_status mpt_primary_visibility(mpt_context* ctx, const mpt_camera* ca
     if (cnt) { if (tl) MPT_LAUNCH_PRIMARY(true, true); else MPT_LAUNCH_PRIMARY(true, false); }
     else { if (tl) MPT_LAUNCH_PRIMARY(false, true); else MPT_LAUNCH_PRIMARY(false, false); }
 #undef MPT_LAUNCH_PRIMARY
+    CU(cudaGetLastError());
+    ctx->stats.kernel_launches++;
+    ctx->stats.rays_primary += uint64_t(width) * height;
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_gbuffer(mpt_context* ctx, const mpt_camera* camera, const mpt_camera* prev_camera, uint32_t width, uint32_t height,
+                               uint32_t instance_mask, const mpt_gbuffer_images* images, void* stream) {
+    if (!ctx || !camera || !images || !width || !height) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!ctx->scene_ready || !ctx->materials_ready) return fail(ctx, MPT_ERR_NOT_READY, "scene or materials not uploaded");
+    if (camera->aperture_radius > 0.f) return fail(ctx, MPT_ERR_UNSUPPORTED, "thin-lens camera is out of scope (pinhole only)");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t tiles = ((width + 7) / 8) * ((height + 3) / 4);
+    const uint32_t blocks = (tiles * 32 + kThreads - 1) / kThreads;
+    const CameraParams cam = to_device_camera(*camera), prev = to_device_camera(prev_camera ? *prev_camera : *camera);
+    const GBufferOut out{(uint2*)images->d_tex0, (PackedHitInfo*)images->d_tex1, (float4*)images->d_tex2, (float4*)images->d_tex3, (float4*)images->d_emission};
+    const bool tl = ctx->view.accel.two_level != 0;
+#define MPT_LAUNCH_GBUFFER(F) do { if (tl) k_gbuffer<F, true><<<blocks, kThreads, 0, st>>>(ctx->view, cam, prev, width, height, instance_mask, out); \
+                                   else k_gbuffer<F, false><<<blocks, kThreads, 0, st>>>(ctx->view, cam, prev, width, height, instance_mask, out); } while (0)
+    if (ctx->feature_union == 0) MPT_LAUNCH_GBUFFER(0u);
+    else if (!(ctx->feature_union & (MPT_GLTF_TRANSMISSION | MPT_GLTF_VOLUME))) MPT_LAUNCH_GBUFFER(0x3Cu);
+    else MPT_LAUNCH_GBUFFER(0x3Fu);
+#undef MPT_LAUNCH_GBUFFER
     CU(cudaGetLastError());
     ctx->stats.kernel_launches++;
     ctx->stats.rays_primary += uint64_t(width) * height;

@@ -62,6 +62,7 @@ constexpr uint32_t kNoTexture = 0xFFFFu;
 struct ShadingPoint { // hit.slang:105-147
     f3 pos;
     f3 face_normal_dec; // decode_normal(encode_normal(surface.face_normal)): what get_face_normal() returns
+    f3 geo_normal;      // surface.face_normal itself (GBuffer grad_z, hit.slang:99-103); dead in the pt kernels
     f3 emission;
     Frame frame;
     bool has_material;
@@ -300,6 +301,8 @@ MPT_DEV f3 xf_vec(const float4* m, f3 v) {
 MPT_DEV void env_shading_point(const SceneView& S, f3 ray_o, f3 ray_d, ShadingPoint& sp) {
     sp.pos = ray_o + ray_d * kEnvDistance;
     sp.face_normal_dec = -ray_d; // never read: has_material is false
+    sp.geo_normal = -ray_d;
+    sp.frame = frame_from_normal(-ray_d); // OrthonormalFrame(-ray.Direction), scene.slang:492
     sp.emission = env_eval(S, ray_d);
     sp.has_material = false;
 }
@@ -367,6 +370,7 @@ MPT_DEV void surface_shading_point(const SceneView& S, f3 ray_o, f3 ray_d, const
         }
     }
     sp.pos = pos;
+    sp.geo_normal = face_normal;
     sp.face_normal_dec = decode_normal(encode_normal(face_normal)); // sp.enc_face_normal round trip, scene.slang:443
     sp.has_material = with_material;
     if (with_material) {
@@ -407,6 +411,14 @@ struct CameraParams {
     float near_plane, far_plane;
     float jitter_x, jitter_y;
 };
+// camera.slang:58-70
+MPT_DEV f2 project_pinhole(const CameraParams& c, f3 world_pos, uint32_t w, uint32_t h) {
+    const f3 d = world_pos - c.position;
+    const float t = dot(c.W, c.W) / dot(d, c.W);
+    const f3 plane_pos = t * d - c.W;
+    const f2 ndc = mk2(dot(plane_pos, c.U) / dot(c.U, c.U), dot(plane_pos, c.V) / dot(c.V, c.V));
+    return mk2((ndc.x + 1.f) / 2.f * float(w) - 0.5f, (ndc.y - 1.f) / -2.f * float(h) - 0.5f);
+}
 // Every operation is individually rounded (no FMA contraction) so that the primary rays are bit-identical to a plain
 // IEEE evaluation of camera.slang:29-56 on the host; primary-visibility parity is then exact up to true ties.
 MPT_DEV f3 normalize_rn(f3 v) {

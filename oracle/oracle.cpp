@@ -719,6 +719,84 @@ struct Scene {
         return r;
     }
 
+    // camera.slang:58-70
+    static float2 project_pinhole(const mpt_camera& c, float3 world_pos, uint32_t w, uint32_t h) {
+        const float3 U(c.U[0], c.U[1], c.U[2]), V(c.V[0], c.V[1], c.V[2]), W(c.W[0], c.W[1], c.W[2]);
+        const float3 d = world_pos - float3(c.position[0], c.position[1], c.position[2]);
+        const float t = dot(W, W) / dot(d, W);
+        const float3 plane_pos = t * d - W;
+        const float2 ndc(dot(plane_pos, U) / dot(U, U), dot(plane_pos, V) / dot(V, V));
+        const float2 p((ndc.x - -1.f) / 2.f, (ndc.y - 1.f) / -2.f);
+        return float2(p.x * float(w) - 0.5f, p.y * float(h) - 0.5f);
+    }
+
+    // One pixel of the GBuffer (Raytraced) node: gbuffer_rt.slang:18-94, stores of gbuffer.slang:152-172.
+    // Textures are sampled at LOD 0 (mpt_texture_upload takes no mip chain), so the ray-differential UV gradients of
+    // gbuffer_rt.slang:41-50 have no consumer and are not evaluated. Static scene: prev_pos = pos (scene.slang:392-401
+    // without HasPrevVertices / IsAnimated).
+    struct GBufferTexel {
+        uint32_t tex0[2];
+        Hit hit; // packed into tex1 by the caller (gbuffer.slang:167-169)
+        float tex2[4], tex3[4], emission[4];
+    };
+    GBufferTexel gbuffer_pixel(const mpt_camera& cam, const mpt_camera& prev_cam, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint32_t mask) const {
+        GBufferTexel g;
+        const Ray ray = generate_camera_ray(cam, x, y, w, h);
+        const Hit hit = trace_ray(ray, mask);
+        g.hit = hit;
+        float3 normal, albedo, emission;
+        float linear_z, delta_z = 0.f;
+        float2 grad_z(0.f, 0.f), mv;
+        bool surface_hit = false;
+        if (hit.valid()) {
+            const mpt_geometry_desc& gd = geometry(hit);
+            if ((gd.flags & MPT_GEOM_USE_ENV_MAP) == 0) {
+                surface_hit = true;
+                const Mesh& m = meshes[gd.mesh];
+                uint32_t ia, ib, ic;
+                m.tri(hit.primitive_id, ia, ib, ic);
+                const Surface surface = get_surface(hit, gd, m.vertices[ia], m.vertices[ib], m.vertices[ic]);
+                const float3 prev_pos = surface.pos;
+                linear_z = length(surface.pos - ray.o);
+                const float3 r_x = generate_camera_ray(cam, x + 1, y, w, h).d, r_y = generate_camera_ray(cam, x, y + 1, w, h).d;
+                const float n_dot_oo = dot(surface.face_normal, surface.pos - ray.o);                          // hit.slang:99-103
+                grad_z = float2(n_dot_oo / dot(surface.face_normal, r_x) - linear_z, n_dot_oo / dot(surface.face_normal, r_y) - linear_z);
+                delta_z = length(prev_pos - float3(prev_cam.position[0], prev_cam.position[1], prev_cam.position[2])) - linear_z;
+                const float2 pp = project_pinhole(prev_cam, prev_pos, w, h);                                     // scene.slang:404-414
+                mv = float2(pp.x - float(x) - cam.jitter[0], pp.y - float(y) - cam.jitter[1]);
+                Frame frame = surface.frame;
+                float3 face_normal = surface.face_normal;
+                bool front_facing = true;
+                if (gd.flags & MPT_GEOM_TWO_SIDED) {
+                    front_facing = dot(-ray.d, surface.face_normal) >= 0.f;
+                    if (!front_facing) { frame.flip_normal(); face_normal = -face_normal; }
+                }
+                ShadingData sd{-ray.d, surface.pos, surface.uv, frame, face_normal, 0, 1.0f, front_facing};
+                Frame mat_frame;
+                float3 mat_emission;
+                const MaterialSample mat = get_material_sample(surface.material_id, sd, mat_emission, mat_frame);
+                normal = mat_frame.n;
+                albedo = mat.get_albedo(mat_frame.to_local(-ray.d));
+                emission = mat_emission; // x exterior_volume.transmittance(linear_z) = 1 (Vacuum)
+            }
+        }
+        if (!surface_hit) {
+            const ShadingPoint sp = make_environment_map_shading_point(ray);
+            linear_z = length(sp.pos - ray.o);
+            const float2 pp = project_pinhole(prev_cam, sp.pos, w, h);
+            mv = float2(pp.x - float(x) - cam.jitter[0], pp.y - float(y) - cam.jitter[1]);
+            normal = sp.shading_frame.n;
+            albedo = sp.emission;
+            emission = sp.emission;
+        }
+        g.tex0[0] = encode_normal(normal);
+        g.tex0[1] = uint32_t(float_to_half(grad_z.x)) | (uint32_t(float_to_half(grad_z.y)) << 16);
+        g.tex2[0] = mv.x; g.tex2[1] = mv.y; g.tex2[2] = std::min(linear_z, 65504.0f); g.tex2[3] = delta_z;
+        g.tex3[0] = albedo.x; g.tex3[1] = albedo.y; g.tex3[2] = albedo.z; g.tex3[3] = 1.f;
+        g.emission[0] = emission.x; g.emission[1] = emission.y; g.emission[2] = emission.z; g.emission[3] = 0.f;
+        return g;
+    }
+
     // render_pt.slang:24-90
     float3 trace_path(Ray ray, ShadingPoint sp, Rng& rng, const mpt_render_params& P, uint64_t* ray_count) const {
         Medium medium; // scene.exterior_volume = Vacuum
@@ -987,6 +1065,25 @@ int oracle_primary_visibility(oracle_context* c, const mpt_camera* cam, uint32_t
         for (uint32_t x = 0; x < w; x++) {
             const Ray r = Scene::generate_camera_ray(*cam, x, uint32_t(y), w, h);
             out[size_t(y) * w + x] = pack_hit(s.trace_ray(r, mask));
+        }
+    return 0;
+}
+
+// GBuffer (Raytraced) node, gbuffer_rt.slang. Any of the output images may be NULL.
+int oracle_gbuffer(oracle_context* c, const mpt_camera* cam, const mpt_camera* prev_cam, uint32_t w, uint32_t h, uint32_t mask, uint32_t* tex0,
+                   void* tex1, float* tex2, float* tex3, float* emission) {
+    const Scene& s = c->scene;
+    if (!prev_cam) prev_cam = cam;
+#pragma omp parallel for schedule(dynamic, 4)
+    for (int y = 0; y < int(h); y++)
+        for (uint32_t x = 0; x < w; x++) {
+            const Scene::GBufferTexel g = s.gbuffer_pixel(*cam, *prev_cam, x, uint32_t(y), w, h, mask);
+            const size_t i = size_t(y) * w + x;
+            if (tex0) { tex0[2 * i] = g.tex0[0]; tex0[2 * i + 1] = g.tex0[1]; }
+            if (tex1) ((PackedHitInfo*)tex1)[i] = pack_hit(g.hit);
+            if (tex2) std::memcpy(tex2 + 4 * i, g.tex2, 16);
+            if (tex3) std::memcpy(tex3 + 4 * i, g.tex3, 16);
+            if (emission) std::memcpy(emission + 4 * i, g.emission, 16);
         }
     return 0;
 }

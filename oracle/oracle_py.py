@@ -86,6 +86,13 @@ class OracleContext:
         assert self.l.oracle_primary_visibility(self.h, C.byref(cam), C.c_uint32(w), C.c_uint32(h), C.c_uint32(mask), _p(out)) == 0
         return out
 
+    def gbuffer(self, cam, w, h, prev_cam=None, mask=0xFF):
+        g = {"tex0": np.zeros((h, w, 2), np.uint32), "tex1": np.zeros((h, w), abi.PACKED_HIT_DTYPE), "tex2": np.zeros((h, w, 4), np.float32),
+             "tex3": np.zeros((h, w, 4), np.float32), "emission": np.zeros((h, w, 4), np.float32)}
+        assert self.l.oracle_gbuffer(self.h, C.byref(cam), C.byref(prev_cam) if prev_cam is not None else None, C.c_uint32(w), C.c_uint32(h),
+                                     C.c_uint32(mask), _p(g["tex0"]), _p(g["tex1"]), _p(g["tex2"]), _p(g["tex3"]), _p(g["emission"])) == 0
+        return g
+
     def trace(self, rays, mask=0xFF, return_t=False):
         rays = np.ascontiguousarray(rays)
         hits = np.zeros(len(rays), abi.HIT_DTYPE)

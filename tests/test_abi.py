@@ -71,7 +71,7 @@ def test_struct_layouts_match_header():
               ("mpt_material_type", abi.MaterialType), ("mpt_camera", abi.Camera), ("mpt_render_params", abi.RenderParams),
               ("mpt_ray", abi.Ray), ("mpt_hit", abi.Hit), ("mpt_stats", abi.Stats), ("mpt_bvh_info", abi.BvhInfo),
               ("mpt_bsdf_check_params", abi.BsdfCheckParams), ("mpt_accumulate_params", abi.AccumulateParams),
-              ("mpt_accumulate_buffers", abi.AccumulateBuffers)]
+              ("mpt_accumulate_buffers", abi.AccumulateBuffers), ("mpt_gbuffer_images", abi.GBufferImages)]
     body = "".join(f'printf("{n} %zu\\n", sizeof({n}));\n' for n, _ in checks)
     for n, t in checks:
         for f, _ in t._fields_:

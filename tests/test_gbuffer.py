@@ -1,0 +1,205 @@
+"""GBuffer (Raytraced) node: the oracle's restatement of gbuffer_rt.slang against independent closed forms,
+and the CUDA kernel (mpt_gbuffer) against the oracle."""
+import numpy as np
+import pytest
+
+from merian_b200 import synthetic
+from merian_b200.scene import MESH_IS_OPAQUE, CameraDesc, DiffuseMaterial, GltfMaterial, Mesh, Node, SceneDescription, SceneTables, upload_scene
+
+from helpers import compare_hits, make_oracle, tables
+
+MISS = 0xFFFFFFFF
+
+
+def _half2(word):
+    w = np.ascontiguousarray(word, dtype=np.uint32)
+    return np.stack([(w & 0xFFFF).astype(np.uint16).view(np.float16), (w >> 16).astype(np.uint16).view(np.float16)], -1).astype(np.float32)
+
+
+def _decode_normal(enc):
+    from merian_b200.scene import device_decode_normal
+    e = np.ascontiguousarray(enc, dtype=np.uint32)
+    return device_decode_normal(e.reshape(-1)).reshape(e.shape + (3,))
+
+
+def _primary_dirs(cam, w, h):
+    px, py = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32))
+    nx = 2 * (px + 0.5 + cam.jitter[0]) / w - 1
+    ny = -2 * (py + 0.5 + cam.jitter[1]) / h + 1
+    U, V, W = (np.array(v[:], np.float32) for v in (cam.U, cam.V, cam.W))
+    d = nx[..., None] * U + ny[..., None] * V + W
+    return d / np.linalg.norm(d, axis=-1, keepdims=True)
+
+
+def _project(cam, pos, w, h):
+    """camera.slang:58-70 in float64."""
+    U, V, W, P = (np.array(v[:], np.float64) for v in (cam.U, cam.V, cam.W, cam.position))
+    d = pos.astype(np.float64) - P
+    t = (W @ W) / (d @ W)
+    plane = t[..., None] * d - W
+    ndc = np.stack([(plane @ U) / (U @ U), (plane @ V) / (V @ V)], -1)
+    p = (ndc - np.array([-1.0, 1.0])) / np.array([2.0, -2.0])
+    return p * np.array([w, h]) - 0.5
+
+
+def _material_scene():
+    """Three glTF quads (dielectric, metal, clearcoat + sheen) and a diffuse-model quad in front of the sky."""
+    def quad(cx, mat):
+        s = 0.45
+        p = np.array([[cx - s, -s, 0], [cx + s, -s, 0], [cx + s, s, 0.3], [cx - s, s, 0.3]], np.float32)
+        n = np.tile(np.array([[0, -0.287348, 0.957826]], np.float32), (4, 1))
+        uv = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float32)
+        return Mesh(positions=p, normals=n, uvs=uv, indices=np.array([[0, 1, 2], [0, 2, 3]], np.uint16), material_id=mat, flags=MESH_IS_OPAQUE)
+    mats = [GltfMaterial(base_color_factor=(0.8, 0.3, 0.2, 1), metallic_factor=0.0, roughness_factor=0.5, emissive_factor=(0.1, 0.2, 0.3)),
+            GltfMaterial(base_color_factor=(0.9, 0.8, 0.3, 1), metallic_factor=1.0, roughness_factor=0.25),
+            GltfMaterial(base_color_factor=(0.2, 0.5, 0.7, 1), metallic_factor=0.2, roughness_factor=0.6, clearcoat={"weight": 0.7, "roughness": 0.15},
+                         sheen={"color": (0.6, 0.5, 0.4), "roughness": 0.5}, iridescence={"factor": 0.6, "ior": 1.35, "thickness_min": 150.0, "thickness_max": 350.0}),
+            DiffuseMaterial((0.25, 0.5, 0.75, 1.0))]
+    meshes = [quad(-1.5 + i, i) for i in range(4)]
+    env = synthetic.sky_env(64, 32, sun_peak=50.0, sun_sigma_deg=10.0, sun_dir=(0.2, 0.3, 1.0))
+    return SceneDescription(meshes=meshes, nodes=[Node([i]) for i in range(4)], materials=mats, env=env,
+                            camera=CameraDesc(position=(0.1, 0.2, 3.0), target=(0.0, 0.0, 0.0), yfov_deg=55.0, aspect=1.5, near=0.01, far=100.0))
+
+
+# ------------------------------------------------------------------------------------------------- oracle vs closed forms
+def test_oracle_gbuffer_static_view(oracle_lib):
+    t = tables("cornell")
+    o = make_oracle(t)
+    cam = t.desc.camera.to_abi(0)
+    w = h = 96
+    g = o.gbuffer(cam, w, h)
+    vis = o.primary_visibility(cam, w, h)
+    assert np.array_equal(g["tex1"], vis)                       # store_hit, gbuffer.slang:167-169
+    hit = vis["instance_id"] != MISS
+    assert hit.mean() > 0.9
+    # same camera for both frames: nothing moves on screen (mv = projection round trip - pixel) and depths agree
+    assert np.abs(g["tex2"][..., :2]).max() < 2e-3
+    assert (g["tex2"][..., 3][hit] == 0).all()
+    assert (g["tex3"][..., 3] == 1).all() and (g["emission"][..., 3] == 0).all()
+    # linear_z is the distance along the primary ray: o + d * z lies on the hit triangle's plane
+    d = _primary_dirs(cam, w, h)
+    z = g["tex2"][..., 2]
+    pos = np.array(cam.position[:], np.float32) + d * z[..., None]
+    assert np.abs(pos[hit]).max() < 1.01 * np.abs(np.concatenate([m.positions for m in t.desc.meshes])).max()
+    # grad_z = screen-space derivative of linear_z (hit.slang:97-103): compare with finite differences inside one triangle
+    gz = _half2(g["tex0"][..., 1])
+    tri_key = vis["primitive_id"].astype(np.int64) | (vis["geometry_index"].astype(np.int64) << 32) | (vis["instance_index"].astype(np.int64) << 48)
+    same_x = hit[:, :-1] & hit[:, 1:] & (tri_key[:, :-1] == tri_key[:, 1:])
+    fd_x = (z[:, 1:] - z[:, :-1])[same_x]
+    assert np.abs(gz[:, :-1, 0][same_x] - fd_x).max() < 2e-3 + 2e-3 * np.abs(fd_x).max()
+    same_y = hit[:-1] & hit[1:] & (tri_key[:-1] == tri_key[1:])
+    fd_y = (z[1:] - z[:-1])[same_y]
+    assert np.abs(gz[:-1, :, 1][same_y] - fd_y).max() < 2e-3 + 2e-3 * np.abs(fd_y).max()
+    # Lambert walls: albedo = base colour (brdf-lambert-diffuse.slang get_albedo); the light is the only emitter
+    mats = t.desc.materials
+    geo_mat = np.array([mat for (_mesh, mat, _flags, _prims) in t.geometries])
+    mat_of = geo_mat[(vis["instance_id"] + vis["geometry_index"])[hit]]
+    em = g["emission"][hit][:, :3]
+    for mid in np.unique(mat_of):
+        sel = mat_of == mid
+        m = mats[mid]
+        ef = np.array(getattr(m, "emissive_factor", (0, 0, 0)), np.float32) * np.float32(getattr(m, "emissive_strength", 1.0))
+        np.testing.assert_allclose(em[sel], np.broadcast_to(ef, em[sel].shape), rtol=1e-6)
+    # normals: unit length after decoding, facing the camera for these one-sided walls
+    n = _decode_normal(g["tex0"][..., 0])
+    assert np.abs(np.linalg.norm(n, axis=-1) - 1).max() < 1e-5
+    assert ((n * -d).sum(-1)[hit] > -1e-3).all()
+
+
+def test_oracle_gbuffer_moving_camera_and_miss(oracle_lib):
+    t = SceneTables(_material_scene())
+    o = make_oracle(t)
+    w, h = 120, 80
+    cam = t.desc.camera.to_abi(0)
+    prev_desc = CameraDesc(position=(0.25, 0.1, 3.2), target=(0.05, 0.0, 0.0), yfov_deg=55.0, aspect=1.5, near=0.01, far=100.0)
+    prev = prev_desc.to_abi(0)
+    g = o.gbuffer(cam, w, h, prev_cam=prev)
+    hit = g["tex1"]["instance_id"] != MISS
+    assert 0.2 < hit.mean() < 0.9
+    d = _primary_dirs(cam, w, h)
+    z = g["tex2"][..., 2]
+    P = np.array(cam.position[:], np.float32)
+    pos = P + d * z[..., None]
+    px, py = np.meshgrid(np.arange(w), np.arange(h))
+    mv_ref = _project(prev, pos, w, h) - np.stack([px, py], -1)
+    assert np.abs(g["tex2"][..., :2][hit] - mv_ref[hit]).max() < 5e-3       # compute_motion_vector, scene.slang:404-414
+    dz_ref = np.linalg.norm(pos - np.array(prev.position[:], np.float32), axis=-1) - z
+    assert np.abs(g["tex2"][..., 3][hit] - dz_ref[hit]).max() < 1e-4        # delta_z, gbuffer_rt.slang:38
+    # miss: the environment shading point (gbuffer_rt.slang:82-93): depth clamps to the f16 ceiling, albedo = emission = sky radiance,
+    # normal = -ray direction, no depth gradient
+    miss = ~hit
+    assert (z[miss] == 65504.0).all() and (g["tex0"][..., 1][miss] == 0).all()
+    assert np.array_equal(g["tex3"][miss][:, :3], g["emission"][miss][:, :3]) and (g["emission"][miss][:, :3] > 0).all()
+    n = _decode_normal(g["tex0"][..., 0])
+    assert np.abs(n[miss] + d[miss]).max() < 2e-4
+    # directional albedo: the conductor's is tinted by its base colour, a dielectric's lies between base colour and 1
+    geo_mat = np.array([mat for (_mesh, mat, _flags, _prims) in t.geometries])
+    mat_of = np.where(hit, geo_mat[np.where(hit, g["tex1"]["instance_id"] + g["tex1"]["geometry_index"], 0)], -1)
+    alb = g["tex3"][..., :3]
+    a_metal = alb[hit & (mat_of == 1)].mean(0)
+    assert a_metal[0] > a_metal[1] > a_metal[2] and 0.2 < a_metal[2] < 0.5
+    a_die = alb[hit & (mat_of == 0)]
+    assert (a_die >= np.array([0.8, 0.3, 0.2]) - 1e-4).all() and (a_die <= 1.0).all()
+    assert np.allclose(alb[hit & (mat_of == 3)], [0.25, 0.5, 0.75])
+    np.testing.assert_allclose(g["emission"][hit & (mat_of == 0)][:, :3], np.broadcast_to([0.1, 0.2, 0.3], (int((hit & (mat_of == 0)).sum()), 3)), rtol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------- CUDA vs oracle
+def _compare_gbuffers(got, ref):
+    mism, bary_err, same = compare_hits(got["tex1"], ref["tex1"])
+    assert mism == 0.0 and bary_err == 0.0
+    hit = ref["tex1"]["instance_id"] != MISS
+    # encoded normals: identical up to one snorm16 step per component (fp32 contraction differs between nvcc and gcc)
+    a, b = got["tex0"][..., 0], ref["tex0"][..., 0]
+    dx = np.abs((a & 0xFFFF).astype(np.int16).astype(np.int32) - (b & 0xFFFF).astype(np.int16).astype(np.int32))
+    dy = np.abs((a >> 16).astype(np.int16).astype(np.int32) - (b >> 16).astype(np.int16).astype(np.int32))
+    assert max(dx.max(), dy.max()) <= 1 and (a != b).mean() < 0.02
+    gz_g, gz_r = _half2(got["tex0"][..., 1]), _half2(ref["tex0"][..., 1])
+    assert np.abs(gz_g - gz_r).max() <= 2e-3 * np.maximum(np.abs(gz_r).max(), 1.0)
+    np.testing.assert_allclose(got["tex2"][..., 2], ref["tex2"][..., 2], rtol=2e-6)
+    assert np.abs(got["tex2"][..., :2][hit] - ref["tex2"][..., :2][hit]).max() < 2e-3
+    assert np.abs(got["tex2"][..., 3][hit] - ref["tex2"][..., 3][hit]).max() < 1e-4 * max(1.0, float(ref["tex2"][..., 2][hit].max()))
+    np.testing.assert_allclose(got["tex3"], ref["tex3"], rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(got["emission"], ref["emission"], rtol=2e-4, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("scene", ["cornell", "materials", "terrain", "rocks"])
+def test_cuda_gbuffer_matches_oracle(gpu_ctx, scene):
+    if scene == "cornell":
+        t, (w, h) = tables("cornell"), (128, 128)
+    elif scene == "materials":
+        t, (w, h) = SceneTables(_material_scene()), (150, 100)
+    elif scene == "terrain":
+        t, (w, h) = tables("terrain", nx=200, ny=100, env_size=(256, 128)), (240, 136)
+    else:
+        t, (w, h) = tables("instanced_rocks", n_instances=60, rock_res=17, env_size=(128, 64)), (160, 90)
+    upload_scene(gpu_ctx, t)
+    o = make_oracle(t)
+    cam = t.desc.camera.to_abi(3)
+    cd = t.desc.camera
+    prev = CameraDesc(position=tuple(np.array(cd.position) + [0.05, 0.02, -0.03]), target=cd.target, up=cd.up, yfov_deg=cd.yfov_deg, aspect=cd.aspect,
+                      near=cd.near, far=cd.far).to_abi(2)
+    _compare_gbuffers(gpu_ctx.gbuffer(cam, w, h, prev_cam=prev), o.gbuffer(cam, w, h, prev_cam=prev))
+    g = gpu_ctx.gbuffer(cam, w, h)  # static view
+    assert np.array_equal(g["tex1"], gpu_ctx.primary_visibility(cam, w, h))
+    hit = g["tex1"]["instance_id"] != MISS
+    assert (g["tex2"][..., 3][hit] == 0).all()
+
+
+@pytest.mark.gpu
+def test_gbuffer_feeds_pt_with_demodulation(gpu_ctx):
+    """The node chain gbuffer -> pt: tex1 and tex3 of mpt_gbuffer drive mpt_render with merian_render_demodulate_albedo
+    (render_pt.slang:119-121); multiplying the albedo back gives the plain image."""
+    import torch
+    from merian_b200 import abi
+    from helpers import render_params
+    t = tables("cornell")
+    upload_scene(gpu_ctx, t)
+    cam = t.desc.camera.to_abi(0)
+    w = h = 96
+    g = gpu_ctx.gbuffer_device(cam, w, h)
+    plain = gpu_ctx.render_device(cam, render_params(w, h, 16), tex1=g["tex1"])
+    demod = gpu_ctx.render_device(cam, render_params(w, h, 16, flags=abi.RENDER_EMISSION_ON_PRIMARY | abi.RENDER_DEMODULATE_ALBEDO), tex1=g["tex1"], albedo=g["tex3"])
+    back = demod[..., :3] * torch.clamp(g["tex3"][..., :3], min=1e-2)
+    assert torch.allclose(back, plain[..., :3], rtol=1e-4, atol=1e-6)
