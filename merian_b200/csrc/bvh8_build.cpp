@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -37,12 +38,19 @@ struct Node2 {
 
 constexpr int NBINS = 16;
 
+// Builder knobs for tuning sessions (host code only; defaults are the measured optimum).
+float env_float(const char* name, float def) {
+    const char* v = std::getenv(name);
+    return v ? float(std::atof(v)) : def;
+}
+
 struct Builder2 {
     const Box* boxes;
     std::vector<float> cent; // 3 per prim
     std::vector<uint32_t> idx;
     std::vector<Node2> nodes;
     int max_leaf;
+    float trav_cost = 1.0f; // SAH: cost of one node test in units of one primitive test
 
     void build(uint32_t n) {
         idx.resize(n);
@@ -104,7 +112,7 @@ struct Builder2 {
             }
             const float parent_area = box.half_area();
             const float leaf_cost = float(j.count);
-            const float split_cost = (parent_area > 0.f && best_axis >= 0) ? 1.0f + best_cost / parent_area : FLT_MAX;
+            const float split_cost = (parent_area > 0.f && best_axis >= 0) ? trav_cost + best_cost / parent_area : FLT_MAX;
             if (int(j.count) <= max_leaf && split_cost >= leaf_cost) { make_leaf(j.node, j.first, j.count); continue; }
 
             uint32_t mid;
@@ -167,7 +175,9 @@ void build_bvh8(const Box* boxes, uint32_t n, Bvh8& out, int max_leaf) {
     }
     Builder2 b2;
     b2.boxes = boxes;
-    b2.max_leaf = std::min(std::max(max_leaf, 1), 3);
+    b2.max_leaf = std::min(std::max(int(env_float("MPT_BVH_MAX_LEAF", float(max_leaf))), 1), 3);
+    b2.trav_cost = env_float("MPT_BVH_TRAV_COST", 1.0f);
+    const int collapse_mode = int(env_float("MPT_BVH_COLLAPSE", 0.f));
     b2.build(n);
     const std::vector<Node2>& n2 = b2.nodes;
 
@@ -192,7 +202,11 @@ void build_bvh8(const Box* boxes, uint32_t n, Bvh8& out, int max_leaf) {
                 float best_area = -1.f;
                 for (int i = 0; i < nch; i++) {
                     if (n2[ch[i]].count > 0) continue;
-                    const float a = n2[ch[i]].box.half_area();
+                    float a = n2[ch[i]].box.half_area();
+                    if (collapse_mode == 1) { // prefer opening nodes whose children are much smaller than they are
+                        const Node2& c = n2[ch[i]];
+                        a = a - 0.5f * (n2[c.left].box.half_area() + n2[c.right].box.half_area());
+                    }
                     if (a > best_area) { best_area = a; best = i; }
                 }
                 if (best < 0) break;

@@ -36,7 +36,8 @@ struct Counters {
     uint32_t qcount[kMaxBounces + 2]; // qcount[b] = rays queued for the extend of bounce b
     uint32_t hcount[kMaxBounces + 2]; // hcount[b] = surface hits found by the extend of bounce b
     uint32_t fetch[kMaxBounces + 2];  // persistent-thread fetch cursors
-    unsigned long long rays_continuation, rays_primary, shaded_hits, nodes_visited, tris_tested;
+    uint32_t scount[kMaxBounces + 2]; // scount[b] = shadow rays queued by the shade of bounce b - 1 (MPT_RENDER_NEE)
+    unsigned long long rays_continuation, rays_primary, shaded_hits, nodes_visited, tris_tested, rays_shadow;
 };
 
 struct PackedHitInfo { // gbuffer.slang:40-61
@@ -55,6 +56,9 @@ struct PathBuffers {
     float4* thr;      // throughput.rgb | current_ior
     float4* rad;      // radiance.rgb | rng state (bits)
     float4* med;      // medium mu_t.rgb | -   (only touched when the scene has transmissive materials)
+    float4* sq_o;     // shadow queue (MPT_RENDER_NEE): origin.xyz | slot (bits)
+    float4* sq_d;     //                                direction.xyz | -
+    float4* sq_c;     //                                MIS-weighted contribution.rgb if the ray reaches the environment | -
 };
 
 struct RenderConst {
@@ -83,13 +87,14 @@ MPT_DEV uint32_t queue_push_index(bool alive, uint32_t* counter) {
 
 // One scattering step of trace_path (render_pt.slang:35-76): BSDF sample, throughput, medium bookkeeping, make_ray.
 template <uint32_t FEAT>
-MPT_DEV bool scatter(const ShadingPoint& sp, f3 ray_d, Rng& rng, f3& throughput, float& current_ior, f3& medium, f3& out_o, f3& out_d) {
+MPT_DEV bool scatter(const ShadingPoint& sp, f3 ray_d, Rng& rng, f3& throughput, float& current_ior, f3& medium, f3& out_o, f3& out_d, float& out_pdf) {
     if (!sp.has_material || all_below(throughput, kThroughputCut)) return false;
     const f3 wi_world = -ray_d;
     const f3 wi = sp.frame.to_local(wi_world);
     f3 wo_l, weight;
     float pdf;
     if (!bsdf_sample_eval<FEAT>(sp.bsdf, wi, rng, wo_l, pdf, weight)) return false;
+    out_pdf = pdf;
     const f3 wo = sp.frame.to_world(wo_l);
     throughput *= weight;
     const bool transmission = wi.z * wo_l.z < 0.f;
@@ -104,6 +109,42 @@ MPT_DEV bool scatter(const ShadingPoint& sp, f3 ray_d, Rng& rng, f3& throughput,
     if (((dot(wi_world, ng) < 0.f) != (wo_ng < 0.f)) != transmission) return false;
     out_o = offset_ray_origin(sp.pos, wo_ng < 0.f ? -ng : ng);
     out_d = wo;
+    return true;
+}
+
+// Next event estimation towards the lat-long environment (MPT_RENDER_NEE; an addition, the reference's pt has none: SURVEY §0.1).
+// One light sample per path vertex from the alias table, combined with the BSDF-sampled continuation by the balance heuristic:
+//   light sample:  T * f*cos * L / (p_light + p_bsdf)   if the shadow ray reaches the environment
+//   BSDF sample that misses all geometry (k_extend):  weight p_bsdf / (p_bsdf + p_light)
+// so the expectation equals the reference estimator's. Emissive surfaces stay BSDF-sampled only. The light sample draws from
+// its own RNG stream (keyed on the path's RNG state), so the BSDF-sampled paths are the same with and without NEE.
+template <uint32_t FEAT>
+MPT_DEV bool nee_environment(const SceneView& S, const ShadingPoint& sp, f3 ray_d, uint32_t rng_state, f3 throughput, f3 medium, f3& so, f3& sd, f3& contrib) {
+    if (S.env_type != 1u || !sp.has_material || all_below(throughput, kThroughputCut)) return false;
+    Rng r = make_pcg(pcg4d16(rng_state, 0x9E3779B9u, 0x7F4A7C15u, 1u));
+    const float u0 = r.next_float(), u1 = r.next_float(), u2 = r.next_float();
+    f3 wo;
+    float p_light;
+    if (!env_sample(S, u0, u1, u2, wo, p_light)) return false;
+    const f3 wi_world = -ray_d;
+    const f3 wi = sp.frame.to_local(wi_world), wo_l = sp.frame.to_local(wo);
+    f3 e;
+    float p_bsdf;
+    bsdf_eval_pdf<FEAT>(sp.bsdf, wi, wo_l, e, p_bsdf);
+    if (!(e.x > 0.f || e.y > 0.f || e.z > 0.f)) return false;
+    const bool transmission = wi.z * wo_l.z < 0.f;
+    const f3 ng = sp.face_normal_dec;
+    const float wo_ng = dot(wo, ng);
+    if (((dot(wi_world, ng) < 0.f) != (wo_ng < 0.f)) != transmission) return false; // ShadingPoint::make_ray, hit.slang:134-147
+    // the medium the shadow segment would cross (same bookkeeping as scatter): an absorbing interior over ENV_MAP_DISTANCE
+    // transmits nothing, exactly like the BSDF-sampled ray that escapes from inside it
+    f3 med = medium;
+    if (transmission) med = (dot(wi_world, ng) >= 0.f) ? sp.absorption : mk3(0.f);
+    if (med.x != 0.f || med.y != 0.f || med.z != 0.f) return false;
+    contrib = throughput * e * env_eval(S, wo) / (p_light + p_bsdf);
+    if (!finite3(contrib) || !(contrib.x > 0.f || contrib.y > 0.f || contrib.z > 0.f)) return false;
+    so = offset_ray_origin(sp.pos, wo_ng < 0.f ? -ng : ng);
+    sd = wo;
     return true;
 }
 
@@ -244,7 +285,7 @@ __global__ void __launch_bounds__(kThreads) k_trace(const __grid_constant__ Scen
 }
 
 // --------------------------------------------------------------------------------------- wavefront: primary shade
-template <uint32_t FEAT>
+template <uint32_t FEAT, bool NEE>
 __global__ void __launch_bounds__(kThreads) k_shade_primary(const __grid_constant__ SceneView S, CameraParams cam, RenderConst rc, const PackedHitInfo* tex1, PathBuffers pb,
                                                             Counters* ctr) {
     const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
@@ -284,13 +325,23 @@ __global__ void __launch_bounds__(kThreads) k_shade_primary(const __grid_constan
         const uint32_t sidx = rc.sample_offset + (rc.pass_first + k) * rc.sample_stride;
         Rng rng = make_pcg(pcg4d16(x, y, rc.frame, sidx)); // render_pt.slang:114
         f3 throughput = mk3(1.f), medium = mk3(0.f), no, nd;
-        float ior = 1.0f;
+        float ior = 1.0f, pdf = 0.f;
         bool alive = false;
-        if (valid && rc.max_path_length > 1) alive = scatter<FEAT>(sp, d, rng, throughput, ior, medium, no, nd);
+        if (NEE) {
+            f3 so, sd, sc;
+            const bool lit = valid && rc.max_path_length > 1 && nee_environment<FEAT>(S, sp, d, rng.state, throughput, medium, so, sd, sc);
+            const uint32_t si = queue_push_index(lit, &ctr->scount[1]);
+            if (lit) {
+                pb.sq_o[si] = make_float4(so.x, so.y, so.z, __uint_as_float(slot));
+                pb.sq_d[si] = make_float4(sd.x, sd.y, sd.z, 0.f);
+                pb.sq_c[si] = make_float4(sc.x, sc.y, sc.z, 0.f);
+            }
+        }
+        if (valid && rc.max_path_length > 1) alive = scatter<FEAT>(sp, d, rng, throughput, ior, medium, no, nd, pdf);
         const uint32_t qi = queue_push_index(alive, &ctr->qcount[1]);
         if (alive) {
             pb.q_o[0][qi] = make_float4(no.x, no.y, no.z, __uint_as_float(slot));
-            pb.q_d[0][qi] = make_float4(nd.x, nd.y, nd.z, kRayTMax);
+            pb.q_d[0][qi] = make_float4(nd.x, nd.y, nd.z, NEE ? pdf : kRayTMax); // continuation rays all have tmax = SCENE_RAY_TMAX
         }
         if (valid) {
             pb.rad[slot] = make_float4(radiance0.x, radiance0.y, radiance0.z, __uint_as_float(rng.state));
@@ -314,7 +365,7 @@ struct ExtendTune {
 #ifndef MPT_EXTEND_MIN_BLOCKS
 #define MPT_EXTEND_MIN_BLOCKS 7
 #endif
-template <bool COUNT, bool MEDIUM, bool TWO_LEVEL>
+template <bool COUNT, bool MEDIUM, bool TWO_LEVEL, bool NEE>
 __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_extend(const __grid_constant__ SceneView S, const float4* __restrict__ q_o, const float4* __restrict__ q_d,
                                                      PathBuffers pb, uint32_t bounce, uint32_t mask, ExtendTune tune, Counters* ctr) {
     const uint32_t n = ctr->qcount[bounce];
@@ -324,6 +375,7 @@ __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_extend(cons
 
     bool active = false, exhausted = false, finished = false;
     uint32_t slot = 0;
+    float pdf_bsdf = 0.f; // NEE only: the density the ray's direction was sampled with (rides in q_d.w)
     while (true) {
         // ---- retire finished rays (the warp is converged here)
         const bool is_hit = finished && T.hit.tri != kMiss;
@@ -349,7 +401,8 @@ __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_extend(cons
                 const float4 m = pb.med[slot];
                 if (m.x != 0.f || m.y != 0.f || m.z != 0.f) throughput *= vexp(-(kEnvDistance * length(T.dir())) * mk3(m.x, m.y, m.z));
             }
-            const f3 e = throughput * env_eval(S, T.dir());
+            f3 e = throughput * env_eval(S, T.dir());
+            if (NEE) e = e * (pdf_bsdf / (pdf_bsdf + env_pdf(S, T.dir()))); // balance heuristic against nee_environment
             float4 ra = pb.rad[slot];
             ra.x += e.x;
             ra.y += e.y;
@@ -369,7 +422,8 @@ __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_extend(cons
                 if (j < n) {
                     const float4 ro = __ldg(q_o + j), rd = __ldg(q_d + j);
                     slot = __float_as_uint(ro.w);
-                    active = T.init(xyz(ro), xyz(rd), 0.f /* SCENE_RAY_TMIN */, rd.w, mask);
+                    if (NEE) pdf_bsdf = rd.w;
+                    active = T.init(xyz(ro), xyz(rd), 0.f /* SCENE_RAY_TMIN */, NEE ? kRayTMax : rd.w, mask);
                     finished = !active; // masked out: a miss
                 } else {
                     exhausted = true;
@@ -394,8 +448,29 @@ __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_extend(cons
     }
 }
 
+// --------------------------------------------------------------------------------------- wavefront: shadow rays (MPT_RENDER_NEE)
+// Visibility towards the environment with the SAME intersection semantics as the continuation rays (back-face culling, masks,
+// alpha test), so that light samples and BSDF samples see the same scene. Unoccluded: add the MIS-weighted contribution.
+template <bool TWO_LEVEL>
+__global__ void __launch_bounds__(kThreads) k_shadow(const __grid_constant__ SceneView S, PathBuffers pb, uint32_t bounce, uint32_t mask, Counters* ctr) {
+    const uint32_t n = ctr->scount[bounce];
+    MaterialAlphaTest at{&S};
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const float4 ro = __ldg(pb.sq_o + j), rd = __ldg(pb.sq_d + j);
+        if (!trace_any<TWO_LEVEL>(S.accel, xyz(ro), xyz(rd), 0.f, kRayTMax, mask, at)) {
+            const float4 c = __ldg(pb.sq_c + j);
+            const uint32_t slot = __float_as_uint(ro.w);
+            float4 ra = pb.rad[slot]; // one shadow ray per slot and bounce: no race
+            ra.x += c.x;
+            ra.y += c.y;
+            ra.z += c.z;
+            pb.rad[slot] = ra;
+        }
+    }
+}
+
 // --------------------------------------------------------------------------------------- wavefront: shade after extend
-template <uint32_t FEAT>
+template <uint32_t FEAT, bool NEE>
 __global__ void __launch_bounds__(kThreads) k_shade_bounce(const __grid_constant__ SceneView S, RenderConst rc, PathBuffers pb, uint32_t bounce, Counters* ctr) {
     const uint32_t n = ctr->hcount[bounce];
     const uint32_t out = bounce & 1u;
@@ -405,9 +480,9 @@ __global__ void __launch_bounds__(kThreads) k_shade_bounce(const __grid_constant
     for (uint32_t base = warp * 32u; base < n; base += warps_total * 32u) {
         const uint32_t j = base + lane_id();
         const bool valid = j < n;
-        bool alive = false;
-        f3 no, nd, throughput, medium = mk3(0.f);
-        float ior = 1.f;
+        bool alive = false, lit = false;
+        f3 no, nd, throughput, medium = mk3(0.f), so, sd, sc;
+        float ior = 1.f, pdf = 0.f;
         uint32_t slot = 0;
         if (valid) {
             const uint4 hw = __ldg(pb.hq_hit + j);
@@ -438,7 +513,8 @@ __global__ void __launch_bounds__(kThreads) k_shade_bounce(const __grid_constant
             }
             const f3 radiance = mk3(ra.x, ra.y, ra.z) + throughput * sp.emission; // :86
             Rng rng = make_pcg(__float_as_uint(ra.w));
-            if (more) alive = scatter<FEAT>(sp, d, rng, throughput, ior, medium, no, nd);
+            if (NEE && more) lit = nee_environment<FEAT>(S, sp, d, rng.state, throughput, medium, so, sd, sc);
+            if (more) alive = scatter<FEAT>(sp, d, rng, throughput, ior, medium, no, nd, pdf);
             pb.rad[slot] = make_float4(radiance.x, radiance.y, radiance.z, __uint_as_float(rng.state));
             if (alive) {
                 pb.thr[slot] = make_float4(throughput.x, throughput.y, throughput.z, ior);
@@ -448,7 +524,15 @@ __global__ void __launch_bounds__(kThreads) k_shade_bounce(const __grid_constant
         const uint32_t qi = queue_push_index(alive, &ctr->qcount[bounce + 1]);
         if (alive) {
             pb.q_o[out][qi] = make_float4(no.x, no.y, no.z, __uint_as_float(slot));
-            pb.q_d[out][qi] = make_float4(nd.x, nd.y, nd.z, kRayTMax);
+            pb.q_d[out][qi] = make_float4(nd.x, nd.y, nd.z, NEE ? pdf : kRayTMax);
+        }
+        if (NEE) {
+            const uint32_t si = queue_push_index(lit, &ctr->scount[bounce + 1]);
+            if (lit) {
+                pb.sq_o[si] = make_float4(so.x, so.y, so.z, __uint_as_float(slot));
+                pb.sq_d[si] = make_float4(sd.x, sd.y, sd.z, 0.f);
+                pb.sq_c[si] = make_float4(sc.x, sc.y, sc.z, 0.f);
+            }
         }
     }
 }
@@ -528,9 +612,10 @@ __global__ void __launch_bounds__(kThreads) k_accumulate(AccumArgs a, const floa
 __global__ void __launch_bounds__(kThreads) k_resolve(RenderConst rc, PathBuffers pb, const float4* albedo, float4* out, AccumArgs acc, Counters* ctr) {
     const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
     if (pix == 0) {
-        unsigned long long rays = 0, shaded = 0;
-        for (int b = 1; b < rc.max_path_length && b < kMaxBounces; b++) { rays += ctr->qcount[b]; shaded += ctr->hcount[b]; }
+        unsigned long long rays = 0, shaded = 0, shadow = 0;
+        for (int b = 1; b < rc.max_path_length && b < kMaxBounces; b++) { rays += ctr->qcount[b]; shaded += ctr->hcount[b]; shadow += ctr->scount[b]; }
         atomicAdd(&ctr->rays_continuation, rays);
+        atomicAdd(&ctr->rays_shadow, shadow);
         atomicAdd(&ctr->shaded_hits, shaded);
     }
     if (pix >= rc.npix) return;
@@ -699,14 +784,15 @@ struct mpt_context {
     std::string error;
     // scene
     DevBuf nodes, tris, tri_attr, geometries, prim_to_tri, instances, tlas_prims, xform, xform_it;
-    DevBuf materials, material_types, texture_table, env_pixels;
+    DevBuf materials, material_types, texture_table, env_pixels, env_alias, env_pmf;
+    bool env_sampling_ready = false;
     std::vector<TextureSlot> textures;
     SceneView view{};
     uint32_t feature_union = 0;
     bool scene_ready = false, materials_ready = false;
     mpt_bvh_info bvh_info{};
     // wavefront pool
-    DevBuf q_o[2], q_d[2], hq_hit, hq_dir, hq_org, thr, rad, med, counters, tex1_internal, stage_tex1, stage_albedo, stage_out;
+    DevBuf q_o[2], q_d[2], hq_hit, hq_dir, hq_org, thr, rad, med, sq_o, sq_d, sq_c, counters, tex1_internal, stage_tex1, stage_albedo, stage_out;
     size_t pool_slots = 0;
     // stats / profiling
     uint32_t profile_flags = 0;
@@ -787,7 +873,7 @@ void harvest_events(mpt_context* ctx) {
     }
 }
 
-mpt_status ensure_pool(mpt_context* ctx, size_t slots, bool need_medium) {
+mpt_status ensure_pool(mpt_context* ctx, size_t slots, bool need_medium, bool need_shadow) {
     if (slots > ctx->pool_slots) {
         for (int i = 0; i < 2; i++) {
             CU(ctx->q_o[i].ensure(slots * sizeof(float4)));
@@ -803,6 +889,11 @@ mpt_status ensure_pool(mpt_context* ctx, size_t slots, bool need_medium) {
         CU(ctx->med.ensure(ctx->pool_slots * sizeof(float4)));
         CU(ctx->hq_org.ensure(ctx->pool_slots * sizeof(float4)));
     }
+    if (need_shadow) {
+        CU(ctx->sq_o.ensure(ctx->pool_slots * sizeof(float4)));
+        CU(ctx->sq_d.ensure(ctx->pool_slots * sizeof(float4)));
+        CU(ctx->sq_c.ensure(ctx->pool_slots * sizeof(float4)));
+    }
     if (!ctx->counters.p) {
         CU(ctx->counters.ensure(sizeof(Counters)));
         CU(cudaMemset(ctx->counters.p, 0, sizeof(Counters)));
@@ -810,7 +901,76 @@ mpt_status ensure_pool(mpt_context* ctx, size_t slots, bool need_medium) {
     return MPT_OK;
 }
 
-template <uint32_t FEAT>
+// Importance table of the lat-long environment for MPT_RENDER_NEE: texel weight = sin(theta) * (luminance, half of it taken
+// from the 3x3 neighbourhood because env_eval interpolates bilinearly between texel centres) + a small uniform floor, turned
+// into an alias table (Vose) so that a draw costs one 8-byte load. Built on first use from the pixels already in HBM.
+mpt_status ensure_env_sampling(mpt_context* ctx) {
+    if (ctx->env_sampling_ready) return MPT_OK;
+    const uint32_t w = ctx->view.env_w, h = ctx->view.env_h;
+    const size_t n = size_t(w) * h;
+    if (ctx->view.env_type != 1u || n == 0) return MPT_OK; // no environment: nee_environment returns false
+    if (n > 0xFFFFFFFFull) return fail(ctx, MPT_ERR_LIMIT, "environment map too large for the alias table");
+    std::vector<float> px(n * 4);
+    CU(cudaMemcpy(px.data(), ctx->env_pixels.p, n * 16, cudaMemcpyDeviceToHost));
+    std::vector<float> lum(n);
+    for (size_t i = 0; i < n; i++) {
+        const float l = 0.299f * px[4 * i] + 0.587f * px[4 * i + 1] + 0.114f * px[4 * i + 2];
+        lum[i] = (l > 0.f && std::isfinite(l)) ? l : 0.f;
+    }
+    std::vector<double> weight(n);
+    double total = 0.0, total_sin = 0.0;
+    for (uint32_t y = 0; y < h; y++) {
+        const double st = std::sin((double(y) + 0.5) / double(h) * 3.14159265358979323846);
+        total_sin += st * w;
+        for (uint32_t x = 0; x < w; x++) {
+            double nb = 0.0;
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++) nb += lum[size_t((y + h + dy) % h) * w + (x + w + dx) % w]; // repeat addressing, scene.cpp:786-789
+            const double v = st * (0.5 * lum[size_t(y) * w + x] + 0.5 * nb / 9.0);
+            weight[size_t(y) * w + x] = v;
+            total += v;
+        }
+    }
+    std::vector<float> pmf(n);
+    const double floor_share = total > 0.0 ? 0.05 : 1.0; // 5 % of the draws are uniform over the sphere
+    for (uint32_t y = 0; y < h; y++) {
+        const double st = std::sin((double(y) + 0.5) / double(h) * 3.14159265358979323846);
+        for (uint32_t x = 0; x < w; x++) {
+            const size_t i = size_t(y) * w + x;
+            pmf[i] = float((1.0 - floor_share) * (total > 0.0 ? weight[i] / total : 0.0) + floor_share * st / total_sin);
+        }
+    }
+    // Vose's alias method
+    std::vector<uint2> alias(n);
+    std::vector<double> scaled(n);
+    std::vector<uint32_t> small, large;
+    small.reserve(n);
+    large.reserve(n);
+    double sum = 0.0;
+    for (size_t i = 0; i < n; i++) sum += pmf[i];
+    for (size_t i = 0; i < n; i++) {
+        scaled[i] = double(pmf[i]) / sum * double(n);
+        (scaled[i] < 1.0 ? small : large).push_back(uint32_t(i));
+    }
+    while (!small.empty() && !large.empty()) {
+        const uint32_t s_i = small.back(), l_i = large.back();
+        small.pop_back();
+        alias[s_i] = make_uint2(fbits(float(scaled[s_i])), l_i);
+        scaled[l_i] = (scaled[l_i] + scaled[s_i]) - 1.0;
+        if (scaled[l_i] < 1.0) { large.pop_back(); small.push_back(l_i); }
+    }
+    for (uint32_t i : large) alias[i] = make_uint2(fbits(1.0f), i);
+    for (uint32_t i : small) alias[i] = make_uint2(fbits(1.0f), i);
+    for (size_t i = 0; i < n; i++) pmf[i] = float(double(pmf[i]) / sum);
+    CU(ctx->env_alias.upload(alias.data(), n * sizeof(uint2)));
+    CU(ctx->env_pmf.upload(pmf.data(), n * sizeof(float)));
+    ctx->view.env_alias = ctx->env_alias.as<uint2>();
+    ctx->view.env_pmf = ctx->env_pmf.as<float>();
+    ctx->env_sampling_ready = true;
+    return MPT_OK;
+}
+
+template <uint32_t FEAT, bool NEE>
 mpt_status run_passes(mpt_context* ctx, const CameraParams& cam, const mpt_render_params& P, const PackedHitInfo* tex1, const float4* albedo,
                       float4* out, const AccumArgs& acc, cudaStream_t st) {
     const uint32_t npix = P.width * P.height;
@@ -823,6 +983,9 @@ mpt_status run_passes(mpt_context* ctx, const CameraParams& cam, const mpt_rende
     pb.thr = ctx->thr.as<float4>();
     pb.rad = ctx->rad.as<float4>();
     pb.med = ctx->med.as<float4>();
+    pb.sq_o = ctx->sq_o.as<float4>();
+    pb.sq_d = ctx->sq_d.as<float4>();
+    pb.sq_c = ctx->sq_c.as<float4>();
     Counters* ctr = ctx->counters.as<Counters>();
     const bool count = ctx->profile_flags & 1u;
     const int L = std::min(P.max_path_length, kMaxBounces);
@@ -844,19 +1007,24 @@ mpt_status run_passes(mpt_context* ctx, const CameraParams& cam, const mpt_rende
         rc.first_pass = first;
         rc.last_pass = (done + k >= total);
         CU(cudaMemsetAsync(ctr, 0, offsetof(Counters, rays_continuation), st));
-        time_launch(ctx, false, st, [&] { k_shade_primary<FEAT><<<pix_blocks, kThreads, 0, st>>>(ctx->view, cam, rc, tex1, pb, ctr); });
+        time_launch(ctx, false, st, [&] { k_shade_primary<FEAT, NEE><<<pix_blocks, kThreads, 0, st>>>(ctx->view, cam, rc, tex1, pb, ctr); });
         ctx->stats.kernel_launches++;
         for (int b = 1; b < L; b++) {
             const uint32_t in = uint32_t(b - 1) & 1u;
+            if (NEE) { // shadow rays of the vertex shaded last: before the extend so that both add to rad[] in stream order
+                if (ctx->view.accel.two_level) k_shadow<true><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, pb, uint32_t(b), P.instance_mask, ctr);
+                else k_shadow<false><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, pb, uint32_t(b), P.instance_mask, ctr);
+                ctx->stats.kernel_launches++;
+            }
             time_launch(ctx, true, st, [&] {
                 constexpr bool MED = (FEAT & F_TRANSMISSION) != 0;
                 const bool tl = ctx->view.accel.two_level != 0;
-#define MPT_LAUNCH_EXTEND(C, TL) k_extend<C, MED, TL><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, pb.q_o[in], pb.q_d[in], pb, uint32_t(b), P.instance_mask, ctx->tune, ctr)
+#define MPT_LAUNCH_EXTEND(C, TL) k_extend<C, MED, TL, NEE><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, pb.q_o[in], pb.q_d[in], pb, uint32_t(b), P.instance_mask, ctx->tune, ctr)
                 if (count) { if (tl) MPT_LAUNCH_EXTEND(true, true); else MPT_LAUNCH_EXTEND(true, false); }
                 else { if (tl) MPT_LAUNCH_EXTEND(false, true); else MPT_LAUNCH_EXTEND(false, false); }
 #undef MPT_LAUNCH_EXTEND
             });
-            time_launch(ctx, false, st, [&] { k_shade_bounce<FEAT><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, rc, pb, uint32_t(b), ctr); });
+            time_launch(ctx, false, st, [&] { k_shade_bounce<FEAT, NEE><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, rc, pb, uint32_t(b), ctr); });
             ctx->stats.kernel_launches += 2;
         }
         k_resolve<<<pix_blocks, kThreads, 0, st>>>(rc, pb, albedo, out, acc, ctr);
@@ -899,7 +1067,7 @@ MPT_API mpt_status mpt_create(int device, mpt_context** out_ctx) {
     ctx->view.min_roughness = kMinRoughness;
     ctx->view.clamp_normals = 1u;
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false, false, false>, kThreads, 0) == cudaSuccess && occ > 0) ctx->extend_blocks_per_sm = uint32_t(occ);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend<false, false, false, false>, kThreads, 0) == cudaSuccess && occ > 0) ctx->extend_blocks_per_sm = uint32_t(occ);
     // tuning knobs for profiling sessions (defaults are the measured optimum on B200)
     auto env_u32 = [](const char* name, uint32_t def) { const char* v = getenv(name); return v ? uint32_t(strtoul(v, nullptr, 10)) : def; };
     ctx->tune.refill = env_u32("MPT_REFILL_THRESHOLD", ctx->tune.refill);
@@ -1185,6 +1353,18 @@ MPT_API mpt_status mpt_env_set(mpt_context* ctx, uint32_t type, const float* to_
     CU(ctx->env_pixels.upload(rgba32f, size_t(width) * height * 16));
     for (int r = 0; r < 3; r++)
         for (int c = 0; c < 3; c++) ctx->view.env_m[r * 3 + c] = to_local[r * 4 + c];
+    {   // inverse of the 3x3 part (local -> world) for the light samples
+        const float* m = ctx->view.env_m;
+        const double det = double(m[0]) * (double(m[4]) * m[8] - double(m[5]) * m[7]) - double(m[1]) * (double(m[3]) * m[8] - double(m[5]) * m[6]) +
+                           double(m[2]) * (double(m[3]) * m[7] - double(m[4]) * m[6]);
+        if (!(std::fabs(det) > 1e-12)) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "environment to_local is singular");
+        const double id = 1.0 / det;
+        float* o = ctx->view.env_inv;
+        o[0] = float((double(m[4]) * m[8] - double(m[5]) * m[7]) * id); o[1] = float((double(m[2]) * m[7] - double(m[1]) * m[8]) * id); o[2] = float((double(m[1]) * m[5] - double(m[2]) * m[4]) * id);
+        o[3] = float((double(m[5]) * m[6] - double(m[3]) * m[8]) * id); o[4] = float((double(m[0]) * m[8] - double(m[2]) * m[6]) * id); o[5] = float((double(m[2]) * m[3] - double(m[0]) * m[5]) * id);
+        o[6] = float((double(m[3]) * m[7] - double(m[4]) * m[6]) * id); o[7] = float((double(m[1]) * m[6] - double(m[0]) * m[7]) * id); o[8] = float((double(m[0]) * m[4] - double(m[1]) * m[3]) * id);
+    }
+    ctx->env_sampling_ready = false;
     ctx->view.env_intensity = intensity;
     ctx->view.env_pixels = ctx->env_pixels.as<float4>();
     ctx->view.env_w = width;
@@ -1266,7 +1446,6 @@ mpt_status render_impl(mpt_context* ctx, const mpt_camera* camera, const mpt_ren
     if (!ctx->scene_ready || !ctx->materials_ready) return fail(ctx, MPT_ERR_NOT_READY, "scene or materials not uploaded");
     if (!P->width || !P->height || P->spp < 0 || P->max_path_length < 1 || P->sample_stride == 0) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "bad render parameters");
     if (camera->aperture_radius > 0.f) return fail(ctx, MPT_ERR_UNSUPPORTED, "thin-lens camera is out of scope (pinhole only)");
-    if (P->flags & MPT_RENDER_NEE) return fail(ctx, MPT_ERR_UNSUPPORTED, "MPT_RENDER_NEE is not implemented yet");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t npix = size_t(P->width) * P->height;
@@ -1278,8 +1457,13 @@ mpt_status render_impl(mpt_context* ctx, const mpt_camera* camera, const mpt_ren
     }
     const size_t want = std::max<size_t>(npix, std::min<size_t>(npix * size_t(std::max(P->spp, 1)), budget));
     const size_t slots = (want / npix) * npix;
-    const mpt_status ps = ensure_pool(ctx, slots, (ctx->feature_union & (MPT_GLTF_TRANSMISSION | MPT_GLTF_VOLUME)) != 0);
+    const bool nee = (P->flags & MPT_RENDER_NEE) != 0 && ctx->view.env_type == 1u;
+    const mpt_status ps = ensure_pool(ctx, slots, (ctx->feature_union & (MPT_GLTF_TRANSMISSION | MPT_GLTF_VOLUME)) != 0, nee);
     if (ps != MPT_OK) return ps;
+    if (nee) {
+        const mpt_status es = ensure_env_sampling(ctx);
+        if (es != MPT_OK) return es;
+    }
     const PackedHitInfo* tex1 = (const PackedHitInfo*)d_tex1;
     if (!tex1) {
         CU(ctx->tex1_internal.ensure(npix * sizeof(PackedHitInfo)));
@@ -1295,10 +1479,12 @@ mpt_status render_impl(mpt_context* ctx, const mpt_camera* camera, const mpt_ren
     }
     // three specialisations of the shading kernels (SURVEY.md §7 "hard parts": Slang drops disabled extensions at compile time):
     // core glTF only / surface extensions / everything incl. transmission + volume (the only one that carries medium state)
-    if (ctx->feature_union == 0) return run_passes<0u>(ctx, cam, *P, tex1, (const float4*)d_albedo, (float4*)d_irradiance, acc, st);
-    if (!(ctx->feature_union & (MPT_GLTF_TRANSMISSION | MPT_GLTF_VOLUME)))
-        return run_passes<0x3Cu>(ctx, cam, *P, tex1, (const float4*)d_albedo, (float4*)d_irradiance, acc, st);
-    return run_passes<0x3Fu>(ctx, cam, *P, tex1, (const float4*)d_albedo, (float4*)d_irradiance, acc, st);
+#define MPT_RUN(F) (nee ? run_passes<F, true>(ctx, cam, *P, tex1, (const float4*)d_albedo, (float4*)d_irradiance, acc, st) \
+                        : run_passes<F, false>(ctx, cam, *P, tex1, (const float4*)d_albedo, (float4*)d_irradiance, acc, st))
+    if (ctx->feature_union == 0) return MPT_RUN(0u);
+    if (!(ctx->feature_union & (MPT_GLTF_TRANSMISSION | MPT_GLTF_VOLUME))) return MPT_RUN(0x3Cu);
+    return MPT_RUN(0x3Fu);
+#undef MPT_RUN
 }
 
 mpt_status make_accum_args(mpt_context* ctx, const mpt_accumulate_params* A, const mpt_accumulate_buffers* B, AccumArgs& a) {
@@ -1453,6 +1639,7 @@ MPT_API mpt_status mpt_get_stats(mpt_context* ctx, mpt_stats* out) {
         Counters c;
         CU(cudaMemcpy(&c, ctx->counters.p, sizeof(Counters), cudaMemcpyDeviceToHost));
         out->rays_continuation += c.rays_continuation;
+        out->rays_shadow += c.rays_shadow;
         out->shaded_hits += c.shaded_hits;
         out->nodes_visited += c.nodes_visited;
         out->tris_tested += c.tris_tested;

@@ -47,6 +47,10 @@ struct SceneView {
     float env_intensity;
     const float4* __restrict__ env_pixels;
     uint32_t env_w, env_h;
+    // environment importance sampling for MPT_RENDER_NEE (built lazily by libmpt; no reference counterpart)
+    const uint2* __restrict__ env_alias;   // per texel: x = probability of keeping the texel (float bits), y = alias texel
+    const float* __restrict__ env_pmf;     // per texel: probability mass (sums to 1)
+    float env_inv[9];                      // inverse of env_m: local -> world
     // MaterialSystem hints (material_system.hpp:83-97)
     float alpha_threshold, min_roughness;
     uint32_t clamp_normals;
@@ -96,6 +100,37 @@ MPT_DEV f3 env_eval(const SceneView& S, f3 dir) {
     const float w00 = (1 - a) * (1 - b), w10 = a * (1 - b), w01 = (1 - a) * b, w11 = a * b;
     return S.env_intensity * mk3(w00 * t00.x + w10 * t10.x + w01 * t01.x + w11 * t11.x, w00 * t00.y + w10 * t10.y + w01 * t01.y + w11 * t11.y,
                                  w00 * t00.z + w10 * t10.z + w01 * t01.z + w11 * t11.z);
+}
+
+// ---- environment importance sampling (MPT_RENDER_NEE). Texel (i, j) of the lat-long map covers u in [i, i+1)/W, v in [j, j+1)/H
+// with uv = world_to_latlong(local dir); solid angle of d(u, v) = 2 pi^2 sin(theta) du dv.
+MPT_DEV float env_pdf(const SceneView& S, f3 dir_world) {
+    const f3 d = normalize(mk3(S.env_m[0] * dir_world.x + S.env_m[1] * dir_world.y + S.env_m[2] * dir_world.z,
+                               S.env_m[3] * dir_world.x + S.env_m[4] * dir_world.y + S.env_m[5] * dir_world.z,
+                               S.env_m[6] * dir_world.x + S.env_m[7] * dir_world.y + S.env_m[8] * dir_world.z));
+    const float sin_theta = sqrtf(fmaxf(0.f, 1.0f - d.y * d.y));
+    if (sin_theta < 1e-6f) return 0.f;
+    const f2 uv = mk2(atan2f(d.x, -d.z) * kInvTwoPi + 0.5f, acosf(clampf(d.y, -1.f, 1.f)) * kInvPi);
+    const uint32_t i = min(uint32_t(fmaxf(uv.x, 0.f) * float(S.env_w)), S.env_w - 1u), j = min(uint32_t(fmaxf(uv.y, 0.f) * float(S.env_h)), S.env_h - 1u);
+    return __ldg(S.env_pmf + size_t(j) * S.env_w + i) * float(S.env_w) * float(S.env_h) / (2.0f * kPi * kPi * sin_theta);
+}
+// Alias-table draw of a texel, uniform position inside it. Returns false when the direction has no usable density.
+MPT_DEV bool env_sample(const SceneView& S, float u0, float u1, float u2, f3& dir_world, float& pdf) {
+    const uint32_t n = S.env_w * S.env_h;
+    const float scaled = u0 * float(n);
+    uint32_t t = min(uint32_t(scaled), n - 1u);
+    const uint2 e = __ldg(S.env_alias + t);
+    if (scaled - float(t) >= __uint_as_float(e.x)) t = e.y;
+    const uint32_t j = t / S.env_w, i = t - j * S.env_w;
+    const float u = (float(i) + u1) / float(S.env_w), v = (float(j) + u2) / float(S.env_h);
+    const float phi = (u - 0.5f) * kTwoPi, theta = v * kPi;
+    const float st = sinf(theta), ct = cosf(theta);
+    if (st < 1e-6f) return false;
+    const f3 l = mk3(st * sinf(phi), ct, -st * cosf(phi)); // inverse of world_to_latlong
+    dir_world = normalize(mk3(S.env_inv[0] * l.x + S.env_inv[1] * l.y + S.env_inv[2] * l.z, S.env_inv[3] * l.x + S.env_inv[4] * l.y + S.env_inv[5] * l.z,
+                              S.env_inv[6] * l.x + S.env_inv[7] * l.y + S.env_inv[8] * l.z));
+    pdf = __ldg(S.env_pmf + t) * float(n) / (2.0f * kPi * kPi * st);
+    return pdf > 0.f;
 }
 
 // ---------------------------------------------------------------- materials

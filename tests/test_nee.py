@@ -1,0 +1,128 @@
+"""MPT_RENDER_NEE: next event estimation towards the environment (alias table over the lat-long texels + balance-heuristic MIS).
+The reference's pt has no NEE, so the contract is "same expectation as the reference estimator": the converged
+NEE image must agree with the converged plain image (GPU) and with the oracle's restatement of render_pt.slang, while the noise
+at equal sample count goes down."""
+import numpy as np
+import pytest
+
+from merian_b200 import abi, synthetic
+from merian_b200.scene import SceneTables, upload_scene
+
+from helpers import luminance, make_oracle, render_params, tables
+
+pytestmark = pytest.mark.gpu
+
+PLAIN = abi.RENDER_EMISSION_ON_PRIMARY
+NEE = abi.RENDER_EMISSION_ON_PRIMARY | abi.RENDER_NEE
+
+
+def _block_mean(img, b=8):
+    h, w = img.shape[:2]
+    return img[:h // b * b, :w // b * b].reshape(h // b, b, w // b, b, -1).mean((1, 3))
+
+
+def _accumulate(ctx, cam, w, h, flags, spp, frames):
+    acc = None
+    for f in range(frames):
+        img = ctx.render_device(cam, render_params(w, h, spp, flags=flags, frame=f)).double()
+        acc = img if acc is None else acc + img
+    return (acc / frames).cpu().numpy()
+
+
+def test_nee_converges_to_the_same_image_as_the_reference_estimator(gpu_ctx):
+    """Broad sun (sigma 10 deg) so that the plain estimator converges too. 8192 spp each on the GPU, 512 spp on the oracle."""
+    d = synthetic.terrain(nx=120, ny=60, env_size=(16, 8))
+    d.env = synthetic.sky_env(256, 128, sun_peak=60.0, sun_sigma_deg=10.0)
+    t = SceneTables(d)
+    upload_scene(gpu_ctx, t)
+    cam = t.desc.camera.to_abi(0)
+    w, h = 128, 72
+    gpu_ctx.reset_stats()
+    plain = _accumulate(gpu_ctx, cam, w, h, PLAIN, 1024, 8)
+    assert gpu_ctx.stats().rays_shadow == 0
+    gpu_ctx.reset_stats()
+    nee = _accumulate(gpu_ctx, cam, w, h, NEE, 1024, 8)
+    st = gpu_ctx.stats()
+    assert st.rays_shadow > 0.3 * st.rays_continuation          # one light sample per shaded vertex that can scatter
+    lp, ln = luminance(plain).mean(), luminance(nee).mean()
+    print(f"mean luminance plain {lp:.5f} nee {ln:.5f}")
+    assert abs(ln - lp) / lp < 5e-3                             # stated tolerance: 0.5 % mean-luminance difference at 8192 spp
+    bp, bn = _block_mean(plain[..., :3]), _block_mean(nee[..., :3])
+    rel = np.abs(bn - bp) / (np.abs(bp) + 1e-2)
+    print(f"8x8 block means: max rel diff {rel.max():.4f}, mean {rel.mean():.5f}")
+    assert rel.max() < 0.05 and rel.mean() < 0.01
+    # against the oracle (render_pt.slang restated, no NEE), 512 spp
+    o = make_oracle(t)
+    ref = o.render(cam, render_params(w, h, 512))
+    lr = luminance(ref).mean()
+    assert abs(ln - lr) / lr < 1e-2
+    rel_o = np.abs(bn - _block_mean(ref[..., :3])) / (np.abs(_block_mean(ref[..., :3])) + 1e-2)
+    assert rel_o.mean() < 0.03
+
+
+def test_nee_reduces_noise_under_a_small_sun(gpu_ctx):
+    """The C3 sky (sun sigma 1 deg, peak 5e4): at equal spp the NEE image is far closer to the converged image."""
+    t = SceneTables(synthetic.terrain(nx=120, ny=60, env_size=(1024, 512)))
+    upload_scene(gpu_ctx, t)
+    cam = t.desc.camera.to_abi(0)
+    w, h = 128, 72
+    ref = _accumulate(gpu_ctx, cam, w, h, NEE, 1024, 16)[..., :3]
+    err = {}
+    for name, flags in (("plain", PLAIN), ("nee", NEE)):
+        img = gpu_ctx.render(cam, render_params(w, h, 32, flags=flags, frame=100))[..., :3]
+        assert np.isfinite(img).all()
+        err[name] = float(np.mean((img - ref) ** 2 / (ref ** 2 + 1e-2)))
+    print("relMSE at 32 spp:", err)
+    assert err["nee"] < 0.25 * err["plain"]
+
+
+def test_nee_without_environment_is_a_no_op(gpu_ctx):
+    t = tables("cornell")
+    upload_scene(gpu_ctx, t)
+    cam = t.desc.camera.to_abi(0)
+    a = gpu_ctx.render(cam, render_params(64, 64, 8, flags=PLAIN))
+    b = gpu_ctx.render(cam, render_params(64, 64, 8, flags=NEE))
+    assert np.array_equal(a, b)
+
+
+def test_nee_two_level_scene_and_rotated_environment(gpu_ctx):
+    """Instanced scene (TLAS path of the shadow kernel) under an environment with a non-identity to_local."""
+    d = synthetic.instanced_rocks(n_instances=40, rock_res=13, env_size=(128, 64))
+    a = np.deg2rad(70.0)
+    R = np.eye(4, dtype=np.float32)
+    R[0, 0], R[0, 2], R[2, 0], R[2, 2] = np.cos(a), np.sin(a), -np.sin(a), np.cos(a)
+    d.env.to_local = R
+    t = SceneTables(d)
+    upload_scene(gpu_ctx, t)
+    cam = t.desc.camera.to_abi(0)
+    w, h = 96, 54
+    plain = _accumulate(gpu_ctx, cam, w, h, PLAIN, 1024, 4)
+    nee = _accumulate(gpu_ctx, cam, w, h, NEE, 1024, 4)
+    lp, ln = luminance(plain).mean(), luminance(nee).mean()
+    print(f"two-level: mean luminance plain {lp:.5f} nee {ln:.5f}")
+    assert abs(ln - lp) / lp < 1e-2
+    rel = np.abs(_block_mean(nee[..., :3]) - _block_mean(plain[..., :3])) / (np.abs(_block_mean(plain[..., :3])) + 1e-2)
+    assert rel.mean() < 0.02
+
+
+def test_nee_with_transmissive_materials_keeps_the_expectation(gpu_ctx):
+    from merian_b200.scene import CameraDesc, GltfMaterial, MESH_IS_OPAQUE, Mesh, Node, SceneDescription
+    glass = GltfMaterial(base_color_factor=(0.9, 0.95, 1.0, 1), metallic_factor=0.0, roughness_factor=0.3, transmission={"weight": 0.8},
+                         volume={"absorption": (0.5, 0.2, 0.1)})
+    floor_m = GltfMaterial(base_color_factor=(0.6, 0.6, 0.6, 1), metallic_factor=0, roughness_factor=1.0)
+    box = synthetic._mesh_from_parts([synthetic._box((0.0, 0.0, 0.0), (0.8, 0.8, 0.25), 20.0, skip_bottom=False)], 0)
+    box.flags |= 0x10  # MESH_TWO_SIDED: transmissive meshes are two-sided (gltf_scene.cpp:659-663)
+    s = 3.0
+    floor = Mesh(positions=np.array([[-s, -s, -0.6], [s, -s, -0.6], [s, s, -0.6], [-s, s, -0.6]], np.float32), normals=np.tile([[0, 0, 1]], (4, 1)).astype(np.float32),
+                 uvs=np.zeros((4, 2), np.float32), indices=np.array([[0, 1, 2], [0, 2, 3]], np.uint16), material_id=1, flags=MESH_IS_OPAQUE, instance_mask=0xFF)
+    box.instance_mask = 0xFF
+    env = synthetic.sky_env(64, 32, sun_peak=50.0, sun_sigma_deg=10.0, sun_dir=(0.2, 0.3, 1.0))
+    t = SceneTables(SceneDescription(meshes=[box, floor], nodes=[Node([0]), Node([1])], materials=[glass, floor_m], env=env,
+                                     camera=CameraDesc(position=(0.1, 0.2, 3.0), target=(0.0, 0.0, 0.0), yfov_deg=50.0, aspect=1.0, near=0.01, far=100.0)))
+    upload_scene(gpu_ctx, t)
+    cam = t.desc.camera.to_abi(0)
+    plain = _accumulate(gpu_ctx, cam, 64, 64, PLAIN, 1024, 4)
+    nee = _accumulate(gpu_ctx, cam, 64, 64, NEE, 1024, 4)
+    lp, ln = luminance(plain).mean(), luminance(nee).mean()
+    print(f"glass: mean luminance plain {lp:.5f} nee {ln:.5f}")
+    assert abs(ln - lp) / lp < 1e-2
