@@ -59,6 +59,46 @@ MPT_API mpt_status mptn_set_shard(mptn_node* node, uint32_t rank, uint32_t world
 MPT_API mpt_status mptn_process(mptn_node* node, const mpt_camera* camera, uint32_t frame, const void* d_tex1,
                                 const void* d_albedo, void* d_irradiance, void* stream, uint32_t* out_events);
 
+/* ---- `GBuffer (Raytraced)` node, host side -------------------------------------------------
+ * GBufferRTNode (include/merian-graph/nodes/gbuffer_rt/gbuffer.hpp:20-75, src/merian-graph/nodes/gbuffer_rt/gbuffer.cpp).
+ * Properties (gbuffer.cpp:155-181): "width", "height" (uint; NEEDS_RECONNECT on change), "0".."7" (instance-mask bits),
+ * "emission format" ("R32G32B32A32Sfloat"). Outputs: "gbuffer" (tex0..tex3) and "emission", both of the node's extent. */
+typedef struct mptn_gbuffer mptn_gbuffer;
+MPT_API mpt_status mptn_gbuffer_create(mpt_context* ctx, mptn_gbuffer** out_node);
+MPT_API void mptn_gbuffer_destroy(mptn_gbuffer* node);
+MPT_API const char* mptn_gbuffer_last_error(const mptn_gbuffer* node);
+MPT_API mpt_status mptn_gbuffer_load_config(mptn_gbuffer* node, const char* json, uint32_t* out_status);
+MPT_API mpt_status mptn_gbuffer_dump_config(mptn_gbuffer* node, char* buf, size_t capacity, size_t* out_len);
+/* GBufferRTNode::pre_process (gbuffer.cpp:104-115): the scene camera's resolution overrides the properties. */
+MPT_API mpt_status mptn_gbuffer_set_resolution(mptn_gbuffer* node, uint32_t width, uint32_t height, uint32_t* out_status);
+MPT_API mpt_status mptn_gbuffer_describe_outputs(mptn_gbuffer* node, uint32_t* out_width, uint32_t* out_height, uint32_t* out_emission_vk_format);
+/* GBufferRTNode::process (gbuffer.cpp:117-146): one mpt_gbuffer over the node's extent; a no-op while the scene is not ready. */
+MPT_API mpt_status mptn_gbuffer_process(mptn_gbuffer* node, const mpt_camera* camera, const mpt_camera* prev_camera,
+                                        const mpt_gbuffer_images* images, void* stream);
+
+/* ---- `Accumulate` node, plain mode, host side ----------------------------------------------
+ * Accumulate (src/merian-graph/nodes/accumulate/accumulate.cpp:153-250). Properties with the reference's keys: "alpha", "max history",
+ * "inf history", "clear", "use motion vectors" (must be false here: same-pixel reuse), "gbuffer check" ("always" | "only if moving" |
+ * "never"), "normal threshold" (radians), "depth threshold", "extended search" (accepted, unused), "firefly filter enable" and
+ * "adaptivity" (must stay off: they remain in the reference node), "hard clamp", "inf clamp"; plus "f32 history" (extension: no 2048 cap).
+ * process(): clears on iteration 0 or after a clear request and reports MPTN_EVENT_CLEAR (accumulate.cpp:154-160). */
+enum { MPTN_EVENT_CLEAR = 0x2 };
+typedef struct mptn_accumulate mptn_accumulate;
+MPT_API mpt_status mptn_accumulate_create(mpt_context* ctx, mptn_accumulate** out_node);
+MPT_API void mptn_accumulate_destroy(mptn_accumulate* node);
+MPT_API const char* mptn_accumulate_last_error(const mptn_accumulate* node);
+MPT_API mpt_status mptn_accumulate_load_config(mptn_accumulate* node, const char* json, uint32_t* out_status);
+MPT_API mpt_status mptn_accumulate_dump_config(mptn_accumulate* node, char* buf, size_t capacity, size_t* out_len);
+MPT_API mpt_status mptn_accumulate_request_clear(mptn_accumulate* node);
+MPT_API mpt_status mptn_accumulate_process(mptn_accumulate* node, uint64_t iteration, uint32_t width, uint32_t height,
+                                           const void* d_src, const mpt_accumulate_buffers* buffers, void* stream,
+                                           uint32_t* out_events);
+/* The pt node and the Accumulate node of one graph fused into one call (mpt_render_accumulate): the irradiance connector between
+ * them (`irradiance->accumulate.src`, examples/gltf.json:155-158) never touches HBM. */
+MPT_API mpt_status mptn_process_accumulate(mptn_node* pt, mptn_accumulate* acc, const mpt_camera* camera, uint32_t frame,
+                                           uint64_t iteration, const void* d_tex1, const void* d_albedo,
+                                           const mpt_accumulate_buffers* buffers, void* stream, uint32_t* out_events);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,7 +17,11 @@ EXPORTS = ["mpt_abi_version", "mpt_create", "mpt_destroy", "mpt_last_error", "mp
            "mpt_set_profiling", "mpt_get_stats", "mpt_reset_stats", "mpt_bvh_get_info", "mpt_bsdf_check",
            # include/mpt_node.h
            "mptn_create", "mptn_destroy", "mptn_last_error", "mptn_load_config", "mptn_dump_config", "mptn_describe_outputs",
-           "mptn_set_shard", "mptn_process"]
+           "mptn_set_shard", "mptn_process",
+           "mptn_gbuffer_create", "mptn_gbuffer_destroy", "mptn_gbuffer_last_error", "mptn_gbuffer_load_config", "mptn_gbuffer_dump_config",
+           "mptn_gbuffer_set_resolution", "mptn_gbuffer_describe_outputs", "mptn_gbuffer_process",
+           "mptn_accumulate_create", "mptn_accumulate_destroy", "mptn_accumulate_last_error", "mptn_accumulate_load_config",
+           "mptn_accumulate_dump_config", "mptn_accumulate_request_clear", "mptn_accumulate_process", "mptn_process_accumulate"]
 
 
 class MptError(RuntimeError):
@@ -73,6 +77,22 @@ def lib():
         l.mptn_describe_outputs.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32] + [C.POINTER(C.c_uint32)] * 3
         l.mptn_set_shard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
         l.mptn_process.argtypes = [C.c_void_p, C.POINTER(abi.Camera), C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]
+        for kind in ("gbuffer", "accumulate"):
+            getattr(l, f"mptn_{kind}_create").argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+            getattr(l, f"mptn_{kind}_destroy").argtypes = [C.c_void_p]
+            getattr(l, f"mptn_{kind}_destroy").restype = None
+            getattr(l, f"mptn_{kind}_last_error").argtypes = [C.c_void_p]
+            getattr(l, f"mptn_{kind}_last_error").restype = C.c_char_p
+            getattr(l, f"mptn_{kind}_load_config").argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint32)]
+            getattr(l, f"mptn_{kind}_dump_config").argtypes = [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]
+        l.mptn_gbuffer_set_resolution.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+        l.mptn_gbuffer_describe_outputs.argtypes = [C.c_void_p] + [C.POINTER(C.c_uint32)] * 3
+        l.mptn_gbuffer_process.argtypes = [C.c_void_p, C.POINTER(abi.Camera), C.POINTER(abi.Camera), C.POINTER(abi.GBufferImages), C.c_void_p]
+        l.mptn_accumulate_request_clear.argtypes = [C.c_void_p]
+        l.mptn_accumulate_process.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.POINTER(abi.AccumulateBuffers), C.c_void_p,
+                                              C.POINTER(C.c_uint32)]
+        l.mptn_process_accumulate.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(abi.Camera), C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p,
+                                              C.POINTER(abi.AccumulateBuffers), C.c_void_p, C.POINTER(C.c_uint32)]
         if l.mpt_abi_version() != abi.MPT_ABI_VERSION:
             raise RuntimeError("libmpt.so ABI version mismatch")
         _lib = l

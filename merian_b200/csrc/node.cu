@@ -321,3 +321,285 @@ MPT_API mpt_status mptn_process(mptn_node* node, const mpt_camera* camera, uint3
 }
 
 } // extern "C"
+
+
+// ====================================================================================== GBuffer (Raytraced) node, host side
+// GBufferRTNode (include/merian-graph/nodes/gbuffer_rt/gbuffer.hpp:20-75, src/merian-graph/nodes/gbuffer_rt/gbuffer.cpp): properties
+// "width" / "height" (when the scene camera dictates no resolution), "0".."7", "emission format"; outputs "gbuffer" + "emission".
+struct mptn_gbuffer {
+    mpt_context* ctx = nullptr;
+    std::string error;
+    uint32_t width = 1920, height = 1080; // gbuffer.hpp:64
+    std::array<bool, 8> mask_enabled{{true, true, true, true, true, true, true, true}};
+    uint32_t emission_format = MPTN_FORMAT_R32G32B32A32_SFLOAT; // gbuffer.hpp:70
+};
+
+// ====================================================================================== Accumulate node (plain mode), host side
+// Accumulate (include/merian-graph/nodes/accumulate/accumulate.hpp, src/merian-graph/nodes/accumulate/accumulate.cpp:153-250).
+struct mptn_accumulate {
+    mpt_context* ctx = nullptr;
+    std::string error;
+    float alpha = 0.0f;            // accumulate.hpp:34
+    float max_history = INFINITY;  // :35
+    float normal_reject_cos = 0.8f; // :36
+    float depth_reject_percent = 0.02f;
+    float hard_clamp = INFINITY;   // :32
+    bool clear = false;
+    bool use_motion_vectors = true; // reference default; the CUDA node supports false only (same-pixel reuse)
+    int gbuffer_check_mode = 0;     // "always" | "only if moving" | "never"
+    bool firefly_filter_enable = false;
+    float adaptivity = 0.0f;
+    bool extended_search = true;    // accepted; the same-pixel check needs no neighbourhood search
+    bool history_f32 = false;       // CUDA-node extension: "f32 history" (no 2048 cap)
+};
+
+namespace {
+template <class N> mpt_status nfail2(N* n, mpt_status s, const std::string& msg) {
+    if (n) n->error = msg;
+    return s;
+}
+struct PropReader {
+    std::map<std::string, JValue> o;
+    std::string err;
+    const JValue* find(const char* key) const { auto it = o.find(key); return it == o.end() ? nullptr : &it->second; }
+    void num(const char* key, float& dst) {
+        if (const JValue* v = find(key)) {
+            if (v->kind != JValue::Number) err = std::string("property '") + key + "' must be a number";
+            else dst = float(v->num);
+        }
+    }
+    void uint(const char* key, uint32_t& dst) {
+        if (const JValue* v = find(key)) {
+            if (v->kind != JValue::Number || v->num < 0) err = std::string("property '") + key + "' must be a non-negative number";
+            else dst = uint32_t(v->num);
+        }
+    }
+    void boolean(const char* key, bool& dst) {
+        if (const JValue* v = find(key)) {
+            if (v->kind != JValue::Bool) err = std::string("property '") + key + "' must be a boolean";
+            else dst = v->b;
+        }
+    }
+};
+std::string jnum(float f) {
+    if (std::isinf(f)) return f > 0 ? "1e999" : "-1e999"; // what nlohmann::json cannot represent either; round-trips through strtod as inf
+    char b[64];
+    std::snprintf(b, sizeof b, "%.9g", double(f));
+    return b;
+}
+mpt_status copy_out(const std::string& s, char* buf, size_t capacity, size_t* out_len) {
+    if (out_len) *out_len = s.size();
+    if (buf && capacity) {
+        const size_t n = std::min(capacity - 1, s.size());
+        std::memcpy(buf, s.data(), n);
+        buf[n] = 0;
+        if (n < s.size()) return MPT_ERR_LIMIT;
+    }
+    return MPT_OK;
+}
+} // namespace
+
+extern "C" {
+
+MPT_API mpt_status mptn_gbuffer_create(mpt_context* ctx, mptn_gbuffer** out_node) {
+    if (!out_node) return MPT_ERR_INVALID_ARGUMENT;
+    *out_node = new mptn_gbuffer();
+    (*out_node)->ctx = ctx;
+    return MPT_OK;
+}
+MPT_API void mptn_gbuffer_destroy(mptn_gbuffer* node) { delete node; }
+MPT_API const char* mptn_gbuffer_last_error(const mptn_gbuffer* node) { return node ? node->error.c_str() : "NULL node"; }
+
+MPT_API mpt_status mptn_gbuffer_load_config(mptn_gbuffer* node, const char* json, uint32_t* out_status) {
+    if (!node || !json) return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (out_status) *out_status = 0;
+    PropReader r;
+    JParser ps(json);
+    if (!ps.object(r.o)) return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "properties JSON: " + ps.err);
+    mptn_gbuffer t = *node;
+    r.uint("width", t.width);   // gbuffer.cpp:160-161
+    r.uint("height", t.height);
+    for (int bit = 0; bit < 8; bit++) r.boolean(std::to_string(bit).c_str(), t.mask_enabled[size_t(bit)]);
+    if (const JValue* v = r.find("emission format")) {
+        if (v->kind != JValue::String) r.err = "property 'emission format' must be a string";
+        else if (v->str == "R32G32B32A32Sfloat") t.emission_format = MPTN_FORMAT_R32G32B32A32_SFLOAT;
+        else if (!v->str.empty()) return nfail2(node, MPT_ERR_UNSUPPORTED, "emission format '" + v->str + "' is not supported (R32G32B32A32Sfloat)");
+    }
+    if (!r.err.empty()) return nfail2(node, MPT_ERR_INVALID_ARGUMENT, r.err);
+    if (!t.width || !t.height) return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "width and height must be non-zero");
+    const bool reconnect = t.width != node->width || t.height != node->height || t.emission_format != node->emission_format;
+    t.error.clear();
+    *node = t;
+    if (out_status && reconnect) *out_status |= MPTN_NEEDS_RECONNECT;
+    return MPT_OK;
+}
+
+MPT_API mpt_status mptn_gbuffer_dump_config(mptn_gbuffer* node, char* buf, size_t capacity, size_t* out_len) {
+    if (!node) return MPT_ERR_INVALID_ARGUMENT;
+    std::string s = "{";
+    for (int bit = 0; bit < 8; bit++) s += "\"" + std::to_string(bit) + "\": " + (node->mask_enabled[size_t(bit)] ? "true" : "false") + ", ";
+    s += std::string("\"emission format\": \"") + format_name(node->emission_format) + "\", ";
+    s += "\"height\": " + std::to_string(node->height) + ", \"width\": " + std::to_string(node->width) + "}";
+    const mpt_status st = copy_out(s, buf, capacity, out_len);
+    return st == MPT_OK ? st : nfail2(node, st, "buffer too small for the configuration");
+}
+
+MPT_API mpt_status mptn_gbuffer_set_resolution(mptn_gbuffer* node, uint32_t width, uint32_t height, uint32_t* out_status) {
+    if (!node || !width || !height) return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "resolution must be non-zero");
+    if (out_status) *out_status = (width != node->width || height != node->height) ? MPTN_NEEDS_RECONNECT : 0u; // pre_process, gbuffer.cpp:104-115
+    node->width = width;
+    node->height = height;
+    return MPT_OK;
+}
+
+MPT_API mpt_status mptn_gbuffer_describe_outputs(mptn_gbuffer* node, uint32_t* out_width, uint32_t* out_height, uint32_t* out_emission_vk_format) {
+    if (!node) return MPT_ERR_INVALID_ARGUMENT;
+    if (out_width) *out_width = node->width;
+    if (out_height) *out_height = node->height;
+    if (out_emission_vk_format) *out_emission_vk_format = node->emission_format;
+    return MPT_OK;
+}
+
+MPT_API mpt_status mptn_gbuffer_process(mptn_gbuffer* node, const mpt_camera* camera, const mpt_camera* prev_camera, const mpt_gbuffer_images* images,
+                                        void* stream) {
+    if (!node || !camera || !images) return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!node->ctx) return nfail2(node, MPT_ERR_NOT_READY, "the node was created without a device context (initialize)");
+    uint32_t mask = 0; // gbuffer.cpp:129-134
+    for (uint32_t bit = 0; bit < 8; bit++)
+        if (node->mask_enabled[bit]) mask |= 1u << bit;
+    const mpt_status s = mpt_gbuffer(node->ctx, camera, prev_camera, node->width, node->height, mask, images, stream);
+    if (s == MPT_ERR_NOT_READY) return MPT_OK; // `if (scene->is_ready())`, gbuffer.cpp:136
+    if (s != MPT_OK) return nfail2(node, s, mpt_last_error(node->ctx));
+    return MPT_OK;
+}
+
+MPT_API mpt_status mptn_accumulate_create(mpt_context* ctx, mptn_accumulate** out_node) {
+    if (!out_node) return MPT_ERR_INVALID_ARGUMENT;
+    *out_node = new mptn_accumulate();
+    (*out_node)->ctx = ctx;
+    return MPT_OK;
+}
+MPT_API void mptn_accumulate_destroy(mptn_accumulate* node) { delete node; }
+MPT_API const char* mptn_accumulate_last_error(const mptn_accumulate* node) { return node ? node->error.c_str() : "NULL node"; }
+
+MPT_API mpt_status mptn_accumulate_load_config(mptn_accumulate* node, const char* json, uint32_t* out_status) {
+    if (!node || !json) return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (out_status) *out_status = 0;
+    PropReader r;
+    JParser ps(json);
+    if (!ps.object(r.o)) return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "properties JSON: " + ps.err);
+    mptn_accumulate t = *node;
+    r.num("alpha", t.alpha);                      // accumulate.cpp:175-177
+    r.num("max history", t.max_history);          // :178-180
+    bool inf_history = std::isinf(t.max_history), clear = false, inf_clamp = false;
+    r.boolean("inf history", inf_history);        // :182-183
+    if (inf_history) t.max_history = INFINITY;
+    r.boolean("clear", clear);                    // :184
+    r.boolean("use motion vectors", t.use_motion_vectors);
+    if (const JValue* v = r.find("gbuffer check")) {
+        if (v->kind != JValue::String) r.err = "property 'gbuffer check' must be a string";
+        else if (v->str == "always") t.gbuffer_check_mode = 0;
+        else if (v->str == "only if moving") t.gbuffer_check_mode = 1;
+        else if (v->str == "never") t.gbuffer_check_mode = 2;
+    }
+    float angle = std::acos(t.normal_reject_cos);
+    r.num("normal threshold", angle);             // radians, :199-202
+    t.normal_reject_cos = std::cos(angle);
+    r.num("depth threshold", t.depth_reject_percent);
+    r.boolean("extended search", t.extended_search);
+    r.boolean("firefly filter enable", t.firefly_filter_enable);
+    r.num("hard clamp", t.hard_clamp);            // :229-233
+    r.boolean("inf clamp", inf_clamp);
+    if (inf_clamp) t.hard_clamp = INFINITY;
+    r.num("adaptivity", t.adaptivity);
+    r.boolean("f32 history", t.history_f32);
+    if (!r.err.empty()) return nfail2(node, MPT_ERR_INVALID_ARGUMENT, r.err);
+    if (!(t.alpha >= 0.f && t.alpha <= 1.f)) return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "alpha must be in [0, 1]");
+    const bool rebuild = t.use_motion_vectors != node->use_motion_vectors || t.gbuffer_check_mode != node->gbuffer_check_mode || t.extended_search != node->extended_search;
+    t.clear = node->clear || clear;
+    t.error.clear();
+    *node = t;
+    if (out_status && rebuild) *out_status |= MPTN_NEEDS_RECONNECT;
+    return MPT_OK;
+}
+
+MPT_API mpt_status mptn_accumulate_dump_config(mptn_accumulate* node, char* buf, size_t capacity, size_t* out_len) {
+    if (!node) return MPT_ERR_INVALID_ARGUMENT;
+    static const char* modes[3] = {"always", "only if moving", "never"};
+    auto b = [](bool v) { return v ? "true" : "false"; };
+    std::string s = "{";
+    s += "\"adaptivity\": " + jnum(node->adaptivity) + ", \"alpha\": " + jnum(node->alpha) + ", \"clear\": false, ";
+    s += "\"depth threshold\": " + jnum(node->depth_reject_percent) + ", \"extended search\": " + b(node->extended_search) + ", ";
+    s += std::string("\"f32 history\": ") + b(node->history_f32) + ", \"firefly filter enable\": " + b(node->firefly_filter_enable) + ", ";
+    s += std::string("\"gbuffer check\": \"") + modes[node->gbuffer_check_mode] + "\", ";
+    s += "\"hard clamp\": " + (std::isinf(node->hard_clamp) ? std::string("0") : jnum(node->hard_clamp)) + ", \"inf clamp\": " + b(std::isinf(node->hard_clamp)) + ", ";
+    s += std::string("\"inf history\": ") + b(std::isinf(node->max_history)) + ", \"max history\": " + (std::isinf(node->max_history) ? std::string("0") : jnum(node->max_history)) + ", ";
+    s += "\"normal threshold\": " + jnum(std::acos(node->normal_reject_cos)) + ", \"use motion vectors\": " + b(node->use_motion_vectors) + "}";
+    const mpt_status st = copy_out(s, buf, capacity, out_len);
+    return st == MPT_OK ? st : nfail2(node, st, "buffer too small for the configuration");
+}
+
+MPT_API mpt_status mptn_accumulate_request_clear(mptn_accumulate* node) { // Accumulate::request_clear, accumulate.cpp:255-257
+    if (!node) return MPT_ERR_INVALID_ARGUMENT;
+    node->clear = true;
+    return MPT_OK;
+}
+
+namespace {
+mpt_status accumulate_params(mptn_accumulate* node, uint64_t iteration, uint32_t width, uint32_t height, mpt_accumulate_params& A, uint32_t* out_events) {
+    if (node->use_motion_vectors) return nfail2(node, MPT_ERR_UNSUPPORTED, "the CUDA Accumulate node reuses the same pixel only: set 'use motion vectors' to false");
+    if (node->firefly_filter_enable || node->adaptivity > 0.f) return nfail2(node, MPT_ERR_UNSUPPORTED, "firefly percentile filter / adaptive alpha stay in the reference node (SURVEY.md 8(f) N2)");
+    if (node->gbuffer_check_mode == 0 && node->history_f32) return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "'f32 history' stores no depth: use 'gbuffer check' = never / only if moving");
+    A = mpt_accumulate_params{};
+    A.width = width; A.height = height;
+    A.alpha = node->alpha; A.max_history = node->max_history; A.hard_clamp = node->hard_clamp;
+    A.normal_reject_cos = node->normal_reject_cos; A.z_reject_percent = node->depth_reject_percent;
+    A.clear = (iteration == 0 || node->clear) ? 1u : 0u;                                          // accumulate.cpp:154-160
+    // same pixel => the motion vector is zero => "only if moving" never checks (accumulate.slang:186-187)
+    A.flags = (node->gbuffer_check_mode == 0 ? MPT_ACC_GBUFFER_CHECK : 0u) | (node->history_f32 ? MPT_ACC_HISTORY_F32 : 0u);
+    if (out_events) *out_events = A.clear ? MPTN_EVENT_CLEAR : 0u;
+    node->clear = false;
+    return MPT_OK;
+}
+} // namespace
+
+MPT_API mpt_status mptn_accumulate_process(mptn_accumulate* node, uint64_t iteration, uint32_t width, uint32_t height, const void* d_src,
+                                           const mpt_accumulate_buffers* buffers, void* stream, uint32_t* out_events) {
+    if (!node || !d_src || !buffers) return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!node->ctx) return nfail2(node, MPT_ERR_NOT_READY, "the node was created without a device context (initialize)");
+    mpt_accumulate_params A;
+    const mpt_status ps = accumulate_params(node, iteration, width, height, A, out_events);
+    if (ps != MPT_OK) return ps;
+    const mpt_status s = mpt_accumulate(node->ctx, &A, d_src, buffers, stream);
+    if (s != MPT_OK) return nfail2(node, s, mpt_last_error(node->ctx));
+    return MPT_OK;
+}
+
+MPT_API mpt_status mptn_process_accumulate(mptn_node* pt, mptn_accumulate* acc, const mpt_camera* camera, uint32_t frame, uint64_t iteration,
+                                           const void* d_tex1, const void* d_albedo, const mpt_accumulate_buffers* buffers, void* stream,
+                                           uint32_t* out_events) {
+    if (!pt || !acc || !camera || !buffers) return nfail2(acc, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (!pt->ctx || pt->ctx != acc->ctx) return nfail2(acc, MPT_ERR_INVALID_ARGUMENT, "both nodes must live on the same device context");
+    if (pt->world > 1) return nfail2(acc, MPT_ERR_INVALID_ARGUMENT, "a sharded pt node writes partial sums: reduce first, then mptn_accumulate_process");
+    if (pt->irradiance_format != MPTN_FORMAT_R32G32B32A32_SFLOAT) return nfail2(acc, MPT_ERR_UNSUPPORTED, "the fused path keeps the irradiance in fp32 registers: set 'irradiance format' to R32G32B32A32Sfloat");
+    uint32_t ev_pt = 0, ev_acc = 0;
+    if (pt->max_path_length != pt->emitted_max_path_length) { pt->emitted_max_path_length = pt->max_path_length; ev_pt |= MPTN_EVENT_BOUNCES_CHANGED; }
+    if (pt->spp < 0 || pt->max_path_length < 1) return nfail2(acc, MPT_ERR_INVALID_ARGUMENT, "samples per pixel must be >= 0 and max path length >= 1");
+    if (pt->demodulate_albedo && !d_albedo) return nfail2(acc, MPT_ERR_INVALID_ARGUMENT, "'demodulate albedo' needs the gbuffer albedo texture");
+    mpt_accumulate_params A;
+    const mpt_status ps = accumulate_params(acc, iteration, pt->width, pt->height, A, &ev_acc);
+    if (ps != MPT_OK) return ps;
+    mpt_render_params P{};
+    P.width = pt->width; P.height = pt->height; P.frame = frame; P.spp = pt->spp; P.max_path_length = pt->max_path_length;
+    for (uint32_t bit = 0; bit < 8; bit++)
+        if (pt->mask_enabled[bit]) P.instance_mask |= 1u << bit;
+    P.flags = (pt->emission_on_primary ? MPT_RENDER_EMISSION_ON_PRIMARY : 0u) | (pt->demodulate_albedo ? MPT_RENDER_DEMODULATE_ALBEDO : 0u);
+    P.sample_offset = 0; P.sample_stride = 1;
+    if (out_events) *out_events = ev_pt | ev_acc;
+    const mpt_status s = mpt_render_accumulate(pt->ctx, camera, &P, d_tex1, pt->demodulate_albedo ? d_albedo : nullptr, &A, buffers, stream);
+    if (s == MPT_ERR_NOT_READY) return MPT_OK;
+    if (s != MPT_OK) return nfail2(acc, s, mpt_last_error(pt->ctx));
+    return MPT_OK;
+}
+
+} // extern "C"
