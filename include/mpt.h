@@ -346,7 +346,11 @@ MPT_API mpt_status mpt_pfm_info(const char* path, uint32_t* width, uint32_t* hei
 MPT_API mpt_status mpt_pfm_load(const char* path, uint32_t desired_channels, float* out, uint64_t capacity_floats);
 /* channels 1, 3 or 4; RGBA is written as RGB (PFM has no alpha); little endian, scale -1. */
 MPT_API mpt_status mpt_pfm_save(const char* path, const float* data, uint32_t width, uint32_t height, uint32_t channels);
-/* Scene::process_pending_env_load for a lat-long .pfm (scene.cpp:775-800): load as RGBA32F and mpt_env_set. */
+/* Radiance RGBE (.hdr), decoded like stb_image's stbi_loadf which image_load_f32 calls (image_io.cpp:226-240): flat or new-style RLE
+ * scanlines, component = mantissa * 2^(e - 136). desired_channels 3 or 4 (alpha = 1). out == NULL: only width / height are returned. */
+MPT_API mpt_status mpt_hdr_load(const char* path, uint32_t desired_channels, uint32_t* width, uint32_t* height, float* out,
+                                uint64_t capacity_floats);
+/* Scene::process_pending_env_load for a lat-long .pfm or .hdr (scene.cpp:775-800): load as RGBA32F and mpt_env_set. */
 MPT_API mpt_status mpt_env_load(mpt_context* ctx, const char* path, const float* to_local, float intensity);
 /* The PFM leg of the `Image Write` node for a float4 device image (e.g. the accumulate output): D2H + mpt_pfm_save. */
 MPT_API mpt_status mpt_image_write(mpt_context* ctx, const char* path, const void* d_rgba32f, uint32_t width,

@@ -13,7 +13,7 @@ _lib = None
 
 EXPORTS = ["mpt_abi_version", "mpt_create", "mpt_destroy", "mpt_last_error", "mpt_scene_upload", "mpt_materials_upload",
            "mpt_materials_set_hints", "mpt_texture_upload", "mpt_env_set", "mpt_primary_visibility", "mpt_gbuffer", "mpt_trace", "mpt_render", "mpt_render_host",
-           "mpt_accumulate", "mpt_render_accumulate", "mpt_pfm_info", "mpt_pfm_load", "mpt_pfm_save", "mpt_env_load", "mpt_image_write",
+           "mpt_accumulate", "mpt_render_accumulate", "mpt_pfm_info", "mpt_pfm_load", "mpt_pfm_save", "mpt_hdr_load", "mpt_env_load", "mpt_image_write",
            "mpt_set_profiling", "mpt_get_stats", "mpt_reset_stats", "mpt_bvh_get_info", "mpt_bsdf_check",
            # include/mpt_node.h
            "mptn_create", "mptn_destroy", "mptn_last_error", "mptn_load_config", "mptn_dump_config", "mptn_describe_outputs",
@@ -60,6 +60,7 @@ def lib():
         l.mpt_pfm_info.argtypes = [C.c_char_p] + [C.POINTER(C.c_uint32)] * 3
         l.mpt_pfm_load.argtypes = [C.c_char_p, C.c_uint32, C.c_void_p, C.c_uint64]
         l.mpt_pfm_save.argtypes = [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+        l.mpt_hdr_load.argtypes = [C.c_char_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_void_p, C.c_uint64]
         l.mpt_env_load.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_float]
         l.mpt_image_write.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
         l.mpt_set_profiling.argtypes = [C.c_void_p, C.c_uint32]

@@ -1,6 +1,7 @@
 // image_io.cpp — see image_io.h.
 #include "image_io.h"
 
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -88,6 +89,69 @@ std::string pfm_save(const char* path, const float* data, int width, int height,
             wr = row.data();
         }
         if (fwrite(wr, sizeof(float), row.size(), f.get()) != row.size()) return std::string("image_io: short write to ") + path;
+    }
+    return {};
+}
+
+std::string hdr_load(const char* path, int desired_channels, int& width, int& height, std::vector<float>& out) {
+    if (desired_channels != 3 && desired_channels != 4) return "image_io: HDR loads as 3 or 4 channels";
+    File f(fopen(path, "rb"));
+    if (!f) return std::string("image_io: cannot open ") + path;
+    auto line = [&](std::string& s) {
+        s.clear();
+        int c;
+        while ((c = fgetc(f.get())) != EOF && c != '\n') s += char(c);
+        return c != EOF || !s.empty();
+    };
+    std::string l;
+    if (!line(l) || (l != "#?RADIANCE" && l != "#?RGBE")) return std::string("image_io: not a Radiance HDR file: ") + path;
+    bool format_ok = false;
+    while (line(l) && !l.empty())
+        if (l == "FORMAT=32-bit_rle_rgbe") format_ok = true;
+    if (!format_ok) return std::string("image_io: unsupported HDR format in ") + path;
+    if (!line(l) || std::sscanf(l.c_str(), "-Y %d +X %d", &height, &width) != 2 || width <= 0 || height <= 0)
+        return std::string("image_io: unsupported HDR data layout in ") + path;
+    const size_t w = size_t(width), h = size_t(height);
+    out.assign(w * h * size_t(desired_channels), 0.f);
+    std::vector<unsigned char> scan(w * 4);
+    auto convert = [&](const unsigned char* rgbe, float* dst) {
+        if (rgbe[3] != 0) {
+            const float f1 = std::ldexp(1.0f, int(rgbe[3]) - (128 + 8));
+            dst[0] = rgbe[0] * f1; dst[1] = rgbe[1] * f1; dst[2] = rgbe[2] * f1;
+        } else {
+            dst[0] = dst[1] = dst[2] = 0.f;
+        }
+        if (desired_channels == 4) dst[3] = 1.f;
+    };
+    for (size_t y = 0; y < h; y++) {
+        unsigned char head[4];
+        if (fread(head, 1, 4, f.get()) != 4) return std::string("image_io: truncated HDR in ") + path;
+        const bool rle = w >= 8 && w < 32768 && head[0] == 2 && head[1] == 2 && !(head[2] & 0x80) && size_t((head[2] << 8) | head[3]) == w;
+        if (!rle) { // flat scanline: the 4 bytes read are the first pixel
+            std::memcpy(scan.data(), head, 4);
+            if (w > 1 && fread(scan.data() + 4, 4, w - 1, f.get()) != w - 1) return std::string("image_io: truncated HDR in ") + path;
+        } else {
+            std::vector<unsigned char> comp(w);
+            for (int k = 0; k < 4; k++) {
+                size_t i = 0;
+                while (i < w) {
+                    int count = fgetc(f.get());
+                    if (count == EOF) return std::string("image_io: truncated HDR in ") + path;
+                    if (count > 128) { // run
+                        const int v = fgetc(f.get());
+                        count -= 128;
+                        if (v == EOF || count == 0 || i + size_t(count) > w) return std::string("image_io: corrupt HDR in ") + path;
+                        for (int z = 0; z < count; z++) comp[i++] = (unsigned char)v;
+                    } else { // dump
+                        if (count == 0 || i + size_t(count) > w) return std::string("image_io: corrupt HDR in ") + path;
+                        if (fread(comp.data() + i, 1, size_t(count), f.get()) != size_t(count)) return std::string("image_io: truncated HDR in ") + path;
+                        i += size_t(count);
+                    }
+                }
+                for (size_t x = 0; x < w; x++) scan[x * 4 + size_t(k)] = comp[x];
+            }
+        }
+        for (size_t x = 0; x < w; x++) convert(&scan[x * 4], &out[(y * w + x) * size_t(desired_channels)]);
     }
     return {};
 }

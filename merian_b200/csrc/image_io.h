@@ -20,4 +20,9 @@ std::string pfm_load(const char* path, int desired_channels, PfmInfo& info, std:
 // data: top-down rows of `channels` (1, 3 or 4) floats; RGBA is written as RGB (PFM has no alpha); little endian, scale -1.
 std::string pfm_save(const char* path, const float* data, int width, int height, int channels);
 
+// Radiance RGBE (.hdr) as image_load_f32 decodes it through stb_image (src/merian/io/image_io.cpp:226-240 -> stbi_loadf): header
+// "#?RADIANCE" / "#?RGBE", "FORMAT=32-bit_rle_rgbe", "-Y h +X w", flat or new-style RLE scanlines, top-down; component =
+// mantissa * 2^(e - 136), (0,0,0,0) -> 0. `desired_channels` 3 or 4 (alpha = 1).
+std::string hdr_load(const char* path, int desired_channels, int& width, int& height, std::vector<float>& out);
+
 } // namespace mpt

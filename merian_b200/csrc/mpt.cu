@@ -16,6 +16,7 @@
 #include "image_io.h"
 #include "shading.cuh"
 
+#include <cctype>
 #include <chrono>
 #include <cstddef>
 #include <cstdio>
@@ -1600,16 +1601,40 @@ MPT_API mpt_status mpt_pfm_save(const char* path, const float* data, uint32_t wi
     return MPT_OK;
 }
 
+MPT_API mpt_status mpt_hdr_load(const char* path, uint32_t desired_channels, uint32_t* width, uint32_t* height, float* out, uint64_t capacity_floats) {
+    mpt_context* ctx = nullptr;
+    if (!path || !width || !height) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    int w = 0, h = 0;
+    std::vector<float> px;
+    const std::string err = hdr_load(path, int(desired_channels), w, h, px);
+    if (!err.empty()) return fail(ctx, MPT_ERR_IO, err);
+    *width = uint32_t(w);
+    *height = uint32_t(h);
+    if (!out) return MPT_OK; // size query
+    if (px.size() > capacity_floats) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "output buffer too small for the image");
+    std::memcpy(out, px.data(), px.size() * sizeof(float));
+    return MPT_OK;
+}
+
 MPT_API mpt_status mpt_env_load(mpt_context* ctx, const char* path, const float* to_local, float intensity) {
     if (!ctx || !path || !to_local) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     const size_t n = std::strlen(path);
-    if (n < 4 || (std::strcmp(path + n - 4, ".pfm") != 0 && std::strcmp(path + n - 4, ".PFM") != 0))
-        return fail(ctx, MPT_ERR_UNSUPPORTED, "mpt_env_load reads .pfm lat-long maps only (decode other formats on the host and call mpt_env_set)");
-    PfmInfo info;
+    auto ends = [&](const char* e) { std::string t(n >= 4 ? path + n - 4 : ""); for (char& c : t) c = char(std::tolower((unsigned char)c)); return t == e; };
     std::vector<float> px;
-    const std::string err = pfm_load(path, 4, info, px); // image_load_f32 -> create_texture_from_rgba32f, scene.cpp:785-789
+    int w = 0, h = 0;
+    std::string err;
+    if (ends(".pfm")) { // image_load_f32 -> create_texture_from_rgba32f, scene.cpp:783-789
+        PfmInfo info;
+        err = pfm_load(path, 4, info, px);
+        w = info.width;
+        h = info.height;
+    } else if (ends(".hdr")) {
+        err = hdr_load(path, 4, w, h, px);
+    } else {
+        return fail(ctx, MPT_ERR_UNSUPPORTED, "mpt_env_load reads .pfm and .hdr lat-long maps (decode 8-bit formats on the host and call mpt_env_set)");
+    }
     if (!err.empty()) return fail(ctx, MPT_ERR_IO, err);
-    return mpt_env_set(ctx, MPT_ENV_LATLONG, to_local, intensity, uint32_t(info.width), uint32_t(info.height), px.data());
+    return mpt_env_set(ctx, MPT_ENV_LATLONG, to_local, intensity, uint32_t(w), uint32_t(h), px.data());
 }
 
 MPT_API mpt_status mpt_image_write(mpt_context* ctx, const char* path, const void* d_rgba32f, uint32_t width, uint32_t height, void* stream) {

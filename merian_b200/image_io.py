@@ -34,3 +34,12 @@ def save_pfm(path, image):
         img = img[..., None]
     h, w, c = img.shape
     _check(lib().mpt_pfm_save(os.fsencode(path), C.c_void_p(img.ctypes.data), w, h, c))
+
+
+def load_hdr(path, desired_channels=3):
+    """Radiance RGBE, decoded as stb_image does for image_load_f32."""
+    w, h = C.c_uint32(), C.c_uint32()
+    _check(lib().mpt_hdr_load(os.fsencode(path), desired_channels, C.byref(w), C.byref(h), None, 0))
+    out = np.empty((h.value, w.value, desired_channels), np.float32)
+    _check(lib().mpt_hdr_load(os.fsencode(path), desired_channels, C.byref(w), C.byref(h), C.c_void_p(out.ctypes.data), out.size))
+    return out

@@ -87,6 +87,70 @@ def test_errors(tmp_path):
         image_io.save_pfm(tmp_path / "two.pfm", np.zeros((2, 2, 2), np.float32))
 
 
+def _rgbe(img):
+    """float RGB -> RGBE bytes (Ward): the shared exponent of the largest component, 8-bit mantissas."""
+    m = img.max(-1)
+    e = np.where(m > 1e-32, np.ceil(np.log2(np.maximum(m, 1e-38)) + 1e-12), -128).astype(np.int32)
+    scale = np.where(m > 1e-32, np.ldexp(1.0, 8 - e), 0.0)
+    out = np.zeros(img.shape[:-1] + (4,), np.uint8)
+    out[..., :3] = np.clip(np.floor(img * scale[..., None]), 0, 255).astype(np.uint8)
+    out[..., 3] = np.where(m > 1e-32, e + 128, 0).astype(np.uint8)
+    return out
+
+
+def _rle_scanline(row):  # new-style RLE: per component, runs of >= 3 equal bytes
+    w = len(row)
+    out = bytearray([2, 2, w >> 8, w & 255])
+    for k in range(4):
+        comp = row[:, k].tolist()
+        i = 0
+        while i < w:
+            run = 1
+            while i + run < w and run < 127 and comp[i + run] == comp[i]:
+                run += 1
+            if run >= 3:
+                out += bytes([128 + run, comp[i]])
+                i += run
+            else:
+                j = i
+                while j < w and j - i < 128:
+                    r = 1
+                    while j + r < w and r < 3 and comp[j + r] == comp[j]:
+                        r += 1
+                    if r >= 3:
+                        break
+                    j += 1
+                out += bytes([j - i]) + bytes(comp[i:j])
+                i = j
+    return bytes(out)
+
+
+@pytest.mark.parametrize("rle,w", [(False, 5), (True, 24), (False, 24)])
+def test_hdr_rgbe_decoding(tmp_path, rle, w):
+    rng = np.random.default_rng(w + int(rle))
+    img = (rng.random((6, w, 3)) * np.array([0.01, 1.0, 3000.0])).astype(np.float32)
+    img[0, :4] = 0.0            # (0,0,0,0) -> 0
+    img[1, :12] = img[1, 0]     # a run for the RLE path
+    rgbe = _rgbe(img)
+    head = b"#?RADIANCE\n# comment\nFORMAT=32-bit_rle_rgbe\nEXPOSURE=1.0\n\n-Y 6 +X %d\n" % w
+    body = b"".join(_rle_scanline(r) for r in rgbe) if rle else rgbe.tobytes()
+    p = tmp_path / "e.hdr"
+    p.write_bytes(head + body)
+    got = image_io.load_hdr(p, 4)
+    ref = rgbe[..., :3].astype(np.float32) * np.ldexp(np.float32(1.0), rgbe[..., 3].astype(np.int32) - 136)[..., None]
+    ref[rgbe[..., 3] == 0] = 0
+    assert np.array_equal(got[..., :3], ref.astype(np.float32)) and (got[..., 3] == 1).all()
+    assert (np.abs(got[..., :3] - img) <= img.max(-1, keepdims=True) * 2.0 ** -7 + 1e-30).all()  # 8-bit mantissa on the shared exponent
+    bad = tmp_path / "bad.hdr"
+    bad.write_bytes(b"#?RADIANCE\nFORMAT=32-bit_rle_xyze\n\n-Y 1 +X 1\n" + bytes(4))
+    with pytest.raises(MptError, match="unsupported HDR format"):
+        image_io.load_hdr(bad)
+    short = tmp_path / "short.hdr"
+    short.write_bytes(head + body[:len(body) // 2])
+    with pytest.raises(MptError, match="truncated|corrupt"):
+        image_io.load_hdr(short)
+
+
 @pytest.mark.gpu
 def test_env_load_and_image_write_on_device(gpu_ctx, tmp_path):
     """A lat-long .pfm loaded by libmpt lights the scene exactly like the same pixels passed to mpt_env_set; the rendered image
