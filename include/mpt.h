@@ -295,6 +295,15 @@ MPT_API mpt_status mpt_render_host(mpt_context* ctx, const mpt_camera* camera,
                                    const mpt_render_params* params, const void* h_tex1,
                                    const void* h_albedo, void* h_irradiance, void* stream);
 
+/* The same with several iterations in flight, the way merian's graph runs (2 by default, examples/gltf.json:39; ring index =
+ * info.get_in_flight_index(), node_process_info.hpp:42-46): _begin enqueues H2D, render and D2H of one iteration and returns;
+ * _end(i) blocks until the irradiance of slot i is in its host buffer. Copies of neighbouring iterations overlap the render.
+ * Host buffers must stay valid (and should be pinned) until _end. in_flight_index < 4. */
+MPT_API mpt_status mpt_render_host_begin(mpt_context* ctx, const mpt_camera* camera, const mpt_render_params* params,
+                                         const void* h_tex1, const void* h_albedo, void* h_irradiance,
+                                         uint32_t in_flight_index);
+MPT_API mpt_status mpt_render_host_end(mpt_context* ctx, uint32_t in_flight_index);
+
 /* ---- Accumulate, plain mode ----------------------------------------------
  * Replaces the accumulate pass of the `Accumulate` node (include/merian-graph/nodes/accumulate/accumulate.slang:103-255,
  * src/merian-graph/nodes/accumulate/accumulate.cpp:153-167) for a signal that is reused at the SAME pixel
@@ -369,8 +378,12 @@ typedef struct mpt_bvh_info {
     uint64_t node_bytes;
     uint64_t triangle_bytes;
     double build_ms;
+    uint64_t max_depth;      /* wide levels on the longest path, deepest BLAS + TLAS (bounds the traversal stack) */
 } mpt_bvh_info;
 MPT_API mpt_status mpt_bvh_get_info(mpt_context* ctx, mpt_bvh_info* out);
+/* Host-only: runs the BVH8 builder over `n` boxes (6 floats each: lo.xyz, hi.xyz) and reports its shape; prim_order (n entries, may be
+ * NULL) receives the leaf order. No device needed. */
+MPT_API mpt_status mpt_bvh8_build_info(const float* boxes, uint32_t n, mpt_bvh_info* out, uint32_t* prim_order);
 
 /* Test hook for the BSDF property suite (tests/test_bsdf.cpp of the reference restated): runs
  * sample_eval / eval / pdf of one BSDF on the device. See merian_b200/csrc/bsdf_check.cu. */

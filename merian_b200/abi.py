@@ -128,7 +128,7 @@ class Stats(C.Structure):
 
 class BvhInfo(C.Structure):
     _fields_ = [("node_count", C.c_uint64), ("triangle_count", C.c_uint64), ("node_bytes", C.c_uint64),
-                ("triangle_bytes", C.c_uint64), ("build_ms", C.c_double)]
+                ("triangle_bytes", C.c_uint64), ("build_ms", C.c_double), ("max_depth", C.c_uint64)]
 
 
 class BsdfCheckParams(C.Structure):

@@ -132,6 +132,14 @@ class Context:
                                            self._stream()))
         return h_out
 
+    def render_host_begin(self, cam, params, h_out, slot, h_tex1=None, h_albedo=None):
+        """One iteration in flight slot `slot` (H2D, render, D2H enqueued; returns immediately). Pair with render_host_end(slot)."""
+        self._check(self.l.mpt_render_host_begin(self.h, C.byref(cam), C.byref(params), C.c_void_p(h_tex1.data_ptr()) if h_tex1 is not None else None,
+                                                 C.c_void_p(h_albedo.data_ptr()) if h_albedo is not None else None, C.c_void_p(h_out.data_ptr()), slot))
+
+    def render_host_end(self, slot):
+        self._check(self.l.mpt_render_host_end(self.h, slot))
+
     # ------------------------------------------------------------------ Accumulate node, plain mode (include/mpt.h)
     @staticmethod
     def _acc_buffers(prev_out, prev_history, out, history, tex0, tex2):

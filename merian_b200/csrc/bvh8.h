@@ -35,7 +35,11 @@ struct Bvh8 {
     std::vector<Bvh8Node> nodes;
     std::vector<uint32_t> prim_order;
     Box bounds;
+    uint32_t depth = 1; // levels of wide nodes on the longest root-to-leaf path (bounds the traversal stack)
 };
+
+// Depth bound build_bvh8 guarantees (by falling back to median splits below the SAH levels for degenerate inputs).
+constexpr uint32_t kMaxBvh8Depth = 14;
 
 // max_leaf: primitives per leaf child (<= 3). Deterministic (no threads inside).
 void build_bvh8(const Box* boxes, uint32_t n, Bvh8& out, int max_leaf = 3);

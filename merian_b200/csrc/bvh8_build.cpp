@@ -38,6 +38,7 @@ struct Node2 {
 
 constexpr int NBINS = 16;
 
+
 // Builder knobs for tuning sessions (host code only; defaults are the measured optimum).
 float env_float(const char* name, float def) {
     const char* v = std::getenv(name);
@@ -50,6 +51,7 @@ struct Builder2 {
     std::vector<uint32_t> idx;
     std::vector<Node2> nodes;
     int max_leaf;
+    uint32_t sah_depth_limit = 0xFFFFFFFFu; // BVH2 levels built with SAH before the builder switches to median splits
     float trav_cost = 1.0f; // SAH: cost of one node test in units of one primitive test
 
     void build(uint32_t n) {
@@ -60,9 +62,9 @@ struct Builder2 {
             for (int a = 0; a < 3; a++) cent[size_t(i) * 3 + a] = 0.5f * (boxes[i].lo[a] + boxes[i].hi[a]);
         nodes.reserve(size_t(n) * 2);
         nodes.emplace_back();
-        struct Job { uint32_t node, first, count; };
+        struct Job { uint32_t node, first, count, depth; };
         std::vector<Job> stack;
-        stack.push_back({0, 0, n});
+        stack.push_back({0, 0, n, 0});
         while (!stack.empty()) {
             const Job j = stack.back();
             stack.pop_back();
@@ -116,7 +118,16 @@ struct Builder2 {
             if (int(j.count) <= max_leaf && split_cost >= leaf_cost) { make_leaf(j.node, j.first, j.count); continue; }
 
             uint32_t mid;
-            if (best_axis >= 0) {
+            if (j.depth >= sah_depth_limit) {
+                // a degenerate SAH chain (one primitive peeled off per level) would outgrow the traversal stack: below this depth
+                // split at the object median of the widest centroid axis, which bounds the remaining depth by log2(count)
+                int a = 0;
+                for (int k = 1; k < 3; k++)
+                    if (cbox.hi[k] - cbox.lo[k] > cbox.hi[a] - cbox.lo[a]) a = k;
+                mid = j.count / 2;
+                std::nth_element(idx.begin() + j.first, idx.begin() + j.first + mid, idx.begin() + j.first + j.count,
+                                 [&](uint32_t p, uint32_t q) { return cent[size_t(p) * 3 + a] < cent[size_t(q) * 3 + a]; });
+            } else if (best_axis >= 0) {
                 const int a = best_axis;
                 const float cmin = cbox.lo[a], cmax = cbox.hi[a];
                 const float k = float(NBINS) * (1.0f - 1e-6f) / (cmax - cmin);
@@ -139,8 +150,8 @@ struct Builder2 {
             nodes[j.node].left = l;
             nodes[j.node].right = l + 1;
             nodes[j.node].count = 0;
-            stack.push_back({l + 1, j.first + mid, j.count - mid});
-            stack.push_back({l, j.first, mid});
+            stack.push_back({l + 1, j.first + mid, j.count - mid, j.depth + 1});
+            stack.push_back({l, j.first, mid, j.depth + 1});
         }
     }
     void make_leaf(uint32_t node, uint32_t first, uint32_t count) {
@@ -160,7 +171,7 @@ inline uint8_t exponent_for(float extent) {
 
 } // namespace
 
-void build_bvh8(const Box* boxes, uint32_t n, Bvh8& out, int max_leaf) {
+static void build_bvh8_once(const Box* boxes, uint32_t n, Bvh8& out, int max_leaf, uint32_t sah_depth_limit) {
     out.nodes.clear();
     out.prim_order.clear();
     B3 all;
@@ -177,18 +188,21 @@ void build_bvh8(const Box* boxes, uint32_t n, Bvh8& out, int max_leaf) {
     b2.boxes = boxes;
     b2.max_leaf = std::min(std::max(int(env_float("MPT_BVH_MAX_LEAF", float(max_leaf))), 1), 3);
     b2.trav_cost = env_float("MPT_BVH_TRAV_COST", 1.0f);
+    b2.sah_depth_limit = sah_depth_limit;
     const int collapse_mode = int(env_float("MPT_BVH_COLLAPSE", 0.f));
     b2.build(n);
     const std::vector<Node2>& n2 = b2.nodes;
 
     out.prim_order.reserve(n);
     out.nodes.reserve(n / 3 + 16);
-    struct Task { uint32_t wide, root2; };
+    struct Task { uint32_t wide, root2, depth; };
     std::vector<Task> queue;
     out.nodes.emplace_back();
-    queue.push_back({0, 0});
+    queue.push_back({0, 0, 1});
+    out.depth = 1;
     for (size_t qi = 0; qi < queue.size(); qi++) {
         const Task t = queue[qi];
+        out.depth = std::max(out.depth, t.depth);
         // ---- gather up to 8 children: repeatedly open the internal child with the largest area
         uint32_t ch[8];
         int nch = 0;
@@ -283,9 +297,20 @@ void build_bvh8(const Box* boxes, uint32_t n, Bvh8& out, int max_leaf) {
         for (int s = 0; s < 8; s++) {
             const int c = child_in_slot[s];
             if (c < 0 || n2[ch[c]].count != 0) continue;
-            queue.push_back({node.child_base + j, ch[c]});
+            queue.push_back({node.child_base + j, ch[c], t.depth + 1});
             j++;
         }
+    }
+}
+
+// The traversal keeps at most two stack entries per wide level (bvh8_traverse.cuh), so the depth must be bounded. SAH trees of
+// real scenes are 8-10 wide levels deep (1 M-triangle terrain: 8); a degenerate input (primitives of geometrically growing size on a
+// line) makes SAH peel one primitive per level. When that happens the tree is rebuilt with SAH only for the top levels and object-median
+// splits below, which bounds the depth by about log8(n) + the SAH levels.
+void build_bvh8(const Box* boxes, uint32_t n, Bvh8& out, int max_leaf) {
+    for (uint32_t limit : {0xFFFFFFFFu, 16u, 8u, 0u}) {
+        build_bvh8_once(boxes, n, out, max_leaf, limit);
+        if (out.depth <= kMaxBvh8Depth) return;
     }
 }
 

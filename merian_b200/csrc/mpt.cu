@@ -795,6 +795,16 @@ struct mpt_context {
     // wavefront pool
     DevBuf q_o[2], q_d[2], hq_hit, hq_dir, hq_org, thr, rad, med, sq_o, sq_d, sq_c, counters, tex1_internal, stage_tex1, stage_albedo, stage_out;
     size_t pool_slots = 0;
+    // frames in flight of mpt_render_host_begin / _end
+    struct InFlight {
+        cudaStream_t copy = nullptr;
+        cudaEvent_t h2d = nullptr, done = nullptr, d2h = nullptr;
+        DevBuf tex1, albedo, out;
+        bool pending = false;
+    };
+    static constexpr uint32_t kMaxInFlight = 4;
+    InFlight in_flight[kMaxInFlight];
+    cudaStream_t compute = nullptr;
     // stats / profiling
     uint32_t profile_flags = 0;
     mpt_stats stats{};
@@ -1086,6 +1096,12 @@ MPT_API void mpt_destroy(mpt_context* ctx) {
         if (t.obj) cudaDestroyTextureObject(t.obj);
         if (t.array) cudaFreeArray(t.array);
     }
+    for (auto& f : ctx->in_flight) {
+        if (f.copy) cudaStreamDestroy(f.copy);
+        for (cudaEvent_t e : {f.h2d, f.done, f.d2h})
+            if (e) cudaEventDestroy(e);
+    }
+    if (ctx->compute) cudaStreamDestroy(ctx->compute);
     for (auto* pool : {&ctx->ev_extend, &ctx->ev_shade})
         for (auto& p : *pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     delete ctx;
@@ -1106,6 +1122,7 @@ MPT_API mpt_status mpt_scene_upload(mpt_context* ctx, const mpt_scene_desc* d) {
     std::vector<uint32_t> blas_root(d->blas_count);
     std::vector<Box> blas_bounds(d->blas_count);
     std::vector<std::vector<uint32_t>> blas_geom_offset(d->blas_count);
+    uint32_t max_blas_depth = 0, tlas_depth = 0;
 
     for (uint32_t bi = 0; bi < d->blas_count; bi++) {
         const mpt_blas_desc& bd = d->blas[bi];
@@ -1138,6 +1155,7 @@ MPT_API mpt_status mpt_scene_upload(mpt_context* ctx, const mpt_scene_desc* d) {
         Bvh8 bvh;
         build_bvh8(boxes.data(), uint32_t(boxes.size()), bvh);
         const uint32_t node_off = uint32_t(nodes.size()), tri_off = uint32_t(tris.size() / 3);
+        max_blas_depth = std::max(max_blas_depth, bvh.depth);
         blas_root[bi] = node_off;
         blas_bounds[bi] = bvh.bounds;
         for (Bvh8Node nd : bvh.nodes) {
@@ -1221,7 +1239,11 @@ MPT_API mpt_status mpt_scene_upload(mpt_context* ctx, const mpt_scene_desc* d) {
             nodes.push_back(nd); // prim_base indexes tlas_prims directly
         }
         tlas_prims = tl.prim_order;
+        tlas_depth = tl.depth;
     }
+    if (2u * (max_blas_depth + tlas_depth) + 2u > uint32_t(kStackSize) - 6u)
+        return fail(ctx, MPT_ERR_LIMIT, "acceleration structure too deep for the traversal stack (BLAS " + std::to_string(max_blas_depth) + " + TLAS " +
+                                            std::to_string(tlas_depth) + " wide levels)");
 
     // ---- geometry table
     std::vector<uint4> geoms(d->geometry_count);
@@ -1268,6 +1290,7 @@ MPT_API mpt_status mpt_scene_upload(mpt_context* ctx, const mpt_scene_desc* d) {
     ctx->bvh_info.triangle_count = tris.size() / 3;
     ctx->bvh_info.node_bytes = nodes.size() * sizeof(Bvh8Node);
     ctx->bvh_info.triangle_bytes = tris.size() * sizeof(float4);
+    ctx->bvh_info.max_depth = max_blas_depth + tlas_depth;
     ctx->bvh_info.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
     ctx->scene_ready = true;
     return MPT_OK;
@@ -1648,6 +1671,60 @@ MPT_API mpt_status mpt_image_write(mpt_context* ctx, const char* path, const voi
     return MPT_OK;
 }
 
+// Several iterations in flight (merian's graph keeps 2 by default, examples/gltf.json:39): the host->device copy of iteration i+1 and
+// the device->host copy of iteration i-1 run on per-slot copy streams while iteration i renders on the context's compute stream (the
+// path pool is shared, so renders are serialised among themselves).
+MPT_API mpt_status mpt_render_host_begin(mpt_context* ctx, const mpt_camera* camera, const mpt_render_params* P, const void* h_tex1, const void* h_albedo,
+                                         void* h_irradiance, uint32_t in_flight_index) {
+    if (!ctx || !camera || !P || !h_irradiance) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (in_flight_index >= mpt_context::kMaxInFlight) return fail(ctx, MPT_ERR_LIMIT, "in_flight_index must be < 4");
+    CU(cudaSetDevice(ctx->device));
+    mpt_context::InFlight& f = ctx->in_flight[in_flight_index];
+    if (f.pending) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "this in-flight slot still holds a frame: call mpt_render_host_end first");
+    if (!ctx->compute) CU(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
+    if (!f.copy) {
+        CU(cudaStreamCreateWithFlags(&f.copy, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&f.h2d, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&f.d2h, cudaEventDisableTiming));
+    }
+    const size_t npix = size_t(P->width) * P->height;
+    CU(f.out.ensure(npix * 16));
+    void* d_tex1 = nullptr;
+    void* d_albedo = nullptr;
+    if (h_tex1) {
+        CU(f.tex1.ensure(npix * 16));
+        CU(cudaMemcpyAsync(f.tex1.p, h_tex1, npix * 16, cudaMemcpyHostToDevice, f.copy));
+        d_tex1 = f.tex1.p;
+    }
+    if (h_albedo) {
+        CU(f.albedo.ensure(npix * 16));
+        CU(cudaMemcpyAsync(f.albedo.p, h_albedo, npix * 16, cudaMemcpyHostToDevice, f.copy));
+        d_albedo = f.albedo.p;
+    }
+    CU(cudaEventRecord(f.h2d, f.copy));
+    CU(cudaStreamWaitEvent(ctx->compute, f.h2d, 0));
+    const mpt_status s = mpt_render(ctx, camera, P, d_tex1, d_albedo, f.out.p, ctx->compute);
+    if (s != MPT_OK) return s;
+    CU(cudaEventRecord(f.done, ctx->compute));
+    CU(cudaStreamWaitEvent(f.copy, f.done, 0));
+    CU(cudaMemcpyAsync(h_irradiance, f.out.p, npix * 16, cudaMemcpyDeviceToHost, f.copy));
+    CU(cudaEventRecord(f.d2h, f.copy));
+    f.pending = true;
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_render_host_end(mpt_context* ctx, uint32_t in_flight_index) {
+    if (!ctx) return MPT_ERR_INVALID_ARGUMENT;
+    if (in_flight_index >= mpt_context::kMaxInFlight) return fail(ctx, MPT_ERR_LIMIT, "in_flight_index must be < 4");
+    mpt_context::InFlight& f = ctx->in_flight[in_flight_index];
+    if (!f.pending) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "no frame is in flight in this slot");
+    CU(cudaSetDevice(ctx->device));
+    f.pending = false;
+    CU(cudaEventSynchronize(f.d2h));
+    return MPT_OK;
+}
+
 MPT_API mpt_status mpt_set_profiling(mpt_context* ctx, uint32_t profile_flags) {
     if (!ctx) return MPT_ERR_INVALID_ARGUMENT;
     ctx->profile_flags = profile_flags;
@@ -1686,6 +1763,23 @@ MPT_API mpt_status mpt_bvh_get_info(mpt_context* ctx, mpt_bvh_info* out) {
     if (!ctx || !out) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!ctx->scene_ready) return fail(ctx, MPT_ERR_NOT_READY, "scene not uploaded");
     *out = ctx->bvh_info;
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_bvh8_build_info(const float* boxes, uint32_t n, mpt_bvh_info* out, uint32_t* prim_order) {
+    mpt_context* ctx = nullptr;
+    if ((!boxes && n) || !out) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    const auto t0 = std::chrono::steady_clock::now();
+    Bvh8 bvh;
+    build_bvh8(reinterpret_cast<const Box*>(boxes), n, bvh);
+    *out = mpt_bvh_info{};
+    out->node_count = bvh.nodes.size();
+    out->triangle_count = bvh.prim_order.size();
+    out->node_bytes = bvh.nodes.size() * sizeof(Bvh8Node);
+    out->triangle_bytes = bvh.prim_order.size() * 48;
+    out->max_depth = bvh.depth;
+    out->build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (prim_order) std::memcpy(prim_order, bvh.prim_order.data(), bvh.prim_order.size() * 4);
     return MPT_OK;
 }
 

@@ -264,6 +264,36 @@ def test_render_host_matches_device_path(gpu_ctx):
     assert np.array_equal(dev, host)
 
 
+def test_iterations_in_flight_equal_the_synchronous_call(gpu_ctx):
+    """mpt_render_host_begin / _end with two slots in flight (merian's default) return the images of mpt_render_host, frame by frame."""
+    t = tables("cornell")
+    upload_scene(gpu_ctx, t)
+    cam = t.desc.camera.to_abi(0)
+    w, h = 96, 64
+    tex1 = gpu_ctx.primary_visibility_device(cam, w, h).cpu().pin_memory()
+    ref = [gpu_ctx.render_host(cam, render_params(w, h, 4, frame=f), h_tex1=tex1).clone() for f in range(5)]
+    outs = [torch.empty((h, w, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    got = []
+    for f in range(5):
+        if f >= 2:
+            gpu_ctx.render_host_end(f % 2)
+            got.append(outs[f % 2].clone())
+        gpu_ctx.render_host_begin(cam, render_params(w, h, 4, frame=f), outs[f % 2], f % 2, h_tex1=tex1)
+    for f in (3, 4):
+        gpu_ctx.render_host_end(f % 2)
+        got.append(outs[f % 2].clone())
+    for f in range(5):
+        assert torch.equal(got[f], ref[f]), f
+    with pytest.raises(MptError):
+        gpu_ctx.render_host_end(0)  # nothing in flight
+    gpu_ctx.render_host_begin(cam, render_params(w, h, 1), outs[0], 0, h_tex1=tex1)
+    with pytest.raises(MptError):
+        gpu_ctx.render_host_begin(cam, render_params(w, h, 1), outs[0], 0, h_tex1=tex1)  # slot busy
+    gpu_ctx.render_host_end(0)
+    with pytest.raises(MptError):
+        gpu_ctx.render_host_begin(cam, render_params(w, h, 1), outs[0], 7, h_tex1=tex1)
+
+
 def test_error_behaviour(gpu_ctx):
     """C-ABI error convention: int status + mpt_last_error, never an exception across the boundary or a silent fallback."""
     from merian_b200.context import Context
