@@ -286,11 +286,14 @@ __global__ void __launch_bounds__(kThreads) k_trace(const __grid_constant__ Scen
 }
 
 // --------------------------------------------------------------------------------------- wavefront: primary shade
+// Core-glTF shading (FEAT = 0) is latency-bound, not register-bound: 8 resident blocks/SM at 64 registers (a few spilled words) beat
+// 5 blocks at 86 registers by 12 % of the shade time (5.84 -> 5.13 ms/frame on C3; 6 blocks: +-0, 10 blocks/48 regs: -3 %, 12 blocks: +3 %
+// slower; profiles/r01f_extend_experiments.md). The extension variants keep the compiler's choice.
 #ifndef MPT_SHADE_MIN_BLOCKS
-#define MPT_SHADE_MIN_BLOCKS 1
+#define MPT_SHADE_MIN_BLOCKS 8
 #endif
 template <uint32_t FEAT, bool NEE>
-__global__ void __launch_bounds__(kThreads, MPT_SHADE_MIN_BLOCKS) k_shade_primary(const __grid_constant__ SceneView S, CameraParams cam, RenderConst rc, const PackedHitInfo* tex1, PathBuffers pb,
+__global__ void __launch_bounds__(kThreads, (FEAT == 0u && !NEE) ? MPT_SHADE_MIN_BLOCKS : 1) k_shade_primary(const __grid_constant__ SceneView S, CameraParams cam, RenderConst rc, const PackedHitInfo* tex1, PathBuffers pb,
                                                             Counters* ctr) {
     const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = pix < rc.npix;
@@ -475,7 +478,7 @@ __global__ void __launch_bounds__(kThreads) k_shadow(const __grid_constant__ Sce
 
 // --------------------------------------------------------------------------------------- wavefront: shade after extend
 template <uint32_t FEAT, bool NEE>
-__global__ void __launch_bounds__(kThreads, MPT_SHADE_MIN_BLOCKS) k_shade_bounce(const __grid_constant__ SceneView S, RenderConst rc, PathBuffers pb, uint32_t bounce, Counters* ctr) {
+__global__ void __launch_bounds__(kThreads, (FEAT == 0u && !NEE) ? MPT_SHADE_MIN_BLOCKS : 1) k_shade_bounce(const __grid_constant__ SceneView S, RenderConst rc, PathBuffers pb, uint32_t bounce, Counters* ctr) {
     const uint32_t n = ctr->hcount[bounce];
     const uint32_t out = bounce & 1u;
     const bool more = int32_t(bounce) + 1 < rc.max_path_length; // with_material, render_pt.slang:80
