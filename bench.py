@@ -141,7 +141,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = w * h * s * args.steps / dt / 1e6
     sample = f"each step = {w}x{h} x {s} spp of the workload (1/128 of a frame), oracle port, {o.num_threads()} threads"
-    print(json.dumps({
+    args.emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -301,10 +301,33 @@ def run_ours(args):
             "clocks": clocks,
             "bvh": {"nodes": bvh.node_count, "node_mb": bvh.node_bytes / 1e6, "triangle_mb": bvh.triangle_bytes / 1e6, "build_ms": bvh.build_ms},
         }
-        print(json.dumps(line))
+        args.emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+class _QuietStdout:
+    """Libraries under us print to the C-level stdout (NCCL writes its version banner there): point fd 1 at stderr while the bench runs
+    and give it back for the ONE JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
 
 
 def main():
@@ -321,10 +344,12 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and not args.small:
         args.warmup = 3  # timing rule: at least 3 warm-up steps
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    with _QuietStdout() as out:
+        args.emit = out.emit
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
 
 
 if __name__ == "__main__":
