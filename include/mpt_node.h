@@ -35,6 +35,7 @@ MPT_API const char* mptn_last_error(const mptn_node* node);
  * Keys (render_pt.cpp:147-187): "samples per pixel" (int), "max path length" (int), "emission on primary" (bool),
  * "shader execution reordering" (bool; accepted, no effect: there is no SER on this device), "demodulate albedo" (bool),
  * "0".."7" (bool, instance-mask bits), "irradiance format" (string: "R32G32B32A32Sfloat" | "R16G16B16A16Sfloat").
+ * One key the reference does not have: "next event estimation" (bool, default false = the reference estimator): MPT_RENDER_NEE.
  * Missing keys keep their value, unknown keys are ignored, UI min/max are NOT applied (properties_json_load.cpp:126-133),
  * a value of the wrong JSON type is an error (nlohmann::json::get throws there). out_status: MPTN_NEEDS_RECONNECT when
  * the irradiance format changed (render_pt.cpp:180-185). */

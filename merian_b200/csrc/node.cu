@@ -144,6 +144,7 @@ struct mptn_node {
     bool emission_on_primary = true;
     bool enable_ser = false;
     bool demodulate_albedo = false;
+    bool nee = false; // "next event estimation": CUDA-node extension (MPT_RENDER_NEE), off = the reference estimator
     std::array<bool, 8> mask_enabled{{true, true, true, true, true, true, true, true}};
     uint32_t irradiance_format = MPTN_FORMAT_R32G32B32A32_SFLOAT;
     // describe_outputs
@@ -206,6 +207,7 @@ MPT_API mpt_status mptn_load_config(mptn_node* node, const char* json, uint32_t*
     want_bool("emission on primary", t.emission_on_primary, e);
     want_bool("shader execution reordering", t.enable_ser, e);
     want_bool("demodulate albedo", t.demodulate_albedo, e);
+    want_bool("next event estimation", t.nee, e);
     for (int bit = 0; bit < 8; bit++) {
         const std::string k = std::to_string(bit);
         want_bool(k.c_str(), t.mask_enabled[size_t(bit)], e);
@@ -238,6 +240,7 @@ MPT_API mpt_status mptn_dump_config(mptn_node* node, char* buf, size_t capacity,
     s += std::string("\"emission on primary\": ") + (node->emission_on_primary ? "true" : "false") + ", ";
     s += std::string("\"irradiance format\": \"") + format_name(node->irradiance_format) + "\", ";
     s += "\"max path length\": " + std::to_string(node->max_path_length) + ", ";
+    s += std::string("\"next event estimation\": ") + (node->nee ? "true" : "false") + ", ";
     s += "\"samples per pixel\": " + std::to_string(node->spp) + ", ";
     s += std::string("\"shader execution reordering\": ") + (node->enable_ser ? "true" : "false") + "}";
     if (out_len) *out_len = s.size();
@@ -287,7 +290,8 @@ MPT_API mpt_status mptn_process(mptn_node* node, const mpt_camera* camera, uint3
     for (uint32_t bit = 0; bit < 8; bit++)
         if (node->mask_enabled[bit]) mask |= 1u << bit;
     P.instance_mask = mask;
-    P.flags = (node->emission_on_primary ? MPT_RENDER_EMISSION_ON_PRIMARY : 0u) | (node->demodulate_albedo ? MPT_RENDER_DEMODULATE_ALBEDO : 0u);
+    P.flags = (node->emission_on_primary ? MPT_RENDER_EMISSION_ON_PRIMARY : 0u) | (node->demodulate_albedo ? MPT_RENDER_DEMODULATE_ALBEDO : 0u) |
+              (node->nee ? MPT_RENDER_NEE : 0u);
     P.sample_offset = 0;
     P.sample_stride = 1;
     P.spp = node->spp;
@@ -593,7 +597,8 @@ MPT_API mpt_status mptn_process_accumulate(mptn_node* pt, mptn_accumulate* acc, 
     P.width = pt->width; P.height = pt->height; P.frame = frame; P.spp = pt->spp; P.max_path_length = pt->max_path_length;
     for (uint32_t bit = 0; bit < 8; bit++)
         if (pt->mask_enabled[bit]) P.instance_mask |= 1u << bit;
-    P.flags = (pt->emission_on_primary ? MPT_RENDER_EMISSION_ON_PRIMARY : 0u) | (pt->demodulate_albedo ? MPT_RENDER_DEMODULATE_ALBEDO : 0u);
+    P.flags = (pt->emission_on_primary ? MPT_RENDER_EMISSION_ON_PRIMARY : 0u) | (pt->demodulate_albedo ? MPT_RENDER_DEMODULATE_ALBEDO : 0u) |
+              (pt->nee ? MPT_RENDER_NEE : 0u);
     P.sample_offset = 0; P.sample_stride = 1;
     if (out_events) *out_events = ev_pt | ev_acc;
     const mpt_status s = mpt_render_accumulate(pt->ctx, camera, &P, d_tex1, pt->demodulate_albedo ? d_albedo : nullptr, &A, buffers, stream);

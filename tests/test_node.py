@@ -13,7 +13,8 @@ from merian_b200._lib import MptError
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 DEFAULTS = {"0": True, "1": True, "2": True, "3": True, "4": True, "5": True, "6": True, "7": True, "demodulate albedo": False,
-            "emission on primary": True, "irradiance format": "R32G32B32A32Sfloat", "max path length": 5, "samples per pixel": 1,
+            "emission on primary": True, "irradiance format": "R32G32B32A32Sfloat", "max path length": 5, "next event estimation": False,
+            "samples per pixel": 1,
             "shader execution reordering": False}
 
 
