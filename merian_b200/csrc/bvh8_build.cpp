@@ -1,4 +1,5 @@
-// bvh8_build.cpp — host builder: binned-SAH BVH2 -> greedy 8-wide collapse -> quantised 80-byte nodes.
+// bvh8_build.cpp — host builder: binned-SAH BVH2 (one primitive per leaf) -> SAH-optimal 8-wide collapse (dynamic program of Ylitie,
+// Karras, Laine 2017, section 4.1, restated from the paper) -> quantised 80-byte nodes.
 // Replaces the driver BLAS/TLAS build of the reference (src/merian-shaders/scene/scene.cpp:1672-1892).
 #include "bvh8.h"
 
@@ -34,6 +35,7 @@ struct Node2 {
     B3 box;
     uint32_t left = 0, right = 0; // internal children
     uint32_t first = 0, count = 0; // leaf range into prim index array (count > 0 => leaf)
+    uint32_t rfirst = 0, rcount = 0; // range of every node (leaf or internal) in the prim index array
 };
 
 constexpr int NBINS = 16;
@@ -74,6 +76,8 @@ struct Builder2 {
                 cbox.grow_pt(&cent[size_t(idx[i]) * 3]);
             }
             nodes[j.node].box = box;
+            nodes[j.node].rfirst = j.first;
+            nodes[j.node].rcount = j.count;
             if (j.count <= 1) { make_leaf(j.node, j.first, j.count); continue; }
 
             // binned SAH over the 3 axes
@@ -186,12 +190,55 @@ static void build_bvh8_once(const Box* boxes, uint32_t n, Bvh8& out, int max_lea
     }
     Builder2 b2;
     b2.boxes = boxes;
-    b2.max_leaf = std::min(std::max(int(env_float("MPT_BVH_MAX_LEAF", float(max_leaf))), 1), 3);
+    const int collapse_mode = int(env_float("MPT_BVH_COLLAPSE", 2.f)); // 2 = SAH-optimal dynamic program (default), 0 = greedy by area
+    b2.max_leaf = collapse_mode == 2 ? 1 : std::min(std::max(int(env_float("MPT_BVH_MAX_LEAF", float(max_leaf))), 1), 3);
     b2.trav_cost = env_float("MPT_BVH_TRAV_COST", 1.0f);
     b2.sah_depth_limit = sah_depth_limit;
-    const int collapse_mode = int(env_float("MPT_BVH_COLLAPSE", 0.f));
     b2.build(n);
     const std::vector<Node2>& n2 = b2.nodes;
+
+    // ---- dynamic program of the SAH-optimal collapse: cost[n][i-1] = C(n, i), the cheapest way to represent BVH2 subtree n as at most i
+    // BVH8 children (leaves of <= 3 primitives or internal nodes); children have larger indices than their parent, so a reverse sweep
+    // is bottom-up.
+    std::vector<float> cost;
+    std::vector<uint8_t> dec, dist8;
+    if (collapse_mode == 2) {
+        const float c_prim = env_float("MPT_BVH_CPRIM", 0.5f), c_node = 1.0f; // measured optimum on C3 (0.15 ... 2.0 within 0.6 %)
+        const size_t nn = n2.size();
+        cost.assign(nn * 7, 0.f);
+        dec.assign(nn * 7, 0);
+        dist8.assign(nn, 1);
+        for (size_t k = nn; k-- > 0;) {
+            const Node2& nd = n2[k];
+            const float area = nd.box.half_area();
+            float* C = &cost[k * 7];
+            uint8_t* D = &dec[k * 7];
+            if (nd.count > 0) { // BVH2 leaf (one primitive)
+                for (int i = 0; i < 7; i++) { C[i] = area * float(nd.count) * c_prim; D[i] = 0; }
+                continue;
+            }
+            const float* L = &cost[size_t(nd.left) * 7];
+            const float* R = &cost[size_t(nd.right) * 7];
+            auto distribute = [&](int j, uint8_t& best_k) { // min over 0 < k < j of C(left, k) + C(right, j - k), slots per side capped at 7
+                float best = FLT_MAX;
+                for (int kk = std::max(1, j - 7); kk <= std::min(j - 1, 7); kk++) {
+                    const float v = L[kk - 1] + R[j - kk - 1];
+                    if (v < best) { best = v; best_k = uint8_t(kk); }
+                }
+                return best;
+            };
+            uint8_t k8 = 1;
+            const float c_internal = distribute(8, k8) + area * c_node;
+            dist8[k] = k8;
+            const float c_leaf = nd.rcount <= 3u ? area * float(nd.rcount) * c_prim : FLT_MAX;
+            if (c_leaf <= c_internal) { C[0] = c_leaf; D[0] = 0; } else { C[0] = c_internal; D[0] = 1; }
+            for (int i = 2; i <= 7; i++) {
+                uint8_t kk = 1;
+                const float cd = distribute(i, kk);
+                if (cd < C[i - 2]) { C[i - 1] = cd; D[i - 1] = kk; } else { C[i - 1] = C[i - 2]; D[i - 1] = 0; }
+            }
+        }
+    }
 
     out.prim_order.reserve(n);
     out.nodes.reserve(n / 3 + 16);
@@ -203,12 +250,32 @@ static void build_bvh8_once(const Box* boxes, uint32_t n, Bvh8& out, int max_lea
     for (size_t qi = 0; qi < queue.size(); qi++) {
         const Task t = queue[qi];
         out.depth = std::max(out.depth, t.depth);
-        // ---- gather up to 8 children: repeatedly open the internal child with the largest area
+        // ---- gather up to 8 children
         uint32_t ch[8];
+        bool ch_leaf[8];
         int nch = 0;
         if (n2[t.root2].count > 0) {
+            ch_leaf[nch] = true;
             ch[nch++] = t.root2; // the BVH2 root itself is a leaf
+        } else if (collapse_mode == 2) {
+            // SAH-optimal collapse (Ylitie, Karras, Laine 2017, section 4.1): follow the decisions of the dynamic program below
+            struct Item { uint32_t node; int slots; };
+            Item work[16];
+            int nw = 0;
+            const int k8 = dist8[t.root2];
+            work[nw++] = {n2[t.root2].right, 8 - k8};
+            work[nw++] = {n2[t.root2].left, k8};
+            while (nw) {
+                Item it = work[--nw];
+                if (n2[it.node].count > 0) { ch_leaf[nch] = true; ch[nch++] = it.node; continue; }
+                while (it.slots > 1 && dec[size_t(it.node) * 7 + size_t(it.slots - 1)] == 0) it.slots--;
+                const uint8_t d = dec[size_t(it.node) * 7 + size_t(it.slots - 1)];
+                if (it.slots == 1) { ch_leaf[nch] = (d == 0); ch[nch++] = it.node; continue; }
+                work[nw++] = {n2[it.node].right, it.slots - int(d)};
+                work[nw++] = {n2[it.node].left, int(d)};
+            }
         } else {
+            // greedy: repeatedly open the internal child with the largest area
             ch[nch++] = n2[t.root2].left;
             ch[nch++] = n2[t.root2].right;
             while (nch < 8) {
@@ -228,6 +295,7 @@ static void build_bvh8_once(const Box* boxes, uint32_t n, Bvh8& out, int max_lea
                 ch[best] = n2[open].left;
                 ch[nch++] = n2[open].right;
             }
+            for (int i = 0; i < nch; i++) ch_leaf[i] = n2[ch[i]].count > 0;
         }
         // ---- slot assignment: slot s is visited first by rays with octant s (direction sign bit set = negative),
         // so it should hold the child that is nearest along d_s: minimise sum of dot(centroid_c - centroid_p, d_s).
@@ -280,15 +348,15 @@ static void build_bvh8_once(const Box* boxes, uint32_t n, Bvh8& out, int max_lea
                 qlo[a][s] = uint8_t(std::min(std::max(lo, 0.0), 255.0));
                 qhi[a][s] = uint8_t(std::min(std::max(hi, 0.0), 255.0));
             }
-            if (cn.count == 0) {
+            if (!ch_leaf[c]) {
                 node.imask |= uint8_t(1u << s);
                 node.meta[s] = uint8_t((1u << 5) | (24u + uint32_t(s)));
                 n_internal++;
             } else {
-                const uint32_t unary = (1u << cn.count) - 1u; // 1, 3, 7
+                const uint32_t unary = (1u << cn.rcount) - 1u; // 1, 3, 7
                 node.meta[s] = uint8_t((unary << 5) | prim_off);
-                for (uint32_t k = 0; k < cn.count; k++) out.prim_order.push_back(b2.idx[cn.first + k]);
-                prim_off += cn.count;
+                for (uint32_t k = 0; k < cn.rcount; k++) out.prim_order.push_back(b2.idx[cn.rfirst + k]);
+                prim_off += cn.rcount;
             }
         }
         out.nodes[t.wide] = node;
@@ -296,7 +364,7 @@ static void build_bvh8_once(const Box* boxes, uint32_t n, Bvh8& out, int max_lea
         uint32_t j = 0;
         for (int s = 0; s < 8; s++) {
             const int c = child_in_slot[s];
-            if (c < 0 || n2[ch[c]].count != 0) continue;
+            if (c < 0 || ch_leaf[c]) continue;
             queue.push_back({node.child_base + j, ch[c], t.depth + 1});
             j++;
         }
