@@ -306,12 +306,14 @@ __global__ void __launch_bounds__(kThreads, (FEAT == 0u && !NEE) ? MPT_SHADE_MIN
     sp.emission = mk3(0.f);
     sp.pos = o;
     bool shaded = false;
+    uint32_t origin_tri = kMiss; // the triangle record the continuation rays leave (k_extend need not test it)
     if (valid) {
         const PackedHitInfo ph = tex1[pix];
         if (ph.instance_id != kMiss) { // Hit::is_valid, hit.slang:53-55
             const uint4 gd = __ldg(S.geometries + ph.instance_id + uint32_t(ph.geometry_index));
             HitRec hr;
             hr.tri = __ldg(S.prim_to_tri + gd.z + ph.primitive_id);
+            origin_tri = hr.tri;
             hr.instance = ph.instance_index;
             const float2 b = __half22float2(ph.bary);
             hr.u = b.x;
@@ -348,7 +350,7 @@ __global__ void __launch_bounds__(kThreads, (FEAT == 0u && !NEE) ? MPT_SHADE_MIN
         const uint32_t qi = queue_push_index(alive, &ctr->qcount[1]);
         if (alive) {
             pb.q_o[0][qi] = make_float4(no.x, no.y, no.z, __uint_as_float(slot));
-            pb.q_d[0][qi] = make_float4(nd.x, nd.y, nd.z, NEE ? pdf : kRayTMax); // continuation rays all have tmax = SCENE_RAY_TMAX
+            pb.q_d[0][qi] = make_float4(nd.x, nd.y, nd.z, NEE ? pdf : __uint_as_float(origin_tri));
         }
         if (valid) {
             pb.rad[slot] = make_float4(radiance0.x, radiance0.y, radiance0.z, __uint_as_float(rng.state));
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_extend(cons
     float pdf_bsdf = 0.f; // NEE only: the density the ray's direction was sampled with (rides in q_d.w)
     while (true) {
         // ---- retire finished rays (the warp is converged here)
-        const bool is_hit = finished && T.hit.tri != kMiss;
+        const bool is_hit = finished && T.found();
         const uint32_t hm = __ballot_sync(0xFFFFFFFFu, is_hit);
         if (hm) {
             const int leader = __ffs(hm) - 1;
@@ -429,8 +431,9 @@ __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_extend(cons
                 if (j < n) {
                     const float4 ro = __ldg(q_o + j), rd = __ldg(q_d + j);
                     slot = __float_as_uint(ro.w);
+                    // continuation rays all have tmax = SCENE_RAY_TMAX; the lane carries the BSDF pdf (NEE) or the triangle the ray leaves
                     if (NEE) pdf_bsdf = rd.w;
-                    active = T.init(xyz(ro), xyz(rd), 0.f /* SCENE_RAY_TMIN */, NEE ? kRayTMax : rd.w, mask);
+                    active = T.init(xyz(ro), xyz(rd), 0.f /* SCENE_RAY_TMIN */, kRayTMax, mask, NEE ? kMiss : __float_as_uint(rd.w));
                     finished = !active; // masked out: a miss
                 } else {
                     exhausted = true;
@@ -490,12 +493,13 @@ __global__ void __launch_bounds__(kThreads, (FEAT == 0u && !NEE) ? MPT_SHADE_MIN
         bool alive = false, lit = false;
         f3 no, nd, throughput, medium = mk3(0.f), so, sd, sc;
         float ior = 1.f, pdf = 0.f;
-        uint32_t slot = 0;
+        uint32_t slot = 0, origin_tri = kMiss;
         if (valid) {
             const uint4 hw = __ldg(pb.hq_hit + j);
             const float4 rd = __ldg(pb.hq_dir + j);
             HitRec hr;
             hr.tri = hw.x;
+            origin_tri = hw.x;
             hr.instance = hw.y;
             hr.u = __uint_as_float(hw.z);
             hr.v = __uint_as_float(hw.w);
@@ -531,7 +535,7 @@ __global__ void __launch_bounds__(kThreads, (FEAT == 0u && !NEE) ? MPT_SHADE_MIN
         const uint32_t qi = queue_push_index(alive, &ctr->qcount[bounce + 1]);
         if (alive) {
             pb.q_o[out][qi] = make_float4(no.x, no.y, no.z, __uint_as_float(slot));
-            pb.q_d[out][qi] = make_float4(nd.x, nd.y, nd.z, NEE ? pdf : kRayTMax);
+            pb.q_d[out][qi] = make_float4(nd.x, nd.y, nd.z, NEE ? pdf : __uint_as_float(origin_tri));
         }
         if (NEE) {
             const uint32_t si = queue_push_index(lit, &ctr->scount[bounce + 1]);
