@@ -205,6 +205,9 @@ static void build_bvh8_once(const Box* boxes, uint32_t n, Bvh8& out, int max_lea
     if (collapse_mode == 2) {
         const float c_prim = env_float("MPT_BVH_CPRIM", 0.5f), c_node = 1.0f; // measured optimum on C3 (0.15 ... 2.0 within 0.6 %)
         const size_t nn = n2.size();
+        cost.assign(nn * 7, 0.f);
+        dec.assign(nn * 7, 0);
+        dist8.assign(nn, 1);
         for (size_t k = nn; k-- > 0;) {
             const Node2& nd = n2[k];
             const float area = nd.box.half_area();
