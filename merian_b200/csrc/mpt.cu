@@ -787,7 +787,7 @@ struct mpt_context {
     int device = 0;
     int sm_count = 148;
     uint32_t extend_blocks_per_sm = 8;
-    ExtendTune tune{16u};
+    ExtendTune tune{14u}; // 12-14 is the optimum with the current traversal (6: -13 %, 8: -5 %, 10: -0.8 %, 16: -1.1 %, 20: -2.6 %, 24: -3.7 %)
     // Path slots in flight, in Mi (128 B of queues + state each, 160 B with a medium). Launches of a few hundred thousand rays
     // are latency-bound (one batch per warp, time = the slowest ray), so bigger passes amortise the tails of the late
     // bounces: 8 / 16 / 32 / 64 Mi slots -> 2379 / 2632 / 2780 / 2859 Msamples/s on C3. 64 Mi slots = 8.6 GB of 180 GB.
