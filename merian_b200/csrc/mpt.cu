@@ -787,6 +787,7 @@ struct mpt_context {
     int device = 0;
     int sm_count = 148;
     uint32_t extend_blocks_per_sm = 8;
+    uint32_t shade_blocks_cap = 64; // MPT_SHADE_BLOCKS_PER_SM (tuning)
     ExtendTune tune{14u}; // 12-14 is the optimum with the current traversal (6: -13 %, 8: -5 %, 10: -0.8 %, 16: -1.1 %, 20: -2.6 %, 24: -3.7 %)
     // Path slots in flight, in Mi (128 B of queues + state each, 160 B with a medium). Launches of a few hundred thousand rays
     // are latency-bound (one batch per warp, time = the slowest ray), so bigger passes amortise the tails of the late
@@ -1011,6 +1012,11 @@ mpt_status run_passes(mpt_context* ctx, const CameraParams& cam, const mpt_rende
     const bool count = ctx->profile_flags & 1u;
     const int L = std::min(P.max_path_length, kMaxBounces);
     const uint32_t persistent_blocks = uint32_t(ctx->sm_count) * ctx->extend_blocks_per_sm;
+    // grid-stride shade kernels: one resident wave of THEIR occupancy (8 blocks/SM for core glTF), not of the extend kernel's
+    int shade_occ = 0;
+    const uint32_t shade_blocks = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&shade_occ, k_shade_bounce<FEAT, NEE>, kThreads, 0) == cudaSuccess && shade_occ > 0)
+                                      ? uint32_t(ctx->sm_count) * std::min(uint32_t(shade_occ), ctx->shade_blocks_cap)
+                                      : persistent_blocks;
     const uint32_t pix_blocks = (npix + kThreads - 1) / kThreads;
 
     RenderConst rc{};
@@ -1045,7 +1051,7 @@ mpt_status run_passes(mpt_context* ctx, const CameraParams& cam, const mpt_rende
                 else { if (tl) MPT_LAUNCH_EXTEND(false, true); else MPT_LAUNCH_EXTEND(false, false); }
 #undef MPT_LAUNCH_EXTEND
             });
-            time_launch(ctx, false, st, [&] { k_shade_bounce<FEAT, NEE><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, rc, pb, uint32_t(b), ctr); });
+            time_launch(ctx, false, st, [&] { k_shade_bounce<FEAT, NEE><<<shade_blocks, kThreads, 0, st>>>(ctx->view, rc, pb, uint32_t(b), ctr); });
             ctx->stats.kernel_launches += 2;
         }
         k_resolve<<<pix_blocks, kThreads, 0, st>>>(rc, pb, albedo, out, acc, ctr);
@@ -1094,6 +1100,7 @@ MPT_API mpt_status mpt_create(int device, mpt_context** out_ctx) {
     ctx->tune.refill = env_u32("MPT_REFILL_THRESHOLD", ctx->tune.refill);
     ctx->pool_mslots = std::max(1u, env_u32("MPT_POOL_MSLOTS", ctx->pool_mslots));
     ctx->extend_blocks_per_sm = std::min(ctx->extend_blocks_per_sm, env_u32("MPT_EXTEND_BLOCKS_PER_SM", ctx->extend_blocks_per_sm));
+    ctx->shade_blocks_cap = std::max(1u, env_u32("MPT_SHADE_BLOCKS_PER_SM", ctx->shade_blocks_cap));
     *out_ctx = ctx;
     return MPT_OK;
 }
