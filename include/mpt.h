@@ -26,7 +26,7 @@ extern "C" {
 #define MPT_API __attribute__((visibility("default")))
 #endif
 
-#define MPT_ABI_VERSION 1u
+#define MPT_ABI_VERSION 2u /* 2: + gbuffer, accumulate, PFM/HDR I/O, iterations in flight, NEE, bvh_info.max_depth */
 
 typedef enum mpt_status {
     MPT_OK = 0,
@@ -166,7 +166,9 @@ enum {
     MPT_RENDER_EMISSION_ON_PRIMARY = 0x1, /* merian_render_emission_on_primary */
     MPT_RENDER_DEMODULATE_ALBEDO = 0x2,   /* merian_render_demodulate_albedo (needs d_albedo) */
     MPT_RENDER_OUTPUT_SUM = 0x4,          /* write sums over the samples instead of means (multi-GPU reduce) */
-    MPT_RENDER_NEE = 0x8                  /* env-map next event estimation with MIS (addition; same expectation) */
+    MPT_RENDER_NEE = 0x8                  /* next event estimation towards the lat-long environment: alias-table light samples + shadow rays,
+                                             balance-heuristic MIS against the BSDF-sampled rays. Not in the reference's pt (it has no NEE):
+                                             same expectation, lower variance; off by default and in every parity / bench number */
 };
 
 typedef struct mpt_render_params {
@@ -250,8 +252,8 @@ MPT_API mpt_status mpt_texture_upload(mpt_context* ctx, uint32_t texture_id, uin
                                       uint32_t wrap_v, uint32_t filter, const void* pixels);
 
 /* Replaces LatLongEnvMap::write_to (env_map.hpp:112-118). `to_local` row-major 4x4; pixels RGBA32F,
- * repeat addressing, bilinear (scene.cpp:786-789). type MPT_ENV_EMPTY ignores the rest. Also builds the
- * alias table used by MPT_RENDER_NEE. */
+ * repeat addressing, bilinear (scene.cpp:786-789). type MPT_ENV_EMPTY ignores the rest. The alias table of
+ * MPT_RENDER_NEE is built from these pixels on the first render that asks for it. */
 MPT_API mpt_status mpt_env_set(mpt_context* ctx, uint32_t type, const float* to_local,
                                float intensity, uint32_t width, uint32_t height,
                                const float* rgba32f);

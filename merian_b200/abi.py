@@ -5,7 +5,7 @@ both sides consume the same scene tables, exactly as the reference's renderer an
 """
 import ctypes as C
 
-MPT_ABI_VERSION = 1
+MPT_ABI_VERSION = 2
 
 # mpt_status
 MPT_OK, MPT_ERR_INVALID_ARGUMENT, MPT_ERR_CUDA, MPT_ERR_NOT_READY, MPT_ERR_UNSUPPORTED, MPT_ERR_LIMIT, MPT_ERR_IO = range(7)

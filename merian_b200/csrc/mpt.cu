@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(kThreads, (FEAT == 0u && !NEE) ? MPT_SHADE_MIN
 
 // --------------------------------------------------------------------------------------- wavefront: extend
 // Persistent warps with per-lane dynamic fetch: a lane whose ray has finished does not wait for the slowest ray of
-// its batch; when fewer than kRefillThreshold lanes of the warp are still traversing, the warp re-converges, all idle
+// its batch; when fewer than tune.refill (14) lanes of the warp are still traversing, the warp re-converges, all idle
 // lanes claim new rays with ONE atomicAdd (ballot + prefix popcount), and traversal resumes.
 struct ExtendTune {
     uint32_t refill;   // re-converge and refill when fewer than this many lanes are still traversing
