@@ -273,6 +273,27 @@ def run_ours(args):
     ctx.render_host(cam, params(args.warmup), h_tex1=h_tex1, h_out=h_outs[0])
     e2e_sync_value = npix * spp / (time.perf_counter() - t0) / 1e6
 
+    # ---- the same frame with MPT_RENDER_NEE (north_star: closest-hit and occlusion queries reported separately and summed); outside
+    # the timed region, not part of `value`
+    nee = None
+    if world == 1:
+        ctx.reset_stats()
+        for i in range(2):
+            ctx.render_device(cam, params(30_000 + i, abi.RENDER_EMISSION_ON_PRIMARY | abi.RENDER_NEE), tex1=tex1, out=out)
+        torch.cuda.synchronize()
+        ctx.reset_stats()
+        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0.record()
+        for i in range(2):
+            ctx.render_device(cam, params(30_002 + i, abi.RENDER_EMISSION_ON_PRIMARY | abi.RENDER_NEE), tex1=tex1, out=out)
+        n1.record()
+        torch.cuda.synchronize()
+        nms = n0.elapsed_time(n1) / 2
+        ns = ctx.stats()
+        nee = {"msamples_per_s": npix * spp / (nms * 1e-3) / 1e6, "ms_per_step": nms,
+               "mrays_closest_hit_per_s": ns.rays_continuation / 2 / (nms * 1e-3) / 1e6, "mrays_occlusion_per_s": ns.rays_shadow / 2 / (nms * 1e-3) / 1e6,
+               "mrays_total_per_s": (ns.rays_continuation + ns.rays_shadow) / 2 / (nms * 1e-3) / 1e6}
+
     if rank == 0:
         peak, peak_src = load_peak()
         extend_ms = st.extend_ms / max(st.extend_launches, 1)
@@ -292,6 +313,7 @@ def run_ours(args):
                              % (bvh.node_bytes / 1e6, 2 * bvh.triangle_bytes / 1e6)},
             "mrays_per_s": mrays,  # continuation rays (primary hits come from the GBuffer texture)
             "rays_per_sample": float(rays[0].item()) / total_samples,
+            "with_nee": nee,  # MPT_RENDER_NEE on the same workload (an addition to the reference estimator; not the headline)
             "roofline": {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_traffic(rays_per_launch), "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
                          "tris_per_ray": tris_per_ray, "rays_per_launch": rays_per_launch, "avg_launch_ms": extend_ms,

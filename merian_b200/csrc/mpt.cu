@@ -38,6 +38,7 @@ struct Counters {
     uint32_t hcount[kMaxBounces + 2]; // hcount[b] = surface hits found by the extend of bounce b
     uint32_t fetch[kMaxBounces + 2];  // persistent-thread fetch cursors
     uint32_t scount[kMaxBounces + 2]; // scount[b] = shadow rays queued by the shade of bounce b - 1 (MPT_RENDER_NEE)
+    uint32_t sfetch[kMaxBounces + 2]; // fetch cursors of the persistent shadow kernel
     unsigned long long rays_continuation, rays_primary, shaded_hits, nodes_visited, tris_tested, rays_shadow;
 };
 
@@ -57,9 +58,9 @@ struct PathBuffers {
     float4* thr;      // throughput.rgb | current_ior
     float4* rad;      // radiance.rgb | rng state (bits)
     float4* med;      // medium mu_t.rgb | -   (only touched when the scene has transmissive materials)
-    float4* sq_o;     // shadow queue (MPT_RENDER_NEE): origin.xyz | slot (bits)
-    float4* sq_d;     //                                direction.xyz | -
-    float4* sq_c;     //                                MIS-weighted contribution.rgb if the ray reaches the environment | -
+    float4* sq_o;     // shadow queue (MPT_RENDER_NEE): origin.xyz | -
+    float4* sq_d;     //                                direction.xyz | triangle record the ray leaves (bits)
+    float4* sq_c;     //                                MIS-weighted contribution.rgb if the ray reaches the environment | slot (bits)
 };
 
 struct RenderConst {
@@ -341,9 +342,9 @@ __global__ void __launch_bounds__(kThreads, (FEAT == 0u && !NEE) ? MPT_SHADE_MIN
             const bool lit = valid && rc.max_path_length > 1 && nee_environment<FEAT>(S, sp, d, rng.state, throughput, medium, so, sd, sc);
             const uint32_t si = queue_push_index(lit, &ctr->scount[1]);
             if (lit) {
-                pb.sq_o[si] = make_float4(so.x, so.y, so.z, __uint_as_float(slot));
-                pb.sq_d[si] = make_float4(sd.x, sd.y, sd.z, 0.f);
-                pb.sq_c[si] = make_float4(sc.x, sc.y, sc.z, 0.f);
+                pb.sq_o[si] = make_float4(so.x, so.y, so.z, 0.f);
+                pb.sq_d[si] = make_float4(sd.x, sd.y, sd.z, __uint_as_float(origin_tri)); // the triangle the shadow ray leaves
+                pb.sq_c[si] = make_float4(sc.x, sc.y, sc.z, __uint_as_float(slot));
             }
         }
         if (valid && rc.max_path_length > 1) alive = scatter<FEAT>(sp, d, rng, throughput, ior, medium, no, nd, pdf);
@@ -460,22 +461,56 @@ __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_extend(cons
 
 // --------------------------------------------------------------------------------------- wavefront: shadow rays (MPT_RENDER_NEE)
 // Visibility towards the environment with the SAME intersection semantics as the continuation rays (back-face culling, masks,
-// alpha test), so that light samples and BSDF samples see the same scene. Unoccluded: add the MIS-weighted contribution.
+// alpha test), so that light samples and BSDF samples see the same scene. Same persistent structure as k_extend (per-lane dynamic
+// fetch from the shadow queue); a ray ends at the first accepted hit. Unoccluded: add the MIS-weighted contribution to the path.
 template <bool TWO_LEVEL>
-__global__ void __launch_bounds__(kThreads) k_shadow(const __grid_constant__ SceneView S, PathBuffers pb, uint32_t bounce, uint32_t mask, Counters* ctr) {
+__global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_shadow(const __grid_constant__ SceneView S, PathBuffers pb, uint32_t bounce, uint32_t mask,
+                                                                            ExtendTune tune, Counters* ctr) {
     const uint32_t n = ctr->scount[bounce];
     MaterialAlphaTest at{&S};
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-        const float4 ro = __ldg(pb.sq_o + j), rd = __ldg(pb.sq_d + j);
-        if (!trace_any<TWO_LEVEL>(S.accel, xyz(ro), xyz(rd), 0.f, kRayTMax, mask, at)) {
+    uint2 stack_mem[kStackSize];
+    Traversal<false, TWO_LEVEL, MaterialAlphaTest> T(S.accel, at, stack_mem);
+    bool active = false, exhausted = false, finished = false;
+    uint32_t j = 0;
+    while (true) {
+        if (finished && !T.found()) {
             const float4 c = __ldg(pb.sq_c + j);
-            const uint32_t slot = __float_as_uint(ro.w);
+            const uint32_t slot = __float_as_uint(c.w);
             float4 ra = pb.rad[slot]; // one shadow ray per slot and bounce: no race
             ra.x += c.x;
             ra.y += c.y;
             ra.z += c.z;
             pb.rad[slot] = ra;
         }
+        finished = false;
+        const uint32_t need = __ballot_sync(0xFFFFFFFFu, !active && !exhausted);
+        if (need) {
+            const int leader = __ffs(need) - 1;
+            uint32_t base = 0;
+            if (int(lane_id()) == leader) base = atomicAdd(&ctr->sfetch[bounce], uint32_t(__popc(need)));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (!active && !exhausted) {
+                j = base + __popc(need & ((1u << lane_id()) - 1u));
+                if (j < n) {
+                    const float4 ro = __ldg(pb.sq_o + j), rd = __ldg(pb.sq_d + j);
+                    active = T.init(xyz(ro), xyz(rd), 0.f, kRayTMax, mask, __float_as_uint(rd.w));
+                    finished = !active; // masked out: nothing can occlude
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        const bool queue_empty = __any_sync(0xFFFFFFFFu, exhausted);
+        if (!__any_sync(0xFFFFFFFFu, active || finished)) break;
+        while (active) {
+            if (T.step() || T.found()) {
+                active = false;
+                finished = true;
+                break;
+            }
+            if (!queue_empty && uint32_t(__popc(__activemask())) < tune.refill) break;
+        }
+        __syncwarp();
     }
 }
 
@@ -540,9 +575,9 @@ __global__ void __launch_bounds__(kThreads, (FEAT == 0u && !NEE) ? MPT_SHADE_MIN
         if (NEE) {
             const uint32_t si = queue_push_index(lit, &ctr->scount[bounce + 1]);
             if (lit) {
-                pb.sq_o[si] = make_float4(so.x, so.y, so.z, __uint_as_float(slot));
-                pb.sq_d[si] = make_float4(sd.x, sd.y, sd.z, 0.f);
-                pb.sq_c[si] = make_float4(sc.x, sc.y, sc.z, 0.f);
+                pb.sq_o[si] = make_float4(so.x, so.y, so.z, 0.f);
+                pb.sq_d[si] = make_float4(sd.x, sd.y, sd.z, __uint_as_float(origin_tri));
+                pb.sq_c[si] = make_float4(sc.x, sc.y, sc.z, __uint_as_float(slot));
             }
         }
     }
@@ -1039,8 +1074,8 @@ mpt_status run_passes(mpt_context* ctx, const CameraParams& cam, const mpt_rende
         for (int b = 1; b < L; b++) {
             const uint32_t in = uint32_t(b - 1) & 1u;
             if (NEE) { // shadow rays of the vertex shaded last: before the extend so that both add to rad[] in stream order
-                if (ctx->view.accel.two_level) k_shadow<true><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, pb, uint32_t(b), P.instance_mask, ctr);
-                else k_shadow<false><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, pb, uint32_t(b), P.instance_mask, ctr);
+                if (ctx->view.accel.two_level) k_shadow<true><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, pb, uint32_t(b), P.instance_mask, ctx->tune, ctr);
+                else k_shadow<false><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, pb, uint32_t(b), P.instance_mask, ctx->tune, ctr);
                 ctx->stats.kernel_launches++;
             }
             time_launch(ctx, true, st, [&] {
