@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kThreads) k_trace(const __grid_constant__ Scen
 #define MPT_SHADE_MIN_BLOCKS 8
 #endif
 template <uint32_t FEAT, bool NEE>
-__global__ void __launch_bounds__(kThreads, (FEAT == 0u && !NEE) ? MPT_SHADE_MIN_BLOCKS : 1) k_shade_primary(const __grid_constant__ SceneView S, CameraParams cam, RenderConst rc, const PackedHitInfo* tex1, PathBuffers pb,
+__global__ void __launch_bounds__(kThreads, FEAT == 0u ? MPT_SHADE_MIN_BLOCKS : 1) k_shade_primary(const __grid_constant__ SceneView S, CameraParams cam, RenderConst rc, const PackedHitInfo* tex1, PathBuffers pb,
                                                             Counters* ctr) {
     const uint32_t pix = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = pix < rc.npix;
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_shadow(cons
 
 // --------------------------------------------------------------------------------------- wavefront: shade after extend
 template <uint32_t FEAT, bool NEE>
-__global__ void __launch_bounds__(kThreads, (FEAT == 0u && !NEE) ? MPT_SHADE_MIN_BLOCKS : 1) k_shade_bounce(const __grid_constant__ SceneView S, RenderConst rc, PathBuffers pb, uint32_t bounce, Counters* ctr) {
+__global__ void __launch_bounds__(kThreads, FEAT == 0u ? MPT_SHADE_MIN_BLOCKS : 1) k_shade_bounce(const __grid_constant__ SceneView S, RenderConst rc, PathBuffers pb, uint32_t bounce, Counters* ctr) {
     const uint32_t n = ctr->hcount[bounce];
     const uint32_t out = bounce & 1u;
     const bool more = int32_t(bounce) + 1 < rc.max_path_length; // with_material, render_pt.slang:80
