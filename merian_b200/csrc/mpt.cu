@@ -382,6 +382,11 @@ __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_extend(cons
     MaterialAlphaTest at{&S};
     uint2 stack_mem[kStackSize];
     Traversal<COUNT, TWO_LEVEL, MaterialAlphaTest> T(S.accel, at, stack_mem);
+    if (TWO_LEVEL) { // world-space ray setup of every thread, word-major: leaving an instance reloads it (8 LDS) instead of redoing 6 divisions
+        __shared__ float s_world[8 * kThreads];
+        T.wcache = s_world + threadIdx.x;
+        T.wcache_stride = kThreads;
+    }
 
     bool active = false, exhausted = false, finished = false;
     uint32_t slot = 0;

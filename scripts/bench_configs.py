@@ -88,9 +88,19 @@ def render_config(name, tables, W, H, spp, L, rank, world, dev, steps, warmup, e
     hits = tex1.cpu().numpy().view(abi.PACKED_HIT_DTYPE).reshape(H, W)
     checks["hit_fraction"] = float((hits["instance_id"] != 0xFFFFFFFF).mean())
 
+    # traversal work per ray (one counting frame) and the extend / shade split (CUDA events inside libmpt)
+    ctx.set_profiling(1)
+    ctx.reset_stats()
+    ctx.render_device(cam, abi.RenderParams(W, H, 5, min(spp, 4), L, 0xFF, abi.RENDER_EMISSION_ON_PRIMARY, 0, 1, 0.0), tex1=tex1)
+    cs = ctx.stats()
+    work = {"nodes_per_ray": cs.nodes_visited / max(cs.rays_continuation, 1), "tris_per_ray": cs.tris_tested / max(cs.rays_continuation, 1)}
+    ctx.set_profiling(2)
     ctx.reset_stats()
     ms = timed(step, steps, warmup, world, dev)
     st = ctx.stats()
+    work["extend_share"] = st.extend_ms / (steps + warmup) / ms
+    work["shade_share"] = st.shade_ms / (steps + warmup) / ms
+    ctx.set_profiling(0)
     rays = torch.tensor([float(st.rays_continuation)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(rays)
@@ -100,7 +110,7 @@ def render_config(name, tables, W, H, spp, L, rank, world, dev, steps, warmup, e
             "msamples_per_s": W * H * spp * world / (ms * 1e-3) / 1e6,
             "mrays_per_s": float(rays.item()) / total_steps / (ms * 1e-3) / 1e6,
             "bvh_nodes": bvh.node_count, "bvh_mb": (bvh.node_bytes + 2 * bvh.triangle_bytes) / 1e6, "bvh_build_ms": bvh.build_ms,
-            "upload_s": upload_s, "checks": checks, "mean_luminance": float((out[..., :3] * torch.tensor([0.299, 0.587, 0.114], device=dev)).sum(-1).mean()) if rank == 0 else None}
+            "upload_s": upload_s, "work": work, "checks": checks, "mean_luminance": float((out[..., :3] * torch.tensor([0.299, 0.587, 0.114], device=dev)).sum(-1).mean()) if rank == 0 else None}
     line.update(extra)
     ctx.close()
     return line
