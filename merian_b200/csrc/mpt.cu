@@ -1248,6 +1248,14 @@ MPT_API mpt_status mpt_scene_upload(mpt_context* ctx, const mpt_scene_desc* d) {
     }
 
     // ---- instances + TLAS
+    // vertex transforms needed for tight instance boxes; beyond the budget (about a second of host time) fall back to box corners
+    uint64_t instance_vertex_work = 0;
+    for (uint32_t i = 0; i < d->instance_count; i++) {
+        if (d->instances[i].blas >= d->blas_count) continue;
+        const mpt_blas_desc& bd = d->blas[d->instances[i].blas];
+        for (uint32_t g = 0; g < bd.mesh_count; g++) instance_vertex_work += d->meshes[bd.meshes[g]].vertex_count;
+    }
+    const bool tight_instance_boxes = instance_vertex_work <= 300000000ull && !getenv("MPT_LOOSE_INSTANCE_BOXES");
     std::vector<InstanceRec> inst(d->instance_count);
     std::vector<Box> ibox(d->instance_count);
     bool identity_single = d->instance_count == 1;
@@ -1268,13 +1276,26 @@ MPT_API mpt_status mpt_scene_upload(mpt_context* ctx, const mpt_scene_desc* d) {
         const Box& ob = blas_bounds[in.blas];
         Box wb;
         for (int a = 0; a < 3; a++) { wb.lo[a] = 3e38f; wb.hi[a] = -3e38f; }
-        for (int k = 0; k < 8; k++) {
-            const float p[3] = {(k & 1) ? ob.hi[0] : ob.lo[0], (k & 2) ? ob.hi[1] : ob.lo[1], (k & 4) ? ob.hi[2] : ob.lo[2]};
+        auto grow = [&](const float* p) {
             for (int a = 0; a < 3; a++) {
                 const float* m = in.transform + a * 4;
                 const float v = m[0] * p[0] + m[1] * p[1] + m[2] * p[2] + m[3];
                 wb.lo[a] = std::min(wb.lo[a], v);
                 wb.hi[a] = std::max(wb.hi[a], v);
+            }
+        };
+        if (tight_instance_boxes) {
+            // the world box of the transformed VERTICES: for a rotated instance it is about half the surface area of the box around the
+            // transformed object-space box, and every false TLAS hit costs an instance entry (ray transform + setup) in k_extend
+            const mpt_blas_desc& bd = d->blas[in.blas];
+            for (uint32_t g = 0; g < bd.mesh_count; g++) {
+                const mpt_mesh_desc& m = d->meshes[bd.meshes[g]];
+                for (uint32_t v = 0; v < m.vertex_count; v++) grow(m.vertices[v].position);
+            }
+        } else {
+            for (int k = 0; k < 8; k++) {
+                const float p[3] = {(k & 1) ? ob.hi[0] : ob.lo[0], (k & 2) ? ob.hi[1] : ob.lo[1], (k & 4) ? ob.hi[2] : ob.lo[2]};
+                grow(p);
             }
         }
         for (int a = 0; a < 3; a++) { // the object-space test is exact; the world box only prunes
