@@ -519,6 +519,69 @@ __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_shadow(cons
     }
 }
 
+// --------------------------------------------------------------------------------------- arbitrary rays, persistent form
+// mpt_trace for incoherent rays: the structure of k_extend (per-lane dynamic fetch: a lane does not wait for the slowest ray of its
+// warp) over the caller's ray array; results land at the ray's own index.
+template <bool COUNT, bool TWO_LEVEL>
+__global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_trace_persistent(const __grid_constant__ SceneView S, const float4* __restrict__ rays, uint32_t n,
+                                                                                      uint32_t mask, uint32_t* hits6, ExtendTune tune, Counters* ctr) {
+    MaterialAlphaTest at{&S};
+    uint2 stack_mem[kStackSize];
+    Traversal<COUNT, TWO_LEVEL, MaterialAlphaTest> T(S.accel, at, stack_mem);
+    bool active = false, exhausted = false, finished = false;
+    uint32_t j = 0;
+    while (true) {
+        if (finished) {
+            uint32_t* o = hits6 + 6 * size_t(j);
+            if (!T.found()) {
+                o[0] = o[1] = o[2] = o[3] = kMiss;
+                o[4] = o[5] = 0u;
+            } else {
+                const float4* tp = S.accel.tris + size_t(T.hit.tri) * 3;
+                o[0] = S.accel.instances[T.hit.instance].custom_index;
+                o[1] = T.hit.instance;
+                o[2] = __float_as_uint(__ldg(tp).w);
+                o[3] = __float_as_uint(__ldg(tp + 1).w);
+                o[4] = __float_as_uint(T.hit.u);
+                o[5] = __float_as_uint(T.hit.v);
+            }
+        }
+        finished = false;
+        const uint32_t need = __ballot_sync(0xFFFFFFFFu, !active && !exhausted);
+        if (need) {
+            const int leader = __ffs(need) - 1;
+            uint32_t base = 0;
+            if (int(lane_id()) == leader) base = atomicAdd(&ctr->fetch[0], uint32_t(__popc(need)));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (!active && !exhausted) {
+                j = base + __popc(need & ((1u << lane_id()) - 1u));
+                if (j < n) {
+                    const float4 ro = __ldg(rays + 2 * size_t(j)), rd = __ldg(rays + 2 * size_t(j) + 1);
+                    active = T.init(xyz(ro), xyz(rd), ro.w, rd.w, mask);
+                    finished = !active;
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        const bool queue_empty = __any_sync(0xFFFFFFFFu, exhausted);
+        if (!__any_sync(0xFFFFFFFFu, active || finished)) break;
+        while (active) {
+            if (T.step()) {
+                active = false;
+                finished = true;
+                break;
+            }
+            if (!queue_empty && uint32_t(__popc(__activemask())) < tune.refill) break;
+        }
+        __syncwarp();
+    }
+    if (COUNT) {
+        atomicAdd(&ctr->nodes_visited, (unsigned long long)T.n_nodes);
+        atomicAdd(&ctr->tris_tested, (unsigned long long)T.n_tris);
+    }
+}
+
 // --------------------------------------------------------------------------------------- wavefront: shade after extend
 template <uint32_t FEAT, bool NEE>
 __global__ void __launch_bounds__(kThreads, FEAT == 0u ? MPT_SHADE_MIN_BLOCKS : 1) k_shade_bounce(const __grid_constant__ SceneView S, RenderConst rc, PathBuffers pb, uint32_t bounce, Counters* ctr) {
@@ -1530,6 +1593,19 @@ MPT_API mpt_status mpt_trace(mpt_context* ctx, const void* d_rays, uint64_t n, u
     if (!ctx->counters.p) { CU(ctx->counters.ensure(sizeof(Counters))); CU(cudaMemset(ctx->counters.p, 0, sizeof(Counters))); }
     const uint32_t blocks = uint32_t((n + kThreads - 1) / kThreads);
     const bool cnt = ctx->profile_flags & 1u, tl = ctx->view.accel.two_level != 0;
+    const uint32_t persistent_blocks = uint32_t(ctx->sm_count) * ctx->extend_blocks_per_sm;
+    if (n < 0xFFFFFFFFull && blocks > persistent_blocks && !getenv("MPT_TRACE_ONE_SHOT")) { // enough rays to fill the machine: per-lane dynamic fetch
+        Counters* ctr = ctx->counters.as<Counters>();
+        CU(cudaMemsetAsync(&ctr->fetch[0], 0, sizeof(uint32_t), st));
+#define MPT_LAUNCH_TRACE_P(C, TL) k_trace_persistent<C, TL><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, (const float4*)d_rays, uint32_t(n), instance_mask, (uint32_t*)d_hits, ctx->tune, ctr)
+        if (cnt) { if (tl) MPT_LAUNCH_TRACE_P(true, true); else MPT_LAUNCH_TRACE_P(true, false); }
+        else { if (tl) MPT_LAUNCH_TRACE_P(false, true); else MPT_LAUNCH_TRACE_P(false, false); }
+#undef MPT_LAUNCH_TRACE_P
+        CU(cudaGetLastError());
+        ctx->stats.kernel_launches++;
+        ctx->stats.rays_continuation += n;
+        return MPT_OK;
+    }
 #define MPT_LAUNCH_TRACE(C, TL) k_trace<C, TL><<<blocks, kThreads, 0, st>>>(ctx->view, (const float4*)d_rays, n, instance_mask, (uint32_t*)d_hits, ctx->counters.as<Counters>())
     if (cnt) { if (tl) MPT_LAUNCH_TRACE(true, true); else MPT_LAUNCH_TRACE(true, false); }
     else { if (tl) MPT_LAUNCH_TRACE(false, true); else MPT_LAUNCH_TRACE(false, false); }

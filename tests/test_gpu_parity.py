@@ -53,6 +53,27 @@ def test_trace_incoherent(gpu_ctx):
     assert d.max() == 0.0  # identical IEEE arithmetic in the triangle test
 
 
+def test_trace_persistent_form_matches_one_shot_and_oracle(gpu_ctx, monkeypatch):
+    """Enough rays to fill the machine take the persistent kernel (per-lane dynamic fetch): same hits as the one-shot kernel, bit for
+    bit, and as the oracle on a sample."""
+    import torch
+    t = tables("terrain", **SMALL_TERRAIN)
+    o = _setup(gpu_ctx, t)
+    cam = t.desc.camera.to_abi(0)
+    rays = synthetic.incoherent_rays(cam, 800, 450)  # 360 000 rays > 148 SMs x 7 blocks x 128 threads
+    rays["origin"] = np.array([0.0, 30.0, 0.0], np.float32)
+    rays["direction"][:, 1] = -np.abs(rays["direction"][:, 1]) - 0.2
+    rays["direction"] /= np.linalg.norm(rays["direction"], axis=1, keepdims=True)
+    got = gpu_ctx.trace(rays)
+    monkeypatch.setenv("MPT_TRACE_ONE_SHOT", "1")
+    one = gpu_ctx.trace(rays)
+    assert np.array_equal(got.view(np.uint32), one.view(np.uint32))
+    ref = o.trace(rays[::7])
+    g = got[::7]
+    same = (ref["primitive_id"] == g["primitive_id"]) & (ref["instance_id"] == g["instance_id"])
+    assert 1 - same.mean() < 1e-4 and np.abs(ref["barycentrics"] - g["barycentrics"])[same].max() == 0.0
+
+
 @pytest.mark.parametrize("scene,kw,w,h,spp", [("cornell", {}, 128, 128, 64), ("terrain", SMALL_TERRAIN, 240, 136, 32)])
 def test_render_matches_oracle(gpu_ctx, scene, kw, w, h, spp):
     t = tables(scene, **kw)
