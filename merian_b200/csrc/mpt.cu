@@ -582,6 +582,76 @@ __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_trace_persi
     }
 }
 
+// --------------------------------------------------------------------------------------- primary visibility, persistent form
+// Camera rays in 8x4-pixel tile order (index j -> tile j / 32, pixel j % 32 inside it) through the per-lane dynamic fetch of k_extend.
+template <bool COUNT, bool TWO_LEVEL>
+__global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_primary_persistent(const __grid_constant__ SceneView S, CameraParams cam, uint32_t w, uint32_t h, uint32_t mask,
+                                                                                        PackedHitInfo* out, ExtendTune tune, Counters* ctr) {
+    const uint32_t tiles_x = (w + 7) / 8, n = tiles_x * ((h + 3) / 4) * 32u;
+    MaterialAlphaTest at{&S};
+    uint2 stack_mem[kStackSize];
+    Traversal<COUNT, TWO_LEVEL, MaterialAlphaTest> T(S.accel, at, stack_mem);
+    bool active = false, exhausted = false, finished = false;
+    uint32_t pix = 0;
+    while (true) {
+        if (finished) {
+            PackedHitInfo p;
+            if (!T.found()) {
+                p.instance_id = kMiss; p.primitive_id = kMiss; p.geometry_index = 0xFFFF; p.instance_index = 0xFFFF;
+                p.bary = __floats2half2_rn(0.f, 0.f);
+            } else {
+                const float4* tp = S.accel.tris + size_t(T.hit.tri) * 3;
+                p.instance_id = S.accel.instances[T.hit.instance].custom_index;
+                p.primitive_id = __float_as_uint(__ldg(tp).w);
+                p.geometry_index = uint16_t(__float_as_uint(__ldg(tp + 1).w));
+                p.instance_index = uint16_t(T.hit.instance);
+                p.bary = __floats2half2_rn(T.hit.u, T.hit.v);
+            }
+            out[pix] = p;
+        }
+        finished = false;
+        const uint32_t need = __ballot_sync(0xFFFFFFFFu, !active && !exhausted);
+        if (need) {
+            const int leader = __ffs(need) - 1;
+            uint32_t base = 0;
+            if (int(lane_id()) == leader) base = atomicAdd(&ctr->fetch[0], uint32_t(__popc(need)));
+            base = __shfl_sync(0xFFFFFFFFu, base, leader);
+            if (!active && !exhausted) {
+                const uint32_t j = base + __popc(need & ((1u << lane_id()) - 1u));
+                if (j >= n) {
+                    exhausted = true;
+                } else {
+                    const uint32_t tile = j >> 5, in = j & 31u;
+                    const uint32_t x = (tile % tiles_x) * 8 + (in & 7u), y = (tile / tiles_x) * 4 + (in >> 3);
+                    if (x < w && y < h) { // else: padding of a partial tile, the lane asks again at the next refill
+                        pix = y * w + x;
+                        f3 o, d;
+                        float tmin, tmax;
+                        camera_ray(cam, x, y, w, h, o, d, tmin, tmax);
+                        active = T.init(o, d, tmin, tmax, mask);
+                        finished = !active;
+                    }
+                }
+            }
+        }
+        const bool queue_empty = __any_sync(0xFFFFFFFFu, exhausted);
+        if (!__any_sync(0xFFFFFFFFu, active || finished || !exhausted)) break; // idle lanes that drew padding pixels fetch again
+        while (active) {
+            if (T.step()) {
+                active = false;
+                finished = true;
+                break;
+            }
+            if (!queue_empty && uint32_t(__popc(__activemask())) < tune.refill) break;
+        }
+        __syncwarp();
+    }
+    if (COUNT) {
+        atomicAdd(&ctr->nodes_visited, (unsigned long long)T.n_nodes);
+        atomicAdd(&ctr->tris_tested, (unsigned long long)T.n_tris);
+    }
+}
+
 // --------------------------------------------------------------------------------------- wavefront: shade after extend
 template <uint32_t FEAT, bool NEE>
 __global__ void __launch_bounds__(kThreads, FEAT == 0u ? MPT_SHADE_MIN_BLOCKS : 1) k_shade_bounce(const __grid_constant__ SceneView S, RenderConst rc, PathBuffers pb, uint32_t bounce, Counters* ctr) {
@@ -1550,6 +1620,19 @@ MPT_API mpt_status mpt_primary_visibility(mpt_context* ctx, const mpt_camera* ca
     const uint32_t blocks = (tiles * 32 + kThreads - 1) / kThreads;
     const CameraParams cam = to_device_camera(*camera);
     const bool cnt = ctx->profile_flags & 1u, tl = ctx->view.accel.two_level != 0;
+    const uint32_t persistent_blocks = uint32_t(ctx->sm_count) * ctx->extend_blocks_per_sm;
+    if (blocks > persistent_blocks && getenv("MPT_PRIMARY_PERSISTENT")) { // opt-in until it has passed the parity tests on a B200
+        Counters* ctr = ctx->counters.as<Counters>();
+        CU(cudaMemsetAsync(&ctr->fetch[0], 0, sizeof(uint32_t), st));
+#define MPT_LAUNCH_PRIMARY_P(C, TL) k_primary_persistent<C, TL><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, cam, width, height, instance_mask, (PackedHitInfo*)d_tex1, ctx->tune, ctr)
+        if (cnt) { if (tl) MPT_LAUNCH_PRIMARY_P(true, true); else MPT_LAUNCH_PRIMARY_P(true, false); }
+        else { if (tl) MPT_LAUNCH_PRIMARY_P(false, true); else MPT_LAUNCH_PRIMARY_P(false, false); }
+#undef MPT_LAUNCH_PRIMARY_P
+        CU(cudaGetLastError());
+        ctx->stats.kernel_launches++;
+        ctx->stats.rays_primary += uint64_t(width) * height;
+        return MPT_OK;
+    }
 #define MPT_LAUNCH_PRIMARY(C, TL) k_primary<C, TL><<<blocks, kThreads, 0, st>>>(ctx->view, cam, width, height, instance_mask, (PackedHitInfo*)d_tex1, ctx->counters.as<Counters>())
     if (cnt) { if (tl) MPT_LAUNCH_PRIMARY(true, true); else MPT_LAUNCH_PRIMARY(true, false); }
     else { if (tl) MPT_LAUNCH_PRIMARY(false, true); else MPT_LAUNCH_PRIMARY(false, false); }

@@ -53,6 +53,24 @@ def test_trace_incoherent(gpu_ctx):
     assert d.max() == 0.0  # identical IEEE arithmetic in the triangle test
 
 
+def test_primary_visibility_persistent_form(gpu_ctx, monkeypatch):
+    """Frames with enough pixels to fill the machine take the persistent kernel; extents that are not multiples of the 8x4 tile leave
+    padding pixels in the fetch order. Same texels as the one-shot kernel, bit for bit, and as the oracle."""
+    t = tables("terrain", **SMALL_TERRAIN)
+    o = _setup(gpu_ctx, t)
+    cam = t.desc.camera.to_abi(0)
+    w, h = 701, 403
+    monkeypatch.setenv("MPT_PRIMARY_PERSISTENT", "1")
+    got = gpu_ctx.primary_visibility(cam, w, h)
+    monkeypatch.delenv("MPT_PRIMARY_PERSISTENT")
+    one = gpu_ctx.primary_visibility(cam, w, h)
+    assert np.array_equal(got.view(np.uint32), one.view(np.uint32))
+    ref = o.primary_visibility(cam, w, h)
+    mism, bary_err, same = compare_hits(got, ref)
+    n_mis, n_ties = edge_ties(got, ref, same)
+    assert n_mis == n_ties and mism < 1e-4 and bary_err == 0.0
+
+
 def test_trace_persistent_form_matches_one_shot_and_oracle(gpu_ctx, monkeypatch):
     """Enough rays to fill the machine take the persistent kernel (per-lane dynamic fetch): same hits as the one-shot kernel, bit for
     bit, and as the oracle on a sample."""
