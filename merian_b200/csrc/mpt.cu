@@ -1621,7 +1621,7 @@ MPT_API mpt_status mpt_primary_visibility(mpt_context* ctx, const mpt_camera* ca
     const CameraParams cam = to_device_camera(*camera);
     const bool cnt = ctx->profile_flags & 1u, tl = ctx->view.accel.two_level != 0;
     const uint32_t persistent_blocks = uint32_t(ctx->sm_count) * ctx->extend_blocks_per_sm;
-    if (blocks > persistent_blocks && getenv("MPT_PRIMARY_PERSISTENT")) { // opt-in until it has passed the parity tests on a B200
+    if (blocks > persistent_blocks && !getenv("MPT_TRACE_ONE_SHOT")) { // enough pixels to fill the machine: per-lane dynamic fetch
         Counters* ctr = ctx->counters.as<Counters>();
         CU(cudaMemsetAsync(&ctr->fetch[0], 0, sizeof(uint32_t), st));
 #define MPT_LAUNCH_PRIMARY_P(C, TL) k_primary_persistent<C, TL><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, cam, width, height, instance_mask, (PackedHitInfo*)d_tex1, ctx->tune, ctr)

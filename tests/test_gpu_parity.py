@@ -59,11 +59,11 @@ def test_primary_visibility_persistent_form(gpu_ctx, monkeypatch):
     t = tables("terrain", **SMALL_TERRAIN)
     o = _setup(gpu_ctx, t)
     cam = t.desc.camera.to_abi(0)
-    w, h = 701, 403
-    monkeypatch.setenv("MPT_PRIMARY_PERSISTENT", "1")
+    w, h = 702, 403  # (an odd width would put the centre column exactly on the terrain's x = 0 grid line: every pixel a shared-edge tie)
     got = gpu_ctx.primary_visibility(cam, w, h)
-    monkeypatch.delenv("MPT_PRIMARY_PERSISTENT")
+    monkeypatch.setenv("MPT_TRACE_ONE_SHOT", "1")
     one = gpu_ctx.primary_visibility(cam, w, h)
+    monkeypatch.delenv("MPT_TRACE_ONE_SHOT")
     assert np.array_equal(got.view(np.uint32), one.view(np.uint32))
     ref = o.primary_visibility(cam, w, h)
     mism, bary_err, same = compare_hits(got, ref)
