@@ -28,6 +28,11 @@ WIDTH, HEIGHT, SPP, MAX_PATH_LENGTH = 1920, 1080, 64, 5
 METRIC = "Msamples/s (1080p pt, path len 5)"
 
 
+def synthetic_version():
+    from merian_b200 import synthetic
+    return synthetic.GENERATOR_VERSION
+
+
 def load_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -307,7 +312,7 @@ def run_ours(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": workload_name(args), "width": W, "height": H, "spp_per_gpu": spp, "spp_total": spp * world,
-                       "max_path_length": MAX_PATH_LENGTH, "triangles": tables.triangle_count, "seed": desc.seed,
+                       "max_path_length": MAX_PATH_LENGTH, "triangles": tables.triangle_count, "seed": desc.seed, "generator": synthetic_version(),
                        "parallelism": f"sample-sharded x{world}, NCCL reduce of the sum buffers" if world > 1 else "single GPU",
                        "l2": "inputs larger than L2: BVH8 %.0f MB + triangle/attribute records %.0f MB + env 134 MB + >1 GB of path state per pass"
                              % (bvh.node_bytes / 1e6, 2 * bvh.triangle_bytes / 1e6)},
