@@ -218,16 +218,26 @@ def run_ours(args):
     bytes_per_ray = 80.0 * nodes_per_ray + 48.0 * tris_per_ray + 48.0  # node + triangle records + ray read (32) + hit write (16)
     ctx.set_profiling(0)
 
-    for i in range(6):  # clocks and caches up before the W warm-up steps the caller asked for (the counting frame above ran slower kernels)
-        ctx.render_device(cam, params(20_000 + i), tex1=tex1, out=out)
-    for i in range(args.warmup):
-        step(i)
-    barrier()
-    ctx.set_profiling(2)  # CUDA-event timing of every extend / shade launch inside the timed region
-    ctx.reset_stats()
+    # The clock sampler is an `nvidia-smi -lms` child process: its start-up (NVML init) takes driver locks that CUDA API calls of this
+    # process can block on, which starves the GPU of launches for hundreds of milliseconds. Start it BEFORE the warm-up and wait for its
+    # first sample, so the timed region only sees the steady 100 ms polling.
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        t_wait = time.perf_counter()
+        while not sampler.lines and time.perf_counter() - t_wait < 5.0:
+            time.sleep(0.05)
+    ctx.set_profiling(2)  # CUDA-event timing of every extend / shade launch; on during the warm-up so that libmpt's event pool is
+    #                       fully created before the timed region (no cudaEventCreate inside it)
+    for i in range(max(6, args.steps + 1)):  # clocks and caches up before the W warm-up steps the caller asked for
+        ctx.render_device(cam, params(20_000 + i), tex1=tex1, out=out)
+    ctx.reset_stats()
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    ctx.reset_stats()
+    if rank == 0:
+        sampler.lines.clear()  # keep only the samples of the timed region
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
