@@ -1,5 +1,5 @@
-// image_io.cpp — see image_io.h.
-#include "image_io.h"
+// float_image_files.cpp — see float_image_files.h.
+#include "float_image_files.h"
 
 #include <cmath>
 #include <cstdint>

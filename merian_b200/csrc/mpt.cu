@@ -13,7 +13,7 @@
 // Queues are double-buffered SoA (origin|slot, direction|tmax); per-path state lives in fixed slots.
 #include "../../include/mpt.h"
 #include "bvh8.h"
-#include "image_io.h"
+#include "float_image_files.h"
 #include "shading.cuh"
 
 #include <cctype>
