@@ -387,6 +387,32 @@ MPT_API mpt_status mpt_bvh_get_info(mpt_context* ctx, mpt_bvh_info* out);
  * NULL) receives the leaf order. No device needed. */
 MPT_API mpt_status mpt_bvh8_build_info(const float* boxes, uint32_t n, mpt_bvh_info* out, uint32_t* prim_order);
 
+/* Host-only (no device needed): the acceleration structure exactly as mpt_scene_upload lays it out in HBM — the BVH8 nodes of every
+ * BLAS and of the TLAS, the triangle records in leaf order, the instance records. Replaces nothing in the reference (its BLAS/TLAS are
+ * opaque driver objects, scene.cpp:1672-1892); it exists so that a CPU checker can walk the SAME tree the device walks (SURVEY.md
+ * §8(d): nodes and triangles per ray are counted by the oracle on this structure) and so that the builder can be tested without a GPU.
+ * The view's pointers stay valid until mpt_host_accel_free. Errors: mpt_last_error(NULL). */
+typedef struct mpt_host_accel mpt_host_accel;
+typedef struct mpt_host_accel_view {
+    const void* nodes;           /* 80-byte BVH8 nodes (layout: merian_b200/csrc/bvh8.h) */
+    uint64_t node_count;
+    const void* tris;            /* 48-byte records: v0|primitive_id, v1|geometry_index, v2|flags (3 x float4) */
+    uint64_t triangle_count;
+    const void* instances;       /* 64-byte records: 3x4 world->object rows, BLAS root, custom index, mask|flags<<8, pad */
+    uint64_t instance_count;
+    const uint32_t* tlas_prims;  /* TLAS leaf record -> instance index */
+    uint64_t tlas_prim_count;
+    const uint32_t* prim_to_tri; /* geometry prim->record table */
+    uint64_t prim_count;
+    uint32_t root;               /* TLAS root (two_level) or the root of the only BLAS */
+    uint32_t two_level;
+    uint32_t max_blas_depth, tlas_depth;
+    double build_ms;
+} mpt_host_accel_view;
+MPT_API mpt_status mpt_host_accel_build(const mpt_scene_desc* scene, mpt_host_accel** out);
+MPT_API mpt_status mpt_host_accel_get(const mpt_host_accel* accel, mpt_host_accel_view* out);
+MPT_API void mpt_host_accel_free(mpt_host_accel* accel);
+
 /* Test hook for the BSDF property suite (tests/test_bsdf.cpp of the reference restated): runs
  * sample_eval / eval / pdf of one BSDF on the device. See merian_b200/csrc/bsdf_check.cu. */
 typedef struct mpt_bsdf_check_params {

@@ -15,6 +15,7 @@ EXPORTS = ["mpt_abi_version", "mpt_create", "mpt_destroy", "mpt_last_error", "mp
            "mpt_materials_set_hints", "mpt_texture_upload", "mpt_env_set", "mpt_primary_visibility", "mpt_gbuffer", "mpt_trace", "mpt_render", "mpt_render_host", "mpt_render_host_begin", "mpt_render_host_end",
            "mpt_accumulate", "mpt_render_accumulate", "mpt_pfm_info", "mpt_pfm_load", "mpt_pfm_save", "mpt_hdr_load", "mpt_env_load", "mpt_image_write",
            "mpt_set_profiling", "mpt_get_stats", "mpt_reset_stats", "mpt_bvh_get_info", "mpt_bvh8_build_info", "mpt_bsdf_check",
+           "mpt_host_accel_build", "mpt_host_accel_get", "mpt_host_accel_free",
            # include/mpt_node.h
            "mptn_create", "mptn_destroy", "mptn_last_error", "mptn_load_config", "mptn_dump_config", "mptn_describe_outputs",
            "mptn_set_shard", "mptn_process",
@@ -70,6 +71,10 @@ def lib():
         l.mpt_reset_stats.argtypes = [C.c_void_p]
         l.mpt_bvh_get_info.argtypes = [C.c_void_p, C.POINTER(abi.BvhInfo)]
         l.mpt_bvh8_build_info.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.BvhInfo), C.c_void_p]
+        l.mpt_host_accel_build.argtypes = [C.POINTER(abi.SceneDesc), C.POINTER(C.c_void_p)]
+        l.mpt_host_accel_get.argtypes = [C.c_void_p, C.POINTER(abi.HostAccelView)]
+        l.mpt_host_accel_free.argtypes = [C.c_void_p]
+        l.mpt_host_accel_free.restype = None
         l.mpt_bsdf_check.argtypes = [C.c_void_p, C.POINTER(abi.BsdfCheckParams), C.c_void_p]
         l.mptn_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         l.mptn_destroy.argtypes = [C.c_void_p]

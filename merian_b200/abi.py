@@ -131,6 +131,13 @@ class BvhInfo(C.Structure):
                 ("triangle_bytes", C.c_uint64), ("build_ms", C.c_double), ("max_depth", C.c_uint64)]
 
 
+class HostAccelView(C.Structure):  # mpt_host_accel_view
+    _fields_ = [("nodes", C.c_void_p), ("node_count", C.c_uint64), ("tris", C.c_void_p), ("triangle_count", C.c_uint64),
+                ("instances", C.c_void_p), ("instance_count", C.c_uint64), ("tlas_prims", C.c_void_p), ("tlas_prim_count", C.c_uint64),
+                ("prim_to_tri", C.c_void_p), ("prim_count", C.c_uint64), ("root", C.c_uint32), ("two_level", C.c_uint32),
+                ("max_blas_depth", C.c_uint32), ("tlas_depth", C.c_uint32), ("build_ms", C.c_double)]
+
+
 class BsdfCheckParams(C.Structure):
     _fields_ = [("bsdf", C.c_uint32), ("wi", C.c_float * 3), ("n_samples", C.c_uint32), ("seed", C.c_uint32),
                 ("albedo", C.c_float * 3), ("alpha", C.c_float), ("f0", C.c_float * 3), ("ior_f0", C.c_float),

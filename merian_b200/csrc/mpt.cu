@@ -14,7 +14,9 @@
 #include "../../include/mpt.h"
 #include "bvh8.h"
 #include "float_image_files.h"
+#include "scene_build.h"
 #include "shading.cuh"
+#include "bvh8_traverse_pooled.cuh"
 
 #include <cctype>
 #include <chrono>
@@ -26,6 +28,27 @@
 #include <vector>
 
 using namespace mpt;
+
+// Queue records and per-path state are written once and read once per bounce (gigabytes per frame), while the BVH nodes and triangle
+// records (tens of MB) are re-read by every ray: mark the former as streaming (ld/st.global.cs, evict-first) so that they do not push
+// the latter out of the 126 MB L2. MPT_STREAM_HINTS=0 builds the plain accesses for A/B runs.
+#ifndef MPT_STREAM_HINTS
+#define MPT_STREAM_HINTS 1
+#endif
+template <class T> __device__ __forceinline__ T ldq(const T* p) {
+#if MPT_STREAM_HINTS
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+template <class T> __device__ __forceinline__ void stq(T* p, T v) {
+#if MPT_STREAM_HINTS
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
 
 // ======================================================================================= device side
 namespace {
@@ -342,22 +365,22 @@ __global__ void __launch_bounds__(kThreads, FEAT == 0u ? MPT_SHADE_MIN_BLOCKS : 
             const bool lit = valid && rc.max_path_length > 1 && nee_environment<FEAT>(S, sp, d, rng.state, throughput, medium, so, sd, sc);
             const uint32_t si = queue_push_index(lit, &ctr->scount[1]);
             if (lit) {
-                pb.sq_o[si] = make_float4(so.x, so.y, so.z, 0.f);
-                pb.sq_d[si] = make_float4(sd.x, sd.y, sd.z, __uint_as_float(origin_tri)); // the triangle the shadow ray leaves
-                pb.sq_c[si] = make_float4(sc.x, sc.y, sc.z, __uint_as_float(slot));
+                stq(&pb.sq_o[si], make_float4(so.x, so.y, so.z, 0.f));
+                stq(&pb.sq_d[si], make_float4(sd.x, sd.y, sd.z, __uint_as_float(origin_tri))); // the triangle the shadow ray leaves
+                stq(&pb.sq_c[si], make_float4(sc.x, sc.y, sc.z, __uint_as_float(slot)));
             }
         }
         if (valid && rc.max_path_length > 1) alive = scatter<FEAT>(sp, d, rng, throughput, ior, medium, no, nd, pdf);
         const uint32_t qi = queue_push_index(alive, &ctr->qcount[1]);
         if (alive) {
-            pb.q_o[0][qi] = make_float4(no.x, no.y, no.z, __uint_as_float(slot));
-            pb.q_d[0][qi] = make_float4(nd.x, nd.y, nd.z, NEE ? pdf : __uint_as_float(origin_tri));
+            stq(&pb.q_o[0][qi], make_float4(no.x, no.y, no.z, __uint_as_float(slot)));
+            stq(&pb.q_d[0][qi], make_float4(nd.x, nd.y, nd.z, NEE ? pdf : __uint_as_float(origin_tri)));
         }
         if (valid) {
-            pb.rad[slot] = make_float4(radiance0.x, radiance0.y, radiance0.z, __uint_as_float(rng.state));
+            stq(&pb.rad[slot], make_float4(radiance0.x, radiance0.y, radiance0.z, __uint_as_float(rng.state)));
             if (alive) {
-                pb.thr[slot] = make_float4(throughput.x, throughput.y, throughput.z, ior);
-                if (FEAT & F_TRANSMISSION) pb.med[slot] = make_float4(medium.x, medium.y, medium.z, 0.f);
+                stq(&pb.thr[slot], make_float4(throughput.x, throughput.y, throughput.z, ior));
+                if (FEAT & F_TRANSMISSION) stq(&pb.med[slot], make_float4(medium.x, medium.y, medium.z, 0.f));
             }
         }
     }
@@ -407,27 +430,27 @@ __global__ void __launch_bounds__(kThreads, (!COUNT && !MEDIUM && !TWO_LEVEL && 
             base = __shfl_sync(0xFFFFFFFFu, base, leader);
             if (is_hit) {
                 const uint32_t hi = base + __popc(hm & ((1u << lane_id()) - 1u));
-                pb.hq_hit[hi] = make_uint4(T.hit.tri, T.hit.instance, __float_as_uint(T.hit.u), __float_as_uint(T.hit.v));
+                stq(&pb.hq_hit[hi], make_uint4(T.hit.tri, T.hit.instance, __float_as_uint(T.hit.u), __float_as_uint(T.hit.v)));
                 const f3 rd = T.dir();
-                pb.hq_dir[hi] = make_float4(rd.x, rd.y, rd.z, __uint_as_float(slot));
-                if (MEDIUM) { const f3 ro = T.org(); pb.hq_org[hi] = make_float4(ro.x, ro.y, ro.z, 0.f); }
+                stq(&pb.hq_dir[hi], make_float4(rd.x, rd.y, rd.z, __uint_as_float(slot)));
+                if (MEDIUM) { const f3 ro = T.org(); stq(&pb.hq_org[hi], make_float4(ro.x, ro.y, ro.z, 0.f)); }
             }
         }
         if (finished && !is_hit && S.env_type != 0u) {
             // miss: _make_environment_map_shading_point (scene.slang:482-498) + render_pt.slang:84-86; the path ends
-            const float4 th = pb.thr[slot];
+            const float4 th = ldq(&pb.thr[slot]);
             f3 throughput = mk3(th.x, th.y, th.z);
             if (MEDIUM) {
-                const float4 m = pb.med[slot];
+                const float4 m = ldq(&pb.med[slot]);
                 if (m.x != 0.f || m.y != 0.f || m.z != 0.f) throughput *= vexp(-(kEnvDistance * length(T.dir())) * mk3(m.x, m.y, m.z));
             }
             f3 e = throughput * env_eval(S, T.dir());
             if (NEE) e = e * (pdf_bsdf / (pdf_bsdf + env_pdf(S, T.dir()))); // balance heuristic against nee_environment
-            float4 ra = pb.rad[slot];
+            float4 ra = ldq(&pb.rad[slot]);
             ra.x += e.x;
             ra.y += e.y;
             ra.z += e.z;
-            pb.rad[slot] = ra;
+            stq(&pb.rad[slot], ra);
         }
         finished = false;
         // ---- refill idle lanes
@@ -440,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, (!COUNT && !MEDIUM && !TWO_LEVEL && 
             if (!active && !exhausted) {
                 const uint32_t j = base + __popc(need & ((1u << lane_id()) - 1u));
                 if (j < n) {
-                    const float4 ro = __ldg(q_o + j), rd = __ldg(q_d + j);
+                    const float4 ro = ldq(q_o + j), rd = ldq(q_d + j);
                     slot = __float_as_uint(ro.w);
                     // continuation rays all have tmax = SCENE_RAY_TMAX; the lane carries the BSDF pdf (NEE) or the triangle the ray leaves
                     if (NEE) pdf_bsdf = rd.w;
@@ -469,6 +492,186 @@ __global__ void __launch_bounds__(kThreads, (!COUNT && !MEDIUM && !TWO_LEVEL && 
     }
 }
 
+// --------------------------------------------------------------------------------------- wavefront: extend, pooled form
+// The organisation described in bvh8_traverse_pooled.cuh: per-warp ray pool in shared memory, converged retire + refill + ray setup,
+// divergent traversal in which a finished lane swaps its record for a READY one with two shared-memory atomics.
+#ifndef MPT_POOL_READY
+#define MPT_POOL_READY 16 // READY records per warp on top of the 32 a warp can be traversing
+#endif
+#ifndef MPT_POOL_SMEM_STACK
+#define MPT_POOL_SMEM_STACK 4 // traversal-stack entries per lane kept in shared memory (deeper ones spill to local memory)
+#endif
+template <bool COUNT, bool MEDIUM, bool TWO_LEVEL, bool NEE>
+__global__ void __launch_bounds__(kThreads, (!COUNT && !MEDIUM && !TWO_LEVEL && !NEE) ? MPT_EXTEND_PLAIN_MIN_BLOCKS : MPT_EXTEND_MIN_BLOCKS)
+k_extend_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ q_o, const float4* __restrict__ q_d, PathBuffers pb, uint32_t bounce, uint32_t mask,
+                ExtendTune tune, Counters* ctr) {
+    constexpr int NE = 32 + MPT_POOL_READY, SS = MPT_POOL_SMEM_STACK, kWarps = kThreads / 32;
+    struct Pool {
+        PoolEntry e[NE];
+        uint8_t ready[NE], done[NE];
+        int ready_head, ready_n, done_n, pad;
+    };
+    __shared__ Pool s_pool[kWarps];
+    __shared__ uint2 s_stack[(SS > 0 ? SS : 1) * kThreads];
+    const uint32_t n = ctr->qcount[bounce];
+    const uint32_t lane = lane_id();
+    const uint32_t lt = (1u << lane) - 1u;
+    Pool& P = s_pool[threadIdx.x >> 5];
+    uint2 lstack[kStackSize - SS];
+    MaterialAlphaTest at{&S};
+    TraversalP<COUNT, TWO_LEVEL, MaterialAlphaTest, SS, kThreads> T(S.accel, at, s_stack + threadIdx.x, lstack);
+    const uint32_t scene_flags = TWO_LEVEL ? 0u : S.accel.instances[0].mask_flags;
+    const bool scene_masked = !TWO_LEVEL && ((scene_flags & 0xFFu) & mask) == 0u; // the only instance is masked out: every ray misses
+
+    // every record starts on the DONE list, marked empty (slot kMiss)
+    for (int i = int(lane); i < NE; i += 32) {
+        P.e[i].a.w = __uint_as_float(kMiss);
+        P.done[i] = uint8_t(i);
+    }
+    if (lane == 0) { P.done_n = NE; P.ready_head = 0; P.ready_n = 0; }
+    __syncwarp();
+
+    bool active = false, exhausted = false;
+    uint32_t my = 0;
+    int ready_n = 0;
+    while (true) {
+        // ======================================================= converged: retire DONE records, refill them, hand READY records to idle lanes
+        const int nd = P.done_n;
+        uint32_t base = 0;
+        if (!exhausted && nd > 0) {
+            if (lane == 0) base = atomicAdd(&ctr->fetch[bounce], uint32_t(nd));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        }
+        int nready = 0;
+#pragma unroll 1
+        for (int r = 0; r * 32 < nd; r++) {
+            const int i = r * 32 + int(lane);
+            const bool have = i < nd;
+            const uint32_t e = have ? uint32_t(P.done[i]) : 0u;
+            PoolEntry& E = P.e[e];
+            // ---- retire
+            uint32_t slot = kMiss;
+            uint4 h = make_uint4(kMiss, kMiss, 0u, 0u);
+            float4 dir = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (have) {
+                slot = __float_as_uint(E.a.w);
+                if (slot != kMiss) {
+                    const float4 hb = E.b;
+                    h = make_uint4(__float_as_uint(hb.x), __float_as_uint(hb.y), __float_as_uint(hb.z), __float_as_uint(hb.w));
+                    dir = E.d;
+                }
+            }
+            const bool is_ray = slot != kMiss, is_hit = is_ray && h.y != kMiss;
+            const uint32_t hm = __ballot_sync(0xFFFFFFFFu, is_hit);
+            if (hm) {
+                uint32_t hb = 0;
+                if (lane == 0) hb = atomicAdd(&ctr->hcount[bounce], uint32_t(__popc(hm)));
+                hb = __shfl_sync(0xFFFFFFFFu, hb, 0);
+                if (is_hit) {
+                    const uint32_t hi = hb + __popc(hm & lt);
+                    stq(&pb.hq_hit[hi], h);
+                    stq(&pb.hq_dir[hi], make_float4(dir.x, dir.y, dir.z, __uint_as_float(slot)));
+                    if (MEDIUM) { const float4 oa = E.a; stq(&pb.hq_org[hi], make_float4(oa.x, oa.y, oa.z, 0.f)); }
+                }
+            }
+            if (is_ray && !is_hit && S.env_type != 0u) {
+                // miss: _make_environment_map_shading_point (scene.slang:482-498) + render_pt.slang:84-86; the path ends
+                const f3 rd = mk3(dir.x, dir.y, dir.z);
+                const float4 th = ldq(&pb.thr[slot]);
+                f3 throughput = mk3(th.x, th.y, th.z);
+                if (MEDIUM) {
+                    const float4 m = ldq(&pb.med[slot]);
+                    if (m.x != 0.f || m.y != 0.f || m.z != 0.f) throughput *= vexp(-(kEnvDistance * length(rd)) * mk3(m.x, m.y, m.z));
+                }
+                f3 ev = throughput * env_eval(S, rd);
+                if (NEE) ev = ev * (dir.w / (dir.w + env_pdf(S, rd))); // balance heuristic against nee_environment
+                float4 ra = ldq(&pb.rad[slot]);
+                ra.x += ev.x;
+                ra.y += ev.y;
+                ra.z += ev.z;
+                stq(&pb.rad[slot], ra);
+            }
+            // ---- refill: the i-th DONE record takes the i-th ray of this warp's claim
+            bool filled = false;
+            if (have) {
+                const uint32_t jn = base + uint32_t(i);
+                if (!exhausted && jn < n) {
+                    const float4 ro = ldq(q_o + jn), rd = ldq(q_d + jn);
+                    if (scene_masked) {
+                        if (S.env_type != 0u) { // same miss shading as above (no medium can be active: nothing was ever hit)
+                            const uint32_t sl = __float_as_uint(ro.w);
+                            const float4 th = ldq(&pb.thr[sl]);
+                            f3 ev = mk3(th.x, th.y, th.z) * env_eval(S, xyz(rd));
+                            if (NEE) ev = ev * (rd.w / (rd.w + env_pdf(S, xyz(rd))));
+                            float4 ra = ldq(&pb.rad[sl]);
+                            ra.x += ev.x;
+                            ra.y += ev.y;
+                            ra.z += ev.z;
+                            stq(&pb.rad[sl], ra);
+                        }
+                    } else {
+                        RaySetup R;
+                        setup_ray(R, xyz(ro), xyz(rd));
+                        E.a = ro; // origin | slot
+                        E.b = make_float4(R.idir.x, R.idir.y, R.idir.z, __uint_as_float(R.octinv4));
+                        E.c = make_float4(R.shear.Sx, R.shear.Sy, R.shear.Sz,
+                                          __uint_as_float(uint32_t(R.shear.kx) | (uint32_t(R.shear.ky) << 2) | (uint32_t(R.shear.kz) << 4)));
+                        E.d = rd; // direction | triangle the ray leaves (or the BSDF pdf with NEE)
+                        filled = true;
+                    }
+                }
+                if (!filled) E.a.w = __uint_as_float(kMiss);
+            }
+            const uint32_t fm = __ballot_sync(0xFFFFFFFFu, filled);
+            if (filled) P.ready[nready + __popc(fm & lt)] = uint8_t(e);
+            nready += __popc(fm);
+        }
+        if (!exhausted && nd > 0 && base + uint32_t(nd) >= n) exhausted = true;
+        __syncwarp();
+        // ---- idle lanes take READY records
+        const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
+        const int k = __popc(idle & lt);
+        if (!active && k < nready) {
+            my = P.ready[k];
+            T.start(&P.e[my], mask, scene_flags, NEE ? kMiss : __float_as_uint(P.e[my].d.w));
+            active = true;
+        }
+        if (lane == 0) {
+            P.done_n = 0;
+            P.ready_n = nready;
+            P.ready_head = min(__popc(idle), nready);
+        }
+        ready_n = nready;
+        __syncwarp();
+        if (!__any_sync(0xFFFFFFFFu, active)) break;
+        // ======================================================= divergent: traverse; a finished lane swaps its record for a READY one
+        while (active) {
+            if (T.step()) {
+                PoolEntry& E = P.e[my];
+                const bool f = T.found();
+                E.b = make_float4(__uint_as_float(f ? T.hit.tri : kMiss), __uint_as_float(T.hit.instance), T.hit.u, T.hit.v);
+                P.done[atomicAdd(&P.done_n, 1)] = uint8_t(my);
+                const int kk = atomicAdd(&P.ready_head, 1);
+                if (kk < ready_n) {
+                    my = P.ready[kk];
+                    T.start(&P.e[my], mask, scene_flags, NEE ? kMiss : __float_as_uint(P.e[my].d.w));
+                } else {
+                    active = false;
+                    break;
+                }
+            }
+            // re-converge for a refill when the READY list is used up and too few lanes are left (never once the queue is exhausted:
+            // the remaining rays just run to completion)
+            if (!exhausted && uint32_t(__popc(__activemask())) < tune.refill && *(volatile int*)&P.ready_head >= ready_n) break;
+        }
+        __syncwarp();
+    }
+    if (COUNT) {
+        atomicAdd(&ctr->nodes_visited, (unsigned long long)T.n_nodes);
+        atomicAdd(&ctr->tris_tested, (unsigned long long)T.n_tris);
+    }
+}
+
 // --------------------------------------------------------------------------------------- wavefront: shadow rays (MPT_RENDER_NEE)
 // Visibility towards the environment with the SAME intersection semantics as the continuation rays (back-face culling, masks,
 // alpha test), so that light samples and BSDF samples see the same scene. Same persistent structure as k_extend (per-lane dynamic
@@ -484,13 +687,13 @@ __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_shadow(cons
     uint32_t j = 0;
     while (true) {
         if (finished && !T.found()) {
-            const float4 c = __ldg(pb.sq_c + j);
+            const float4 c = ldq(pb.sq_c + j);
             const uint32_t slot = __float_as_uint(c.w);
-            float4 ra = pb.rad[slot]; // one shadow ray per slot and bounce: no race
+            float4 ra = ldq(&pb.rad[slot]); // one shadow ray per slot and bounce: no race
             ra.x += c.x;
             ra.y += c.y;
             ra.z += c.z;
-            pb.rad[slot] = ra;
+            stq(&pb.rad[slot], ra);
         }
         finished = false;
         const uint32_t need = __ballot_sync(0xFFFFFFFFu, !active && !exhausted);
@@ -502,7 +705,7 @@ __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_shadow(cons
             if (!active && !exhausted) {
                 j = base + __popc(need & ((1u << lane_id()) - 1u));
                 if (j < n) {
-                    const float4 ro = __ldg(pb.sq_o + j), rd = __ldg(pb.sq_d + j);
+                    const float4 ro = ldq(pb.sq_o + j), rd = ldq(pb.sq_d + j);
                     active = T.init(xyz(ro), xyz(rd), 0.f, kRayTMax, mask, __float_as_uint(rd.w));
                     finished = !active; // masked out: nothing can occlude
                 } else {
@@ -529,7 +732,7 @@ __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_shadow(cons
 // warp) over the caller's ray array; results land at the ray's own index.
 template <bool COUNT, bool TWO_LEVEL>
 __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_trace_persistent(const __grid_constant__ SceneView S, const float4* __restrict__ rays, uint32_t n,
-                                                                                      uint32_t mask, uint32_t* hits6, ExtendTune tune, Counters* ctr) {
+                                                                                      uint32_t mask, uint32_t* hits6, ExtendTune tune, Counters* ctr, uint32_t* fetch) {
     MaterialAlphaTest at{&S};
     uint2 stack_mem[kStackSize];
     Traversal<COUNT, TWO_LEVEL, MaterialAlphaTest> T(S.accel, at, stack_mem);
@@ -556,7 +759,7 @@ __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_trace_persi
         if (need) {
             const int leader = __ffs(need) - 1;
             uint32_t base = 0;
-            if (int(lane_id()) == leader) base = atomicAdd(&ctr->fetch[0], uint32_t(__popc(need)));
+            if (int(lane_id()) == leader) base = atomicAdd(fetch, uint32_t(__popc(need)));
             base = __shfl_sync(0xFFFFFFFFu, base, leader);
             if (!active && !exhausted) {
                 j = base + __popc(need & ((1u << lane_id()) - 1u));
@@ -591,7 +794,7 @@ __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_trace_persi
 // Camera rays in 8x4-pixel tile order (index j -> tile j / 32, pixel j % 32 inside it) through the per-lane dynamic fetch of k_extend.
 template <bool COUNT, bool TWO_LEVEL>
 __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_primary_persistent(const __grid_constant__ SceneView S, CameraParams cam, uint32_t w, uint32_t h, uint32_t mask,
-                                                                                        PackedHitInfo* out, ExtendTune tune, Counters* ctr) {
+                                                                                        PackedHitInfo* out, ExtendTune tune, Counters* ctr, uint32_t* fetch) {
     const uint32_t tiles_x = (w + 7) / 8, n = tiles_x * ((h + 3) / 4) * 32u;
     MaterialAlphaTest at{&S};
     uint2 stack_mem[kStackSize];
@@ -619,7 +822,7 @@ __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_primary_per
         if (need) {
             const int leader = __ffs(need) - 1;
             uint32_t base = 0;
-            if (int(lane_id()) == leader) base = atomicAdd(&ctr->fetch[0], uint32_t(__popc(need)));
+            if (int(lane_id()) == leader) base = atomicAdd(fetch, uint32_t(__popc(need)));
             base = __shfl_sync(0xFFFFFFFFu, base, leader);
             if (!active && !exhausted) {
                 const uint32_t j = base + __popc(need & ((1u << lane_id()) - 1u));
@@ -673,8 +876,8 @@ __global__ void __launch_bounds__(kThreads, FEAT == 0u ? MPT_SHADE_MIN_BLOCKS : 
         float ior = 1.f, pdf = 0.f;
         uint32_t slot = 0, origin_tri = kMiss;
         if (valid) {
-            const uint4 hw = __ldg(pb.hq_hit + j);
-            const float4 rd = __ldg(pb.hq_dir + j);
+            const uint4 hw = ldq(pb.hq_hit + j);
+            const float4 rd = ldq(pb.hq_dir + j);
             HitRec hr;
             hr.tri = hw.x;
             origin_tri = hw.x;
@@ -682,16 +885,16 @@ __global__ void __launch_bounds__(kThreads, FEAT == 0u ? MPT_SHADE_MIN_BLOCKS : 
             hr.u = __uint_as_float(hw.z);
             hr.v = __uint_as_float(hw.w);
             slot = __float_as_uint(rd.w);
-            const float4 th = pb.thr[slot];
-            const float4 ra = pb.rad[slot];
+            const float4 th = ldq(&pb.thr[slot]);
+            const float4 ra = ldq(&pb.rad[slot]);
             throughput = mk3(th.x, th.y, th.z);
             ior = th.w;
             const f3 d = xyz(rd);
             f3 o = mk3(0.f);
             if (FEAT & F_TRANSMISSION) {
-                const float4 m = pb.med[slot];
+                const float4 m = ldq(&pb.med[slot]);
                 medium = mk3(m.x, m.y, m.z);
-                o = xyz(__ldg(pb.hq_org + j));
+                o = xyz(ldq(pb.hq_org + j));
             }
             ShadingPoint sp;
             surface_shading_point<FEAT>(S, o, d, hr, ior, more, sp);
@@ -704,23 +907,23 @@ __global__ void __launch_bounds__(kThreads, FEAT == 0u ? MPT_SHADE_MIN_BLOCKS : 
             Rng rng = make_pcg(__float_as_uint(ra.w));
             if (NEE && more) lit = nee_environment<FEAT>(S, sp, d, rng.state, throughput, medium, so, sd, sc);
             if (more) alive = scatter<FEAT>(sp, d, rng, throughput, ior, medium, no, nd, pdf);
-            pb.rad[slot] = make_float4(radiance.x, radiance.y, radiance.z, __uint_as_float(rng.state));
+            stq(&pb.rad[slot], make_float4(radiance.x, radiance.y, radiance.z, __uint_as_float(rng.state)));
             if (alive) {
-                pb.thr[slot] = make_float4(throughput.x, throughput.y, throughput.z, ior);
-                if (FEAT & F_TRANSMISSION) pb.med[slot] = make_float4(medium.x, medium.y, medium.z, 0.f);
+                stq(&pb.thr[slot], make_float4(throughput.x, throughput.y, throughput.z, ior));
+                if (FEAT & F_TRANSMISSION) stq(&pb.med[slot], make_float4(medium.x, medium.y, medium.z, 0.f));
             }
         }
         const uint32_t qi = queue_push_index(alive, &ctr->qcount[bounce + 1]);
         if (alive) {
-            pb.q_o[out][qi] = make_float4(no.x, no.y, no.z, __uint_as_float(slot));
-            pb.q_d[out][qi] = make_float4(nd.x, nd.y, nd.z, NEE ? pdf : __uint_as_float(origin_tri));
+            stq(&pb.q_o[out][qi], make_float4(no.x, no.y, no.z, __uint_as_float(slot)));
+            stq(&pb.q_d[out][qi], make_float4(nd.x, nd.y, nd.z, NEE ? pdf : __uint_as_float(origin_tri)));
         }
         if (NEE) {
             const uint32_t si = queue_push_index(lit, &ctr->scount[bounce + 1]);
             if (lit) {
-                pb.sq_o[si] = make_float4(so.x, so.y, so.z, 0.f);
-                pb.sq_d[si] = make_float4(sd.x, sd.y, sd.z, __uint_as_float(origin_tri));
-                pb.sq_c[si] = make_float4(sc.x, sc.y, sc.z, __uint_as_float(slot));
+                stq(&pb.sq_o[si], make_float4(so.x, so.y, so.z, 0.f));
+                stq(&pb.sq_d[si], make_float4(sd.x, sd.y, sd.z, __uint_as_float(origin_tri)));
+                stq(&pb.sq_c[si], make_float4(sc.x, sc.y, sc.z, __uint_as_float(slot)));
             }
         }
     }
@@ -821,7 +1024,7 @@ __global__ void __launch_bounds__(kThreads) k_resolve(RenderConst rc, PathBuffer
         m2 = prev.w;
     }
     for (uint32_t k = 0; k < rc.pass_k; k++) {
-        const float4 r = pb.rad[k * rc.npix + pix];
+        const float4 r = ldq(&pb.rad[k * rc.npix + pix]);
         const f3 contrib = mk3(r.x, r.y, r.z) / demod;
         if (finite3(contrib)) { // !any(isnan) && !any(isinf), render_pt.slang:117
             irr += contrib;
@@ -967,6 +1170,9 @@ struct mpt_context {
     uint32_t extend_blocks_per_sm = 7;       // resident blocks of the persistent kernels in general
     uint32_t extend_plain_blocks_per_sm = 8; // ... of the plain k_extend variant
     uint32_t shade_blocks_cap = 64; // MPT_SHADE_BLOCKS_PER_SM (tuning)
+    bool extend_pooled = true;    // k_extend_pooled (per-warp ray pool in shared memory); MPT_EXTEND_LEGACY=1 selects the round-1 kernel for A/B runs
+    ExtendTune tune_pooled{24u};  // pooled form: re-converge when the READY list is empty and fewer than this many lanes are traversing
+    uint32_t pooled_blocks_per_sm = 8, pooled_plain_blocks_per_sm = 8;
     ExtendTune tune{14u}; // 12-14 is the optimum with the current traversal (6: -13 %, 8: -5 %, 10: -0.8 %, 16: -1.1 %, 20: -2.6 %, 24: -3.7 %)
     // Path slots in flight, in Mi (128 B of queues + state each, 160 B with a medium). Launches of a few hundred thousand rays
     // are latency-bound (one batch per warp, time = the slowest ray), so bigger passes amortise the tails of the late
@@ -974,7 +1180,10 @@ struct mpt_context {
     uint32_t pool_mslots = 64;
     std::string error;
     // scene
-    DevBuf nodes, tris, tri_attr, geometries, prim_to_tri, instances, tlas_prims, xform, xform_it;
+    DevBuf accel_mem; // BVH8 nodes, then (256-byte aligned) the triangle records
+    size_t accel_bytes = 0;
+    size_t l2_window_bytes = 0; // > 0: persisting-L2 access-policy window over accel_mem while a frame's kernels run (MPT_L2_PERSIST)
+    DevBuf tri_attr, geometries, prim_to_tri, instances, tlas_prims, xform, xform_it;
     DevBuf materials, material_types, texture_table, env_pixels, env_alias, env_pmf;
     bool env_sampling_ready = false;
     std::vector<TextureSlot> textures;
@@ -995,6 +1204,10 @@ struct mpt_context {
     static constexpr uint32_t kMaxInFlight = 4;
     InFlight in_flight[kMaxInFlight];
     cudaStream_t compute = nullptr;
+    // fetch cursors of the persistent mpt_trace / mpt_primary_visibility kernels: their own words (a ring of 64, one per launch), so
+    // that a launch on a caller's stream never shares a cursor with a frame rendering on ctx->compute (whose passes clear `counters`)
+    DevBuf cursors;
+    uint32_t cursor_next = 0;
     // stats / profiling
     uint32_t profile_flags = 0;
     mpt_stats stats{};
@@ -1015,6 +1228,21 @@ mpt_status fail(mpt_context* c, mpt_status s, const std::string& msg) {
         if (e__ != cudaSuccess) return fail(ctx, MPT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
     } while (0)
 
+// Upload / set entry points copy on the legacy stream, which does not order against ctx->compute (a non-blocking stream) or a caller's
+// stream: wait for every frame this context still has on the device before any table is overwritten or freed.
+cudaError_t quiesce(mpt_context* ctx) {
+    if (ctx->compute) {
+        const cudaError_t e = cudaStreamSynchronize(ctx->compute);
+        if (e != cudaSuccess) return e;
+    }
+    for (auto& f : ctx->in_flight)
+        if (f.copy) {
+            const cudaError_t e = cudaStreamSynchronize(f.copy);
+            if (e != cudaSuccess) return e;
+        }
+    return cudaDeviceSynchronize(); // renders issued on caller-provided streams
+}
+
 CameraParams to_device_camera(const mpt_camera& c) {
     CameraParams p;
     p.position = {c.position[0], c.position[1], c.position[2]};
@@ -1028,20 +1256,7 @@ CameraParams to_device_camera(const mpt_camera& c) {
     return p;
 }
 
-void invert_affine(const float* m, float* o) { // row-major 3x4
-    const double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], i = m[10];
-    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
-    const double id = 1.0 / det;
-    const double r[9] = {(e * i - f * h) * id, (c * h - b * i) * id, (b * f - c * e) * id, (f * g - d * i) * id, (a * i - c * g) * id,
-                         (c * d - a * f) * id, (d * h - e * g) * id, (b * g - a * h) * id, (a * e - b * d) * id};
-    for (int row = 0; row < 3; row++) {
-        for (int col = 0; col < 3; col++) o[row * 4 + col] = float(r[row * 3 + col]);
-        o[row * 4 + 3] = float(-(r[row * 3] * m[3] + r[row * 3 + 1] * m[7] + r[row * 3 + 2] * m[11]));
-    }
-}
-
 inline uint32_t fbits(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
-inline float bitsf(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 
 template <class F> void time_launch(mpt_context* ctx, bool is_extend, cudaStream_t st, F&& launch) {
     if (!(ctx->profile_flags & 2u)) { launch(); return; }
@@ -1099,6 +1314,15 @@ mpt_status ensure_pool(mpt_context* ctx, size_t slots, bool need_medium, bool ne
         CU(ctx->counters.ensure(sizeof(Counters)));
         CU(cudaMemset(ctx->counters.p, 0, sizeof(Counters)));
     }
+    return MPT_OK;
+}
+
+mpt_status next_cursor(mpt_context* ctx, cudaStream_t st, uint32_t** out) {
+    constexpr uint32_t kRing = 64;
+    if (!ctx->cursors.p) CU(ctx->cursors.ensure(kRing * sizeof(uint32_t)));
+    uint32_t* c = ctx->cursors.as<uint32_t>() + (ctx->cursor_next++ % kRing);
+    CU(cudaMemsetAsync(c, 0, sizeof(uint32_t), st));
+    *out = c;
     return MPT_OK;
 }
 
@@ -1203,6 +1427,17 @@ mpt_status run_passes(mpt_context* ctx, const CameraParams& cam, const mpt_rende
     rc.instance_mask = P.instance_mask; rc.flags = P.flags; rc.sample_offset = P.sample_offset; rc.sample_stride = P.sample_stride;
     rc.spp = P.spp;
 
+    // persisting-L2 window over the BVH nodes + triangle records for this frame's kernels (the queues stream past it: stq / ldq)
+    const bool l2_window = ctx->l2_window_bytes > 0 && ctx->accel_bytes > 0;
+    if (l2_window) {
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow.base_ptr = ctx->accel_mem.p;
+        av.accessPolicyWindow.num_bytes = std::min(ctx->accel_bytes, ctx->l2_window_bytes);
+        av.accessPolicyWindow.hitRatio = float(std::min(1.0, double(ctx->l2_window_bytes) / double(ctx->accel_bytes)));
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        CU(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
     const uint32_t total = uint32_t(std::max(P.spp, 0));
     uint32_t done = 0;
     bool first = true;
@@ -1225,8 +1460,14 @@ mpt_status run_passes(mpt_context* ctx, const CameraParams& cam, const mpt_rende
             time_launch(ctx, true, st, [&] {
                 constexpr bool MED = (FEAT & F_TRANSMISSION) != 0;
                 const bool tl = ctx->view.accel.two_level != 0;
-                const uint32_t grid = (!count && !MED && !tl && !NEE) ? uint32_t(ctx->sm_count) * ctx->extend_plain_blocks_per_sm : persistent_blocks;
-#define MPT_LAUNCH_EXTEND(C, TL) k_extend<C, MED, TL, NEE><<<grid, kThreads, 0, st>>>(ctx->view, pb.q_o[in], pb.q_d[in], pb, uint32_t(b), P.instance_mask, ctx->tune, ctr)
+                const bool plain = !count && !MED && !tl && !NEE;
+                const uint32_t grid = uint32_t(ctx->sm_count) * (ctx->extend_pooled ? (plain ? ctx->pooled_plain_blocks_per_sm : ctx->pooled_blocks_per_sm)
+                                                                                     : (plain ? ctx->extend_plain_blocks_per_sm : ctx->extend_blocks_per_sm));
+#define MPT_LAUNCH_EXTEND(C, TL)                                                                                                                          \
+    do {                                                                                                                                                \
+        if (ctx->extend_pooled) k_extend_pooled<C, MED, TL, NEE><<<grid, kThreads, 0, st>>>(ctx->view, pb.q_o[in], pb.q_d[in], pb, uint32_t(b), P.instance_mask, ctx->tune_pooled, ctr); \
+        else k_extend<C, MED, TL, NEE><<<grid, kThreads, 0, st>>>(ctx->view, pb.q_o[in], pb.q_d[in], pb, uint32_t(b), P.instance_mask, ctx->tune, ctr);              \
+    } while (0)
                 if (count) { if (tl) MPT_LAUNCH_EXTEND(true, true); else MPT_LAUNCH_EXTEND(true, false); }
                 else { if (tl) MPT_LAUNCH_EXTEND(false, true); else MPT_LAUNCH_EXTEND(false, false); }
 #undef MPT_LAUNCH_EXTEND
@@ -1240,6 +1481,11 @@ mpt_status run_passes(mpt_context* ctx, const CameraParams& cam, const mpt_rende
         first = false;
     } while (done < total);
     CU(cudaGetLastError());
+    if (l2_window) {
+        cudaStreamAttrValue av{};
+        av.accessPolicyWindow.num_bytes = 0;
+        CU(cudaStreamSetAttribute(st, cudaStreamAttributeAccessPolicyWindow, &av));
+    }
     ctx->stats.samples += uint64_t(npix) * total;
     return MPT_OK;
 }
@@ -1279,6 +1525,22 @@ MPT_API mpt_status mpt_create(int device, mpt_context** out_ctx) {
     // tuning knobs for profiling sessions (defaults are the measured optimum on B200)
     auto env_u32 = [](const char* name, uint32_t def) { const char* v = getenv(name); return v ? uint32_t(strtoul(v, nullptr, 10)) : def; };
     ctx->tune.refill = env_u32("MPT_REFILL_THRESHOLD", ctx->tune.refill);
+    ctx->tune_pooled.refill = env_u32("MPT_POOLED_REFILL_THRESHOLD", ctx->tune_pooled.refill);
+    ctx->extend_pooled = env_u32("MPT_EXTEND_LEGACY", 0u) == 0u;
+    if (env_u32("MPT_L2_PERSIST", 0u)) {
+        // B200: 126 MB L2. Reserve a persisting carve-out and remember the largest window the device accepts.
+        int max_persist = 0, max_window = 0;
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+        const size_t want = size_t(env_u32("MPT_L2_PERSIST_MB", 64u)) << 20;
+        const size_t carve = std::min(want, size_t(std::max(max_persist, 0)));
+        if (carve > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, carve) == cudaSuccess) ctx->l2_window_bytes = std::min(carve, size_t(std::max(max_window, 0)));
+        cudaGetLastError();
+    }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend_pooled<false, false, true, false>, kThreads, 0) == cudaSuccess && occ > 0) ctx->pooled_blocks_per_sm = uint32_t(occ);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_extend_pooled<false, false, false, false>, kThreads, 0) == cudaSuccess && occ > 0) ctx->pooled_plain_blocks_per_sm = uint32_t(occ);
+    ctx->pooled_blocks_per_sm = std::min(ctx->pooled_blocks_per_sm, env_u32("MPT_EXTEND_BLOCKS_PER_SM", ctx->pooled_blocks_per_sm));
+    ctx->pooled_plain_blocks_per_sm = std::min(ctx->pooled_plain_blocks_per_sm, env_u32("MPT_EXTEND_BLOCKS_PER_SM", ctx->pooled_plain_blocks_per_sm));
     ctx->pool_mslots = std::max(1u, env_u32("MPT_POOL_MSLOTS", ctx->pool_mslots));
     ctx->extend_blocks_per_sm = std::min(ctx->extend_blocks_per_sm, env_u32("MPT_EXTEND_BLOCKS_PER_SM", ctx->extend_blocks_per_sm));
     ctx->extend_plain_blocks_per_sm = std::min(ctx->extend_plain_blocks_per_sm, env_u32("MPT_EXTEND_BLOCKS_PER_SM", ctx->extend_plain_blocks_per_sm));
@@ -1310,191 +1572,44 @@ MPT_API mpt_status mpt_scene_upload(mpt_context* ctx, const mpt_scene_desc* d) {
     if (!ctx || !d) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     CU(cudaSetDevice(ctx->device));
     ctx->scene_ready = false;
-    if (d->instance_count == 0 || d->blas_count == 0) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "scene has no instances");
-    if (d->instance_count > 0xFFFFu) return fail(ctx, MPT_ERR_LIMIT, "more than 65535 TLAS instances (PackedHitInfo.instance_index is 16 bit, gbuffer.slang:44)");
-    const auto t_start = std::chrono::steady_clock::now();
-
-    std::vector<Bvh8Node> nodes;
-    std::vector<float4> tris;
-    std::vector<uint4> attrs;
-    std::vector<uint32_t> prim_to_tri;
-    std::vector<uint32_t> blas_root(d->blas_count);
-    std::vector<Box> blas_bounds(d->blas_count);
-    std::vector<std::vector<uint32_t>> blas_geom_offset(d->blas_count);
-    uint32_t max_blas_depth = 0, tlas_depth = 0;
-
-    for (uint32_t bi = 0; bi < d->blas_count; bi++) {
-        const mpt_blas_desc& bd = d->blas[bi];
-        if (bd.mesh_count > 0xFFFFu) return fail(ctx, MPT_ERR_LIMIT, "more than 65535 geometries in one BLAS (PackedHitInfo.geometry_index is 16 bit)");
-        struct Ref { uint32_t geom, prim; };
-        std::vector<Ref> refs;
-        std::vector<Box> boxes;
-        blas_geom_offset[bi].resize(bd.mesh_count);
-        for (uint32_t g = 0; g < bd.mesh_count; g++) {
-            if (bd.meshes[g] >= d->mesh_count) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "BLAS references a mesh out of range");
-            const mpt_mesh_desc& m = d->meshes[bd.meshes[g]];
-            blas_geom_offset[bi][g] = uint32_t(prim_to_tri.size() + refs.size());
-            for (uint32_t p = 0; p < m.primitive_count; p++) {
-                uint32_t ia, ib, ic;
-                if (m.index_flag == MPT_GEOM_INDEX_U32) { const uint32_t* ix = (const uint32_t*)m.indices + size_t(p) * 3; ia = ix[0]; ib = ix[1]; ic = ix[2]; }
-                else if (m.index_flag == MPT_GEOM_INDEX_U16) { const uint16_t* ix = (const uint16_t*)m.indices + size_t(p) * 3; ia = ix[0]; ib = ix[1]; ic = ix[2]; }
-                else if (m.index_flag == MPT_GEOM_INDEX_U8) { const uint8_t* ix = (const uint8_t*)m.indices + size_t(p) * 3; ia = ix[0]; ib = ix[1]; ic = ix[2]; }
-                else { ia = p * 3; ib = ia + 1; ic = ia + 2; }
-                if (ia >= m.vertex_count || ib >= m.vertex_count || ic >= m.vertex_count) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "vertex index out of range");
-                Box bx;
-                for (int a = 0; a < 3; a++) {
-                    const float x0 = m.vertices[ia].position[a], x1 = m.vertices[ib].position[a], x2 = m.vertices[ic].position[a];
-                    bx.lo[a] = std::min(x0, std::min(x1, x2));
-                    bx.hi[a] = std::max(x0, std::max(x1, x2));
-                }
-                boxes.push_back(bx);
-                refs.push_back({g, p});
-            }
-        }
-        Bvh8 bvh;
-        build_bvh8(boxes.data(), uint32_t(boxes.size()), bvh);
-        const uint32_t node_off = uint32_t(nodes.size()), tri_off = uint32_t(tris.size() / 3);
-        max_blas_depth = std::max(max_blas_depth, bvh.depth);
-        blas_root[bi] = node_off;
-        blas_bounds[bi] = bvh.bounds;
-        for (Bvh8Node nd : bvh.nodes) {
-            nd.child_base += node_off;
-            nd.prim_base += tri_off;
-            nodes.push_back(nd);
-        }
-        const size_t p2t_base = prim_to_tri.size();
-        prim_to_tri.resize(p2t_base + refs.size());
-        for (uint32_t k = 0; k < bvh.prim_order.size(); k++) {
-            const uint32_t ri = bvh.prim_order[k];
-            const Ref r = refs[ri];
-            const mpt_mesh_desc& m = d->meshes[bd.meshes[r.geom]];
-            uint32_t ix[3];
-            if (m.index_flag == MPT_GEOM_INDEX_U32) { const uint32_t* q = (const uint32_t*)m.indices + size_t(r.prim) * 3; ix[0] = q[0]; ix[1] = q[1]; ix[2] = q[2]; }
-            else if (m.index_flag == MPT_GEOM_INDEX_U16) { const uint16_t* q = (const uint16_t*)m.indices + size_t(r.prim) * 3; ix[0] = q[0]; ix[1] = q[1]; ix[2] = q[2]; }
-            else if (m.index_flag == MPT_GEOM_INDEX_U8) { const uint8_t* q = (const uint8_t*)m.indices + size_t(r.prim) * 3; ix[0] = q[0]; ix[1] = q[1]; ix[2] = q[2]; }
-            else { ix[0] = r.prim * 3; ix[1] = ix[0] + 1; ix[2] = ix[0] + 2; }
-            const uint32_t w[3] = {r.prim, r.geom, m.opaque ? 0u : kTriNonOpaque};
-            uint32_t aw[12] = {0};
-            for (int c = 0; c < 3; c++) {
-                const mpt_packed_vertex& v = m.vertices[ix[c]];
-                tris.push_back(make_float4(v.position[0], v.position[1], v.position[2], bitsf(w[c])));
-                aw[c * 3 + 0] = v.encoded_normal;
-                aw[c * 3 + 1] = uint32_t(v.uv[0]) | (uint32_t(v.uv[1]) << 16);
-                aw[c * 3 + 2] = v.encoded_tangent;
-            }
-            attrs.push_back(make_uint4(aw[0], aw[1], aw[2], aw[3]));
-            attrs.push_back(make_uint4(aw[4], aw[5], aw[6], aw[7]));
-            attrs.push_back(make_uint4(aw[8], 0, 0, 0));
-            prim_to_tri[p2t_base + ri] = tri_off + k;
-        }
+    // uploads use the legacy stream; a frame of mpt_render_host_begin may still be reading the old arrays on ctx->compute
+    CU(quiesce(ctx));
+    HostAccel H;
+    {
+        std::string err;
+        const mpt_status bs = build_host_accel(d, H, uint32_t(kStackSize), err);
+        if (bs != MPT_OK) return fail(ctx, bs, err);
     }
+    const auto& nodes = H.nodes;
+    const auto& tris = H.tris;
+    const auto& attrs = H.attrs;
+    const auto& prim_to_tri = H.prim_to_tri;
+    const auto& inst = H.instances;
+    const auto& tlas_prims = H.tlas_prims;
+    const auto& geoms = H.geoms;
+    const uint32_t root = H.root;
+    const bool identity_single = H.two_level == 0;
+    const uint32_t max_blas_depth = H.max_blas_depth, tlas_depth = H.tlas_depth;
 
-    // ---- instances + TLAS
-    // vertex transforms needed for tight instance boxes; beyond the budget (about a second of host time) fall back to box corners
-    uint64_t instance_vertex_work = 0;
-    for (uint32_t i = 0; i < d->instance_count; i++) {
-        if (d->instances[i].blas >= d->blas_count) continue;
-        const mpt_blas_desc& bd = d->blas[d->instances[i].blas];
-        for (uint32_t g = 0; g < bd.mesh_count; g++) instance_vertex_work += d->meshes[bd.meshes[g]].vertex_count;
-    }
-    const bool tight_instance_boxes = instance_vertex_work <= 300000000ull && !getenv("MPT_LOOSE_INSTANCE_BOXES");
-    std::vector<InstanceRec> inst(d->instance_count);
-    std::vector<Box> ibox(d->instance_count);
-    bool identity_single = d->instance_count == 1;
-    for (uint32_t i = 0; i < d->instance_count; i++) {
-        const mpt_instance_desc& in = d->instances[i];
-        if (in.blas >= d->blas_count) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "instance references a BLAS out of range");
-        float inv[12];
-        invert_affine(in.transform, inv);
-        inst[i].inv0 = make_float4(inv[0], inv[1], inv[2], inv[3]);
-        inst[i].inv1 = make_float4(inv[4], inv[5], inv[6], inv[7]);
-        inst[i].inv2 = make_float4(inv[8], inv[9], inv[10], inv[11]);
-        inst[i].blas_root = blas_root[in.blas];
-        inst[i].custom_index = in.instance_custom_index;
-        inst[i].mask_flags = (in.mask & 0xFFu) | ((in.flags & 0xFFu) << 8);
-        inst[i].pad = 0;
-        static const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
-        if (std::memcmp(in.transform, ident, sizeof(ident)) != 0) identity_single = false;
-        const Box& ob = blas_bounds[in.blas];
-        Box wb;
-        for (int a = 0; a < 3; a++) { wb.lo[a] = 3e38f; wb.hi[a] = -3e38f; }
-        auto grow = [&](const float* p) {
-            for (int a = 0; a < 3; a++) {
-                const float* m = in.transform + a * 4;
-                const float v = m[0] * p[0] + m[1] * p[1] + m[2] * p[2] + m[3];
-                wb.lo[a] = std::min(wb.lo[a], v);
-                wb.hi[a] = std::max(wb.hi[a], v);
-            }
-        };
-        if (tight_instance_boxes) {
-            // the world box of the transformed VERTICES: for a rotated instance it is about half the surface area of the box around the
-            // transformed object-space box, and every false TLAS hit costs an instance entry (ray transform + setup) in k_extend
-            const mpt_blas_desc& bd = d->blas[in.blas];
-            for (uint32_t g = 0; g < bd.mesh_count; g++) {
-                const mpt_mesh_desc& m = d->meshes[bd.meshes[g]];
-                for (uint32_t v = 0; v < m.vertex_count; v++) grow(m.vertices[v].position);
-            }
-        } else {
-            for (int k = 0; k < 8; k++) {
-                const float p[3] = {(k & 1) ? ob.hi[0] : ob.lo[0], (k & 2) ? ob.hi[1] : ob.lo[1], (k & 4) ? ob.hi[2] : ob.lo[2]};
-                grow(p);
-            }
-        }
-        for (int a = 0; a < 3; a++) { // the object-space test is exact; the world box only prunes
-            const float pad = (wb.hi[a] - wb.lo[a]) * 1e-5f + 1e-6f;
-            wb.lo[a] -= pad;
-            wb.hi[a] += pad;
-        }
-        ibox[i] = wb;
-    }
-    std::vector<uint32_t> tlas_prims;
-    uint32_t root = blas_root[d->instances[0].blas];
-    if (!identity_single) {
-        Bvh8 tl;
-        build_bvh8(ibox.data(), d->instance_count, tl);
-        const uint32_t node_off = uint32_t(nodes.size());
-        root = node_off;
-        for (Bvh8Node nd : tl.nodes) {
-            nd.child_base += node_off;
-            nodes.push_back(nd); // prim_base indexes tlas_prims directly
-        }
-        tlas_prims = tl.prim_order;
-        tlas_depth = tl.depth;
-    }
-    if (2u * (max_blas_depth + tlas_depth) + 2u > uint32_t(kStackSize) - 6u)
-        return fail(ctx, MPT_ERR_LIMIT, "acceleration structure too deep for the traversal stack (BLAS " + std::to_string(max_blas_depth) + " + TLAS " +
-                                            std::to_string(tlas_depth) + " wide levels)");
-
-    // ---- geometry table
-    std::vector<uint4> geoms(d->geometry_count);
-    for (uint32_t g = 0; g < d->geometry_count; g++)
-        geoms[g] = make_uint4(uint32_t(d->geometries[g].material_id) | (uint32_t(d->geometries[g].flags) << 16), d->geometries[g].primitive_count, 0u, 0u);
-    for (uint32_t i = 0; i < d->instance_count; i++) {
-        const mpt_instance_desc& in = d->instances[i];
-        const mpt_blas_desc& bd = d->blas[in.blas];
-        for (uint32_t g = 0; g < bd.mesh_count; g++) {
-            const uint32_t gid = in.instance_custom_index + g;
-            if (gid >= d->geometry_count) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "instance_custom_index + geometry_index exceeds the geometry table");
-            if (d->geometries[gid].mesh != bd.meshes[g]) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "geometry table does not match the BLAS mesh list");
-            geoms[gid].z = blas_geom_offset[in.blas][g];
-        }
-    }
-
-    CU(ctx->nodes.upload(nodes.data(), nodes.size() * sizeof(Bvh8Node)));
-    CU(ctx->tris.upload(tris.data(), tris.size() * sizeof(float4)));
-    CU(ctx->tri_attr.upload(attrs.data(), attrs.size() * sizeof(uint4)));
+    // nodes and triangle records share one allocation so that one L2 access-policy window can cover both (run_passes)
+    const size_t node_bytes = (nodes.size() * sizeof(Bvh8Node) + 255) & ~size_t(255), tri_bytes = tris.size() * sizeof(HostVec4);
+    CU(ctx->accel_mem.ensure(node_bytes + std::max<size_t>(tri_bytes, 16)));
+    CU(cudaMemcpy(ctx->accel_mem.p, nodes.data(), nodes.size() * sizeof(Bvh8Node), cudaMemcpyHostToDevice));
+    if (tri_bytes) CU(cudaMemcpy(ctx->accel_mem.as<char>() + node_bytes, tris.data(), tri_bytes, cudaMemcpyHostToDevice));
+    ctx->accel_bytes = node_bytes + tri_bytes;
+    CU(ctx->tri_attr.upload(attrs.data(), attrs.size() * sizeof(HostUVec4)));
     CU(ctx->prim_to_tri.upload(prim_to_tri.data(), prim_to_tri.size() * 4));
-    CU(ctx->instances.upload(inst.data(), inst.size() * sizeof(InstanceRec)));
+    CU(ctx->instances.upload(inst.data(), inst.size() * sizeof(HostInstanceRec)));
     CU(ctx->tlas_prims.upload(tlas_prims.data(), tlas_prims.size() * 4));
-    CU(ctx->geometries.upload(geoms.data(), geoms.size() * sizeof(uint4)));
+    CU(ctx->geometries.upload(geoms.data(), geoms.size() * sizeof(HostUVec4)));
     std::vector<float> ident(size_t(d->instance_count) * 16, 0.f);
     for (uint32_t i = 0; i < d->instance_count; i++) ident[i * 16] = ident[i * 16 + 5] = ident[i * 16 + 10] = ident[i * 16 + 15] = 1.f;
     CU(ctx->xform.upload(d->instance_transforms ? d->instance_transforms : ident.data(), size_t(d->instance_count) * 64));
     CU(ctx->xform_it.upload(d->inverse_transposed_instance_transforms ? d->inverse_transposed_instance_transforms : ident.data(), size_t(d->instance_count) * 64));
 
     SceneView& v = ctx->view;
-    v.accel.nodes = ctx->nodes.as<float4>();
-    v.accel.tris = ctx->tris.as<float4>();
+    v.accel.nodes = ctx->accel_mem.as<float4>();
+    v.accel.tris = reinterpret_cast<const float4*>(ctx->accel_mem.as<char>() + node_bytes);
     v.accel.instances = ctx->instances.as<InstanceRec>();
     v.accel.tlas_prims = ctx->tlas_prims.as<uint32_t>();
     v.accel.root = root;
@@ -1509,9 +1624,9 @@ MPT_API mpt_status mpt_scene_upload(mpt_context* ctx, const mpt_scene_desc* d) {
     ctx->bvh_info.node_count = nodes.size();
     ctx->bvh_info.triangle_count = tris.size() / 3;
     ctx->bvh_info.node_bytes = nodes.size() * sizeof(Bvh8Node);
-    ctx->bvh_info.triangle_bytes = tris.size() * sizeof(float4);
+    ctx->bvh_info.triangle_bytes = tris.size() * sizeof(HostVec4);
     ctx->bvh_info.max_depth = max_blas_depth + tlas_depth;
-    ctx->bvh_info.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
+    ctx->bvh_info.build_ms = H.build_ms;
     ctx->scene_ready = true;
     return MPT_OK;
 }
@@ -1521,6 +1636,7 @@ MPT_API mpt_status mpt_materials_upload(mpt_context* ctx, const void* entries, u
     if (!ctx || (!entries && material_count) || !types) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     if (entry_size % 4 != 0 || entry_size < 20) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "material entry size must be a multiple of 4 and hold header + base colour");
     CU(cudaSetDevice(ctx->device));
+    CU(quiesce(ctx));
     ctx->feature_union = 0;
     std::vector<uint2> tt(type_count);
     for (uint32_t i = 0; i < type_count; i++) {
@@ -1558,6 +1674,7 @@ MPT_API mpt_status mpt_texture_upload(mpt_context* ctx, uint32_t texture_id, uin
     if (!ctx || !pixels || width == 0 || height == 0) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "bad texture");
     if (texture_id >= 0xFFFFu) return fail(ctx, MPT_ERR_LIMIT, "TextureID is 16 bit");
     CU(cudaSetDevice(ctx->device));
+    CU(quiesce(ctx));
     if (ctx->textures.size() <= texture_id) ctx->textures.resize(texture_id + 1);
     TextureSlot& slot = ctx->textures[texture_id];
     if (slot.obj) { cudaDestroyTextureObject(slot.obj); slot.obj = 0; }
@@ -1591,6 +1708,7 @@ MPT_API mpt_status mpt_env_set(mpt_context* ctx, uint32_t type, const float* to_
                                const float* rgba32f) {
     if (!ctx) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL context");
     CU(cudaSetDevice(ctx->device));
+    CU(quiesce(ctx));
     if (type == MPT_ENV_EMPTY) { ctx->view.env_type = 0; return MPT_OK; }
     if (type != MPT_ENV_LATLONG) return fail(ctx, MPT_ERR_UNSUPPORTED, "only Empty and LatLong environment maps are supported");
     if (!to_local || !rgba32f || !width || !height) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "bad env map");
@@ -1632,8 +1750,9 @@ MPT_API mpt_status mpt_primary_visibility(mpt_context* ctx, const mpt_camera* ca
     const uint32_t persistent_blocks = uint32_t(ctx->sm_count) * ctx->extend_blocks_per_sm;
     if (blocks > persistent_blocks && !getenv("MPT_TRACE_ONE_SHOT")) { // enough pixels to fill the machine: per-lane dynamic fetch
         Counters* ctr = ctx->counters.as<Counters>();
-        CU(cudaMemsetAsync(&ctr->fetch[0], 0, sizeof(uint32_t), st));
-#define MPT_LAUNCH_PRIMARY_P(C, TL) k_primary_persistent<C, TL><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, cam, width, height, instance_mask, (PackedHitInfo*)d_tex1, ctx->tune, ctr)
+        uint32_t* cursor = nullptr;
+        { const mpt_status cs = next_cursor(ctx, st, &cursor); if (cs != MPT_OK) return cs; }
+#define MPT_LAUNCH_PRIMARY_P(C, TL) k_primary_persistent<C, TL><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, cam, width, height, instance_mask, (PackedHitInfo*)d_tex1, ctx->tune, ctr, cursor)
         if (cnt) { if (tl) MPT_LAUNCH_PRIMARY_P(true, true); else MPT_LAUNCH_PRIMARY_P(true, false); }
         else { if (tl) MPT_LAUNCH_PRIMARY_P(false, true); else MPT_LAUNCH_PRIMARY_P(false, false); }
 #undef MPT_LAUNCH_PRIMARY_P
@@ -1688,8 +1807,9 @@ MPT_API mpt_status mpt_trace(mpt_context* ctx, const void* d_rays, uint64_t n, u
     const uint32_t persistent_blocks = uint32_t(ctx->sm_count) * ctx->extend_blocks_per_sm;
     if (n < 0xFFFFFFFFull && blocks > persistent_blocks && !getenv("MPT_TRACE_ONE_SHOT")) { // enough rays to fill the machine: per-lane dynamic fetch
         Counters* ctr = ctx->counters.as<Counters>();
-        CU(cudaMemsetAsync(&ctr->fetch[0], 0, sizeof(uint32_t), st));
-#define MPT_LAUNCH_TRACE_P(C, TL) k_trace_persistent<C, TL><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, (const float4*)d_rays, uint32_t(n), instance_mask, (uint32_t*)d_hits, ctx->tune, ctr)
+        uint32_t* cursor = nullptr;
+        { const mpt_status cs = next_cursor(ctx, st, &cursor); if (cs != MPT_OK) return cs; }
+#define MPT_LAUNCH_TRACE_P(C, TL) k_trace_persistent<C, TL><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, (const float4*)d_rays, uint32_t(n), instance_mask, (uint32_t*)d_hits, ctx->tune, ctr, cursor)
         if (cnt) { if (tl) MPT_LAUNCH_TRACE_P(true, true); else MPT_LAUNCH_TRACE_P(true, false); }
         else { if (tl) MPT_LAUNCH_TRACE_P(false, true); else MPT_LAUNCH_TRACE_P(false, false); }
 #undef MPT_LAUNCH_TRACE_P
@@ -1715,6 +1835,7 @@ mpt_status render_impl(mpt_context* ctx, const mpt_camera* camera, const mpt_ren
     if (!ctx || !camera || !P || !d_irradiance) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!ctx->scene_ready || !ctx->materials_ready) return fail(ctx, MPT_ERR_NOT_READY, "scene or materials not uploaded");
     if (!P->width || !P->height || P->spp < 0 || P->max_path_length < 1 || P->sample_stride == 0) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "bad render parameters");
+    if (P->max_path_length > kMaxBounces) return fail(ctx, MPT_ERR_LIMIT, "max_path_length above 64 (per-bounce queue counters)");
     if (camera->aperture_radius > 0.f) return fail(ctx, MPT_ERR_UNSUPPORTED, "thin-lens camera is out of scope (pinhole only)");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -1966,8 +2087,8 @@ MPT_API mpt_status mpt_render_host_end(mpt_context* ctx, uint32_t in_flight_inde
     mpt_context::InFlight& f = ctx->in_flight[in_flight_index];
     if (!f.pending) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "no frame is in flight in this slot");
     CU(cudaSetDevice(ctx->device));
-    f.pending = false;
     CU(cudaEventSynchronize(f.d2h));
+    f.pending = false; // only once the copies are known to be complete
     return MPT_OK;
 }
 
@@ -2011,6 +2132,42 @@ MPT_API mpt_status mpt_bvh_get_info(mpt_context* ctx, mpt_bvh_info* out) {
     *out = ctx->bvh_info;
     return MPT_OK;
 }
+
+struct mpt_host_accel {
+    HostAccel a;
+};
+
+MPT_API mpt_status mpt_host_accel_build(const mpt_scene_desc* scene, mpt_host_accel** out) {
+    if (!scene || !out) return fail(nullptr, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    *out = nullptr;
+    mpt_host_accel* h = nullptr;
+    try {
+        h = new mpt_host_accel();
+        std::string err;
+        const mpt_status s = build_host_accel(scene, h->a, uint32_t(kStackSize), err);
+        if (s != MPT_OK) { delete h; return fail(nullptr, s, err); }
+    } catch (...) {
+        delete h;
+        return fail(nullptr, MPT_ERR_LIMIT, "out of host memory while building the acceleration structure");
+    }
+    *out = h;
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_host_accel_get(const mpt_host_accel* h, mpt_host_accel_view* v) {
+    if (!h || !v) return fail(nullptr, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    const HostAccel& a = h->a;
+    v->nodes = a.nodes.data(); v->node_count = a.nodes.size();
+    v->tris = a.tris.data(); v->triangle_count = a.tris.size() / 3;
+    v->instances = a.instances.data(); v->instance_count = a.instances.size();
+    v->tlas_prims = a.tlas_prims.data(); v->tlas_prim_count = a.tlas_prims.size();
+    v->prim_to_tri = a.prim_to_tri.data(); v->prim_count = a.prim_to_tri.size();
+    v->root = a.root; v->two_level = a.two_level; v->max_blas_depth = a.max_blas_depth; v->tlas_depth = a.tlas_depth;
+    v->build_ms = a.build_ms;
+    return MPT_OK;
+}
+
+MPT_API void mpt_host_accel_free(mpt_host_accel* h) { delete h; }
 
 MPT_API mpt_status mpt_bvh8_build_info(const float* boxes, uint32_t n, mpt_bvh_info* out, uint32_t* prim_order) {
     mpt_context* ctx = nullptr;

@@ -872,6 +872,8 @@ inline std::array<float, 12> invert_affine(const float* m) {
 
 } // namespace orc
 
+#include "oracle_bvh8.hpp" // walker over the product's BVH8 (counts nodes / triangles per ray for the roofline)
+
 // ---- BSDF property suite: tests/bsdf/bsdf-checks.slang:30-135 restated ---------------------------
 using namespace orc;
 namespace {
@@ -1214,6 +1216,37 @@ int oracle_accumulate(const mpt_accumulate_params* A, const float* src_img, cons
             encode_history(1.0f, history + 2 * i);
         }
     }
+    return 0;
+}
+
+// Closest hits of `n` rays over the acceleration structure libmpt.so built (mpt_host_accel_get), with per-ray work counters summed
+// into counts5 = {rays, node tests, triangle tests, instance entries, deepest stack}. `c` may be NULL when every geometry is opaque.
+// skip_records (nullable): per ray, the triangle record it leaves (not tested, like the device's origin-triangle rule).
+int oracle_bvh8_trace(oracle_context* c, const mpt_host_accel_view* accel, const mpt_ray* rays, uint64_t n, uint32_t mask, const uint32_t* skip_records,
+                      mpt_hit* hits, float* t_out, uint32_t* records_out, uint64_t* counts5) {
+    const Bvh8Walker W(*accel, c ? &c->scene : nullptr);
+    uint64_t nodes = 0, tris = 0, entries = 0, max_stack = 0;
+#pragma omp parallel for schedule(dynamic, 256) reduction(+ : nodes, tris, entries) reduction(max : max_stack)
+    for (int64_t i = 0; i < int64_t(n); i++) {
+        const Ray r{float3(rays[i].origin[0], rays[i].origin[1], rays[i].origin[2]), rays[i].tmin,
+                    float3(rays[i].direction[0], rays[i].direction[1], rays[i].direction[2]), rays[i].tmax};
+        Bvh8Counts cnt;
+        float t;
+        Bvh8Walker::State st;
+        st.best_t = r.tmax;
+        const uint32_t skip = skip_records ? skip_records[i] : 0xFFFFFFFFu;
+        if (accel->two_level) W.walk(accel->root, true, r.o, r.d, r.tmin, mask, 0, 0xFFFFFFFFu, st, 0);
+        else if ((W.inst[0].mask_flags & 0xFFu) & mask) W.walk(accel->root, false, r.o, r.d, r.tmin, mask, 0, skip, st, 0);
+        cnt = st.cnt;
+        t = st.best.valid() ? st.best_t : -1.f;
+        const Hit& h = st.best;
+        if (hits) hits[i] = {h.instance_id, h.instance_index, h.primitive_id, h.geometry_index, {h.bary.x, h.bary.y}};
+        if (t_out) t_out[i] = t;
+        if (records_out) records_out[i] = st.best_record;
+        nodes += cnt.nodes; tris += cnt.tris; entries += cnt.instance_entries;
+        max_stack = std::max(max_stack, cnt.max_stack);
+    }
+    if (counts5) { counts5[0] = n; counts5[1] = nodes; counts5[2] = tris; counts5[3] = entries; counts5[4] = max_stack; }
     return 0;
 }
 

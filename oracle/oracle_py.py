@@ -16,7 +16,7 @@ _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 
 
 def build(force: bool = False):
-    srcs = [os.path.join(_HERE, f) for f in ("oracle.cpp", "oracle_math.hpp", "oracle_bsdf.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle.cpp", "oracle_math.hpp", "oracle_bsdf.hpp", "oracle_bvh8.hpp")]
     if not force and os.path.exists(_LIB_PATH) and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return _LIB_PATH
     subprocess.check_call(["make", "-C", _HERE, "-s"], env={**os.environ, "MAKEFLAGS": ""})
@@ -99,6 +99,19 @@ class OracleContext:
         t = np.zeros(len(rays), np.float32)
         assert self.l.oracle_trace(self.h, _p(rays), C.c_uint64(len(rays)), C.c_uint32(mask), _p(hits), _p(t)) == 0
         return (hits, t) if return_t else hits
+
+    def bvh8_trace(self, accel_view, rays, mask=0xFF, skip_records=None):
+        """Closest hits over the PRODUCT's BVH8 (merian_b200.host_accel.HostAccel.view) with work counters.
+        Returns (hits, t, records, counts) with counts = dict(rays, nodes, tris, instance_entries, max_stack)."""
+        rays = np.ascontiguousarray(rays)
+        n = len(rays)
+        hits = np.zeros(n, abi.HIT_DTYPE)
+        t = np.zeros(n, np.float32)
+        rec = np.zeros(n, np.uint32)
+        cnt = np.zeros(5, np.uint64)
+        skip = None if skip_records is None else np.ascontiguousarray(skip_records, np.uint32)
+        assert self.l.oracle_bvh8_trace(self.h, C.byref(accel_view), _p(rays), C.c_uint64(n), C.c_uint32(mask), _p(skip), _p(hits), _p(t), _p(rec), _p(cnt)) == 0
+        return hits, t, rec, dict(zip(("rays", "nodes", "tris", "instance_entries", "max_stack"), (int(x) for x in cnt)))
 
     def render(self, cam, params, tex1=None, albedo=None):
         out = np.zeros((params.height, params.width, 4), np.float32)
