@@ -387,6 +387,37 @@ MPT_API mpt_status mpt_bvh_get_info(mpt_context* ctx, mpt_bvh_info* out);
  * NULL) receives the leaf order. No device needed. */
 MPT_API mpt_status mpt_bvh8_build_info(const float* boxes, uint32_t n, mpt_bvh_info* out, uint32_t* prim_order);
 
+/* ---- multi-GPU: the one exchange step of the path -------------------------------------------------------------
+ * A frame is sharded by sample index (mpt_render_params.sample_offset / sample_stride + MPT_RENDER_OUTPUT_SUM): every GPU renders its
+ * share of the samples of ALL pixels into a private sum buffer; the buffers are combined with ONE NCCL reduce over NVLink per frame and
+ * normalised once. The reference has no multi-device path (render_pt.slang:113-122 loops over a pixel's samples in one thread); these
+ * entry points are what lets a C++ host (one merian process per GPU) shard the node without Python.
+ *
+ * mpt_comm owns (or adopts) one ncclComm_t and a side stream. mpt_reduce_begin enqueues, BEHIND the work already submitted to
+ * `render_stream`, on the side stream:  reduce(sum) -> divide by spp_total (receiving ranks) -> optional copy to the pinned host buffer
+ * h_out. The caller may submit the next frame to render_stream right away (it overlaps the reduce) as long as it renders into a different
+ * buffer. mpt_reduce_end makes a stream wait for the result; mpt_reduce_wait blocks the host until it (and the host copy) is complete.
+ * NCCL is resolved at run time (dlopen libnccl.so.2; MPT_NCCL_LIBRARY overrides the name); without it the calls return
+ * MPT_ERR_UNSUPPORTED. Errors: mpt_comm_last_error (NULL: errors of the calls that take no mpt_comm). */
+#define MPT_COMM_UNIQUE_ID_BYTES 128
+enum {
+    MPT_REDUCE_ALL_RANKS = 0x1, /* ncclAllReduce: every rank receives the frame (each feeds its own Vulkan consumer) */
+    MPT_REDUCE_KEEP_SUM = 0x2   /* do not divide by spp_total */
+};
+typedef struct mpt_comm mpt_comm;
+MPT_API mpt_status mpt_comm_unique_id(uint8_t id[MPT_COMM_UNIQUE_ID_BYTES]); /* rank 0 calls it and hands the bytes to the other ranks */
+MPT_API mpt_status mpt_comm_create(int device, const uint8_t id[MPT_COMM_UNIQUE_ID_BYTES], int rank, int world, mpt_comm** out);
+MPT_API mpt_status mpt_comm_adopt(int device, void* nccl_comm, int rank, int world, mpt_comm** out); /* an ncclComm_t the host already has */
+MPT_API void mpt_comm_destroy(mpt_comm* comm);
+MPT_API const char* mpt_comm_last_error(const mpt_comm* comm);
+MPT_API mpt_status mpt_comm_info(uint32_t* nccl_version);
+/* d_partial_sum: this rank's RGBA32F sums (width*height float4). d_out: where the combined frame lands on the receiving rank(s) (may be
+ * d_partial_sum itself); ignored elsewhere. h_out: optional pinned host buffer on the receiving rank(s). */
+MPT_API mpt_status mpt_reduce_begin(mpt_comm* comm, const void* d_partial_sum, void* d_out, void* h_out, uint32_t width, uint32_t height,
+                                    uint32_t spp_total, int root, uint32_t flags, void* render_stream);
+MPT_API mpt_status mpt_reduce_end(mpt_comm* comm, void* stream);
+MPT_API mpt_status mpt_reduce_wait(mpt_comm* comm);
+
 /* Host-only (no device needed): the acceleration structure exactly as mpt_scene_upload lays it out in HBM — the BVH8 nodes of every
  * BLAS and of the TLAS, the triangle records in leaf order, the instance records. Replaces nothing in the reference (its BLAS/TLAS are
  * opaque driver objects, scene.cpp:1672-1892); it exists so that a CPU checker can walk the SAME tree the device walks (SURVEY.md

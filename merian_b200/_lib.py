@@ -16,6 +16,8 @@ EXPORTS = ["mpt_abi_version", "mpt_create", "mpt_destroy", "mpt_last_error", "mp
            "mpt_accumulate", "mpt_render_accumulate", "mpt_pfm_info", "mpt_pfm_load", "mpt_pfm_save", "mpt_hdr_load", "mpt_env_load", "mpt_image_write",
            "mpt_set_profiling", "mpt_get_stats", "mpt_reset_stats", "mpt_bvh_get_info", "mpt_bvh8_build_info", "mpt_bsdf_check",
            "mpt_host_accel_build", "mpt_host_accel_get", "mpt_host_accel_free",
+           "mpt_comm_unique_id", "mpt_comm_create", "mpt_comm_adopt", "mpt_comm_destroy", "mpt_comm_last_error", "mpt_comm_info",
+           "mpt_reduce_begin", "mpt_reduce_end", "mpt_reduce_wait",
            # include/mpt_node.h
            "mptn_create", "mptn_destroy", "mptn_last_error", "mptn_load_config", "mptn_dump_config", "mptn_describe_outputs",
            "mptn_set_shard", "mptn_process",
@@ -75,6 +77,17 @@ def lib():
         l.mpt_host_accel_get.argtypes = [C.c_void_p, C.POINTER(abi.HostAccelView)]
         l.mpt_host_accel_free.argtypes = [C.c_void_p]
         l.mpt_host_accel_free.restype = None
+        l.mpt_comm_unique_id.argtypes = [C.c_void_p]
+        l.mpt_comm_create.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        l.mpt_comm_adopt.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        l.mpt_comm_destroy.argtypes = [C.c_void_p]
+        l.mpt_comm_destroy.restype = None
+        l.mpt_comm_last_error.argtypes = [C.c_void_p]
+        l.mpt_comm_last_error.restype = C.c_char_p
+        l.mpt_comm_info.argtypes = [C.POINTER(C.c_uint32)]
+        l.mpt_reduce_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p]
+        l.mpt_reduce_end.argtypes = [C.c_void_p, C.c_void_p]
+        l.mpt_reduce_wait.argtypes = [C.c_void_p]
         l.mpt_bsdf_check.argtypes = [C.c_void_p, C.POINTER(abi.BsdfCheckParams), C.c_void_p]
         l.mptn_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         l.mptn_destroy.argtypes = [C.c_void_p]

@@ -42,6 +42,9 @@ RENDER_DEMODULATE_ALBEDO = 0x2
 RENDER_OUTPUT_SUM = 0x4
 RENDER_NEE = 0x8
 
+COMM_UNIQUE_ID_BYTES = 128
+REDUCE_ALL_RANKS, REDUCE_KEEP_SUM = 0x1, 0x2
+
 
 class PackedVertex(C.Structure):  # scene-data.slangh:75-80, 24 bytes
     _pack_ = 4

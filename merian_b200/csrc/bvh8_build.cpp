@@ -55,6 +55,7 @@ struct Builder2 {
     int max_leaf;
     uint32_t sah_depth_limit = 0xFFFFFFFFu; // BVH2 levels built with SAH before the builder switches to median splits
     float trav_cost = 1.0f; // SAH: cost of one node test in units of one primitive test
+    float balance = 0.f;    // SAH candidates must leave at least this fraction of the primitives on the smaller side (0 = plain SAH)
 
     void build(uint32_t n) {
         idx.resize(n);
@@ -112,6 +113,7 @@ struct Builder2 {
                     acc.grow(bb[b]);
                     cnt += bc[b];
                     if (cnt == 0 || rc[b + 1] == 0) continue;
+                    if (float(std::min(cnt, rc[b + 1])) < balance * float(j.count)) continue;
                     const float cost = acc.half_area() * float(cnt) + ra[b + 1] * float(rc[b + 1]);
                     if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = b; }
                 }
@@ -194,6 +196,7 @@ static void build_bvh8_once(const Box* boxes, uint32_t n, Bvh8& out, int max_lea
     b2.max_leaf = collapse_mode == 2 ? 1 : std::min(std::max(int(env_float("MPT_BVH_MAX_LEAF", float(max_leaf))), 1), 3);
     b2.trav_cost = env_float("MPT_BVH_TRAV_COST", 1.0f);
     b2.sah_depth_limit = sah_depth_limit;
+    b2.balance = env_float("MPT_BVH_BALANCE", 0.f);
     b2.build(n);
     const std::vector<Node2>& n2 = b2.nodes;
 
@@ -376,6 +379,10 @@ static void build_bvh8_once(const Box* boxes, uint32_t n, Bvh8& out, int max_lea
 // line) makes SAH peel one primitive per level. When that happens the tree is rebuilt with SAH only for the top levels and object-median
 // splits below, which bounds the depth by about log8(n) + the SAH levels.
 void build_bvh8(const Box* boxes, uint32_t n, Bvh8& out, int max_leaf) {
+    if (std::getenv("MPT_BVH_SAH_DEPTH")) { // tuning sessions: SAH for the top levels only, object-median splits below
+        build_bvh8_once(boxes, n, out, max_leaf, uint32_t(env_float("MPT_BVH_SAH_DEPTH", 64.f)));
+        if (out.depth <= kMaxBvh8Depth) return;
+    }
     for (uint32_t limit : {0xFFFFFFFFu, 16u, 8u, 0u}) {
         build_bvh8_once(boxes, n, out, max_leaf, limit);
         if (out.depth <= kMaxBvh8Depth) return;

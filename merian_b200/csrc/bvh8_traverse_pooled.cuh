@@ -20,21 +20,13 @@
 
 namespace mpt {
 
-// One pooled ray record: 64 bytes of shared memory.
+// One pooled ray record: 64 bytes of shared memory (shared memory is carved out of the SM's L1, which the traversal lives on: the pool
+// is kept as small as the measurements allow, see k_extend_pooled).
 struct alignas(16) PoolEntry {
-    float4 a; // origin.xyz | ray index in the queue (bits)
-    float4 b; // world-space 1/direction.xyz | octinv4 (bits); after the ray finished: hit record tri | instance | u | v
-    float4 c; // shear Sx, Sy, Sz | kx | ky << 2 | kz << 4 (bits)
-    float4 d; // direction.xyz | the queue record's w lane (triangle the ray leaves, or the BSDF pdf with NEE)
-};
-
-constexpr int kPoolEntries = 64;
-
-struct WarpPool { // per warp, in shared memory
-    PoolEntry e[kPoolEntries];
-    uint8_t ready[kPoolEntries];
-    uint8_t done[kPoolEntries];
-    int ready_head, ready_n, done_n, pad;
+    float4 a; // origin.xyz | path slot (bits); slot 0xFFFFFFFF = the record holds no ray
+    float4 b; // 1/direction.xyz | the triangle record the ray leaves (bits); after the ray finished: hit record tri | instance | u | v
+    float4 c; // shear Sx, Sy, Sz | kx | ky << 2 | kz << 4 | octant << 8 (bits)
+    float4 d; // direction.xyz | the queue record's w lane again (with NEE: the BSDF pdf)
 };
 
 // One node test: visits the child at `bit` of a node group (child_base, parent_imask), intersects its 8 child boxes and returns the new
@@ -122,23 +114,25 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
     }
     MPT_DEV uint2 top() const { return (SS > 0 && sp - 1 < SS) ? sst[(sp - 1) * STRIDE] : lst[sp - 1 - SS]; }
 
-    MPT_DEV void load_world_setup() {
-        const float4 a = ent->a, b = ent->b;
+    // returns the record's b.w lane (the triangle the ray leaves)
+    MPT_DEV uint32_t load_world_setup() {
+        const float4 a = ent->a, b = ent->b, c = ent->c;
         o = mk3(a.x, a.y, a.z);
         idir = mk3(b.x, b.y, b.z);
-        octinv4 = __float_as_uint(b.w);
+        const uint32_t kk = __float_as_uint(c.w);
+        octinv4 = (7u - ((kk >> 8) & 7u)) * 0x01010101u;
         if (TWO_LEVEL) {
-            const float4 c = ent->c;
             shear.Sx = c.x; shear.Sy = c.y; shear.Sz = c.z;
-            const uint32_t kk = __float_as_uint(c.w);
             shear.kx = int(kk & 3u); shear.ky = int((kk >> 2) & 3u); shear.kz = int((kk >> 4) & 3u);
         }
+        return __float_as_uint(b.w);
     }
 
-    // scene_flags: mask_flags of instance 0 (single-level scenes)
-    MPT_DEV void start(const PoolEntry* e, uint32_t mask, uint32_t scene_flags, uint32_t skip_tri) {
+    // scene_flags: mask_flags of instance 0 (single-level scenes). use_skip: leave out the triangle the ray starts on (record lane b.w)
+    MPT_DEV void start(const PoolEntry* e, uint32_t mask, uint32_t scene_flags, bool use_skip) {
         ent = e;
-        load_world_setup();
+        const uint32_t leaves = load_world_setup();
+        const uint32_t skip_tri = use_skip ? leaves : kMiss;
         best_t = kRayTMaxPooled();
         ray_mask = mask;
         hit.tri = TWO_LEVEL ? kMiss : skip_tri;

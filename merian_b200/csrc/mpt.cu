@@ -29,9 +29,12 @@
 
 using namespace mpt;
 
-// Queue records and per-path state are written once and read once per bounce (gigabytes per frame), while the BVH nodes and triangle
-// records (tens of MB) are re-read by every ray: mark the former as streaming (ld/st.global.cs, evict-first) so that they do not push
-// the latter out of the 126 MB L2. MPT_STREAM_HINTS=0 builds the plain accesses for A/B runs.
+// Ray / hit / shadow queue records are written once and read once per bounce (gigabytes per frame), while the BVH nodes and triangle
+// records (tens of MB) are re-read by every ray. Queue READS are marked streaming (ld.global.cs: the line is dead after the read).
+// Measured on C3 (profiles/r02a_ab.jsonl, r02b_ab.jsonl) with streaming marks on reads AND writes of queues AND path state: extend
+// -1.5 % but shade +10 % (5.10 -> 5.65 ms: what a kernel writes evict-first is gone from L2 when the next kernel wants it), so writes and
+// the read-modify-write path state stay plain. The persisting-L2 window (MPT_L2_PERSIST=1) is opt-in: it left extend unchanged and
+// doubled the shade time (the 64 MB carve-out is taken from the L2 that also holds attribute records, environment texels, path state).
 #ifndef MPT_STREAM_HINTS
 #define MPT_STREAM_HINTS 1
 #endif
@@ -40,13 +43,6 @@ template <class T> __device__ __forceinline__ T ldq(const T* p) {
     return __ldcs(p);
 #else
     return *p;
-#endif
-}
-template <class T> __device__ __forceinline__ void stq(T* p, T v) {
-#if MPT_STREAM_HINTS
-    __stcs(p, v);
-#else
-    *p = v;
 #endif
 }
 
@@ -365,22 +361,22 @@ __global__ void __launch_bounds__(kThreads, FEAT == 0u ? MPT_SHADE_MIN_BLOCKS : 
             const bool lit = valid && rc.max_path_length > 1 && nee_environment<FEAT>(S, sp, d, rng.state, throughput, medium, so, sd, sc);
             const uint32_t si = queue_push_index(lit, &ctr->scount[1]);
             if (lit) {
-                stq(&pb.sq_o[si], make_float4(so.x, so.y, so.z, 0.f));
-                stq(&pb.sq_d[si], make_float4(sd.x, sd.y, sd.z, __uint_as_float(origin_tri))); // the triangle the shadow ray leaves
-                stq(&pb.sq_c[si], make_float4(sc.x, sc.y, sc.z, __uint_as_float(slot)));
+                pb.sq_o[si] = make_float4(so.x, so.y, so.z, 0.f);
+                pb.sq_d[si] = make_float4(sd.x, sd.y, sd.z, __uint_as_float(origin_tri)); // the triangle the shadow ray leaves
+                pb.sq_c[si] = make_float4(sc.x, sc.y, sc.z, __uint_as_float(slot));
             }
         }
         if (valid && rc.max_path_length > 1) alive = scatter<FEAT>(sp, d, rng, throughput, ior, medium, no, nd, pdf);
         const uint32_t qi = queue_push_index(alive, &ctr->qcount[1]);
         if (alive) {
-            stq(&pb.q_o[0][qi], make_float4(no.x, no.y, no.z, __uint_as_float(slot)));
-            stq(&pb.q_d[0][qi], make_float4(nd.x, nd.y, nd.z, NEE ? pdf : __uint_as_float(origin_tri)));
+            pb.q_o[0][qi] = make_float4(no.x, no.y, no.z, __uint_as_float(slot));
+            pb.q_d[0][qi] = make_float4(nd.x, nd.y, nd.z, NEE ? pdf : __uint_as_float(origin_tri));
         }
         if (valid) {
-            stq(&pb.rad[slot], make_float4(radiance0.x, radiance0.y, radiance0.z, __uint_as_float(rng.state)));
+            pb.rad[slot] = make_float4(radiance0.x, radiance0.y, radiance0.z, __uint_as_float(rng.state));
             if (alive) {
-                stq(&pb.thr[slot], make_float4(throughput.x, throughput.y, throughput.z, ior));
-                if (FEAT & F_TRANSMISSION) stq(&pb.med[slot], make_float4(medium.x, medium.y, medium.z, 0.f));
+                pb.thr[slot] = make_float4(throughput.x, throughput.y, throughput.z, ior);
+                if (FEAT & F_TRANSMISSION) pb.med[slot] = make_float4(medium.x, medium.y, medium.z, 0.f);
             }
         }
     }
@@ -430,27 +426,27 @@ __global__ void __launch_bounds__(kThreads, (!COUNT && !MEDIUM && !TWO_LEVEL && 
             base = __shfl_sync(0xFFFFFFFFu, base, leader);
             if (is_hit) {
                 const uint32_t hi = base + __popc(hm & ((1u << lane_id()) - 1u));
-                stq(&pb.hq_hit[hi], make_uint4(T.hit.tri, T.hit.instance, __float_as_uint(T.hit.u), __float_as_uint(T.hit.v)));
+                pb.hq_hit[hi] = make_uint4(T.hit.tri, T.hit.instance, __float_as_uint(T.hit.u), __float_as_uint(T.hit.v));
                 const f3 rd = T.dir();
-                stq(&pb.hq_dir[hi], make_float4(rd.x, rd.y, rd.z, __uint_as_float(slot)));
-                if (MEDIUM) { const f3 ro = T.org(); stq(&pb.hq_org[hi], make_float4(ro.x, ro.y, ro.z, 0.f)); }
+                pb.hq_dir[hi] = make_float4(rd.x, rd.y, rd.z, __uint_as_float(slot));
+                if (MEDIUM) { const f3 ro = T.org(); pb.hq_org[hi] = make_float4(ro.x, ro.y, ro.z, 0.f); }
             }
         }
         if (finished && !is_hit && S.env_type != 0u) {
             // miss: _make_environment_map_shading_point (scene.slang:482-498) + render_pt.slang:84-86; the path ends
-            const float4 th = ldq(&pb.thr[slot]);
+            const float4 th = pb.thr[slot];
             f3 throughput = mk3(th.x, th.y, th.z);
             if (MEDIUM) {
-                const float4 m = ldq(&pb.med[slot]);
+                const float4 m = pb.med[slot];
                 if (m.x != 0.f || m.y != 0.f || m.z != 0.f) throughput *= vexp(-(kEnvDistance * length(T.dir())) * mk3(m.x, m.y, m.z));
             }
             f3 e = throughput * env_eval(S, T.dir());
             if (NEE) e = e * (pdf_bsdf / (pdf_bsdf + env_pdf(S, T.dir()))); // balance heuristic against nee_environment
-            float4 ra = ldq(&pb.rad[slot]);
+            float4 ra = pb.rad[slot];
             ra.x += e.x;
             ra.y += e.y;
             ra.z += e.z;
-            stq(&pb.rad[slot], ra);
+            pb.rad[slot] = ra;
         }
         finished = false;
         // ---- refill idle lanes
@@ -495,37 +491,45 @@ __global__ void __launch_bounds__(kThreads, (!COUNT && !MEDIUM && !TWO_LEVEL && 
 // --------------------------------------------------------------------------------------- wavefront: extend, pooled form
 // The organisation described in bvh8_traverse_pooled.cuh: per-warp ray pool in shared memory, converged retire + refill + ray setup,
 // divergent traversal in which a finished lane swaps its record for a READY one with two shared-memory atomics.
+// Measured on C3 (profiles/r02a_*): node test 27.0 of 32 lanes (round 1: 22.8), extend 36.6 -> 32.9 ms per frame with the stack in
+// local memory; shared memory is taken from L1, and every KB costs: READY 32 instead of 16: +1.7 %, 4 / 8 stack entries per lane in
+// shared memory: +4.5 % / +4.1 %; READY 8: +6 % (the pool runs dry), READY 24: +3 %. 48-byte records (direction and path slot re-read
+// from the queue when the ray retires) were slower than 64-byte ones: the converged phase then chains two dependent DRAM latencies.
+// Postponing the primitive section to every 2nd / 4th loop iteration: +7 % / +34 % (the hit distance lags, rays take more iterations).
 #ifndef MPT_POOL_READY
 #define MPT_POOL_READY 16 // READY records per warp on top of the 32 a warp can be traversing
 #endif
 #ifndef MPT_POOL_SMEM_STACK
-#define MPT_POOL_SMEM_STACK 4 // traversal-stack entries per lane kept in shared memory (deeper ones spill to local memory)
+#define MPT_POOL_SMEM_STACK 0 // traversal-stack entries per lane kept in shared memory (the rest: local memory, i.e. L1)
 #endif
 template <bool COUNT, bool MEDIUM, bool TWO_LEVEL, bool NEE>
 __global__ void __launch_bounds__(kThreads, (!COUNT && !MEDIUM && !TWO_LEVEL && !NEE) ? MPT_EXTEND_PLAIN_MIN_BLOCKS : MPT_EXTEND_MIN_BLOCKS)
 k_extend_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ q_o, const float4* __restrict__ q_d, PathBuffers pb, uint32_t bounce, uint32_t mask,
                 ExtendTune tune, Counters* ctr) {
     constexpr int NE = 32 + MPT_POOL_READY, SS = MPT_POOL_SMEM_STACK, kWarps = kThreads / 32;
+    using Trav = TraversalP<COUNT, TWO_LEVEL, MaterialAlphaTest, SS, kThreads>;
+    using Entry = PoolEntry;
     struct Pool {
-        PoolEntry e[NE];
+        Entry e[NE];
         uint8_t ready[NE], done[NE];
         int ready_head, ready_n, done_n, pad;
     };
     __shared__ Pool s_pool[kWarps];
-    __shared__ uint2 s_stack[(SS > 0 ? SS : 1) * kThreads];
+    __shared__ uint2 s_stack[(SS > 0 ? SS : 1) * (SS > 0 ? kThreads : 1)];
     const uint32_t n = ctr->qcount[bounce];
     const uint32_t lane = lane_id();
     const uint32_t lt = (1u << lane) - 1u;
     Pool& P = s_pool[threadIdx.x >> 5];
     uint2 lstack[kStackSize - SS];
     MaterialAlphaTest at{&S};
-    TraversalP<COUNT, TWO_LEVEL, MaterialAlphaTest, SS, kThreads> T(S.accel, at, s_stack + threadIdx.x, lstack);
+    Trav T(S.accel, at, s_stack + (SS > 0 ? threadIdx.x : 0), lstack);
     const uint32_t scene_flags = TWO_LEVEL ? 0u : S.accel.instances[0].mask_flags;
     const bool scene_masked = !TWO_LEVEL && ((scene_flags & 0xFFu) & mask) == 0u; // the only instance is masked out: every ray misses
+    constexpr uint32_t kNoRay = 0xFFFFFFFFu;
 
-    // every record starts on the DONE list, marked empty (slot kMiss)
+    // every record starts on the DONE list, marked empty (path slot kNoRay)
     for (int i = int(lane); i < NE; i += 32) {
-        P.e[i].a.w = __uint_as_float(kMiss);
+        P.e[i].a.w = __uint_as_float(kNoRay);
         P.done[i] = uint8_t(i);
     }
     if (lane == 0) { P.done_n = NE; P.ready_head = 0; P.ready_n = 0; }
@@ -548,20 +552,18 @@ k_extend_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ 
             const int i = r * 32 + int(lane);
             const bool have = i < nd;
             const uint32_t e = have ? uint32_t(P.done[i]) : 0u;
-            PoolEntry& E = P.e[e];
+            Entry& E = P.e[e];
             // ---- retire
-            uint32_t slot = kMiss;
+            const uint32_t slot = have ? __float_as_uint(E.a.w) : kNoRay;
+            const bool is_ray = slot != kNoRay;
             uint4 h = make_uint4(kMiss, kMiss, 0u, 0u);
             float4 dir = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (have) {
-                slot = __float_as_uint(E.a.w);
-                if (slot != kMiss) {
-                    const float4 hb = E.b;
-                    h = make_uint4(__float_as_uint(hb.x), __float_as_uint(hb.y), __float_as_uint(hb.z), __float_as_uint(hb.w));
-                    dir = E.d;
-                }
+            if (is_ray) {
+                const float4 hb = E.b;
+                h = make_uint4(__float_as_uint(hb.x), __float_as_uint(hb.y), __float_as_uint(hb.z), __float_as_uint(hb.w));
+                dir = E.d; // direction | the BSDF pdf (NEE)
             }
-            const bool is_ray = slot != kMiss, is_hit = is_ray && h.y != kMiss;
+            const bool is_hit = is_ray && h.y != kMiss;
             const uint32_t hm = __ballot_sync(0xFFFFFFFFu, is_hit);
             if (hm) {
                 uint32_t hb = 0;
@@ -569,27 +571,27 @@ k_extend_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ 
                 hb = __shfl_sync(0xFFFFFFFFu, hb, 0);
                 if (is_hit) {
                     const uint32_t hi = hb + __popc(hm & lt);
-                    stq(&pb.hq_hit[hi], h);
-                    stq(&pb.hq_dir[hi], make_float4(dir.x, dir.y, dir.z, __uint_as_float(slot)));
-                    if (MEDIUM) { const float4 oa = E.a; stq(&pb.hq_org[hi], make_float4(oa.x, oa.y, oa.z, 0.f)); }
+                    pb.hq_hit[hi] = h;
+                    pb.hq_dir[hi] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(slot));
+                    if (MEDIUM) { const float4 oa = E.a; pb.hq_org[hi] = make_float4(oa.x, oa.y, oa.z, 0.f); }
                 }
             }
             if (is_ray && !is_hit && S.env_type != 0u) {
                 // miss: _make_environment_map_shading_point (scene.slang:482-498) + render_pt.slang:84-86; the path ends
                 const f3 rd = mk3(dir.x, dir.y, dir.z);
-                const float4 th = ldq(&pb.thr[slot]);
+                const float4 th = pb.thr[slot];
                 f3 throughput = mk3(th.x, th.y, th.z);
                 if (MEDIUM) {
-                    const float4 m = ldq(&pb.med[slot]);
+                    const float4 m = pb.med[slot];
                     if (m.x != 0.f || m.y != 0.f || m.z != 0.f) throughput *= vexp(-(kEnvDistance * length(rd)) * mk3(m.x, m.y, m.z));
                 }
                 f3 ev = throughput * env_eval(S, rd);
                 if (NEE) ev = ev * (dir.w / (dir.w + env_pdf(S, rd))); // balance heuristic against nee_environment
-                float4 ra = ldq(&pb.rad[slot]);
+                float4 ra = pb.rad[slot];
                 ra.x += ev.x;
                 ra.y += ev.y;
                 ra.z += ev.z;
-                stq(&pb.rad[slot], ra);
+                pb.rad[slot] = ra;
             }
             // ---- refill: the i-th DONE record takes the i-th ray of this warp's claim
             bool filled = false;
@@ -600,27 +602,28 @@ k_extend_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ 
                     if (scene_masked) {
                         if (S.env_type != 0u) { // same miss shading as above (no medium can be active: nothing was ever hit)
                             const uint32_t sl = __float_as_uint(ro.w);
-                            const float4 th = ldq(&pb.thr[sl]);
+                            const float4 th = pb.thr[sl];
                             f3 ev = mk3(th.x, th.y, th.z) * env_eval(S, xyz(rd));
                             if (NEE) ev = ev * (rd.w / (rd.w + env_pdf(S, xyz(rd))));
-                            float4 ra = ldq(&pb.rad[sl]);
+                            float4 ra = pb.rad[sl];
                             ra.x += ev.x;
                             ra.y += ev.y;
                             ra.z += ev.z;
-                            stq(&pb.rad[sl], ra);
+                            pb.rad[sl] = ra;
                         }
                     } else {
                         RaySetup R;
                         setup_ray(R, xyz(ro), xyz(rd));
-                        E.a = ro; // origin | slot
-                        E.b = make_float4(R.idir.x, R.idir.y, R.idir.z, __uint_as_float(R.octinv4));
+                        const uint32_t oct = 7u - (R.octinv4 & 0xFFu);
+                        E.a = ro; // origin | path slot
+                        E.b = make_float4(R.idir.x, R.idir.y, R.idir.z, rd.w); // rd.w: the triangle the ray leaves (the BSDF pdf with NEE)
                         E.c = make_float4(R.shear.Sx, R.shear.Sy, R.shear.Sz,
-                                          __uint_as_float(uint32_t(R.shear.kx) | (uint32_t(R.shear.ky) << 2) | (uint32_t(R.shear.kz) << 4)));
-                        E.d = rd; // direction | triangle the ray leaves (or the BSDF pdf with NEE)
+                                          __uint_as_float(uint32_t(R.shear.kx) | (uint32_t(R.shear.ky) << 2) | (uint32_t(R.shear.kz) << 4) | (oct << 8)));
+                        E.d = rd;
                         filled = true;
                     }
                 }
-                if (!filled) E.a.w = __uint_as_float(kMiss);
+                if (!filled) E.a.w = __uint_as_float(kNoRay);
             }
             const uint32_t fm = __ballot_sync(0xFFFFFFFFu, filled);
             if (filled) P.ready[nready + __popc(fm & lt)] = uint8_t(e);
@@ -633,7 +636,7 @@ k_extend_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ 
         const int k = __popc(idle & lt);
         if (!active && k < nready) {
             my = P.ready[k];
-            T.start(&P.e[my], mask, scene_flags, NEE ? kMiss : __float_as_uint(P.e[my].d.w));
+            T.start(&P.e[my], mask, scene_flags, !NEE);
             active = true;
         }
         if (lane == 0) {
@@ -647,14 +650,14 @@ k_extend_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ 
         // ======================================================= divergent: traverse; a finished lane swaps its record for a READY one
         while (active) {
             if (T.step()) {
-                PoolEntry& E = P.e[my];
+                Entry& E = P.e[my];
                 const bool f = T.found();
                 E.b = make_float4(__uint_as_float(f ? T.hit.tri : kMiss), __uint_as_float(T.hit.instance), T.hit.u, T.hit.v);
                 P.done[atomicAdd(&P.done_n, 1)] = uint8_t(my);
                 const int kk = atomicAdd(&P.ready_head, 1);
                 if (kk < ready_n) {
                     my = P.ready[kk];
-                    T.start(&P.e[my], mask, scene_flags, NEE ? kMiss : __float_as_uint(P.e[my].d.w));
+                    T.start(&P.e[my], mask, scene_flags, !NEE);
                 } else {
                     active = false;
                     break;
@@ -689,11 +692,11 @@ __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_shadow(cons
         if (finished && !T.found()) {
             const float4 c = ldq(pb.sq_c + j);
             const uint32_t slot = __float_as_uint(c.w);
-            float4 ra = ldq(&pb.rad[slot]); // one shadow ray per slot and bounce: no race
+            float4 ra = pb.rad[slot]; // one shadow ray per slot and bounce: no race
             ra.x += c.x;
             ra.y += c.y;
             ra.z += c.z;
-            stq(&pb.rad[slot], ra);
+            pb.rad[slot] = ra;
         }
         finished = false;
         const uint32_t need = __ballot_sync(0xFFFFFFFFu, !active && !exhausted);
@@ -885,14 +888,14 @@ __global__ void __launch_bounds__(kThreads, FEAT == 0u ? MPT_SHADE_MIN_BLOCKS : 
             hr.u = __uint_as_float(hw.z);
             hr.v = __uint_as_float(hw.w);
             slot = __float_as_uint(rd.w);
-            const float4 th = ldq(&pb.thr[slot]);
-            const float4 ra = ldq(&pb.rad[slot]);
+            const float4 th = pb.thr[slot];
+            const float4 ra = pb.rad[slot];
             throughput = mk3(th.x, th.y, th.z);
             ior = th.w;
             const f3 d = xyz(rd);
             f3 o = mk3(0.f);
             if (FEAT & F_TRANSMISSION) {
-                const float4 m = ldq(&pb.med[slot]);
+                const float4 m = pb.med[slot];
                 medium = mk3(m.x, m.y, m.z);
                 o = xyz(ldq(pb.hq_org + j));
             }
@@ -907,23 +910,23 @@ __global__ void __launch_bounds__(kThreads, FEAT == 0u ? MPT_SHADE_MIN_BLOCKS : 
             Rng rng = make_pcg(__float_as_uint(ra.w));
             if (NEE && more) lit = nee_environment<FEAT>(S, sp, d, rng.state, throughput, medium, so, sd, sc);
             if (more) alive = scatter<FEAT>(sp, d, rng, throughput, ior, medium, no, nd, pdf);
-            stq(&pb.rad[slot], make_float4(radiance.x, radiance.y, radiance.z, __uint_as_float(rng.state)));
+            pb.rad[slot] = make_float4(radiance.x, radiance.y, radiance.z, __uint_as_float(rng.state));
             if (alive) {
-                stq(&pb.thr[slot], make_float4(throughput.x, throughput.y, throughput.z, ior));
-                if (FEAT & F_TRANSMISSION) stq(&pb.med[slot], make_float4(medium.x, medium.y, medium.z, 0.f));
+                pb.thr[slot] = make_float4(throughput.x, throughput.y, throughput.z, ior);
+                if (FEAT & F_TRANSMISSION) pb.med[slot] = make_float4(medium.x, medium.y, medium.z, 0.f);
             }
         }
         const uint32_t qi = queue_push_index(alive, &ctr->qcount[bounce + 1]);
         if (alive) {
-            stq(&pb.q_o[out][qi], make_float4(no.x, no.y, no.z, __uint_as_float(slot)));
-            stq(&pb.q_d[out][qi], make_float4(nd.x, nd.y, nd.z, NEE ? pdf : __uint_as_float(origin_tri)));
+            pb.q_o[out][qi] = make_float4(no.x, no.y, no.z, __uint_as_float(slot));
+            pb.q_d[out][qi] = make_float4(nd.x, nd.y, nd.z, NEE ? pdf : __uint_as_float(origin_tri));
         }
         if (NEE) {
             const uint32_t si = queue_push_index(lit, &ctr->scount[bounce + 1]);
             if (lit) {
-                stq(&pb.sq_o[si], make_float4(so.x, so.y, so.z, 0.f));
-                stq(&pb.sq_d[si], make_float4(sd.x, sd.y, sd.z, __uint_as_float(origin_tri)));
-                stq(&pb.sq_c[si], make_float4(sc.x, sc.y, sc.z, __uint_as_float(slot)));
+                pb.sq_o[si] = make_float4(so.x, so.y, so.z, 0.f);
+                pb.sq_d[si] = make_float4(sd.x, sd.y, sd.z, __uint_as_float(origin_tri));
+                pb.sq_c[si] = make_float4(sc.x, sc.y, sc.z, __uint_as_float(slot));
             }
         }
     }
@@ -1024,7 +1027,7 @@ __global__ void __launch_bounds__(kThreads) k_resolve(RenderConst rc, PathBuffer
         m2 = prev.w;
     }
     for (uint32_t k = 0; k < rc.pass_k; k++) {
-        const float4 r = ldq(&pb.rad[k * rc.npix + pix]);
+        const float4 r = pb.rad[k * rc.npix + pix];
         const f3 contrib = mk3(r.x, r.y, r.z) / demod;
         if (finite3(contrib)) { // !any(isnan) && !any(isinf), render_pt.slang:117
             irr += contrib;

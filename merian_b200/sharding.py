@@ -58,3 +58,63 @@ def render_sharded(render, cam, params: abi.RenderParams, rank: int, world: int,
     if total > 0 and not (params.flags & abi.RENDER_OUTPUT_SUM):
         out.mul_(1.0 / total)
     return out
+
+
+class ShardComm:
+    """The library's own NCCL path (mpt_comm_* / mpt_reduce_* of include/mpt.h): one communicator + side stream per process.
+
+    `exchange_id(id_bytes_or_None) -> bytes` distributes rank 0's NCCL unique id to the other ranks out of band (torch.distributed
+    broadcast in bench.py; a C++ host would use its own channel). The reduce runs on the library's side stream behind the render."""
+
+    def __init__(self, device: int, rank: int, world: int, exchange_id):
+        import ctypes as C
+
+        from ._lib import MptError, lib
+        self.l, self.rank, self.world = lib(), rank, world
+        buf = (C.c_uint8 * abi.COMM_UNIQUE_ID_BYTES)()
+        if rank == 0:
+            st = self.l.mpt_comm_unique_id(buf)
+            if st != abi.MPT_OK:
+                raise MptError(st, self.l.mpt_comm_last_error(None).decode())
+        raw = exchange_id(bytes(buf) if rank == 0 else None)
+        buf = (C.c_uint8 * abi.COMM_UNIQUE_ID_BYTES).from_buffer_copy(raw)
+        self.h = C.c_void_p()
+        st = self.l.mpt_comm_create(device, buf, rank, world, C.byref(self.h))
+        if st != abi.MPT_OK:
+            raise MptError(st, self.l.mpt_comm_last_error(None).decode())
+
+    def _check(self, st):
+        if st != abi.MPT_OK:
+            from ._lib import MptError
+            raise MptError(st, self.l.mpt_comm_last_error(self.h).decode())
+
+    def reduce_begin(self, partial_sum, out, width, height, spp_total, root=0, flags=0, stream=None, h_out=None):
+        """partial_sum / out: torch CUDA tensors (H, W, 4) float32; h_out: pinned host tensor or None."""
+        import ctypes as C
+
+        import torch
+        st = stream if stream is not None else torch.cuda.current_stream(partial_sum.device).cuda_stream
+        self._check(self.l.mpt_reduce_begin(self.h, C.c_void_p(partial_sum.data_ptr()), C.c_void_p(out.data_ptr()) if out is not None else None,
+                                            C.c_void_p(h_out.data_ptr()) if h_out is not None else None, width, height, spp_total, root, flags,
+                                            C.c_void_p(st)))
+
+    def reduce_end(self, stream=None):
+        import ctypes as C
+
+        import torch
+        st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
+        self._check(self.l.mpt_reduce_end(self.h, C.c_void_p(st)))
+
+    def reduce_wait(self):
+        self._check(self.l.mpt_reduce_wait(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.l.mpt_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
