@@ -373,6 +373,12 @@ MPT_API mpt_status mpt_set_profiling(mpt_context* ctx, uint32_t profile_flags);
 MPT_API mpt_status mpt_get_stats(mpt_context* ctx, mpt_stats* out);
 MPT_API mpt_status mpt_reset_stats(mpt_context* ctx);
 
+/* Measurement hook (bench.py, tests): copies to the host the ray queue that the LAST extend launch of the last rendered frame consumed,
+ * i.e. the continuation rays of bounce = max_path_length - 1 of that frame's last pass (earlier queues have been overwritten by then).
+ * h_leaves (nullable) receives, per ray, the triangle record the ray starts on (the device does not test it; undefined for NEE frames).
+ * *count = rays in that queue; at most `capacity` are copied. SURVEY.md §8(d): the oracle counts nodes / triangles per ray on these rays. */
+MPT_API mpt_status mpt_debug_ray_queue(mpt_context* ctx, uint32_t bounce, mpt_ray* h_rays, uint32_t* h_leaves, uint64_t capacity, uint64_t* count);
+
 /* Introspection used by tests and DESIGN.md figures. */
 typedef struct mpt_bvh_info {
     uint64_t node_count;     /* 80-byte BVH8 nodes over all BLAS + TLAS */

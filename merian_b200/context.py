@@ -171,6 +171,18 @@ class Context:
     def reset_stats(self):
         self._check(self.l.mpt_reset_stats(self.h))
 
+    def debug_ray_queue(self, bounce, capacity=None):
+        """The continuation rays the last extend launch of the last frame consumed (bounce = max_path_length - 1) and the triangle
+        record each of them starts on. Returns (rays RAY_DTYPE array, leaves uint32 array)."""
+        n = C.c_uint64(0)
+        self._check(self.l.mpt_debug_ray_queue(self.h, bounce, None, None, 0, C.byref(n)))
+        m = int(n.value) if capacity is None else min(int(n.value), capacity)
+        rays = np.zeros(m, abi.RAY_DTYPE)
+        leaves = np.zeros(m, np.uint32)
+        if m:
+            self._check(self.l.mpt_debug_ray_queue(self.h, bounce, _hp(rays), _hp(leaves), m, C.byref(n)))
+        return rays, leaves
+
     def bvh_info(self) -> abi.BvhInfo:
         b = abi.BvhInfo()
         self._check(self.l.mpt_bvh_get_info(self.h, C.byref(b)))

@@ -19,7 +19,11 @@ struct alignas(16) Bvh8Node {
     uint8_t imask;            // bit i set: child slot i is an internal node
     uint32_t child_base;      // index of the first internal child (absolute into the node array)
     uint32_t prim_base;       // index of the first primitive record referenced by leaf children (absolute)
-    uint8_t meta[8];          // internal: 0b001sssss with sssss = 24 + slot; leaf: unary count (1,3,7) << 5 | offset; empty: 0
+    uint32_t leaf_bits;       // 3 bits per child slot s at 3s: unary count (1, 3, 7) of a leaf child's primitives, 0 for inner / empty slots.
+                              // The records of the leaf children lie back to back in slot order from prim_base: the primitive at bit b
+                              // is record prim_base + popcount(leaf_bits & ((1 << b) - 1)). Fixed bit positions let the traversal turn
+                              // its 8-bit "child hit" mask into primitive bits with three shift-or steps instead of a shift per child.
+    uint32_t reserved;
     uint8_t qlox[8], qloy[8], qloz[8];
     uint8_t qhix[8], qhiy[8], qhiz[8];
 };

@@ -338,7 +338,7 @@ static void build_bvh8_once(const Box* boxes, uint32_t n, Bvh8& out, int max_lea
         const double sc[3] = {std::ldexp(1.0, int(node.ex) - 127), std::ldexp(1.0, int(node.ey) - 127), std::ldexp(1.0, int(node.ez) - 127)};
         node.child_base = uint32_t(out.nodes.size());
         node.prim_base = uint32_t(out.prim_order.size());
-        uint32_t n_internal = 0, prim_off = 0;
+        uint32_t n_internal = 0;
         uint8_t* qlo[3] = {node.qlox, node.qloy, node.qloz};
         uint8_t* qhi[3] = {node.qhix, node.qhiy, node.qhiz};
         for (int s = 0; s < 8; s++) {
@@ -353,13 +353,11 @@ static void build_bvh8_once(const Box* boxes, uint32_t n, Bvh8& out, int max_lea
             }
             if (!ch_leaf[c]) {
                 node.imask |= uint8_t(1u << s);
-                node.meta[s] = uint8_t((1u << 5) | (24u + uint32_t(s)));
                 n_internal++;
             } else {
                 const uint32_t unary = (1u << cn.rcount) - 1u; // 1, 3, 7
-                node.meta[s] = uint8_t((unary << 5) | prim_off);
+                node.leaf_bits |= unary << (3 * s);
                 for (uint32_t k = 0; k < cn.rcount; k++) out.prim_order.push_back(b2.idx[cn.rfirst + k]);
-                prim_off += cn.rcount;
             }
         }
         out.nodes[t.wide] = node;

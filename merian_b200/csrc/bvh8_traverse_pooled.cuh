@@ -29,88 +29,51 @@ struct alignas(16) PoolEntry {
     float4 d; // direction.xyz | the queue record's w lane again (with NEE: the BSDF pdf)
 };
 
-// One node test: visits the child at `bit` of a node group (child_base, parent_imask), intersects its 8 child boxes and returns the new
-// node group G and the primitives it uncovered (fresh; fresh.y == 0: none). Same arithmetic as Traversal::step section 1 (comments there).
-// TMIN_ZERO: the ray's tmin is 0 (continuation rays), the lower clamp is the 0 already inside tn.
-template <bool TMIN_ZERO>
-MPT_DEV void bvh8_node_test(const AccelView& A, uint32_t child_base, uint32_t parent_imask, uint32_t bit, f3 o, f3 idir, uint32_t octinv4, float tlo, float thi,
-                            uint2& G, uint2& fresh) {
-    const uint32_t slot = (bit - 24u) ^ (octinv4 & 0xFFu);
-    const uint32_t rel = __popc(parent_imask & ~(0xFFFFFFFFu << slot));
-    const uint32_t ni = child_base + rel;
-    const float4* np = A.nodes + size_t(ni) * 5;
-    const float4 n0 = __ldg(np + 0), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-    const uint32_t eimask = __float_as_uint(n0.w);
-    const float aix = __uint_as_float((eimask & 0xFFu) << 23) * idir.x;
-    const float aiy = __uint_as_float(((eimask >> 8) & 0xFFu) << 23) * idir.y;
-    const float aiz = __uint_as_float(((eimask >> 16) & 0xFFu) << 23) * idir.z;
-    const float ox = fmaf(-32768.0f, aix, (n0.x - o.x) * idir.x);
-    const float oy = fmaf(-32768.0f, aiy, (n0.y - o.y) * idir.y);
-    const float oz = fmaf(-32768.0f, aiz, (n0.z - o.z) * idir.z);
-    const float ex = 0.00390625f * fabsf(aix), ey = 0.00390625f * fabsf(aiy), ez = 0.00390625f * fabsf(aiz);
-    const float oxn = ox - ex, oxf = ox + ex, oyn = oy - ey, oyf = oy + ey, ozn = oz - ez, ozf = oz + ez;
-    const uint32_t bias = A.prmt_bias;
-    const uint32_t imask = eimask >> 24;
-    uint32_t hitmask = 0;
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
-        const uint32_t meta4 = __float_as_uint(half ? n1.w : n1.z);
-        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
-        const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
-        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-        const uint32_t qlox = __float_as_uint(half ? n2.y : n2.x), qloy = __float_as_uint(half ? n2.w : n2.z);
-        const uint32_t qloz = __float_as_uint(half ? n3.y : n3.x), qhix = __float_as_uint(half ? n3.w : n3.z);
-        const uint32_t qhiy = __float_as_uint(half ? n4.y : n4.x), qhiz = __float_as_uint(half ? n4.w : n4.z);
-        const uint32_t nearx = idir.x < 0.f ? qhix : qlox, farx = idir.x < 0.f ? qlox : qhix;
-        const uint32_t neary = idir.y < 0.f ? qhiy : qloy, fary = idir.y < 0.f ? qloy : qhiy;
-        const uint32_t nearz = idir.z < 0.f ? qhiz : qloz, farz = idir.z < 0.f ? qloz : qhiz;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const float t0x = fmaf(byte_biased(nearx, bias, j), aix, oxn), t1x = fmaf(byte_biased(farx, bias, j), aix, oxf);
-            const float t0y = fmaf(byte_biased(neary, bias, j), aiy, oyn), t1y = fmaf(byte_biased(fary, bias, j), aiy, oyf);
-            const float t0z = fmaf(byte_biased(nearz, bias, j), aiz, ozn), t1z = fmaf(byte_biased(farz, bias, j), aiz, ozf);
-            const float tn = fmaxf(fmaxf(t0x, t0y), fmaxf(t0z, 0.f)) * 0.9999995f;
-            const float tf = fminf(fminf(t1x, t1y), t1z) * 1.0000005f;
-            if ((TMIN_ZERO ? tn : fmaxf(tn, tlo)) <= fminf(tf, thi)) {
-                const uint32_t cb = (child_bits4 >> (8 * j)) & 0xFFu;
-                const uint32_t bi = (bit_index4 >> (8 * j)) & 0xFFu;
-                hitmask |= cb << bi;
-            }
-        }
-    }
-    G.x = __float_as_uint(n1.x);
-    G.y = (hitmask & 0xFF000000u) | imask;
-    fresh = make_uint2(__float_as_uint(n1.y), hitmask & 0x00FFFFFFu);
-}
+// Resumable closest-hit traversal fed from a per-warp ray pool. One step() = at most one node test and one primitive test, as in
+// Traversal (bvh8_traverse.cuh), with two differences: node groups and parked primitive groups live on SEPARATE stacks — refilling the
+// current groups is then a pair of predicated pops instead of a loop that has to tell the entry kinds apart (10 % of the round-1
+// kernel's instructions, at 8.6 of 32 lanes) — and the shear constants of the watertight test are read from the ray record when a
+// triangle is tested (single-level scenes) instead of occupying registers through the node tests.
+// SS = node-stack entries kept in shared memory (per lane, stride STRIDE uint2); 0 = all in local memory (measured best, see k_extend_pooled).
+constexpr int kPrimStackSize = 24; // parked primitive groups: at most one per node test while another group is pending
 
-// Resumable closest-hit traversal fed from a WarpPool. SS = stack entries kept in shared memory (per lane, stride STRIDE uint2).
 template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struct TraversalP {
     const AccelView& A;
     const AlphaTest& alpha_test;
-    uint2* sst;            // shared-memory part of the stack: entry i at sst[i * STRIDE]
-    uint2* lst;            // local-memory overflow: entry i >= SS at lst[i - SS]
+    uint2* sst;            // shared-memory part of the node stack: entry i at sst[i * STRIDE]
+    uint2* lst;            // local-memory part: entry i >= SS at lst[i - SS]
+    uint4* pst;            // parked primitive groups (local memory): first record | hits (slot space) + stack height << 24 | leaf_bits | -
     const PoolEntry* ent;  // the record this lane is traversing
     f3 o, idir;            // current-space ray (object space inside an instance)
-    uint32_t octinv4;
+    uint32_t perm;         // make_perm(octant) of the current-space ray
     Shear shear;           // TWO_LEVEL only (registers); single-level scenes read the record's shear when a triangle is tested
     float best_t;
     uint32_t ray_mask;
-    int sp;
-    uint2 G, Gt;
+    int sp, psp, pbase;    // node stack pointer; primitive stack pointer and its floor inside the current instance
+    uint2 G;               // current node group: x = first inner child, y = hits << 24 | imask
+    uint2 Gt;              // pending primitive group: x = first primitive record of its node, y = hit primitives (slot-space bits)
+    uint32_t Gv;           //   ... and the node's leaf_bits: the primitive at bit b is record Gt.x + popc(Gv & ((1 << b) - 1)). Kept in a
+                           //   register: re-reading it from the node when a primitive is tested put a second dependent load in front of
+                           //   the triangle fetch (long-scoreboard stalls per issue 2.3 -> 3.9, extend +3.5 %, profiles/r02d_*)
     bool in_blas, force_opaque;
     int cull;
     uint32_t cur_instance;
     HitRec hit;
     uint32_t n_nodes, n_tris;
 
-    MPT_DEV TraversalP(const AccelView& a, const AlphaTest& at, uint2* s, uint2* l) : A(a), alpha_test(at), sst(s), lst(l), ent(nullptr), n_nodes(0), n_tris(0) {}
+    MPT_DEV TraversalP(const AccelView& a, const AlphaTest& at, uint2* s, uint2* l, uint4* p)
+        : A(a), alpha_test(at), sst(s), lst(l), pst(p), ent(nullptr), n_nodes(0), n_tris(0) {}
     MPT_DEV bool found() const { return hit.instance != kMiss; }
 
     MPT_DEV void push(uint2 v) {
         if (SS > 0 && sp < SS) sst[sp * STRIDE] = v;
         else lst[sp - SS] = v;
         sp++;
+    }
+    MPT_DEV void unpark() {
+        const uint4 p = pst[--psp];
+        Gt = make_uint2(p.x, p.y & 0x00FFFFFFu);
+        Gv = p.z;
     }
     MPT_DEV uint2 top() const { return (SS > 0 && sp - 1 < SS) ? sst[(sp - 1) * STRIDE] : lst[sp - 1 - SS]; }
 
@@ -120,7 +83,7 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
         o = mk3(a.x, a.y, a.z);
         idir = mk3(b.x, b.y, b.z);
         const uint32_t kk = __float_as_uint(c.w);
-        octinv4 = (7u - ((kk >> 8) & 7u)) * 0x01010101u;
+        perm = make_perm((kk >> 8) & 7u);
         if (TWO_LEVEL) {
             shear.Sx = c.x; shear.Sy = c.y; shear.Sz = c.z;
             shear.kx = int(kk & 3u); shear.ky = int((kk >> 2) & 3u); shear.kz = int((kk >> 4) & 3u);
@@ -132,13 +95,14 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
     MPT_DEV void start(const PoolEntry* e, uint32_t mask, uint32_t scene_flags, bool use_skip) {
         ent = e;
         const uint32_t leaves = load_world_setup();
-        const uint32_t skip_tri = use_skip ? leaves : kMiss;
-        best_t = kRayTMaxPooled();
+        best_t = 1e7f; // SCENE_RAY_TMAX, hit.slang:8 (continuation rays: tmin 0)
         ray_mask = mask;
-        hit.tri = TWO_LEVEL ? kMiss : skip_tri;
+        hit.tri = (TWO_LEVEL || !use_skip) ? kMiss : leaves;
         hit.instance = kMiss;
         hit.u = hit.v = 0.f;
         sp = 0;
+        psp = 0;
+        pbase = 0;
         in_blas = !TWO_LEVEL;
         cur_instance = 0;
         cull = 0;
@@ -150,38 +114,44 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
         }
         G = make_uint2(A.root, 0x80000000u);
         Gt = make_uint2(0u, 0u);
+        Gv = 0u;
     }
-    static MPT_DEV float kRayTMaxPooled() { return 1e7f; } // SCENE_RAY_TMAX, hit.slang:8 (continuation rays: tmin 0)
 
     MPT_DEV bool step() {
         // ---------------------------------------------------------------- 1. one node test
         if (G.y & 0xFF000000u) {
             const uint32_t bit = 31u - uint32_t(__clz(G.y));
-            uint2 rest = G;
-            rest.y &= ~(1u << bit);
-            if (rest.y & 0xFF000000u) push(rest);
+            G.y &= ~(1u << bit);
+            if (G.y & 0xFF000000u) push(G);
+            const uint32_t slot = (bit - 24u) ^ (perm >> 24);
+            const uint32_t ni = G.x + uint32_t(__popc(G.y & ~(0xFFFFFFFFu << slot)));
             if (COUNT) n_nodes++;
-            uint2 fresh;
-            bvh8_node_test<true>(A, G.x, G.y & 0xFFu, bit, o, idir, octinv4, 0.f, best_t, G, fresh);
-            if (fresh.y) {
-                if (Gt.y) push(fresh); // one group is already pending: park the new one
-                else Gt = fresh;
+            uint32_t leaf;
+            uint2 pl; // first primitive record, leaf_bits
+            bvh8_node_test<true>(A, ni, o, idir, perm, 0.f, best_t, G, leaf, &pl);
+            if (leaf) {
+                if (Gt.y) pst[psp++] = make_uint4(pl.x, leaf | (uint32_t(sp) << 24), pl.y, 0u); // one group is already pending: park the new one
+                else { Gt = make_uint2(pl.x, leaf); Gv = pl.y; }
             }
         }
-        // the stack top this lane will need in section 3, loaded before the primitive test (single-level scenes: section 2 never pushes)
+        // the node-stack top this lane will need in section 3, loaded before the primitive test so that the local-memory latency hides
+        // behind it (single-level scenes only: entering an instance in section 2 pushes)
         uint2 pre_top = make_uint2(0u, 0u);
         const bool pre_valid = !TWO_LEVEL && (G.y & 0xFF000000u) == 0u && sp > 0;
         if (pre_valid) pre_top = top();
         // ---------------------------------------------------------------- 2. one primitive of the pending group
+        // (all of it when the primitive stack is nearly full, so that parking can never overflow)
         if (Gt.y) {
             do {
                 const uint32_t i = 31u - uint32_t(__clz(Gt.y));
                 Gt.y &= ~(1u << i);
+                const uint32_t rec = Gt.x + uint32_t(__popc(Gv & ((1u << i) - 1u)));
                 if (!TWO_LEVEL || in_blas) {
-                    const uint32_t ti = Gt.x + i;
-                    if (TWO_LEVEL || ti != hit.tri) {
+                    // single-level scenes: not the triangle the ray leaves (nor, trivially, the current closest hit). Two-level scenes test
+                    // everything: the same record index occurs in every instance of a BLAS, so equality with hit.tri says nothing there
+                    if (TWO_LEVEL || rec != hit.tri) {
                         if (COUNT) n_tris++;
-                        const float4* tp = A.tris + size_t(ti) * 3;
+                        const float4* tp = A.tris + size_t(rec) * 3;
                         const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
                         Shear s;
                         if (TWO_LEVEL) {
@@ -194,9 +164,9 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
                         }
                         float t, u, v;
                         if (intersect_triangle(s, o, xyz(a), xyz(b), xyz(c), cull, 0.f, best_t, t, u, v)) {
-                            if (force_opaque || !(__float_as_uint(c.w) & kTriNonOpaque) || !alpha_test(ti, cur_instance, u, v)) {
+                            if (force_opaque || !(__float_as_uint(c.w) & kTriNonOpaque) || !alpha_test(rec, cur_instance, u, v)) {
                                 best_t = t;
-                                hit.tri = ti;
+                                hit.tri = rec;
                                 hit.instance = cur_instance;
                                 hit.u = u;
                                 hit.v = v;
@@ -205,21 +175,24 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
                     }
                 } else {
                     // TLAS leaf: enter the instance
-                    const uint32_t inst = __ldg(A.tlas_prims + Gt.x + i);
+                    const uint32_t inst = __ldg(A.tlas_prims + rec);
                     const InstanceRec* ip = A.instances + inst;
                     const uint4 meta = __ldg(reinterpret_cast<const uint4*>(ip) + 3);
                     if (((meta.z & 0xFFu) & ray_mask) == 0) continue;
                     const float4 r0 = __ldg(&ip->inv0), r1 = __ldg(&ip->inv1), r2 = __ldg(&ip->inv2);
                     if (G.y & 0xFF000000u) push(G);
-                    if (Gt.y) push(Gt);
-                    push(make_uint2(0u, 0u)); // sentinel: leave the instance
+                    if (Gt.y) pst[psp++] = make_uint4(Gt.x, Gt.y | (uint32_t(sp) << 24), Gv, 0u);
+                    push(make_uint2(uint32_t(pbase), 0u)); // sentinel: leave the instance (x = the TLAS level's primitive-stack floor)
+                    pbase = psp;
                     const float4 wa = ent->a, wd = ent->d;
                     const f3 org_w = mk3(wa.x, wa.y, wa.z), dir_w = mk3(wd.x, wd.y, wd.z);
+                    // world -> object, every product and sum rounded separately (no FMA contraction) so that the object-space
+                    // ray, and with it the barycentrics, are bit-identical to a plain IEEE evaluation on the host
                     const f3 oo = mk3(affine_rn(r0, org_w, r0.w), affine_rn(r1, org_w, r1.w), affine_rn(r2, org_w, r2.w));
                     const f3 od = mk3(linear_rn(r0, dir_w), linear_rn(r1, dir_w), linear_rn(r2, dir_w));
                     RaySetup R;
                     setup_ray(R, oo, od);
-                    o = R.o; idir = R.idir; octinv4 = R.octinv4; shear = R.shear;
+                    o = R.o; idir = R.idir; perm = R.perm; shear = R.shear;
                     cur_instance = inst;
                     const uint32_t fl = meta.z >> 8;
                     cull = (fl & 1u) ? 2 : ((fl & 2u) ? 1 : 0);
@@ -228,27 +201,31 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
                     G = make_uint2(meta.x, 0x80000000u);
                     Gt = make_uint2(0u, 0u);
                 }
-            } while (Gt.y && sp > kStackSize - 6);
+            } while (Gt.y && psp > kPrimStackSize - 4);
         }
-        // ---------------------------------------------------------------- 3. refill the groups from the stack
+        // ---------------------------------------------------------------- 3. refill the groups from the stacks
+        // A parked primitive group remembers the node-stack height it was uncovered at (top byte of y): node groups below that height
+        // wait until it has been tested — the order of the single-stack traversal (a group uncovered deeper in the tree is tested before
+        // the walk moves on to the siblings of its ancestors), which keeps the hit distance fresh: taking sibling groups first cost
+        // +1.4 % node tests and +4.6 % triangle tests on C3 (profiles/r02d_ab.jsonl).
+        if (Gt.y == 0u && psp > pbase) unpark();
         bool first_pop = true;
-        while ((G.y & 0xFF000000u) == 0) {
-            if (sp == 0) return Gt.y == 0;
+        while ((G.y & 0xFF000000u) == 0u) {
+            if (sp == 0) return Gt.y == 0u; // nothing left to visit: finished once the pending primitives are done
+            if (psp > pbase && (pst[psp - 1].y >> 24) >= uint32_t(sp)) break;
             const uint2 t = (pre_valid && first_pop) ? pre_top : top();
             first_pop = false;
-            if (t.y & 0xFF000000u) {
+            if (t.y & 0xFF000000u) { // a node group
                 G = t;
                 --sp;
                 break;
             }
-            if (Gt.y) break;
-            --sp;
-            if (t.y) {
-                Gt = t;
-            } else if (TWO_LEVEL) { // sentinel: back to the TLAS with the world-space ray of the record
-                load_world_setup();
-                in_blas = false;
-            }
+            if (!TWO_LEVEL || Gt.y) break; // the sentinel: the instance's pending primitives go first
+            --sp;                          // back to the TLAS with the world-space ray of the record
+            pbase = int(t.x);
+            load_world_setup();
+            in_blas = false;
+            if (psp > pbase) unpark();
         }
         return false;
     }

@@ -521,8 +521,9 @@ k_extend_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ 
     const uint32_t lt = (1u << lane) - 1u;
     Pool& P = s_pool[threadIdx.x >> 5];
     uint2 lstack[kStackSize - SS];
+    uint4 pstack[kPrimStackSize];
     MaterialAlphaTest at{&S};
-    Trav T(S.accel, at, s_stack + (SS > 0 ? threadIdx.x : 0), lstack);
+    Trav T(S.accel, at, s_stack + (SS > 0 ? threadIdx.x : 0), lstack, pstack);
     const uint32_t scene_flags = TWO_LEVEL ? 0u : S.accel.instances[0].mask_flags;
     const bool scene_masked = !TWO_LEVEL && ((scene_flags & 0xFFu) & mask) == 0u; // the only instance is masked out: every ray misses
     constexpr uint32_t kNoRay = 0xFFFFFFFFu;
@@ -614,7 +615,7 @@ k_extend_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ 
                     } else {
                         RaySetup R;
                         setup_ray(R, xyz(ro), xyz(rd));
-                        const uint32_t oct = 7u - (R.octinv4 & 0xFFu);
+                        const uint32_t oct = 7u - (R.perm >> 24);
                         E.a = ro; // origin | path slot
                         E.b = make_float4(R.idir.x, R.idir.y, R.idir.z, rd.w); // rd.w: the triangle the ray leaves (the BSDF pdf with NEE)
                         E.c = make_float4(R.shear.Sx, R.shear.Sy, R.shear.Sz,
@@ -2126,6 +2127,34 @@ MPT_API mpt_status mpt_reset_stats(mpt_context* ctx) {
     harvest_events(ctx);
     ctx->stats = mpt_stats{};
     if (ctx->counters.p) CU(cudaMemset(ctx->counters.p, 0, sizeof(Counters)));
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_debug_ray_queue(mpt_context* ctx, uint32_t bounce, mpt_ray* h_rays, uint32_t* h_leaves, uint64_t capacity, uint64_t* count) {
+    if (!ctx || !count) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    if (bounce < 1 || bounce > uint32_t(kMaxBounces) || !ctx->counters.p || !ctx->pool_slots) return fail(ctx, MPT_ERR_NOT_READY, "no frame has been rendered");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    uint32_t n = 0;
+    CU(cudaMemcpy(&n, &ctx->counters.as<Counters>()->qcount[bounce], sizeof(n), cudaMemcpyDeviceToHost));
+    *count = n;
+    if (!h_rays || capacity == 0) return MPT_OK;
+    const size_t m = size_t(std::min<uint64_t>(n, capacity));
+    try {
+        std::vector<float4> o(m), d(m);
+        const uint32_t parity = (bounce - 1u) & 1u;
+        CU(cudaMemcpy(o.data(), ctx->q_o[parity].p, m * sizeof(float4), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(d.data(), ctx->q_d[parity].p, m * sizeof(float4), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < m; i++) {
+            h_rays[i].origin[0] = o[i].x; h_rays[i].origin[1] = o[i].y; h_rays[i].origin[2] = o[i].z;
+            h_rays[i].tmin = 0.f; // SCENE_RAY_TMIN / SCENE_RAY_TMAX, hit.slang:7-8
+            h_rays[i].direction[0] = d[i].x; h_rays[i].direction[1] = d[i].y; h_rays[i].direction[2] = d[i].z;
+            h_rays[i].tmax = kRayTMax;
+            if (h_leaves) h_leaves[i] = fbits(d[i].w);
+        }
+    } catch (...) {
+        return fail(ctx, MPT_ERR_LIMIT, "out of host memory");
+    }
     return MPT_OK;
 }
 

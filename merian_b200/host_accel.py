@@ -9,7 +9,7 @@ import numpy as np
 from . import abi
 from ._lib import MptError, lib
 
-NODE_DTYPE = np.dtype([("p", "<f4", 3), ("e", "u1", 3), ("imask", "u1"), ("child_base", "<u4"), ("prim_base", "<u4"), ("meta", "u1", 8),
+NODE_DTYPE = np.dtype([("p", "<f4", 3), ("e", "u1", 3), ("imask", "u1"), ("child_base", "<u4"), ("prim_base", "<u4"), ("leaf_bits", "<u4"), ("reserved", "<u4"),
                        ("qlo", "u1", (3, 8)), ("qhi", "u1", (3, 8))])
 assert NODE_DTYPE.itemsize == 80
 

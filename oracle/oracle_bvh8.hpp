@@ -23,7 +23,8 @@ struct Bvh8NodeRaw { // 80 bytes
     uint8_t e[3];
     uint8_t imask;
     uint32_t child_base, prim_base;
-    uint8_t meta[8];
+    uint32_t leaf_bits; // 3 bits per slot: unary primitive count of a leaf child (1, 3, 7); 0 for inner / empty slots
+    uint32_t reserved;
     uint8_t qlo[3][8]; // qlox, qloy, qloz
     uint8_t qhi[3][8]; // qhix, qhiy, qhiz
 };
@@ -62,7 +63,7 @@ struct Bvh8Walker {
     uint32_t test_node(const Bvh8NodeRaw& n, const double o[3], const double idir[3], double tlo, double thi) const {
         uint32_t hits = 0;
         for (int s = 0; s < 8; s++) {
-            if (n.meta[s] == 0) continue;
+            if (!((n.imask >> s) & 1u) && !((n.leaf_bits >> (3 * s)) & 7u)) continue; // empty slot
             double tn = tlo, tf = thi;
             for (int a = 0; a < 3; a++) {
                 const double sc = std::ldexp(1.0, int(n.e[a]) - 127);
@@ -107,7 +108,8 @@ struct Bvh8Walker {
             for (int r = 7; r >= 0; r--) {
                 const uint32_t s = uint32_t(r) ^ octinv;
                 if (!(hits & (1u << s)) || (n.imask & (1u << s))) continue;
-                const uint32_t off = n.meta[s] & 0x1Fu, unary = n.meta[s] >> 5;
+                const uint32_t unary = (n.leaf_bits >> (3 * s)) & 7u;
+                const uint32_t off = uint32_t(__builtin_popcount(n.leaf_bits & ((1u << (3 * s)) - 1u))); // records of the leaf slots below s
                 const uint32_t count = unary == 7u ? 3u : (unary == 3u ? 2u : 1u);
                 for (uint32_t k = 0; k < count; k++) {
                     const uint32_t rec = n.prim_base + off + k;

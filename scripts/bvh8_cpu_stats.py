@@ -86,8 +86,9 @@ def main():
     acc = HostAccel(tables)
     wall = time.perf_counter() - t0
     nodes = acc.nodes
-    nchild = (nodes["meta"] != 0).sum(1)
     ninner = np.array([bin(int(m)).count("1") for m in nodes["imask"]])
+    lb = nodes["leaf_bits"].astype(np.uint32)
+    nchild = ninner + sum((((lb >> np.uint32(3 * s)) & np.uint32(7)) != 0).astype(np.int64) for s in range(8))
     o = OracleContext()
     cam = desc.camera.to_abi(0)
     pr = camera_rays(cam, args.width, args.height)

@@ -88,12 +88,15 @@ def test_host_accel_covers_every_primitive():
     # every leaf child's records lie inside the record array and leaf ranges are disjoint
     covered = np.zeros(acc.view.triangle_count, np.int32)
     for nd in nodes:
+        lb, first = int(nd["leaf_bits"]), int(nd["prim_base"])
+        assert lb >> 24 == 0
         for s in range(8):
-            m = int(nd["meta"][s])
-            if m == 0 or (int(nd["imask"]) >> s) & 1:
+            m = (lb >> (3 * s)) & 7
+            if m == 0:
                 continue
-            count = {1: 1, 3: 2, 7: 3}[m >> 5]
-            first = int(nd["prim_base"]) + (m & 31)
-            covered[first:first + count] += 1
+            assert not (int(nd["imask"]) >> s) & 1  # a slot is an inner child or a leaf, never both
+            count = {1: 1, 3: 2, 7: 3}[m]
+            covered[first:first + count] += 1  # records of the leaf slots lie back to back in slot order
+            first += count
     assert (covered == 1).all()
     acc.close()
