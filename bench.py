@@ -9,7 +9,9 @@ A "step" = one frame = width*height*spp paths through mpt_render (primary hits f
   python bench.py --impl reference ...                          the reference arm: the CPU restatement of the
                                                                 reference's algorithm (oracle/) on the host cores
 Multi-GPU: one process per GPU (torchrun); the scene is replicated, rank r renders sample indices r, r+N, ...
-(weak scaling: 64 spp per GPU, 64*N spp per frame) into a private sum buffer; one NCCL reduce to rank 0 per frame.
+into a private sum buffer; one NCCL reduce to rank 0 per frame, issued by libmpt.so itself (mpt_reduce_begin) on a side
+stream so that it overlaps the next frame's render. --scaling weak (default): 64 spp per GPU, 64*N per frame;
+--scaling strong: 64 spp per frame split over the N GPUs.
 """
 import argparse
 import json
@@ -41,15 +43,21 @@ def load_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def load_traffic(rays_per_launch):
-    """ncu `dram__bytes_read.sum + dram__bytes_write.sum` of k_extend from the committed `--set full` capture
-    (profiles/extend_traffic.json holds it per ray), scaled to the rays of this run's average launch; or None."""
+def load_traffic():
+    """ncu `dram__bytes_read.sum + dram__bytes_write.sum` of k_extend, averaged over the extend launches of one timed step of THIS
+    command (profiles/extend_traffic.json, written by scripts/extend_traffic_from_ncu.py from a `--set full` capture); or None."""
     p = os.path.join(ROOT, "profiles", "extend_traffic.json")
     if os.path.exists(p):
         with open(p) as f:
-            per_ray = json.load(f).get("dram_bytes_per_ray")
-        return per_ray * rays_per_launch if per_ray else None
+            return json.load(f).get("dram_bytes_per_launch")
     return None
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
 
 
 class ClockSampler:
@@ -107,6 +115,7 @@ def cpu_baseline(tables, width, height, spp, seconds_hint=15.0):
     from merian_b200.scene import upload_scene
     from oracle.oracle_py import OracleContext
     o = OracleContext()
+    o.set_num_threads(host_threads())  # all host cores, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)
     upload_scene(o, tables)
     cam = tables.desc.camera.to_abi(0)
     w, h, s = width // 4, height // 4, 8
@@ -163,11 +172,47 @@ def workload_name(args):
             f"max path length {MAX_PATH_LENGTH}" if not args.small else "C3-small (harness test)")
 
 
+def oracle_work_per_ray(ctx, tables, oracle, cam, W, H):
+    """nodes / triangles per ray counted by the CPU oracle walking the SAME BVH8 (mpt_host_accel_build emits what
+    mpt_scene_upload puts in HBM) over the SAME continuation rays: a reduced frame (W/4 x H/4, 4 spp) is rendered with max path length
+    2 .. 5, the ray queue the last extend launch consumed is copied back each time (bounce 1 .. 4: the RNG is keyed on (pixel, frame,
+    sample), so these are the rays of the one full-length frame), and the oracle's walker counts on them. The device's own counters over
+    the same frame are returned next to it."""
+    import torch
+    from merian_b200 import abi
+    from merian_b200.host_accel import HostAccel
+    w, h, spp = max(W // 4, 8), max(H // 4, 8), 4
+    acc = HostAccel(tables)
+    tex1 = ctx.primary_visibility_device(cam, w, h)
+    P = lambda L: abi.RenderParams(w, h, 77, spp, L, 0xFF, abi.RENDER_EMISSION_ON_PRIMARY, 0, 1, 0.0)
+    tot = {"rays": 0, "nodes": 0, "tris": 0}
+    for L in range(2, MAX_PATH_LENGTH + 1):
+        ctx.render_device(cam, P(L), tex1=tex1)
+        torch.cuda.synchronize()
+        rays, leaves = ctx.debug_ray_queue(L - 1)
+        if len(rays) == 0:
+            continue
+        _, _, _, cnt = oracle.bvh8_trace(acc.view, rays, skip_records=None if acc.view.two_level else leaves)
+        for k in tot:
+            tot[k] += cnt[k]
+    ctx.set_profiling(1)
+    ctx.reset_stats()
+    ctx.render_device(cam, P(MAX_PATH_LENGTH), tex1=tex1)
+    cs = ctx.stats()
+    ctx.set_profiling(0)
+    acc.close()
+    r = max(tot["rays"], 1)
+    rd = max(cs.rays_continuation, 1)
+    return {"rays": tot["rays"], "nodes_per_ray": tot["nodes"] / r, "tris_per_ray": tot["tris"] / r, "device_rays": int(cs.rays_continuation),
+            "device_nodes_per_ray": cs.nodes_visited / rd, "device_tris_per_ray": cs.tris_tested / rd,
+            "sample": f"{w}x{h} x {spp} spp, same scene / camera / path length"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from merian_b200 import abi
+    from merian_b200 import abi, sharding
     from merian_b200.context import Context
     from merian_b200.scene import upload_scene
 
@@ -184,39 +229,79 @@ def run_ours(args):
     upload_scene(ctx, tables)
     bvh = ctx.bvh_info()
     desc = tables.desc
-    W, H, spp = args.width, args.height, args.spp
+    W, H = args.width, args.height
     npix = W * H
+    strong = args.scaling == "strong"
+    # weak scaling: args.spp per GPU, args.spp * N per frame; strong scaling: args.spp per frame, split over the N GPUs
+    spp_total = args.spp if strong else args.spp * world
+    spp_rank = sharding.shard_counts(spp_total, world)[rank]
 
     def params(frame, flags=abi.RENDER_EMISSION_ON_PRIMARY):
         if world > 1:
-            return abi.RenderParams(W, H, frame, spp, MAX_PATH_LENGTH, 0xFF, flags | abi.RENDER_OUTPUT_SUM, rank, world, 0.0)
-        return abi.RenderParams(W, H, frame, spp, MAX_PATH_LENGTH, 0xFF, flags, 0, 1, 0.0)
+            return abi.RenderParams(W, H, frame, spp_rank, MAX_PATH_LENGTH, 0xFF, flags | abi.RENDER_OUTPUT_SUM, rank, world, 0.0)
+        return abi.RenderParams(W, H, frame, spp_total, MAX_PATH_LENGTH, 0xFF, flags, 0, 1, 0.0)
 
     cam = desc.camera.to_abi(0)
     tex1 = ctx.primary_visibility_device(cam, W, H)  # the GBuffer node's product (gbuffer_rt.slang), resident in HBM
-    out = torch.empty((H, W, 4), dtype=torch.float32, device=dev)
-
-    def step(frame):
-        ctx.render_device(cam, params(frame), tex1=tex1, out=out)
-        if world > 1:
-            dist.reduce(out, dst=0, op=dist.ReduceOp.SUM)  # NCCL over NVLink: accumulation buffers -> rank 0
+    # two frames in flight: frame i's partial sums are being reduced on the library's side stream while frame i + 1 renders
+    sums = [torch.empty((H, W, 4), dtype=torch.float32, device=dev) for _ in range(2)]
+    outs = [torch.empty((H, W, 4), dtype=torch.float32, device=dev) for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
+    comm = None
+    if world > 1:
+        def exchange(raw):  # rank 0's NCCL unique id -> every rank (out of band: torch.distributed is only plumbing here)
+            t = torch.zeros(abi.COMM_UNIQUE_ID_BYTES, dtype=torch.uint8, device=dev)
             if rank == 0:
-                out.mul_(1.0 / (spp * world))
+                t.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+            dist.broadcast(t, src=0)
+            return bytes(t.cpu().numpy().tobytes())
+        comm = sharding.ShardComm(local_rank, rank, world, exchange)  # mpt_comm_create: NCCL inside libmpt.so
+    in_flight = [False]
+
+    def step(i, h_out=None, h_tex1=None, d_tex1=tex1):
+        """One frame. Multi-GPU: render this rank's samples into sums[i % 2], then mpt_reduce_begin (reduce -> normalise -> optional
+        copy to the host buffer, on the side stream); the previous frame's reduce is joined first (one communicator, one reduce at a time)."""
+        b = i % 2
+        if h_tex1 is not None:
+            d_tex1.copy_(h_tex1, non_blocking=True)
+        if world == 1:
+            ctx.render_device(cam, params(i), tex1=d_tex1, out=sums[b])
+            if h_out is not None:
+                h_out.copy_(sums[b], non_blocking=True)
+            return
+        ctx.render_device(cam, params(i), tex1=d_tex1, out=sums[b])
+        if in_flight[0]:
+            comm.reduce_wait()
+        comm.reduce_begin(sums[b], outs[b], W, H, spp_total, root=0, h_out=h_out if rank == 0 else None)
+        in_flight[0] = True
+
+    def drain():
+        if world > 1 and in_flight[0]:
+            comm.reduce_wait()
+            in_flight[0] = False
 
     def barrier():
+        drain()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- algorithmic work per ray: one instrumented (counting) frame outside the timed region
+    # ---- algorithmic work per ray, outside the timed region: the oracle's count (roofline numerator) and the device's own
+    work = None
+    oracle = None
+    base = None
+    if rank == 0 and not args.no_cpu_baseline:
+        base, oracle, _ = cpu_baseline(tables, W, H, args.spp)  # also the oracle context (scene uploaded) for the walker below
+        work = oracle_work_per_ray(ctx, tables, oracle, cam, W, H)
     ctx.set_profiling(1)
     ctx.reset_stats()
-    ctx.render_device(cam, params(10_000), tex1=tex1, out=out)
+    ctx.render_device(cam, params(10_000), tex1=tex1, out=sums[0])
     cs = ctx.stats()
     rays_c = max(cs.rays_continuation, 1)
-    nodes_per_ray, tris_per_ray = cs.nodes_visited / rays_c, cs.tris_tested / rays_c
-    bytes_per_ray = 80.0 * nodes_per_ray + 48.0 * tris_per_ray + 48.0  # node + triangle records + ray read (32) + hit write (16)
+    dev_nodes_per_ray, dev_tris_per_ray = cs.nodes_visited / rays_c, cs.tris_tested / rays_c
     ctx.set_profiling(0)
+    nodes_per_ray = work["nodes_per_ray"] if work else dev_nodes_per_ray
+    tris_per_ray = work["tris_per_ray"] if work else dev_tris_per_ray
+    bytes_per_ray = 80.0 * nodes_per_ray + 48.0 * tris_per_ray + 48.0  # node + triangle records + ray read (32) + hit write (16)
 
     # The clock sampler is an `nvidia-smi -lms` child process: its start-up (NVML init) takes driver locks that CUDA API calls of this
     # process can block on, which starves the GPU of launches for hundreds of milliseconds. Start it BEFORE the warm-up and wait for its
@@ -230,7 +315,7 @@ def run_ours(args):
     ctx.set_profiling(2)  # CUDA-event timing of every extend / shade launch; on during the warm-up so that libmpt's event pool is
     #                       fully created before the timed region (no cudaEventCreate inside it)
     for i in range(max(6, args.steps + 1)):  # clocks and caches up before the W warm-up steps the caller asked for
-        ctx.render_device(cam, params(20_000 + i), tex1=tex1, out=out)
+        ctx.render_device(cam, params(20_000 + i), tex1=tex1, out=sums[i % 2])
     ctx.reset_stats()
     for i in range(args.warmup):
         step(i)
@@ -243,6 +328,9 @@ def run_ours(args):
     ev0.record()
     for i in range(args.steps):
         step(args.warmup + i)
+    if world > 1:
+        comm.reduce_end()  # the timing stream waits for the last frame's reduce + normalise: ev1 is behind the whole job
+        in_flight[0] = False
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -253,40 +341,61 @@ def run_ours(args):
     st = ctx.stats()
     ctx.set_profiling(0)
 
-    rays = torch.tensor([float(st.rays_continuation), float(st.shaded_hits), float(st.kernel_launches)], device=dev, dtype=torch.float64)
+    launches = float(st.kernel_launches) + (2.0 * args.steps if (world > 1 and rank == 0) else (1.0 * args.steps if world > 1 else 0.0))  # + NCCL reduce, k_normalise
+    rays = torch.tensor([float(st.rays_continuation), float(st.shaded_hits), launches], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(rays, op=dist.ReduceOp.SUM)
-    total_samples = npix * spp * world * args.steps
+    total_samples = npix * spp_total * args.steps
     value = total_samples / (ms * 1e-3) / 1e6
     mrays = float(rays[0].item()) / (ms * 1e-3) / 1e6
 
-    # ---- end to end through the C-ABI with HOST buffers: H2D GBuffer hits, render, D2H irradiance, every step, with two iterations in
-    # flight as merian's graph runs them (examples/gltf.json:39): mpt_render_host_begin / _end. A step is complete when its irradiance
-    # is in host memory; the timed region covers e2e_steps complete steps.
+    # ---- end to end with HOST buffers, every step: H2D of the GBuffer hit texture from pinned memory, render, (multi-GPU: reduce +
+    # normalise,) D2H of the irradiance into pinned memory on rank 0 — two iterations in flight as merian's graph runs them
+    # (examples/gltf.json:39). One GPU: mpt_render_host_begin / _end (the C-ABI's host-buffer entry points). Several GPUs: the same
+    # copies around mpt_render + mpt_reduce_begin(h_out); a step is complete when rank 0 holds the normalised frame in host memory.
     h_tex1 = tex1.cpu().pin_memory()
     h_outs = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
-    e2e_steps = max(2, min(args.steps, 4))
-    ctx.render_host(cam, params(0), h_tex1=h_tex1, h_out=h_outs[0])  # warm (allocates the staging buffers)
-    for s_ in range(2):
-        ctx.render_host_begin(cam, params(s_), h_outs[s_], s_, h_tex1=h_tex1)
-    for s_ in range(2):
-        ctx.render_host_end(s_)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e2e_steps):
-        if i >= 2:
+    e2e_steps = max(2, args.steps)
+    if world == 1:
+        ctx.render_host(cam, params(0), h_tex1=h_tex1, h_out=h_outs[0])  # warm (allocates the staging buffers)
+        for s_ in range(2):
+            ctx.render_host_begin(cam, params(s_), h_outs[s_], s_, h_tex1=h_tex1)
+        for s_ in range(2):
+            ctx.render_host_end(s_)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            if i >= 2:
+                ctx.render_host_end(i % 2)
+            ctx.render_host_begin(cam, params(args.warmup + i), h_outs[i % 2], i % 2, h_tex1=h_tex1)
+        for i in range(max(e2e_steps - 2, 0), e2e_steps):
             ctx.render_host_end(i % 2)
-        ctx.render_host_begin(cam, params(args.warmup + i), h_outs[i % 2], i % 2, h_tex1=h_tex1)
-    for i in range(max(e2e_steps - 2, 0), e2e_steps):
-        ctx.render_host_end(i % 2)
-    e2e_dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        e2e_dt = time.perf_counter() - t0
+    else:
+        d_tex1s = [torch.empty_like(tex1) for _ in range(2)]
+        for i in range(2):
+            step(i, h_out=h_outs[i % 2], h_tex1=h_tex1, d_tex1=d_tex1s[i % 2])
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps):
+            step(args.warmup + i, h_out=h_outs[i % 2], h_tex1=h_tex1, d_tex1=d_tex1s[i % 2])
+        drain()  # rank 0: the last frame is in host memory; other ranks: their last contribution has been sent
+        torch.cuda.synchronize()
+        e2e_dt = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_dt], device=dev, dtype=torch.float64)
     if world > 1:
-        dist.all_reduce(e2e_dt, op=dist.ReduceOp.MAX)
-    e2e_value = npix * spp * world * e2e_steps / float(e2e_dt.item()) / 1e6
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = npix * spp_total * e2e_steps / float(e2e_t.item()) / 1e6
     # the synchronous call (one iteration in flight), reported next to it
-    t0 = time.perf_counter()
-    ctx.render_host(cam, params(args.warmup), h_tex1=h_tex1, h_out=h_outs[0])
-    e2e_sync_value = npix * spp / (time.perf_counter() - t0) / 1e6
+    e2e_sync_value = None
+    if world == 1:
+        best = None
+        for rep in range(3):  # best of three: the first call after the pipelined loop pays for the stream switch
+            t0 = time.perf_counter()
+            ctx.render_host(cam, params(args.warmup + rep), h_tex1=h_tex1, h_out=h_outs[0])
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+        e2e_sync_value = npix * spp_total / best / 1e6
 
     # ---- the same frame with MPT_RENDER_NEE (north_star: closest-hit and occlusion queries reported separately and summed); outside
     # the timed region, not part of `value`
@@ -294,18 +403,18 @@ def run_ours(args):
     if world == 1:
         ctx.reset_stats()
         for i in range(2):
-            ctx.render_device(cam, params(30_000 + i, abi.RENDER_EMISSION_ON_PRIMARY | abi.RENDER_NEE), tex1=tex1, out=out)
+            ctx.render_device(cam, params(30_000 + i, abi.RENDER_EMISSION_ON_PRIMARY | abi.RENDER_NEE), tex1=tex1, out=sums[0])
         torch.cuda.synchronize()
         ctx.reset_stats()
         n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n0.record()
         for i in range(2):
-            ctx.render_device(cam, params(30_002 + i, abi.RENDER_EMISSION_ON_PRIMARY | abi.RENDER_NEE), tex1=tex1, out=out)
+            ctx.render_device(cam, params(30_002 + i, abi.RENDER_EMISSION_ON_PRIMARY | abi.RENDER_NEE), tex1=tex1, out=sums[0])
         n1.record()
         torch.cuda.synchronize()
         nms = n0.elapsed_time(n1) / 2
         ns = ctx.stats()
-        nee = {"msamples_per_s": npix * spp / (nms * 1e-3) / 1e6, "ms_per_step": nms,
+        nee = {"msamples_per_s": npix * spp_total / (nms * 1e-3) / 1e6, "ms_per_step": nms,
                "mrays_closest_hit_per_s": ns.rays_continuation / 2 / (nms * 1e-3) / 1e6, "mrays_occlusion_per_s": ns.rays_shadow / 2 / (nms * 1e-3) / 1e6,
                "mrays_total_per_s": (ns.rays_continuation + ns.rays_shadow) / 2 / (nms * 1e-3) / 1e6}
 
@@ -314,33 +423,37 @@ def run_ours(args):
         extend_ms = st.extend_ms / max(st.extend_launches, 1)
         rays_per_launch = st.rays_continuation / max(st.extend_launches, 1)
         achieved = bytes_per_ray * rays_per_launch / (extend_ms * 1e-3) / 1e9 if extend_ms > 0 else 0.0
-        base = None
-        if world == 1 and not args.no_cpu_baseline:
-            base, _, _ = cpu_baseline(tables, W, H, spp)
         line = {
             "metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": workload_name(args), "width": W, "height": H, "spp_per_gpu": spp, "spp_total": spp * world,
+            "config": {"workload": workload_name(args), "width": W, "height": H, "spp_per_gpu": spp_rank, "spp_total": spp_total,
                        "max_path_length": MAX_PATH_LENGTH, "triangles": tables.triangle_count, "seed": desc.seed, "generator": synthetic_version(),
-                       "parallelism": f"sample-sharded x{world}, NCCL reduce of the sum buffers" if world > 1 else "single GPU",
+                       "parallelism": (f"sample-sharded x{world}, one NCCL reduce of the sum buffers per frame inside libmpt.so (mpt_reduce_begin), "
+                                       "overlapped with the next frame's render") if world > 1 else "single GPU",
                        "l2": "inputs larger than L2: BVH8 %.0f MB + triangle/attribute records %.0f MB + env 134 MB + >1 GB of path state per pass"
                              % (bvh.node_bytes / 1e6, 2 * bvh.triangle_bytes / 1e6)},
             "mrays_per_s": mrays,  # continuation rays (primary hits come from the GBuffer texture)
             "rays_per_sample": float(rays[0].item()) / total_samples,
             "with_nee": nee,  # MPT_RENDER_NEE on the same workload (an addition to the reference estimator; not the headline)
-            "roofline": {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": load_traffic(rays_per_launch), "peak_source": peak_src, "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray,
-                         "tris_per_ray": tris_per_ray, "rays_per_launch": rays_per_launch, "avg_launch_ms": extend_ms,
+            "roofline": {"bound": "hbm", "kernel": "k_extend_pooled", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": load_traffic(), "peak_source": peak_src, "bytes_per_ray": bytes_per_ray,
+                         "counted_by": "oracle BVH8 walker on the device's ray queues" if work else "device counters (no oracle in this run)",
+                         "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
+                         "nodes_per_ray_device": dev_nodes_per_ray, "tris_per_ray_device": dev_tris_per_ray, "oracle_sample": work,
+                         "rays_per_launch": rays_per_launch, "avg_launch_ms": extend_ms,
                          "extend_share_of_step": st.extend_ms / ms if ms > 0 else None, "shade_share_of_step": st.shade_ms / ms if ms > 0 else None},
             "cpu_baseline": base,
-            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": npix * 16, "d2h_bytes_per_step": npix * 16,
-                    "iterations_in_flight": 2, "synchronous_call_value": e2e_sync_value},
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": npix * 16 * world, "d2h_bytes_per_step": npix * 16,
+                    "iterations_in_flight": 2, "steps": e2e_steps, "synchronous_call_value": e2e_sync_value,
+                    "includes_reduce": world > 1},
             "gpu_launches": int(rays[2].item()),
             "clocks": clocks,
             "bvh": {"nodes": bvh.node_count, "node_mb": bvh.node_bytes / 1e6, "triangle_mb": bvh.triangle_bytes / 1e6, "build_ms": bvh.build_ms},
         }
         args.emit(json.dumps(line))
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -380,6 +493,8 @@ def main():
     ap.add_argument("--spp", type=int, default=SPP)
     ap.add_argument("--small", action="store_true", help="tiny scene (harness test only; not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="multi-GPU: weak = --spp per GPU (default, the driver's scaling run), strong = --spp per frame split over the GPUs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours" and not args.small:
         args.warmup = 3  # timing rule: at least 3 warm-up steps

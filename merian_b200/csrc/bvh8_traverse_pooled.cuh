@@ -207,7 +207,10 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
         // A parked primitive group remembers the node-stack height it was uncovered at (top byte of y): node groups below that height
         // wait until it has been tested — the order of the single-stack traversal (a group uncovered deeper in the tree is tested before
         // the walk moves on to the siblings of its ancestors), which keeps the hit distance fresh: taking sibling groups first cost
-        // +1.4 % node tests and +4.6 % triangle tests on C3 (profiles/r02d_ab.jsonl).
+        // +1.4 % node tests and +4.6 % triangle tests on C3 (profiles/r02d_ab.jsonl). The stricter rule "never go back to a stacked node
+        // group while ANY primitive is pending" brings the counts down to the oracle's immediate-test traversal (11.03 nodes, 3.57
+        // triangles per ray) but costs 2-4 % time on every scene tried (C1, C3, C5: profiles/r02h_drain_first.jsonl): lanes idle through
+        // node sections while they drain.
         if (Gt.y == 0u && psp > pbase) unpark();
         bool first_pop = true;
         while ((G.y & 0xFF000000u) == 0u) {

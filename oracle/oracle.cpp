@@ -1250,6 +1250,15 @@ int oracle_bvh8_trace(oracle_context* c, const mpt_host_accel_view* accel, const
     return 0;
 }
 
+// bench.py --impl reference sets the thread count itself: under torchrun every rank inherits OMP_NUM_THREADS=1
+void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_num_threads() {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -123,6 +123,9 @@ class OracleContext:
     def num_threads(self):
         return self.l.oracle_num_threads()
 
+    def set_num_threads(self, n):
+        self.l.oracle_set_num_threads(C.c_int(int(n)))
+
 
 def accumulate(acc_params, src, prev_out=None, prev_history=None, tex0=None, tex2=None):
     """Accumulate node, plain path (accumulate.slang). Returns (out float32 (H, W, 4), history uint32 (H, W, 2))."""

@@ -15,13 +15,24 @@ from merian_b200 import abi  # noqa: E402
 from merian_b200.context import Context  # noqa: E402
 from merian_b200.scene import upload_scene  # noqa: E402
 
-KNOBS = ("MPT_EXTEND_LEGACY", "MPT_POOLED_REFILL_THRESHOLD", "MPT_POOLED_TRI_MASK", "MPT_L2_PERSIST", "MPT_L2_PERSIST_MB", "MPT_TRI_VOTE", "MPT_PREFETCH", "MPT_REFILL_THRESHOLD", "MPT_POOL_MSLOTS", "MPT_EXTEND_BLOCKS_PER_SM", "MPT_BVH_MAX_LEAF", "MPT_BVH_TRAV_COST", "MPT_BVH_COLLAPSE", "MPT_BVH_CPRIM", "MPT_SHADE_BLOCKS_PER_SM")
+KNOBS = ("MPT_EXTEND_LEGACY", "MPT_POOLED_REFILL_THRESHOLD", "MPT_POOLED_DRAIN_FIRST", "MPT_L2_PERSIST", "MPT_L2_PERSIST_MB", "MPT_TRI_VOTE", "MPT_PREFETCH", "MPT_REFILL_THRESHOLD", "MPT_POOL_MSLOTS", "MPT_EXTEND_BLOCKS_PER_SM", "MPT_BVH_MAX_LEAF", "MPT_BVH_TRAV_COST", "MPT_BVH_COLLAPSE", "MPT_BVH_CPRIM", "MPT_SHADE_BLOCKS_PER_SM")
 
 
 def main():
     settings = sys.argv[1:] or [""]
-    tables = bench.build_scene(False)
+    scene = os.environ.get("SWEEP_SCENE", "c3")  # c3 (bench workload) | c1 (Cornell box) | c5 (instanced rocks, two-level) | small (200x100 terrain)
     W, H, spp, L = bench.WIDTH, bench.HEIGHT, bench.SPP, bench.MAX_PATH_LENGTH
+    if scene == "c3":
+        tables = bench.build_scene(False)
+    else:
+        from merian_b200 import synthetic
+        from merian_b200.scene import SceneTables
+        if scene == "c1":
+            tables, W, H, spp = SceneTables(synthetic.cornell()), 1024, 1024, 64
+        elif scene == "c5":
+            tables, W, H, spp = SceneTables(synthetic.instanced_rocks(n_instances=1000, rock_res=71, seed=5, env_size=(1024, 512))), 3840, 2160, 8
+        else:
+            tables, spp = SceneTables(synthetic.terrain(nx=200, ny=100, env_size=(256, 128))), 32
     dev = torch.device("cuda", 0)
     ref_img = None
     for s in settings:
@@ -62,7 +73,7 @@ def main():
             ref_img = img
         else:
             diff = float((img[..., :3] - ref_img[..., :3]).abs().mean() / ref_img[..., :3].abs().mean())
-        print(json.dumps({"setting": s, "msamples_per_s": W * H * spp / ms / 1e3, "ms_per_frame": ms, "extend_ms_per_frame": st.extend_ms / n,
+        print(json.dumps({"scene": scene, "setting": s, "msamples_per_s": W * H * spp / ms / 1e3, "ms_per_frame": ms, "extend_ms_per_frame": st.extend_ms / n,
                           "shade_ms_per_frame": st.shade_ms / n, "nodes_per_ray": npr, "tris_per_ray": tpr, "rel_mean_abs_diff_vs_first": diff}), flush=True)
         ctx.close()
         del ctx

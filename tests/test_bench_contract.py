@@ -30,3 +30,15 @@ def test_reference_arm_prints_one_json_line():
 def test_other_ranks_stay_silent():
     r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"}, "--gpus", "2")
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_reference_arm_uses_all_host_cores_whatever_omp_num_threads_says():
+    """torchrun exports OMP_NUM_THREADS=1 to every rank (round-1 review: the N >= 2 reference lines ran on one thread)."""
+    r = _run({"OMP_NUM_THREADS": "1"})
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([l for l in r.stdout.splitlines() if l.strip()][0])
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count()
+    assert d["cpu_baseline"]["cores"] == n
