@@ -255,29 +255,39 @@ def run_ours(args):
             dist.broadcast(t, src=0)
             return bytes(t.cpu().numpy().tobytes())
         comm = sharding.ShardComm(local_rank, rank, world, exchange)  # mpt_comm_create: NCCL inside libmpt.so
-    in_flight = [False]
+    pending = [False, False]  # a reduce is in flight in slot b (reading sums[b], writing outs[b] / the host buffer)
 
     def step(i, h_out=None, h_tex1=None, d_tex1=tex1):
-        """One frame. Multi-GPU: render this rank's samples into sums[i % 2], then mpt_reduce_begin (reduce -> normalise -> optional
-        copy to the host buffer, on the side stream); the previous frame's reduce is joined first (one communicator, one reduce at a time)."""
+        """One frame. Multi-GPU: render this rank's samples into sums[i % 2], then mpt_reduce_begin(slot i % 2): reduce -> normalise ->
+        optional copy to the host buffer, on the library's side stream, overlapping the next frame's render. The host never blocks on the
+        previous frame (that would leave a single frame queued on the GPU, and every host hiccup would stall it): before a sum buffer is
+        rendered into again, the render STREAM waits for the reduce that read it (mpt_reduce_end), or — when the frames land in host
+        buffers, which the host reuses — the host waits for that two-frames-old reduce (mpt_reduce_wait)."""
         b = i % 2
+        if world > 1 and pending[b]:
+            if h_out is not None:
+                comm.reduce_wait(slot=b)
+            else:
+                comm.reduce_end(slot=b)
+            pending[b] = False
         if h_tex1 is not None:
             d_tex1.copy_(h_tex1, non_blocking=True)
+        ctx.render_device(cam, params(i), tex1=d_tex1, out=sums[b])
         if world == 1:
-            ctx.render_device(cam, params(i), tex1=d_tex1, out=sums[b])
             if h_out is not None:
                 h_out.copy_(sums[b], non_blocking=True)
             return
-        ctx.render_device(cam, params(i), tex1=d_tex1, out=sums[b])
-        if in_flight[0]:
-            comm.reduce_wait()
-        comm.reduce_begin(sums[b], outs[b], W, H, spp_total, root=0, h_out=h_out if rank == 0 else None)
-        in_flight[0] = True
+        comm.reduce_begin(sums[b], outs[b], W, H, spp_total, root=0, h_out=h_out if rank == 0 else None, slot=b)
+        pending[b] = True
 
-    def drain():
-        if world > 1 and in_flight[0]:
-            comm.reduce_wait()
-            in_flight[0] = False
+    def drain(on_stream=False):
+        for b in range(2):
+            if world > 1 and pending[b]:
+                if on_stream:
+                    comm.reduce_end(slot=b)
+                else:
+                    comm.reduce_wait(slot=b)
+                pending[b] = False
 
     def barrier():
         drain()
@@ -325,12 +335,16 @@ def run_ours(args):
         sampler.lines.clear()  # keep only the samples of the timed region
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    # One more untimed step goes in front of the timed ones, behind the barrier: right after a synchronize the GPU's queue is empty, and a
+    # host thread that is held up for a few ms before it gets the first launch out (observed: 10-80 ms, about once per second of run time,
+    # in every mode and also on one GPU, profiles/r02j_reduce_modes.jsonl) would put that idle gap inside the timed region. With a
+    # frame already executing, the K timed steps are all enqueued long before the GPU reaches them; ev0 is recorded in stream order
+    # behind the lead-in frame, so the timed region is exactly K steps of device time.
+    step(args.warmup)
     ev0.record()
     for i in range(args.steps):
-        step(args.warmup + i)
-    if world > 1:
-        comm.reduce_end()  # the timing stream waits for the last frame's reduce + normalise: ev1 is behind the whole job
-        in_flight[0] = False
+        step(args.warmup + 1 + i)
+    drain(on_stream=True)  # the timing stream waits for the last frames' reduce + normalise: ev1 is behind the whole job
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -341,8 +355,9 @@ def run_ours(args):
     st = ctx.stats()
     ctx.set_profiling(0)
 
-    launches = float(st.kernel_launches) + (2.0 * args.steps if (world > 1 and rank == 0) else (1.0 * args.steps if world > 1 else 0.0))  # + NCCL reduce, k_normalise
-    rays = torch.tensor([float(st.rays_continuation), float(st.shaded_hits), launches], device=dev, dtype=torch.float64)
+    timed_share = args.steps / (args.steps + 1.0)  # libmpt's counters also saw the lead-in step
+    launches = float(st.kernel_launches) * timed_share + (2.0 * args.steps if (world > 1 and rank == 0) else (1.0 * args.steps if world > 1 else 0.0))  # + NCCL reduce, k_normalise
+    rays = torch.tensor([float(st.rays_continuation) * timed_share, float(st.shaded_hits) * timed_share, launches], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(rays, op=dist.ReduceOp.SUM)
     total_samples = npix * spp_total * args.steps
@@ -429,6 +444,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args), "width": W, "height": H, "spp_per_gpu": spp_rank, "spp_total": spp_total,
                        "max_path_length": MAX_PATH_LENGTH, "triangles": tables.triangle_count, "seed": desc.seed, "generator": synthetic_version(),
+                       "timing": "CUDA events around exactly `steps` steps, max over ranks; barrier + synchronize, then one untimed lead-in step in front of ev0 (keeps the queue non-empty while the host enqueues the timed steps)",
                        "parallelism": (f"sample-sharded x{world}, one NCCL reduce of the sum buffers per frame inside libmpt.so (mpt_reduce_begin), "
                                        "overlapped with the next frame's render") if world > 1 else "single GPU",
                        "l2": "inputs larger than L2: BVH8 %.0f MB + triangle/attribute records %.0f MB + env 134 MB + >1 GB of path state per pass"
@@ -442,7 +458,8 @@ def run_ours(args):
                          "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
                          "nodes_per_ray_device": dev_nodes_per_ray, "tris_per_ray_device": dev_tris_per_ray, "oracle_sample": work,
                          "rays_per_launch": rays_per_launch, "avg_launch_ms": extend_ms,
-                         "extend_share_of_step": st.extend_ms / ms if ms > 0 else None, "shade_share_of_step": st.shade_ms / ms if ms > 0 else None},
+                         "extend_share_of_step": st.extend_ms * timed_share / ms if ms > 0 else None,
+                         "shade_share_of_step": st.shade_ms * timed_share / ms if ms > 0 else None},
             "cpu_baseline": base,
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": npix * 16 * world, "d2h_bytes_per_step": npix * 16,
                     "iterations_in_flight": 2, "steps": e2e_steps, "synchronous_call_value": e2e_sync_value,

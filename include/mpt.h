@@ -402,7 +402,9 @@ MPT_API mpt_status mpt_bvh8_build_info(const float* boxes, uint32_t n, mpt_bvh_i
  * mpt_comm owns (or adopts) one ncclComm_t and a side stream. mpt_reduce_begin enqueues, BEHIND the work already submitted to
  * `render_stream`, on the side stream:  reduce(sum) -> divide by spp_total (receiving ranks) -> optional copy to the pinned host buffer
  * h_out. The caller may submit the next frame to render_stream right away (it overlaps the reduce) as long as it renders into a different
- * buffer. mpt_reduce_end makes a stream wait for the result; mpt_reduce_wait blocks the host until it (and the host copy) is complete.
+ * buffer. Up to 4 reduces may be in flight, one per `slot` (like in_flight_index of mpt_render_host_begin; the side stream runs them in
+ * issue order). mpt_reduce_end makes a stream wait for a slot's result — e.g. the render stream, before the frame that reuses that slot's
+ * sum buffer; mpt_reduce_wait blocks the host until it (and the host copy) is complete. Both release the slot.
  * NCCL is resolved at run time (dlopen libnccl.so.2; MPT_NCCL_LIBRARY overrides the name); without it the calls return
  * MPT_ERR_UNSUPPORTED. Errors: mpt_comm_last_error (NULL: errors of the calls that take no mpt_comm). */
 #define MPT_COMM_UNIQUE_ID_BYTES 128
@@ -420,9 +422,9 @@ MPT_API mpt_status mpt_comm_info(uint32_t* nccl_version);
 /* d_partial_sum: this rank's RGBA32F sums (width*height float4). d_out: where the combined frame lands on the receiving rank(s) (may be
  * d_partial_sum itself); ignored elsewhere. h_out: optional pinned host buffer on the receiving rank(s). */
 MPT_API mpt_status mpt_reduce_begin(mpt_comm* comm, const void* d_partial_sum, void* d_out, void* h_out, uint32_t width, uint32_t height,
-                                    uint32_t spp_total, int root, uint32_t flags, void* render_stream);
-MPT_API mpt_status mpt_reduce_end(mpt_comm* comm, void* stream);
-MPT_API mpt_status mpt_reduce_wait(mpt_comm* comm);
+                                    uint32_t spp_total, int root, uint32_t flags, void* render_stream, uint32_t slot);
+MPT_API mpt_status mpt_reduce_end(mpt_comm* comm, uint32_t slot, void* stream);
+MPT_API mpt_status mpt_reduce_wait(mpt_comm* comm, uint32_t slot);
 
 /* Host-only (no device needed): the acceleration structure exactly as mpt_scene_upload lays it out in HBM — the BVH8 nodes of every
  * BLAS and of the TLAS, the triangle records in leaf order, the instance records. Replaces nothing in the reference (its BLAS/TLAS are

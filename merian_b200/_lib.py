@@ -86,9 +86,10 @@ def lib():
         l.mpt_comm_last_error.argtypes = [C.c_void_p]
         l.mpt_comm_last_error.restype = C.c_char_p
         l.mpt_comm_info.argtypes = [C.POINTER(C.c_uint32)]
-        l.mpt_reduce_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p]
-        l.mpt_reduce_end.argtypes = [C.c_void_p, C.c_void_p]
-        l.mpt_reduce_wait.argtypes = [C.c_void_p]
+        l.mpt_reduce_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p,
+                                       C.c_uint32]
+        l.mpt_reduce_end.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        l.mpt_reduce_wait.argtypes = [C.c_void_p, C.c_uint32]
         l.mpt_bsdf_check.argtypes = [C.c_void_p, C.POINTER(abi.BsdfCheckParams), C.c_void_p]
         l.mptn_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         l.mptn_destroy.argtypes = [C.c_void_p]

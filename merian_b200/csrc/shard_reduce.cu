@@ -3,7 +3,9 @@
 // frame without Python: `mpt_comm_*` wraps one ncclComm_t + a side stream, `mpt_reduce_begin` issues
 //     ncclReduce(sum of the partial sums -> root)  ->  divide by the total sample count  ->  optional copy to a pinned host buffer
 // on the side stream behind the render that produced the partial sums, so that the next frame's render overlaps it;
-// `mpt_reduce_end` / `mpt_reduce_wait` join it. The reference has no multi-device path (render_pt.slang:113-122 loops over the samples
+// `mpt_reduce_end` / `mpt_reduce_wait` join it. Up to four reduces may be in flight (slots): a host that blocks on frame i - 1 before it
+// enqueues frame i + 1 keeps only one frame queued on the GPU, and every host hiccup then stalls the device (measured on 2 GPUs: 16-33 ms
+// spikes, profiles/r02j_reduce_modes.jsonl); with slots the render stream itself waits for the reduce that last read a sum buffer. The reference has no multi-device path (render_pt.slang:113-122 loops over the samples
 // of a pixel in one thread); the partition by sample index is ours, the estimator is unchanged.
 //
 // NCCL is resolved at run time (dlopen of libnccl.so.2): in a process that already carries a copy (PyTorch bundles its own) that copy
@@ -88,8 +90,10 @@ struct mpt_comm {
     ncclComm_t comm = nullptr;
     bool owns_comm = false;
     cudaStream_t side = nullptr;
-    cudaEvent_t ready = nullptr, done = nullptr;
-    bool pending = false;
+    cudaEvent_t ready = nullptr;
+    static constexpr uint32_t kSlots = 4; // reduces in flight (the side stream runs them in order)
+    cudaEvent_t done[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+    bool pending[kSlots] = {false, false, false, false};
     std::string error;
 };
 
@@ -120,11 +124,13 @@ mpt_status make_comm(int device, int rank, int world, mpt_comm** out) {
     c->device = device; c->rank = rank; c->world = world;
     cudaError_t e = cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming);
+    for (uint32_t i = 0; i < mpt_comm::kSlots && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming);
     if (e != cudaSuccess) {
         const std::string msg = std::string("mpt_comm: ") + cudaGetErrorString(e);
         if (c->side) cudaStreamDestroy(c->side);
         if (c->ready) cudaEventDestroy(c->ready);
+        for (cudaEvent_t ev : c->done)
+            if (ev) cudaEventDestroy(ev);
         delete c;
         return cfail(nullptr, MPT_ERR_CUDA, msg);
     }
@@ -185,15 +191,17 @@ MPT_API void mpt_comm_destroy(mpt_comm* c) {
     if (c->comm && c->owns_comm && nccl()) nccl()->CommDestroy(c->comm);
     if (c->side) cudaStreamDestroy(c->side);
     if (c->ready) cudaEventDestroy(c->ready);
-    if (c->done) cudaEventDestroy(c->done);
+    for (cudaEvent_t ev : c->done)
+        if (ev) cudaEventDestroy(ev);
     delete c;
 }
 
 MPT_API mpt_status mpt_reduce_begin(mpt_comm* c, const void* d_partial_sum, void* d_out, void* h_out, uint32_t width, uint32_t height, uint32_t spp_total,
-                                    int root, uint32_t flags, void* render_stream) {
+                                    int root, uint32_t flags, void* render_stream, uint32_t slot) {
     if (!c || !d_partial_sum || !width || !height) return cfail(c, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     if (root < 0 || root >= c->world) return cfail(c, MPT_ERR_INVALID_ARGUMENT, "root out of range");
-    if (c->pending) return cfail(c, MPT_ERR_INVALID_ARGUMENT, "a reduce is already in flight on this communicator: call mpt_reduce_end / mpt_reduce_wait first");
+    if (slot >= mpt_comm::kSlots) return cfail(c, MPT_ERR_LIMIT, "slot must be < 4");
+    if (c->pending[slot]) return cfail(c, MPT_ERR_INVALID_ARGUMENT, "this slot still holds a reduce: call mpt_reduce_end / mpt_reduce_wait on it first");
     const bool all = (flags & MPT_REDUCE_ALL_RANKS) != 0, is_root = all || c->rank == root;
     if (is_root && !d_out) return cfail(c, MPT_ERR_INVALID_ARGUMENT, "d_out is NULL on a rank that receives the frame");
     CCU(cudaSetDevice(c->device));
@@ -215,26 +223,28 @@ MPT_API mpt_status mpt_reduce_begin(mpt_comm* c, const void* d_partial_sum, void
         }
         if (h_out) CCU(cudaMemcpyAsync(h_out, d_out, count * sizeof(float), cudaMemcpyDeviceToHost, c->side));
     }
-    CCU(cudaEventRecord(c->done, c->side));
-    c->pending = true;
+    CCU(cudaEventRecord(c->done[slot], c->side));
+    c->pending[slot] = true;
     return MPT_OK;
 }
 
-MPT_API mpt_status mpt_reduce_end(mpt_comm* c, void* stream) {
+MPT_API mpt_status mpt_reduce_end(mpt_comm* c, uint32_t slot, void* stream) {
     if (!c) return MPT_ERR_INVALID_ARGUMENT;
-    if (!c->pending) return cfail(c, MPT_ERR_INVALID_ARGUMENT, "no reduce is in flight");
+    if (slot >= mpt_comm::kSlots) return cfail(c, MPT_ERR_LIMIT, "slot must be < 4");
+    if (!c->pending[slot]) return cfail(c, MPT_ERR_INVALID_ARGUMENT, "no reduce is in flight in this slot");
     CCU(cudaSetDevice(c->device));
-    CCU(cudaStreamWaitEvent((cudaStream_t)stream, c->done, 0));
-    c->pending = false;
+    CCU(cudaStreamWaitEvent((cudaStream_t)stream, c->done[slot], 0));
+    c->pending[slot] = false;
     return MPT_OK;
 }
 
-MPT_API mpt_status mpt_reduce_wait(mpt_comm* c) {
+MPT_API mpt_status mpt_reduce_wait(mpt_comm* c, uint32_t slot) {
     if (!c) return MPT_ERR_INVALID_ARGUMENT;
-    if (!c->pending) return cfail(c, MPT_ERR_INVALID_ARGUMENT, "no reduce is in flight");
+    if (slot >= mpt_comm::kSlots) return cfail(c, MPT_ERR_LIMIT, "slot must be < 4");
+    if (!c->pending[slot]) return cfail(c, MPT_ERR_INVALID_ARGUMENT, "no reduce is in flight in this slot");
     CCU(cudaSetDevice(c->device));
-    CCU(cudaEventSynchronize(c->done));
-    c->pending = false;
+    CCU(cudaEventSynchronize(c->done[slot]));
+    c->pending[slot] = false;
     return MPT_OK;
 }
 

@@ -88,7 +88,7 @@ class ShardComm:
             from ._lib import MptError
             raise MptError(st, self.l.mpt_comm_last_error(self.h).decode())
 
-    def reduce_begin(self, partial_sum, out, width, height, spp_total, root=0, flags=0, stream=None, h_out=None):
+    def reduce_begin(self, partial_sum, out, width, height, spp_total, root=0, flags=0, stream=None, h_out=None, slot=0):
         """partial_sum / out: torch CUDA tensors (H, W, 4) float32; h_out: pinned host tensor or None."""
         import ctypes as C
 
@@ -96,17 +96,17 @@ class ShardComm:
         st = stream if stream is not None else torch.cuda.current_stream(partial_sum.device).cuda_stream
         self._check(self.l.mpt_reduce_begin(self.h, C.c_void_p(partial_sum.data_ptr()), C.c_void_p(out.data_ptr()) if out is not None else None,
                                             C.c_void_p(h_out.data_ptr()) if h_out is not None else None, width, height, spp_total, root, flags,
-                                            C.c_void_p(st)))
+                                            C.c_void_p(st), slot))
 
-    def reduce_end(self, stream=None):
+    def reduce_end(self, slot=0, stream=None):
         import ctypes as C
 
         import torch
         st = stream if stream is not None else torch.cuda.current_stream().cuda_stream
-        self._check(self.l.mpt_reduce_end(self.h, C.c_void_p(st)))
+        self._check(self.l.mpt_reduce_end(self.h, slot, C.c_void_p(st)))
 
-    def reduce_wait(self):
-        self._check(self.l.mpt_reduce_wait(self.h))
+    def reduce_wait(self, slot=0):
+        self._check(self.l.mpt_reduce_wait(self.h, slot))
 
     def close(self):
         if getattr(self, "h", None):

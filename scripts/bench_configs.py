@@ -39,6 +39,7 @@ def timed(fn, steps, warmup, world, dev):
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fn()  # untimed lead-in step: the timed ones are enqueued while it runs (bench.py explains why)
     e0.record()
     for _ in range(steps):
         fn()
@@ -98,13 +99,13 @@ def render_config(name, tables, W, H, spp, L, rank, world, dev, steps, warmup, e
     ctx.reset_stats()
     ms = timed(step, steps, warmup, world, dev)
     st = ctx.stats()
-    work["extend_share"] = st.extend_ms / (steps + warmup) / ms
-    work["shade_share"] = st.shade_ms / (steps + warmup) / ms
+    work["extend_share"] = st.extend_ms / (steps + warmup + 1) / ms
+    work["shade_share"] = st.shade_ms / (steps + warmup + 1) / ms
     ctx.set_profiling(0)
     rays = torch.tensor([float(st.rays_continuation)], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(rays)
-    total_steps = steps + warmup
+    total_steps = steps + warmup + 1
     line = {"config": name, "n_gpus": world, "width": W, "height": H, "spp_per_gpu": spp, "spp_total": spp * world, "max_path_length": L,
             "triangles": tables.triangle_count, "instances": len(tables.instances), "ms_per_frame": ms,
             "msamples_per_s": W * H * spp * world / (ms * 1e-3) / 1e6,

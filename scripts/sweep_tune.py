@@ -60,6 +60,7 @@ def main():
         ctx.set_profiling(2)
         ctx.reset_stats()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ctx.render_device(cam, P(2), tex1=tex1, out=out)  # lead-in frame: the timed ones are enqueued while it runs (see bench.py)
         e0.record()
         n = 4
         for i in range(n):
@@ -73,8 +74,8 @@ def main():
             ref_img = img
         else:
             diff = float((img[..., :3] - ref_img[..., :3]).abs().mean() / ref_img[..., :3].abs().mean())
-        print(json.dumps({"scene": scene, "setting": s, "msamples_per_s": W * H * spp / ms / 1e3, "ms_per_frame": ms, "extend_ms_per_frame": st.extend_ms / n,
-                          "shade_ms_per_frame": st.shade_ms / n, "nodes_per_ray": npr, "tris_per_ray": tpr, "rel_mean_abs_diff_vs_first": diff}), flush=True)
+        print(json.dumps({"scene": scene, "setting": s, "msamples_per_s": W * H * spp / ms / 1e3, "ms_per_frame": ms, "extend_ms_per_frame": st.extend_ms / (n + 1),
+                          "shade_ms_per_frame": st.shade_ms / (n + 1), "nodes_per_ray": npr, "tris_per_ray": tpr, "rel_mean_abs_diff_vs_first": diff}), flush=True)
         ctx.close()
         del ctx
 

@@ -31,11 +31,19 @@ def test_single_rank_reduce_normalises_and_lands_in_host_memory(gpu_ctx):
     assert torch.equal(out, want)  # sum / spp with the division k_resolve uses: bit-identical to the unsharded frame
     assert np.array_equal(h_out.numpy(), want.cpu().numpy())
     # stream-side join, in place, un-normalised
-    comm.reduce_begin(part, part, w, h, total, root=0, flags=abi.REDUCE_KEEP_SUM)
-    comm.reduce_end()
+    comm.reduce_begin(part, part, w, h, total, root=0, flags=abi.REDUCE_KEEP_SUM, slot=1)
+    comm.reduce_end(slot=1)
     torch.cuda.synchronize()
     assert torch.allclose(part / total, want, rtol=1e-6, atol=0)
-    # protocol errors are reported, not swallowed
+    # two reduces in flight in different slots; the same slot twice is refused; protocol errors are reported, not swallowed
+    a, b = part.clone(), part.clone()
+    comm.reduce_begin(a, a, w, h, total, slot=0)
+    comm.reduce_begin(b, b, w, h, total, slot=1)
     with pytest.raises(Exception):
-        comm.reduce_wait()
+        comm.reduce_begin(b, b, w, h, total, slot=1)
+    comm.reduce_wait(slot=0)
+    comm.reduce_wait(slot=1)
+    assert torch.equal(a, b)
+    with pytest.raises(Exception):
+        comm.reduce_wait(slot=0)
     comm.close()
