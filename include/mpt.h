@@ -26,7 +26,8 @@ extern "C" {
 #define MPT_API __attribute__((visibility("default")))
 #endif
 
-#define MPT_ABI_VERSION 2u /* 2: + gbuffer, accumulate, PFM/HDR I/O, iterations in flight, NEE, bvh_info.max_depth */
+#define MPT_ABI_VERSION 3u /* 2: + gbuffer, accumulate, PFM/HDR I/O, iterations in flight, NEE, bvh_info.max_depth
+                              3: + external memory / semaphore import, mpt_comm_* / mpt_reduce_*, host accel export, ray-queue read-back */
 
 typedef enum mpt_status {
     MPT_OK = 0,
@@ -393,6 +394,38 @@ MPT_API mpt_status mpt_bvh_get_info(mpt_context* ctx, mpt_bvh_info* out);
  * NULL) receives the leaf order. No device needed. */
 MPT_API mpt_status mpt_bvh8_build_info(const float* boxes, uint32_t n, mpt_bvh_info* out, uint32_t* prim_order);
 
+/* ---- Vulkan <-> CUDA interop (north_star; SURVEY.md §8(b) "cross-API sync options" (2)) ------------------------------------------
+ * The merian node shares its output with the rest of the graph without a host round trip: it allocates an exportable VkBuffer
+ * (VkExportMemoryAllocateInfo, VK_EXTERNAL_MEMORY_HANDLE_TYPE_OPAQUE_FD_BIT; vkGetMemoryFdKHR) and two exportable TIMELINE semaphores
+ * (VkExportSemaphoreCreateInfo, VK_EXTERNAL_SEMAPHORE_HANDLE_TYPE_OPAQUE_FD_BIT; vkGetSemaphoreFdKHR), imports them once, and per
+ * iteration replaces `submission.sync_to_cpu_and_back` (include/merian/vk/command/submission.hpp:101-114) by: raw queue submit that
+ * signals S_vk = n (include/merian/vk/command/queue.hpp:29-30) -> mpt_wait_external_semaphore(S_vk, n, stream) -> mpt_render(..., d_ptr,
+ * stream) -> mpt_signal_external_semaphore(S_cu, n, stream) -> the graph's next submit waits S_cu = n. merian's own TimelineSemaphore
+ * cannot be used: its handle type has a private, non-exportable constructor (include/merian/vk/sync/semaphore_timeline.hpp:10-29), so the
+ * node owns its semaphores; the device extensions VK_KHR_external_memory_fd + VK_KHR_external_semaphore_fd are requested through
+ * DeviceSupportInfo::check (include/merian/vk/extension/extension.hpp:70-78). A successful import takes ownership of the descriptor
+ * (do not close it); a failed one leaves it with the caller. INTEGRATION.md §3 has the Vulkan side line by line. */
+enum {
+    MPT_EXTERNAL_MEMORY_OPAQUE_FD = 0,   /* vkGetMemoryFdKHR, VK_EXTERNAL_MEMORY_HANDLE_TYPE_OPAQUE_FD_BIT */
+    MPT_EXTERNAL_MEMORY_CUDA_VMM_FD = 1  /* cuMemExportToShareableHandle(CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR): a CUDA-only host; size must
+                                            be a multiple of the allocation granularity */
+};
+enum { MPT_EXTERNAL_MEMORY_DEDICATED = 0x1 /* the VkDeviceMemory is a dedicated allocation (VkMemoryDedicatedAllocateInfo) */ };
+enum {
+    MPT_EXTERNAL_SEMAPHORE_OPAQUE_FD = 0,  /* binary VkSemaphore exported as OPAQUE_FD */
+    MPT_EXTERNAL_SEMAPHORE_TIMELINE_FD = 1 /* VK_SEMAPHORE_TYPE_TIMELINE exported as OPAQUE_FD */
+};
+typedef struct mpt_external_memory mpt_external_memory;
+typedef struct mpt_external_semaphore mpt_external_semaphore;
+MPT_API mpt_status mpt_import_external_memory_fd(mpt_context* ctx, int fd, uint64_t size, uint32_t handle_type, uint32_t flags,
+                                                 mpt_external_memory** out, void** d_ptr);
+MPT_API mpt_status mpt_release_external_memory(mpt_context* ctx, mpt_external_memory* memory);
+MPT_API mpt_status mpt_import_external_semaphore_fd(mpt_context* ctx, int fd, uint32_t handle_type, mpt_external_semaphore** out);
+/* `value`: the timeline value to wait for / to signal (ignored for binary semaphores). Enqueued on `stream`. */
+MPT_API mpt_status mpt_wait_external_semaphore(mpt_context* ctx, mpt_external_semaphore* semaphore, uint64_t value, void* stream);
+MPT_API mpt_status mpt_signal_external_semaphore(mpt_context* ctx, mpt_external_semaphore* semaphore, uint64_t value, void* stream);
+MPT_API mpt_status mpt_release_external_semaphore(mpt_context* ctx, mpt_external_semaphore* semaphore);
+
 /* ---- multi-GPU: the one exchange step of the path -------------------------------------------------------------
  * A frame is sharded by sample index (mpt_render_params.sample_offset / sample_stride + MPT_RENDER_OUTPUT_SUM): every GPU renders its
  * share of the samples of ALL pixels into a private sum buffer; the buffers are combined with ONE NCCL reduce over NVLink per frame and
@@ -455,7 +488,10 @@ MPT_API void mpt_host_accel_free(mpt_host_accel* accel);
 /* Test hook for the BSDF property suite (tests/test_bsdf.cpp of the reference restated): runs
  * sample_eval / eval / pdf of one BSDF on the device. See merian_b200/csrc/bsdf_check.cu. */
 typedef struct mpt_bsdf_check_params {
-    uint32_t bsdf;        /* 0 Lambert, 1 GGX, 2 GGX aniso, 3 FresnelMix, 4 IridescentFresnelMix, 5 IridescentRoughDielectric, 6 Sheen, 7 glTF full */
+    uint32_t bsdf;        /* 0 Lambert, 1 GGX, 2 GGX aniso, 3 FresnelMix<GGX, Lambert>, 4 IridescentFresnelMix, 5 IridescentRoughDielectric,
+                           * 6 SheenBRDF alone (oracle only: on the device the sheen lobe exists only inside SheenLayer, MPT_ERR_UNSUPPORTED),
+                           * 7 the whole GltfBSDF nest (metallic 0.5, clearcoat 0.5, sheen 0.5 * albedo, iridescence as given, no transmission),
+                           * 8 Conductor, 9 SheenLayer<dielectric> with sheen colour = albedo */
     float wi[3];
     uint32_t n_samples;
     uint32_t seed;

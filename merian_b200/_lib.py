@@ -18,6 +18,8 @@ EXPORTS = ["mpt_abi_version", "mpt_create", "mpt_destroy", "mpt_last_error", "mp
            "mpt_host_accel_build", "mpt_host_accel_get", "mpt_host_accel_free",
            "mpt_comm_unique_id", "mpt_comm_create", "mpt_comm_adopt", "mpt_comm_destroy", "mpt_comm_last_error", "mpt_comm_info",
            "mpt_reduce_begin", "mpt_reduce_end", "mpt_reduce_wait",
+           "mpt_import_external_memory_fd", "mpt_release_external_memory", "mpt_import_external_semaphore_fd", "mpt_wait_external_semaphore",
+           "mpt_signal_external_semaphore", "mpt_release_external_semaphore",
            # include/mpt_node.h
            "mptn_create", "mptn_destroy", "mptn_last_error", "mptn_load_config", "mptn_dump_config", "mptn_describe_outputs",
            "mptn_set_shard", "mptn_process",
@@ -90,6 +92,12 @@ def lib():
                                        C.c_uint32]
         l.mpt_reduce_end.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         l.mpt_reduce_wait.argtypes = [C.c_void_p, C.c_uint32]
+        l.mpt_import_external_memory_fd.argtypes = [C.c_void_p, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        l.mpt_release_external_memory.argtypes = [C.c_void_p, C.c_void_p]
+        l.mpt_import_external_semaphore_fd.argtypes = [C.c_void_p, C.c_int, C.c_uint32, C.POINTER(C.c_void_p)]
+        l.mpt_wait_external_semaphore.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        l.mpt_signal_external_semaphore.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        l.mpt_release_external_semaphore.argtypes = [C.c_void_p, C.c_void_p]
         l.mpt_bsdf_check.argtypes = [C.c_void_p, C.POINTER(abi.BsdfCheckParams), C.c_void_p]
         l.mptn_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         l.mptn_destroy.argtypes = [C.c_void_p]

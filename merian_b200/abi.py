@@ -5,7 +5,7 @@ both sides consume the same scene tables, exactly as the reference's renderer an
 """
 import ctypes as C
 
-MPT_ABI_VERSION = 2
+MPT_ABI_VERSION = 3
 
 # mpt_status
 MPT_OK, MPT_ERR_INVALID_ARGUMENT, MPT_ERR_CUDA, MPT_ERR_NOT_READY, MPT_ERR_UNSUPPORTED, MPT_ERR_LIMIT, MPT_ERR_IO = range(7)
@@ -42,6 +42,9 @@ RENDER_DEMODULATE_ALBEDO = 0x2
 RENDER_OUTPUT_SUM = 0x4
 RENDER_NEE = 0x8
 
+EXTERNAL_MEMORY_OPAQUE_FD, EXTERNAL_MEMORY_CUDA_VMM_FD = 0, 1
+EXTERNAL_MEMORY_DEDICATED = 0x1
+EXTERNAL_SEMAPHORE_OPAQUE_FD, EXTERNAL_SEMAPHORE_TIMELINE_FD = 0, 1
 COMM_UNIQUE_ID_BYTES = 128
 REDUCE_ALL_RANKS, REDUCE_KEEP_SUM = 0x1, 0x2
 

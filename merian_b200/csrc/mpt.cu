@@ -15,6 +15,7 @@
 #include "bvh8.h"
 #include "float_image_files.h"
 #include "scene_build.h"
+#include "mpt_internal.h"
 #include "shading.cuh"
 #include "bvh8_traverse_pooled.cuh"
 
@@ -1049,8 +1050,7 @@ __global__ void __launch_bounds__(kThreads) k_resolve(RenderConst rc, PathBuffer
 template <uint32_t FEAT> MPT_DEV bool check_sample(const Bsdf& b, f3 wi, Rng& rng, f3& wo, float& pdf, f3& w) {
     return bsdf_sample_eval<FEAT>(b, wi, rng, wo, pdf, w);
 }
-__global__ void k_bsdf_check(mpt_bsdf_check_params P, float* out) {
-    constexpr uint32_t FEAT = 0x3F;
+template <uint32_t FEAT> __global__ void k_bsdf_check(mpt_bsdf_check_params P, float* out) {
     Bsdf b;
     b.gltf = 1u;
     b.base = mk3(P.albedo[0], P.albedo[1], P.albedo[2]);
@@ -1066,6 +1066,15 @@ __global__ void k_bsdf_check(mpt_bsdf_check_params P, float* out) {
     case 4: b.iri = P.iridescence; break;                                          // IridescentFresnelMix<GGX, Lambert>, eta 1/1.5
     case 5: b.tw = 1.f; b.f0 = 0.04f; b.iri = P.iridescence; break;                // IridescentRoughDielectric
     case 8: b.metallic = 1.f; b.base = mk3(P.f0[0], P.f0[1], P.f0[2]); break;      // Conductor: Schlick(f0) * GGX
+    case 3: break;                                                                 // FresnelMix<GGX, Lambert>: the kernel is instantiated without
+                                                                                   // the iridescence feature (gltf-material.slang:64-90 prunes it)
+    case 9:                                                                        // SheenLayer<dielectric>: sheen colour = albedo over the same base
+        b.sheen_col = b.base; b.sheen_alpha = P.alpha; b.max_sheen = fmaxf(b.base.x, fmaxf(b.base.y, b.base.z));
+        break;
+    case 7:                                                                        // the whole GltfBSDF nest (no transmission: reciprocity holds)
+        b.metallic = 0.5f; b.ay = P.alpha_bitangent > 0.f ? P.alpha_bitangent : P.alpha; b.coat_w = 0.5f; b.iri = P.iridescence;
+        b.sheen_col = 0.5f * b.base; b.sheen_alpha = P.alpha; b.max_sheen = 0.5f * fmaxf(b.base.x, fmaxf(b.base.y, b.base.z));
+        break;
     default: break;
     }
     const f3 wi = mk3(P.wi[0], P.wi[1], P.wi[2]);
@@ -1495,6 +1504,9 @@ mpt_status run_passes(mpt_context* ctx, const CameraParams& cam, const mpt_rende
 }
 
 } // namespace
+
+int mpt_internal_device(const mpt_context* ctx) { return ctx->device; }
+mpt_status mpt_internal_fail(mpt_context* ctx, mpt_status status, const char* message) { return fail(ctx, status, message ? message : ""); }
 
 // ======================================================================================= C-ABI
 extern "C" {
@@ -2220,11 +2232,13 @@ MPT_API mpt_status mpt_bvh8_build_info(const float* boxes, uint32_t n, mpt_bvh_i
 
 MPT_API mpt_status mpt_bsdf_check(mpt_context* ctx, const mpt_bsdf_check_params* p, float* out16) {
     if (!ctx || !p || !out16) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
-    if (p->bsdf == 3 || p->bsdf == 6 || p->bsdf == 7 || p->bsdf > 8) return fail(ctx, MPT_ERR_UNSUPPORTED, "BSDF configuration is not a sub-tree of GltfBSDF");
+    if (p->bsdf == 6 || p->bsdf > 9)
+        return fail(ctx, MPT_ERR_UNSUPPORTED, "not a sub-tree of GltfBSDF that can be isolated (SheenBRDF alone: use 9, SheenLayer over the dielectric)");
     CU(cudaSetDevice(ctx->device));
     DevBuf o;
     CU(o.ensure(64));
-    k_bsdf_check<<<1, 1>>>(*p, o.as<float>());
+    if (p->bsdf == 3) k_bsdf_check<0u><<<1, 1>>>(*p, o.as<float>());
+    else k_bsdf_check<0x3Fu><<<1, 1>>>(*p, o.as<float>());
     CU(cudaGetLastError());
     CU(cudaMemcpy(out16, o.p, 64, cudaMemcpyDeviceToHost));
     return MPT_OK;

@@ -1336,6 +1336,22 @@ int oracle_bsdf_check(const mpt_bsdf_check_params* p, float* out16) {
     case 5: bsdf_checks(IridescentRoughDielectricBSDF(p->alpha, 1.0f / 1.5f, albedo, float3(0.04f), 1.3f, 400.0f, p->iridescence), wi, p->n_samples, p->seed, out16); break;
     case 6: bsdf_checks(SheenBRDF(albedo, p->alpha), wi, p->n_samples, p->seed, out16); break;
     case 8: bsdf_checks(ConductorFresnelBSDF<GGXBRDF>(GGXBRDF(p->alpha), f0), wi, p->n_samples, p->seed, out16); break;
+    case 7:
+    case 9: {
+        // the nest GltfMaterial::get_sample builds (gltf-material.slang:18-27, 153-308), with the factors mpt.h states for these codes
+        const bool full = p->bsdf == 7;
+        const float eta = 1.0f / 1.5f, iri = full ? p->iridescence : 0.f, metallic = full ? 0.5f : 0.f, coat_w = full ? 0.5f : 0.f;
+        const float2 spec_alpha(p->alpha, full && p->alpha_bitangent > 0.f ? p->alpha_bitangent : p->alpha);
+        const float3 sheen_col = full ? albedo * 0.5f : albedo;
+        const GltfOpaqueDielectric od(SpecularBRDF(spec_alpha), LambertDiffuseBRDF(albedo), p->ior_f0, eta, 1.3f, 400.0f, iri);
+        const GltfDielectric diel(od, IridescentRoughDielectricBSDF(p->alpha, eta, albedo, float3(p->ior_f0), 1.3f, 400.0f, iri), 0.f);
+        const GltfReflective refl(diel, GltfConductor(SpecularBRDF(spec_alpha), albedo, 1.3f, 400.0f, iri), metallic);
+        const float max_sheen = std::max(sheen_col.x, std::max(sheen_col.y, sheen_col.z));
+        const GltfSheened sheened(SheenBRDF(sheen_col, p->alpha), refl, p->alpha, max_sheen);
+        const float coat_alpha = DEFAULT_MIN_ROUGHNESS * DEFAULT_MIN_ROUGHNESS;
+        bsdf_checks(GltfBSDF(sheened, GltfCoated(SpecularBRDF(coat_alpha), sheened, GLTF_DIELECTRIC_IOR_F0), coat_w), wi, p->n_samples, p->seed, out16);
+        break;
+    }
     default: return 1;
     }
     return 0;

@@ -19,7 +19,7 @@ QUADRATURE_TOL = 1e-3
 ALBEDO_REL_TOL = 0.15
 
 # mpt_bsdf_check_params.bsdf
-LAMBERT, GGX, GGX_ANISO, FRESNEL_MIX, IRIDESCENT_MIX, ROUGH_DIELECTRIC, SHEEN, CONDUCTOR = 0, 1, 2, 3, 4, 5, 6, 8
+LAMBERT, GGX, GGX_ANISO, FRESNEL_MIX, IRIDESCENT_MIX, ROUGH_DIELECTRIC, SHEEN, GLTF_FULL, CONDUCTOR, SHEEN_LAYER = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 
 
 def wi_zenith(deg, azimuth_deg=0.0):
@@ -102,6 +102,16 @@ def cases(include_albedo=True):
         for nm, wi in (("Normal", WI_NORMAL), ("Grazing", WI_GRAZING)):
             out.append((f"Conductor{a}{nm}", dict(bsdf=CONDUCTOR, alpha=a, f0=(0.95, 0.64, 0.54), wi=wi),
                         [sample_pdf_match, sample_eval_consistent, reciprocal, energy_conserving] + A, None))
+    # Not in the reference's suite: the sheen lobe as it is reachable from GltfBSDF (SheenLayer over the dielectric; the device cannot
+    # isolate SheenBRDF) and the whole nest. The reference's property checks that hold for a layered BSDF; both arms build the same nest.
+    for a in (0.09, 0.3, 0.5, 1.0):
+        for nm, wi in (("Normal", WI_NORMAL), ("Grazing", WI_GRAZING)):
+            out.append((f"SheenLayerAlpha{a}{nm}", dict(bsdf=SHEEN_LAYER, albedo=(0.8, 0.5, 0.2), alpha=a, wi=wi),
+                        [sample_pdf_match, sample_eval_consistent, energy_conserving], None))
+    for s in (0.0, 1.0):
+        for nm, wi in (("Normal", wi_zenith(20, 30)), ("Grazing", wi_zenith(75, 30))):
+            out.append((f"GltfFull{s}{nm}", dict(bsdf=GLTF_FULL, albedo=(0.8, 0.5, 0.2), alpha=0.3, alpha_bitangent=0.1, iridescence=s, wi=wi),
+                        [sample_eval_consistent, energy_conserving], None))
     return out
 
 
