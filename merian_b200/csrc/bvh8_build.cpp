@@ -1,13 +1,20 @@
 // bvh8_build.cpp — host builder: binned-SAH BVH2 (one primitive per leaf) -> SAH-optimal 8-wide collapse (dynamic program of Ylitie,
 // Karras, Laine 2017, section 4.1, restated from the paper) -> quantised 80-byte nodes.
-// Replaces the driver BLAS/TLAS build of the reference (src/merian-shaders/scene/scene.cpp:1672-1892).
+// Replaces the driver BLAS/TLAS build of the reference (src/merian-shaders/scene/scene.cpp:1672-1892), which runs on the device per
+// geometry change; here it runs on the host cores, in parallel (OpenMP tasks over subtrees, level-synchronous emission); per-phase
+// times in profiles/r02_bvh_build.md. The output is a deterministic function of the input boxes (thread timing only permutes the
+// numbering of the intermediate BVH2 nodes).
 #include "bvh8.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 #include <numeric>
 
 namespace mpt {
@@ -18,7 +25,7 @@ struct B3 {
     void grow(const Box& b) {
         for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); }
     }
-    void grow(const B3& b) {
+    void grow(const B3& b) { // growing by an empty box (lo = FLT_MAX, hi = -FLT_MAX) is a no-op
         for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); }
     }
     void grow_pt(const float* p) {
@@ -31,15 +38,41 @@ struct B3 {
     }
 };
 
-struct Node2 {
-    B3 box;
-    uint32_t left = 0, right = 0; // internal children
-    uint32_t first = 0, count = 0; // leaf range into prim index array (count > 0 => leaf)
-    uint32_t rfirst = 0, rcount = 0; // range of every node (leaf or internal) in the prim index array
+struct Box6 { // a B3 without constructors, so that arrays of nodes need no initialisation pass
+    float lo[3], hi[3];
+    float half_area() const {
+        const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (dx < 0) return 0.f;
+        return dx * dy + dy * dz + dz * dx;
+    }
+};
+struct Node2 { // trivially constructible: the 2n-node array is allocated uninitialised and first touched by the thread that builds the node
+    Box6 box;
+    uint32_t left, right;    // internal children
+    uint32_t count;          // > 0: BVH2 leaf (one primitive, or up to 3 with coincident centroids)
+    uint32_t rfirst, rcount; // range of every node (leaf or internal) in the prim index array
+};
+template <class T> struct RawArray { // uninitialised storage for trivially constructible T
+    T* p = nullptr;
+    size_t n = 0;
+    ~RawArray() { std::free(p); }
+    bool alloc(size_t count) {
+        std::free(p);
+        n = count;
+        p = static_cast<T*>(std::malloc(std::max<size_t>(count, 1) * sizeof(T)));
+        return p != nullptr;
+    }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+    T* data() { return p; }
 };
 
 constexpr int NBINS = 16;
-
+constexpr uint32_t kSmallNode = 8;              // at most this many primitives: exact sweep over sorted centroids instead of binning
+constexpr uint32_t kTaskGrain = 4096;           // subtrees below this size are built by the thread that reaches them
+constexpr uint32_t kParallelBinning = 1u << 17; // nodes above this size bin their primitives with several tasks
+constexpr uint32_t kLocalSubtree = 16384;       // subtrees of at most this many primitives are built from private contiguous copies
+constexpr uint32_t kMaxRecursion = 256;         // SAH levels before the builder switches to median splits (bounds the recursion depth)
 
 // Builder knobs for tuning sessions (host code only; defaults are the measured optimum).
 float env_float(const char* name, float def) {
@@ -47,122 +80,335 @@ float env_float(const char* name, float def) {
     return v ? float(std::atof(v)) : def;
 }
 
-struct Builder2 {
-    const Box* boxes;
-    std::vector<float> cent; // 3 per prim
-    std::vector<uint32_t> idx;
-    std::vector<Node2> nodes;
-    int max_leaf;
-    uint32_t sah_depth_limit = 0xFFFFFFFFu; // BVH2 levels built with SAH before the builder switches to median splits
-    float trav_cost = 1.0f; // SAH: cost of one node test in units of one primitive test
-    float balance = 0.f;    // SAH candidates must leave at least this fraction of the primitives on the smaller side (0 = plain SAH)
+// BVH2 (binned SAH, 16 bins, the three axes binned in ONE pass; exact sweep for nodes of <= 8 primitives) with the dynamic program of the
+// wide collapse evaluated in post-order inside the same task tree: cost[n][i-1] = C(n, i), the cheapest way to represent BVH2 subtree n
+// as at most i BVH8 children (leaves of <= 3 primitives, or internal nodes).
+// Parallel: every split of a large node spawns an OpenMP task for one child; nodes come from a pre-sized array through an atomic
+// counter. A job carries its box and centroid box (accumulated from the parent's bins), so a node costs one binning pass and one
+// partition pass.
+struct Builder {
+    const Box* boxes = nullptr;
+    RawArray<float> cent; // 3 per prim
+    RawArray<uint32_t> idx;
+    RawArray<Node2> nodes;
+    RawArray<float> cost;         // 7 per node
+    RawArray<uint8_t> dec, dist8; // 7 per node; 1 per node
+    uint32_t node_count = 0;
+    std::atomic<uint32_t> next_node{1};
+    uint32_t sah_depth_limit = kMaxRecursion;
+    float balance = 0.f; // SAH candidates must leave at least this fraction of the primitives on the smaller side (0 = plain SAH)
+    float c_prim = 0.5f, c_node = 1.0f;
+
+    struct Job { uint32_t node, first, count, depth; B3 box, cbox; };
+    // The arrays a subtree is built from: the global ones, or — once a subtree is small enough to live in L2 — private contiguous copies
+    // of its primitives' boxes and centroids (the global index array is a random permutation by then, and every level of the tree would
+    // gather 36 bytes per primitive from all over memory again). `first0`: position in the global index array of local position 0.
+    struct View { const Box* boxes; const float* cent; uint32_t* idx; uint32_t first0; };
+    struct Bins {
+        B3 bb[3][NBINS], cb[3][NBINS];
+        uint32_t bc[3][NBINS];
+        Bins() { std::memset(bc, 0, sizeof(bc)); }
+        void merge(const Bins& o) {
+            for (int a = 0; a < 3; a++)
+                for (int b = 0; b < NBINS; b++) {
+                    if (!o.bc[a][b]) continue;
+                    bb[a][b].grow(o.bb[a][b]);
+                    cb[a][b].grow(o.cb[a][b]);
+                    bc[a][b] += o.bc[a][b];
+                }
+        }
+    };
 
     void build(uint32_t n) {
-        idx.resize(n);
-        std::iota(idx.begin(), idx.end(), 0u);
-        cent.resize(size_t(n) * 3);
-        for (uint32_t i = 0; i < n; i++)
-            for (int a = 0; a < 3; a++) cent[size_t(i) * 3 + a] = 0.5f * (boxes[i].lo[a] + boxes[i].hi[a]);
-        nodes.reserve(size_t(n) * 2);
-        nodes.emplace_back();
-        struct Job { uint32_t node, first, count, depth; };
-        std::vector<Job> stack;
-        stack.push_back({0, 0, n, 0});
-        while (!stack.empty()) {
-            const Job j = stack.back();
-            stack.pop_back();
-            B3 box, cbox;
-            for (uint32_t i = j.first; i < j.first + j.count; i++) {
-                box.grow(boxes[idx[i]]);
-                cbox.grow_pt(&cent[size_t(idx[i]) * 3]);
+        const auto t0 = std::chrono::steady_clock::now();
+        const size_t nn = size_t(n) * 2 + 1;
+        if (!idx.alloc(n) || !cent.alloc(size_t(n) * 3) || !nodes.alloc(nn) || !cost.alloc(nn * 7) || !dec.alloc(nn * 7) || !dist8.alloc(nn))
+            throw std::bad_alloc();
+        B3 box, cbox;
+#pragma omp parallel
+        {
+            B3 lb, lc;
+#pragma omp for schedule(static) nowait
+            for (int64_t i = 0; i < int64_t(n); i++) {
+                idx[size_t(i)] = uint32_t(i);
+                float c[3];
+                for (int a = 0; a < 3; a++) c[a] = cent[size_t(i) * 3 + a] = 0.5f * (boxes[i].lo[a] + boxes[i].hi[a]);
+                lb.grow(boxes[i]);
+                lc.grow_pt(c);
             }
-            nodes[j.node].box = box;
-            nodes[j.node].rfirst = j.first;
-            nodes[j.node].rcount = j.count;
-            if (j.count <= 1) { make_leaf(j.node, j.first, j.count); continue; }
+#pragma omp critical
+            {
+                box.grow(lb);
+                cbox.grow(lc);
+            }
+        }
+        if (std::getenv("MPT_BUILD_TIMING"))
+            std::fprintf(stderr, "[bvh8_build] alloc + centroids %.1f ms; ", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        const View global{boxes, cent.data(), idx.data(), 0u};
+#pragma omp parallel
+#pragma omp single
+        build_node(Job{0, 0, n, 0, box, cbox}, global);
+        node_count = next_node.load();
+    }
 
-            // binned SAH over the 3 axes
+    void bin_range(const Job& j, const View& V, uint32_t first, uint32_t last, const float* k, const bool* axis_ok, Bins& B) const {
+        const Box* boxes = V.boxes;
+        const float* cent = V.cent;
+        const uint32_t* idx = V.idx;
+        for (uint32_t i = first; i < last; i++) {
+            const uint32_t p = idx[i];
+            const float* c = &cent[size_t(p) * 3];
+            for (int a = 0; a < 3; a++) {
+                if (!axis_ok[a]) continue;
+                int b = int((c[a] - j.cbox.lo[a]) * k[a]);
+                b = std::min(std::max(b, 0), NBINS - 1);
+                B.bc[a][b]++;
+                B.bb[a][b].grow(boxes[p]);
+                B.cb[a][b].grow_pt(c);
+            }
+        }
+    }
+
+    // the dynamic program for one node whose children are done
+    void collapse_cost(uint32_t k) {
+        const Node2& nd = nodes[k];
+        const float area = nd.box.half_area();
+        float* C = &cost[size_t(k) * 7];
+        uint8_t* D = &dec[size_t(k) * 7];
+        if (nd.count > 0) { // BVH2 leaf
+            for (int i = 0; i < 7; i++) { C[i] = area * float(nd.count) * c_prim; D[i] = 0; }
+            return;
+        }
+        const float* L = &cost[size_t(nd.left) * 7];
+        const float* R = &cost[size_t(nd.right) * 7];
+        auto distribute = [&](int j, uint8_t& best_k) { // min over 0 < k < j of C(left, k) + C(right, j - k), slots per side capped at 7
+            float best = FLT_MAX;
+            for (int kk = std::max(1, j - 7); kk <= std::min(j - 1, 7); kk++) {
+                const float v = L[kk - 1] + R[j - kk - 1];
+                if (v < best) { best = v; best_k = uint8_t(kk); }
+            }
+            return best;
+        };
+        uint8_t k8 = 1;
+        const float c_internal = distribute(8, k8) + area * c_node;
+        dist8[k] = k8;
+        const float c_leaf = nd.rcount <= 3u ? area * float(nd.rcount) * c_prim : FLT_MAX;
+        if (c_leaf <= c_internal) { C[0] = c_leaf; D[0] = 0; } else { C[0] = c_internal; D[0] = 1; }
+        for (int i = 2; i <= 7; i++) {
+            uint8_t kk = 1;
+            const float cd = distribute(i, kk);
+            if (cd < C[i - 2]) { C[i - 1] = cd; D[i - 1] = kk; } else { C[i - 1] = C[i - 2]; D[i - 1] = 0; }
+        }
+    }
+
+    static void set_box(Node2& nd, const B3& b) {
+        for (int a = 0; a < 3; a++) { nd.box.lo[a] = b.lo[a]; nd.box.hi[a] = b.hi[a]; }
+    }
+    void make_leaf(uint32_t node, uint32_t count) {
+        nodes[node].count = count;
+        collapse_cost(node);
+    }
+
+    // SAH split of a small node: exact sweep over the primitives sorted by centroid, per axis. Returns false if no axis separates them.
+    bool split_small(const Job& j, const View& V, uint32_t& mid, B3& lbox, B3& lcb, B3& rbox, B3& rcb) {
+        const Box* boxes = V.boxes;
+        const float* cent = V.cent;
+        uint32_t* idx = V.idx;
+        const uint32_t n = j.count;
+        if (n == 2) { // one possible split; keep the index order when the centroids allow it
+            const uint32_t p = idx[j.first], q = idx[j.first + 1];
+            bool differ = false;
+            for (int a = 0; a < 3; a++) differ |= cent[size_t(p) * 3 + a] != cent[size_t(q) * 3 + a];
+            if (!differ) return false;
+            lbox.grow(boxes[p]); lcb.grow_pt(&cent[size_t(p) * 3]);
+            rbox.grow(boxes[q]); rcb.grow_pt(&cent[size_t(q) * 3]);
+            mid = 1;
+            return true;
+        }
+        uint32_t order[kSmallNode], best_order[kSmallNode];
+        float best_cost = FLT_MAX;
+        uint32_t best_mid = 0;
+        for (int a = 0; a < 3; a++) {
+            if (!(j.cbox.hi[a] > j.cbox.lo[a])) continue;
+            for (uint32_t i = 0; i < n; i++) order[i] = idx[j.first + i];
+            std::sort(order, order + n, [&](uint32_t p, uint32_t q) {
+                const float cp = cent[size_t(p) * 3 + a], cq = cent[size_t(q) * 3 + a];
+                return cp < cq || (cp == cq && p < q);
+            });
+            float ra[kSmallNode];
+            B3 acc;
+            for (uint32_t i = n - 1; i > 0; i--) { acc.grow(boxes[order[i]]); ra[i] = acc.half_area(); }
+            acc = B3();
+            for (uint32_t i = 0; i + 1 < n; i++) {
+                acc.grow(boxes[order[i]]);
+                if (float(std::min(i + 1, n - i - 1)) < balance * float(n)) continue;
+                const float c = acc.half_area() * float(i + 1) + ra[i + 1] * float(n - i - 1);
+                if (c < best_cost) { best_cost = c; best_mid = i + 1; std::memcpy(best_order, order, n * sizeof(uint32_t)); }
+            }
+        }
+        if (best_mid == 0) return false;
+        for (uint32_t i = 0; i < n; i++) {
+            idx[j.first + i] = best_order[i];
+            B3& bx = i < best_mid ? lbox : rbox;
+            B3& cb = i < best_mid ? lcb : rcb;
+            bx.grow(boxes[best_order[i]]);
+            cb.grow_pt(&cent[size_t(best_order[i]) * 3]);
+        }
+        mid = best_mid;
+        return true;
+    }
+
+    // j.first is a position in V.idx; the node records the position in the GLOBAL index array
+    void build_node(Job j, const View& V) {
+        Node2& nd = nodes[j.node];
+        set_box(nd, j.box);
+        nd.left = nd.right = 0;
+        nd.rfirst = V.first0 + j.first;
+        nd.rcount = j.count;
+        if (j.count <= 1) { make_leaf(j.node, j.count); return; }
+        if (V.first0 == 0 && V.idx == idx.data() && j.count <= kLocalSubtree && j.count > kSmallNode) {
+            // small enough for L2: build this subtree from private contiguous copies, then write the resulting order back
+            std::vector<Box> lb(j.count);
+            std::vector<float> lc(size_t(j.count) * 3);
+            std::vector<uint32_t> li(j.count), lg(j.count);
+            for (uint32_t i = 0; i < j.count; i++) {
+                const uint32_t p = idx[j.first + i];
+                lg[i] = p;
+                li[i] = i;
+                lb[i] = boxes[p];
+                for (int a = 0; a < 3; a++) lc[size_t(i) * 3 + a] = cent[size_t(p) * 3 + a];
+            }
+            const View local{lb.data(), lc.data(), li.data(), j.first};
+            Job lj = j;
+            lj.first = 0;
+            build_subtree(lj, local);
+            for (uint32_t i = 0; i < j.count; i++) idx[j.first + i] = lg[li[i]];
+            return;
+        }
+        build_subtree(j, V);
+    }
+
+    void build_subtree(Job j, const View& V) {
+        Node2& nd = nodes[j.node];
+        const Box* boxes = V.boxes;
+        const float* cent = V.cent;
+        uint32_t* const idx = V.idx;
+        set_box(nd, j.box);
+        nd.left = nd.right = 0;
+        nd.rfirst = V.first0 + j.first;
+        nd.rcount = j.count;
+        if (j.count <= 1) { make_leaf(j.node, j.count); return; }
+
+        uint32_t mid = 0;
+        Job lj{0, 0, 0, j.depth + 1, B3(), B3()}, rj = lj;
+        bool have_child_boxes = false;
+        if (j.depth >= sah_depth_limit) {
+            // a degenerate SAH chain (one primitive peeled off per level) would outgrow the traversal stack: below this depth
+            // split at the object median of the widest centroid axis, which bounds the remaining depth by log2(count)
+            int a = 0;
+            for (int q = 1; q < 3; q++)
+                if (j.cbox.hi[q] - j.cbox.lo[q] > j.cbox.hi[a] - j.cbox.lo[a]) a = q;
+            mid = j.count / 2;
+            std::nth_element(idx + j.first, idx + j.first + mid, idx + j.first + j.count, [&](uint32_t p, uint32_t q) {
+                const float cp = cent[size_t(p) * 3 + a], cq = cent[size_t(q) * 3 + a];
+                return cp < cq || (cp == cq && p < q);
+            });
+        } else if (j.count <= kSmallNode) {
+            have_child_boxes = split_small(j, V, mid, lj.box, lj.cbox, rj.box, rj.cbox);
+        } else {
+            // binned SAH over the 3 axes, one pass (several tasks for the largest nodes)
+            float k[3];
+            bool axis_ok[3];
+            for (int a = 0; a < 3; a++) {
+                axis_ok[a] = j.cbox.hi[a] > j.cbox.lo[a];
+                k[a] = axis_ok[a] ? float(NBINS) * (1.0f - 1e-6f) / (j.cbox.hi[a] - j.cbox.lo[a]) : 0.f;
+            }
+            Bins B;
+            if (j.count >= kParallelBinning) {
+                constexpr int kParts = 16;
+                std::vector<Bins> part(kParts);
+                for (int t = 0; t < kParts; t++) {
+                    const uint32_t f = j.first + uint32_t(uint64_t(j.count) * t / kParts), l = j.first + uint32_t(uint64_t(j.count) * (t + 1) / kParts);
+                    Bins* dst = &part[t];
+#pragma omp task default(shared) firstprivate(f, l, dst)
+                    bin_range(j, V, f, l, k, axis_ok, *dst);
+                }
+#pragma omp taskwait
+                for (int t = 0; t < kParts; t++) B.merge(part[t]); // fixed order: deterministic
+            } else {
+                bin_range(j, V, j.first, j.first + j.count, k, axis_ok, B);
+            }
             float best_cost = FLT_MAX;
             int best_axis = -1, best_bin = -1;
             for (int a = 0; a < 3; a++) {
-                const float cmin = cbox.lo[a], cmax = cbox.hi[a];
-                if (!(cmax > cmin)) continue;
-                B3 bb[NBINS];
-                uint32_t bc[NBINS] = {0};
-                const float k = float(NBINS) * (1.0f - 1e-6f) / (cmax - cmin);
-                for (uint32_t i = j.first; i < j.first + j.count; i++) {
-                    const uint32_t p = idx[i];
-                    int b = int((cent[size_t(p) * 3 + a] - cmin) * k);
-                    b = std::min(std::max(b, 0), NBINS - 1);
-                    bb[b].grow(boxes[p]);
-                    bc[b]++;
-                }
+                if (!axis_ok[a]) continue;
                 float ra[NBINS];
                 uint32_t rc[NBINS];
                 B3 acc;
                 uint32_t cnt = 0;
                 for (int b = NBINS - 1; b > 0; b--) {
-                    acc.grow(bb[b]);
-                    cnt += bc[b];
+                    acc.grow(B.bb[a][b]);
+                    cnt += B.bc[a][b];
                     ra[b] = acc.half_area();
                     rc[b] = cnt;
                 }
                 acc = B3();
                 cnt = 0;
                 for (int b = 0; b < NBINS - 1; b++) {
-                    acc.grow(bb[b]);
-                    cnt += bc[b];
+                    acc.grow(B.bb[a][b]);
+                    cnt += B.bc[a][b];
                     if (cnt == 0 || rc[b + 1] == 0) continue;
                     if (float(std::min(cnt, rc[b + 1])) < balance * float(j.count)) continue;
-                    const float cost = acc.half_area() * float(cnt) + ra[b + 1] * float(rc[b + 1]);
-                    if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = b; }
+                    const float c = acc.half_area() * float(cnt) + ra[b + 1] * float(rc[b + 1]);
+                    if (c < best_cost) { best_cost = c; best_axis = a; best_bin = b; }
                 }
             }
-            const float parent_area = box.half_area();
-            const float leaf_cost = float(j.count);
-            const float split_cost = (parent_area > 0.f && best_axis >= 0) ? trav_cost + best_cost / parent_area : FLT_MAX;
-            if (int(j.count) <= max_leaf && split_cost >= leaf_cost) { make_leaf(j.node, j.first, j.count); continue; }
-
-            uint32_t mid;
-            if (j.depth >= sah_depth_limit) {
-                // a degenerate SAH chain (one primitive peeled off per level) would outgrow the traversal stack: below this depth
-                // split at the object median of the widest centroid axis, which bounds the remaining depth by log2(count)
-                int a = 0;
-                for (int k = 1; k < 3; k++)
-                    if (cbox.hi[k] - cbox.lo[k] > cbox.hi[a] - cbox.lo[a]) a = k;
-                mid = j.count / 2;
-                std::nth_element(idx.begin() + j.first, idx.begin() + j.first + mid, idx.begin() + j.first + j.count,
-                                 [&](uint32_t p, uint32_t q) { return cent[size_t(p) * 3 + a] < cent[size_t(q) * 3 + a]; });
-            } else if (best_axis >= 0) {
+            if (best_axis >= 0) {
                 const int a = best_axis;
-                const float cmin = cbox.lo[a], cmax = cbox.hi[a];
-                const float k = float(NBINS) * (1.0f - 1e-6f) / (cmax - cmin);
-                auto it = std::partition(idx.begin() + j.first, idx.begin() + j.first + j.count, [&](uint32_t p) {
-                    int b = int((cent[size_t(p) * 3 + a] - cmin) * k);
+                const float cmin = j.cbox.lo[a], ka = k[a];
+                auto it = std::partition(idx + j.first, idx + j.first + j.count, [&](uint32_t p) {
+                    int b = int((cent[size_t(p) * 3 + a] - cmin) * ka);
                     b = std::min(std::max(b, 0), NBINS - 1);
                     return b <= best_bin;
                 });
-                mid = uint32_t(it - idx.begin()) - j.first;
-            } else {
-                mid = 0;
+                mid = uint32_t(it - idx) - j.first;
+                for (int b = 0; b < NBINS; b++) { // the children's boxes are unions of the bins on either side of the split
+                    Job& t = b <= best_bin ? lj : rj;
+                    t.box.grow(B.bb[a][b]);
+                    t.cbox.grow(B.cb[a][b]);
+                }
+                have_child_boxes = true;
             }
-            if (mid == 0 || mid == j.count) { // all centroids coincide: split the index range in half
-                if (int(j.count) <= max_leaf) { make_leaf(j.node, j.first, j.count); continue; }
-                mid = j.count / 2;
-            }
-            const uint32_t l = uint32_t(nodes.size());
-            nodes.emplace_back();
-            nodes.emplace_back();
-            nodes[j.node].left = l;
-            nodes[j.node].right = l + 1;
-            nodes[j.node].count = 0;
-            stack.push_back({l + 1, j.first + mid, j.count - mid, j.depth + 1});
-            stack.push_back({l, j.first, mid, j.depth + 1});
         }
-    }
-    void make_leaf(uint32_t node, uint32_t first, uint32_t count) {
-        nodes[node].first = first;
-        nodes[node].count = count;
+        if (mid == 0 || mid == j.count) { // all centroids coincide: one BVH2 leaf of up to 3 primitives, else split the index range in half
+            if (j.count <= 3u) { make_leaf(j.node, j.count); return; }
+            mid = j.count / 2;
+            have_child_boxes = false;
+        }
+        const uint32_t l = next_node.fetch_add(2);
+        nd.left = l;
+        nd.right = l + 1;
+        nd.count = 0;
+        lj.node = l; lj.first = j.first; lj.count = mid;
+        rj.node = l + 1; rj.first = j.first + mid; rj.count = j.count - mid;
+        if (!have_child_boxes) {
+            lj.box = lj.cbox = rj.box = rj.cbox = B3();
+            for (Job* t : {&lj, &rj})
+                for (uint32_t i = t->first; i < t->first + t->count; i++) {
+                    t->box.grow(boxes[idx[i]]);
+                    t->cbox.grow_pt(&cent[size_t(idx[i]) * 3]);
+                }
+        }
+        if (rj.count > kTaskGrain && lj.count > kTaskGrain) {
+#pragma omp task default(shared) firstprivate(rj)
+            build_node(rj, V);
+            build_node(lj, V);
+#pragma omp taskwait
+        } else {
+            build_node(lj, V);
+            build_node(rj, V);
+        }
+        collapse_cost(j.node);
     }
 };
 
@@ -175,214 +421,188 @@ inline uint8_t exponent_for(float extent) {
     return uint8_t(e);
 }
 
+// One wide node under construction: its (up to 8) children as BVH2 subtrees, slot-assigned and quantised.
+struct Wide {
+    uint32_t root2 = 0; // BVH2 subtree this wide node stands for
+    uint32_t child[8];  // BVH2 node per slot (valid where slot_used)
+    uint8_t slot_used = 0, slot_leaf = 0;
+    uint32_t n_internal = 0, n_prims = 0;
+    Bvh8Node node;
+};
+
 } // namespace
 
-static void build_bvh8_once(const Box* boxes, uint32_t n, Bvh8& out, int max_leaf, uint32_t sah_depth_limit) {
+static void build_bvh8_once(const Box* boxes, uint32_t n, Bvh8& out, uint32_t sah_depth_limit) {
     out.nodes.clear();
     out.prim_order.clear();
-    B3 all;
-    for (uint32_t i = 0; i < n; i++) all.grow(boxes[i]);
-    for (int a = 0; a < 3; a++) { out.bounds.lo[a] = n ? all.lo[a] : 0.f; out.bounds.hi[a] = n ? all.hi[a] : 0.f; }
+    out.depth = 1;
     if (n == 0) {
+        for (int a = 0; a < 3; a++) out.bounds.lo[a] = out.bounds.hi[a] = 0.f;
         Bvh8Node root;
         std::memset(&root, 0, sizeof(root));
         root.ex = root.ey = root.ez = 1;
         out.nodes.push_back(root);
         return;
     }
-    Builder2 b2;
+    Builder b2;
     b2.boxes = boxes;
-    const int collapse_mode = int(env_float("MPT_BVH_COLLAPSE", 2.f)); // 2 = SAH-optimal dynamic program (default), 0 = greedy by area
-    b2.max_leaf = collapse_mode == 2 ? 1 : std::min(std::max(int(env_float("MPT_BVH_MAX_LEAF", float(max_leaf))), 1), 3);
-    b2.trav_cost = env_float("MPT_BVH_TRAV_COST", 1.0f);
-    b2.sah_depth_limit = sah_depth_limit;
+    b2.sah_depth_limit = std::min(sah_depth_limit, kMaxRecursion);
     b2.balance = env_float("MPT_BVH_BALANCE", 0.f);
+    b2.c_prim = env_float("MPT_BVH_CPRIM", 0.5f); // measured optimum on C3 (0.15 ... 2.0 within 0.6 %)
+    const bool timing = std::getenv("MPT_BUILD_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+    auto t_phase = now();
     b2.build(n);
-    const std::vector<Node2>& n2 = b2.nodes;
+    if (timing) { std::fprintf(stderr, "[bvh8_build] n=%u bvh2 + collapse dp %.1f ms", n, ms_since(t_phase)); t_phase = now(); }
+    const RawArray<Node2>& n2 = b2.nodes;
+    const RawArray<uint8_t>& dec = b2.dec;
+    for (int a = 0; a < 3; a++) { out.bounds.lo[a] = n2[0].box.lo[a]; out.bounds.hi[a] = n2[0].box.hi[a]; }
 
-    // ---- dynamic program of the SAH-optimal collapse: cost[n][i-1] = C(n, i), the cheapest way to represent BVH2 subtree n as at most i
-    // BVH8 children (leaves of <= 3 primitives or internal nodes); children have larger indices than their parent, so a reverse sweep
-    // is bottom-up.
-    std::vector<float> cost;
-    std::vector<uint8_t> dec, dist8;
-    if (collapse_mode == 2) {
-        const float c_prim = env_float("MPT_BVH_CPRIM", 0.5f), c_node = 1.0f; // measured optimum on C3 (0.15 ... 2.0 within 0.6 %)
-        const size_t nn = n2.size();
-        cost.assign(nn * 7, 0.f);
-        dec.assign(nn * 7, 0);
-        dist8.assign(nn, 1);
-        for (size_t k = nn; k-- > 0;) {
-            const Node2& nd = n2[k];
-            const float area = nd.box.half_area();
-            float* C = &cost[k * 7];
-            uint8_t* D = &dec[k * 7];
-            if (nd.count > 0) { // BVH2 leaf (one primitive)
-                for (int i = 0; i < 7; i++) { C[i] = area * float(nd.count) * c_prim; D[i] = 0; }
-                continue;
-            }
-            const float* L = &cost[size_t(nd.left) * 7];
-            const float* R = &cost[size_t(nd.right) * 7];
-            auto distribute = [&](int j, uint8_t& best_k) { // min over 0 < k < j of C(left, k) + C(right, j - k), slots per side capped at 7
-                float best = FLT_MAX;
-                for (int kk = std::max(1, j - 7); kk <= std::min(j - 1, 7); kk++) {
-                    const float v = L[kk - 1] + R[j - kk - 1];
-                    if (v < best) { best = v; best_k = uint8_t(kk); }
-                }
-                return best;
-            };
-            uint8_t k8 = 1;
-            const float c_internal = distribute(8, k8) + area * c_node;
-            dist8[k] = k8;
-            const float c_leaf = nd.rcount <= 3u ? area * float(nd.rcount) * c_prim : FLT_MAX;
-            if (c_leaf <= c_internal) { C[0] = c_leaf; D[0] = 0; } else { C[0] = c_internal; D[0] = 1; }
-            for (int i = 2; i <= 7; i++) {
-                uint8_t kk = 1;
-                const float cd = distribute(i, kk);
-                if (cd < C[i - 2]) { C[i - 1] = cd; D[i - 1] = kk; } else { C[i - 1] = C[i - 2]; D[i - 1] = 0; }
-            }
-        }
-    }
-
-    out.prim_order.reserve(n);
-    out.nodes.reserve(n / 3 + 16);
-    struct Task { uint32_t wide, root2, depth; };
-    std::vector<Task> queue;
-    out.nodes.emplace_back();
-    queue.push_back({0, 0, 1});
-    out.depth = 1;
-    for (size_t qi = 0; qi < queue.size(); qi++) {
-        const Task t = queue[qi];
-        out.depth = std::max(out.depth, t.depth);
-        // ---- gather up to 8 children
-        uint32_t ch[8];
-        bool ch_leaf[8];
-        int nch = 0;
-        if (n2[t.root2].count > 0) {
-            ch_leaf[nch] = true;
-            ch[nch++] = t.root2; // the BVH2 root itself is a leaf
-        } else if (collapse_mode == 2) {
-            // SAH-optimal collapse (Ylitie, Karras, Laine 2017, section 4.1): follow the decisions of the dynamic program below
-            struct Item { uint32_t node; int slots; };
-            Item work[16];
-            int nw = 0;
-            const int k8 = dist8[t.root2];
-            work[nw++] = {n2[t.root2].right, 8 - k8};
-            work[nw++] = {n2[t.root2].left, k8};
-            while (nw) {
-                Item it = work[--nw];
-                if (n2[it.node].count > 0) { ch_leaf[nch] = true; ch[nch++] = it.node; continue; }
-                while (it.slots > 1 && dec[size_t(it.node) * 7 + size_t(it.slots - 1)] == 0) it.slots--;
-                const uint8_t d = dec[size_t(it.node) * 7 + size_t(it.slots - 1)];
-                if (it.slots == 1) { ch_leaf[nch] = (d == 0); ch[nch++] = it.node; continue; }
-                work[nw++] = {n2[it.node].right, it.slots - int(d)};
-                work[nw++] = {n2[it.node].left, int(d)};
-            }
-        } else {
-            // greedy: repeatedly open the internal child with the largest area
-            ch[nch++] = n2[t.root2].left;
-            ch[nch++] = n2[t.root2].right;
-            while (nch < 8) {
-                int best = -1;
-                float best_area = -1.f;
-                for (int i = 0; i < nch; i++) {
-                    if (n2[ch[i]].count > 0) continue;
-                    float a = n2[ch[i]].box.half_area();
-                    if (collapse_mode == 1) { // prefer opening nodes whose children are much smaller than they are
-                        const Node2& c = n2[ch[i]];
-                        a = a - 0.5f * (n2[c.left].box.half_area() + n2[c.right].box.half_area());
-                    }
-                    if (a > best_area) { best_area = a; best = i; }
-                }
-                if (best < 0) break;
-                const uint32_t open = ch[best];
-                ch[best] = n2[open].left;
-                ch[nch++] = n2[open].right;
-            }
-            for (int i = 0; i < nch; i++) ch_leaf[i] = n2[ch[i]].count > 0;
-        }
-        // ---- slot assignment: slot s is visited first by rays with octant s (direction sign bit set = negative),
-        // so it should hold the child that is nearest along d_s: minimise sum of dot(centroid_c - centroid_p, d_s).
-        const B3& pb = n2[t.root2].box;
-        float pc[3];
-        for (int a = 0; a < 3; a++) pc[a] = 0.5f * (pb.lo[a] + pb.hi[a]);
-        float cost[8][8];
-        for (int c = 0; c < nch; c++) {
-            const B3& cb = n2[ch[c]].box;
-            float d[3];
-            for (int a = 0; a < 3; a++) d[a] = 0.5f * (cb.lo[a] + cb.hi[a]) - pc[a];
-            for (int s = 0; s < 8; s++)
-                cost[c][s] = ((s & 1) ? -d[0] : d[0]) + ((s & 2) ? -d[1] : d[1]) + ((s & 4) ? -d[2] : d[2]);
-        }
-        int slot_of[8], child_in_slot[8];
-        for (int i = 0; i < 8; i++) { slot_of[i] = -1; child_in_slot[i] = -1; }
-        for (int k = 0; k < nch; k++) {
-            float bc = FLT_MAX;
-            int bi = -1, bs = -1;
-            for (int c = 0; c < nch; c++) {
-                if (slot_of[c] >= 0) continue;
-                for (int s = 0; s < 8; s++) {
-                    if (child_in_slot[s] >= 0) continue;
-                    if (cost[c][s] < bc) { bc = cost[c][s]; bi = c; bs = s; }
-                }
-            }
-            slot_of[bi] = bs;
-            child_in_slot[bs] = bi;
-        }
-        // ---- encode
-        Bvh8Node node;
-        std::memset(&node, 0, sizeof(node));
-        node.px = pb.lo[0]; node.py = pb.lo[1]; node.pz = pb.lo[2];
-        node.ex = exponent_for(pb.hi[0] - pb.lo[0]);
-        node.ey = exponent_for(pb.hi[1] - pb.lo[1]);
-        node.ez = exponent_for(pb.hi[2] - pb.lo[2]);
-        const double sc[3] = {std::ldexp(1.0, int(node.ex) - 127), std::ldexp(1.0, int(node.ey) - 127), std::ldexp(1.0, int(node.ez) - 127)};
-        node.child_base = uint32_t(out.nodes.size());
-        node.prim_base = uint32_t(out.prim_order.size());
-        uint32_t n_internal = 0;
-        uint8_t* qlo[3] = {node.qlox, node.qloy, node.qloz};
-        uint8_t* qhi[3] = {node.qhix, node.qhiy, node.qhiz};
-        for (int s = 0; s < 8; s++) {
-            const int c = child_in_slot[s];
-            if (c < 0) continue;
-            const Node2& cn = n2[ch[c]];
-            for (int a = 0; a < 3; a++) {
-                const double lo = std::floor((double(cn.box.lo[a]) - double(pb.lo[a])) / sc[a]);
-                const double hi = std::ceil((double(cn.box.hi[a]) - double(pb.lo[a])) / sc[a]);
-                qlo[a][s] = uint8_t(std::min(std::max(lo, 0.0), 255.0));
-                qhi[a][s] = uint8_t(std::min(std::max(hi, 0.0), 255.0));
-            }
-            if (!ch_leaf[c]) {
-                node.imask |= uint8_t(1u << s);
-                n_internal++;
+    // ---- emission, one level of wide nodes at a time: the nodes of a level are independent (children, slot assignment, quantisation in
+    // parallel); a prefix sum over the level then gives every node its child_base / prim_base in breadth-first order.
+    std::vector<Wide> level(1), next;
+    level[0].root2 = 0;
+    uint32_t depth = 0;
+    while (!level.empty()) {
+        depth++;
+        const size_t base_index = out.nodes.size();
+#pragma omp parallel for schedule(dynamic, 64) if (level.size() > 256)
+        for (int64_t li = 0; li < int64_t(level.size()); li++) {
+            Wide& w = level[size_t(li)];
+            // ---- gather up to 8 children along the decisions of the dynamic program (Ylitie, Karras, Laine 2017, section 4.1)
+            uint32_t ch[8];
+            bool ch_leaf[8];
+            int nch = 0;
+            if (n2[w.root2].count > 0) { // the BVH2 root itself is a leaf
+                ch_leaf[nch] = true;
+                ch[nch++] = w.root2;
             } else {
-                const uint32_t unary = (1u << cn.rcount) - 1u; // 1, 3, 7
-                node.leaf_bits |= unary << (3 * s);
-                for (uint32_t k = 0; k < cn.rcount; k++) out.prim_order.push_back(b2.idx[cn.rfirst + k]);
+                struct Item { uint32_t node; int slots; };
+                Item work[16];
+                int nw = 0;
+                const int k8 = b2.dist8[w.root2];
+                work[nw++] = {n2[w.root2].right, 8 - k8};
+                work[nw++] = {n2[w.root2].left, k8};
+                while (nw) {
+                    Item it = work[--nw];
+                    if (n2[it.node].count > 0) { ch_leaf[nch] = true; ch[nch++] = it.node; continue; }
+                    while (it.slots > 1 && dec[size_t(it.node) * 7 + size_t(it.slots - 1)] == 0) it.slots--;
+                    const uint8_t d = dec[size_t(it.node) * 7 + size_t(it.slots - 1)];
+                    if (it.slots == 1) { ch_leaf[nch] = (d == 0); ch[nch++] = it.node; continue; }
+                    work[nw++] = {n2[it.node].right, it.slots - int(d)};
+                    work[nw++] = {n2[it.node].left, int(d)};
+                }
+            }
+            // ---- slot assignment: slot s is visited first by rays with octant s (direction sign bit set = negative),
+            // so it should hold the child that is nearest along d_s: minimise sum of dot(centroid_c - centroid_p, d_s).
+            const Box6& pb = n2[w.root2].box;
+            float pc[3];
+            for (int a = 0; a < 3; a++) pc[a] = 0.5f * (pb.lo[a] + pb.hi[a]);
+            float cst[8][8];
+            for (int c = 0; c < nch; c++) {
+                const Box6& cb = n2[ch[c]].box;
+                float d[3];
+                for (int a = 0; a < 3; a++) d[a] = 0.5f * (cb.lo[a] + cb.hi[a]) - pc[a];
+                for (int s = 0; s < 8; s++) cst[c][s] = ((s & 1) ? -d[0] : d[0]) + ((s & 2) ? -d[1] : d[1]) + ((s & 4) ? -d[2] : d[2]);
+            }
+            int slot_of[8], child_in_slot[8];
+            for (int i = 0; i < 8; i++) { slot_of[i] = -1; child_in_slot[i] = -1; }
+            for (int k = 0; k < nch; k++) {
+                float bc = FLT_MAX;
+                int bi = -1, bs = -1;
+                for (int c = 0; c < nch; c++) {
+                    if (slot_of[c] >= 0) continue;
+                    for (int s = 0; s < 8; s++) {
+                        if (child_in_slot[s] >= 0) continue;
+                        if (cst[c][s] < bc) { bc = cst[c][s]; bi = c; bs = s; }
+                    }
+                }
+                slot_of[bi] = bs;
+                child_in_slot[bs] = bi;
+            }
+            // ---- encode (child_base / prim_base are filled in after the prefix sum)
+            Bvh8Node& node = w.node;
+            std::memset(&node, 0, sizeof(node));
+            node.px = pb.lo[0]; node.py = pb.lo[1]; node.pz = pb.lo[2];
+            node.ex = exponent_for(pb.hi[0] - pb.lo[0]);
+            node.ey = exponent_for(pb.hi[1] - pb.lo[1]);
+            node.ez = exponent_for(pb.hi[2] - pb.lo[2]);
+            const double sc[3] = {std::ldexp(1.0, int(node.ex) - 127), std::ldexp(1.0, int(node.ey) - 127), std::ldexp(1.0, int(node.ez) - 127)};
+            uint8_t* qlo[3] = {node.qlox, node.qloy, node.qloz};
+            uint8_t* qhi[3] = {node.qhix, node.qhiy, node.qhiz};
+            w.slot_used = w.slot_leaf = 0;
+            w.n_internal = w.n_prims = 0;
+            for (int s = 0; s < 8; s++) {
+                const int c = child_in_slot[s];
+                if (c < 0) continue;
+                const Node2& cn = n2[ch[c]];
+                w.child[s] = ch[c];
+                w.slot_used |= uint8_t(1u << s);
+                for (int a = 0; a < 3; a++) {
+                    const double lo = std::floor((double(cn.box.lo[a]) - double(pb.lo[a])) / sc[a]);
+                    const double hi = std::ceil((double(cn.box.hi[a]) - double(pb.lo[a])) / sc[a]);
+                    qlo[a][s] = uint8_t(std::min(std::max(lo, 0.0), 255.0));
+                    qhi[a][s] = uint8_t(std::min(std::max(hi, 0.0), 255.0));
+                }
+                if (!ch_leaf[c]) {
+                    node.imask |= uint8_t(1u << s);
+                    w.n_internal++;
+                } else {
+                    const uint32_t unary = (1u << cn.rcount) - 1u; // 1, 3, 7
+                    node.leaf_bits |= unary << (3 * s);
+                    w.slot_leaf |= uint8_t(1u << s);
+                    w.n_prims += cn.rcount;
+                }
             }
         }
-        out.nodes[t.wide] = node;
-        out.nodes.resize(out.nodes.size() + n_internal);
-        uint32_t j = 0;
-        for (int s = 0; s < 8; s++) {
-            const int c = child_in_slot[s];
-            if (c < 0 || ch_leaf[c]) continue;
-            queue.push_back({node.child_base + j, ch[c], t.depth + 1});
-            j++;
+        // ---- prefix sums: breadth-first numbering of the next level and of the primitive records
+        const size_t next_base = base_index + level.size();
+        size_t child_cursor = next_base, prim_cursor = out.prim_order.size();
+        std::vector<size_t> next_first(level.size());
+        for (size_t li = 0; li < level.size(); li++) {
+            Wide& w = level[li];
+            w.node.child_base = uint32_t(child_cursor);
+            w.node.prim_base = uint32_t(prim_cursor);
+            next_first[li] = child_cursor - next_base;
+            child_cursor += w.n_internal;
+            prim_cursor += w.n_prims;
         }
+        out.nodes.resize(next_base);
+        out.prim_order.resize(prim_cursor);
+        next.assign(child_cursor - next_base, Wide());
+#pragma omp parallel for schedule(static) if (level.size() > 256)
+        for (int64_t li = 0; li < int64_t(level.size()); li++) {
+            const Wide& w = level[size_t(li)];
+            out.nodes[base_index + size_t(li)] = w.node;
+            size_t nf = next_first[size_t(li)], pf = w.node.prim_base;
+            for (int s = 0; s < 8; s++) {
+                if (!(w.slot_used & (1u << s))) continue;
+                if (w.slot_leaf & (1u << s)) {
+                    const Node2& cn = n2[w.child[s]];
+                    for (uint32_t k = 0; k < cn.rcount; k++) out.prim_order[pf++] = b2.idx[cn.rfirst + k];
+                } else {
+                    next[nf++].root2 = w.child[s];
+                }
+            }
+        }
+        level.swap(next);
     }
+    out.depth = depth;
+    if (timing) std::fprintf(stderr, ", emit %.1f ms (%zu nodes, %u levels)\n", ms_since(t_phase), out.nodes.size(), depth);
 }
 
-// The traversal keeps at most two stack entries per wide level (bvh8_traverse.cuh), so the depth must be bounded. SAH trees of
+// The traversal keeps a bounded number of stack entries per wide level (bvh8_traverse.cuh), so the depth must be bounded. SAH trees of
 // real scenes are 8-10 wide levels deep (1 M-triangle terrain: 8); a degenerate input (primitives of geometrically growing size on a
 // line) makes SAH peel one primitive per level. When that happens the tree is rebuilt with SAH only for the top levels and object-median
 // splits below, which bounds the depth by about log8(n) + the SAH levels.
-void build_bvh8(const Box* boxes, uint32_t n, Bvh8& out, int max_leaf) {
+void build_bvh8(const Box* boxes, uint32_t n, Bvh8& out, int /*max_leaf*/) {
     if (std::getenv("MPT_BVH_SAH_DEPTH")) { // tuning sessions: SAH for the top levels only, object-median splits below
-        build_bvh8_once(boxes, n, out, max_leaf, uint32_t(env_float("MPT_BVH_SAH_DEPTH", 64.f)));
+        build_bvh8_once(boxes, n, out, uint32_t(env_float("MPT_BVH_SAH_DEPTH", 64.f)));
         if (out.depth <= kMaxBvh8Depth) return;
     }
     for (uint32_t limit : {0xFFFFFFFFu, 16u, 8u, 0u}) {
-        build_bvh8_once(boxes, n, out, max_leaf, limit);
+        build_bvh8_once(boxes, n, out, limit);
         if (out.depth <= kMaxBvh8Depth) return;
     }
 }
