@@ -251,6 +251,23 @@ MPT_API mpt_status mpt_materials_set_hints(mpt_context* ctx, float alpha_test_th
 MPT_API mpt_status mpt_texture_upload(mpt_context* ctx, uint32_t texture_id, uint32_t width,
                                       uint32_t height, uint32_t format, uint32_t wrap_u,
                                       uint32_t wrap_v, uint32_t filter, const void* pixels);
+/* The same with a mip chain: mipmap_mode != MPT_MIPMAP_NONE allocates floor(log2(max(w, h))) + 1 levels and fills them the way
+ * create_texture_from_rgba8(..., generate_mipmaps) does (resource_allocator.cpp:298-313: cmd_generate_mipmaps = a linear blit per level,
+ * include/merian/vk/utils/blits.hpp:101-168). Which textures get one is the loader's decision (GLTFScene: the glTF sampler's *_MIPMAP_*
+ * minFilter, gltf_scene.cpp:212-248, 583-593). Only the GBuffer node samples with screen-space gradients (GradLODSampler,
+ * gbuffer_rt.slang:41-66); `pt` reads LOD 0 of every texture (LOD0Sampler, textures.slang:338-366). */
+enum { MPT_MIPMAP_NONE = 0, MPT_MIPMAP_NEAREST = 1, MPT_MIPMAP_LINEAR = 2 }; /* VkSamplerMipmapMode + "has a chain" */
+MPT_API mpt_status mpt_texture_upload_ex(mpt_context* ctx, uint32_t texture_id, uint32_t width, uint32_t height, uint32_t format, uint32_t wrap_u,
+                                         uint32_t wrap_v, uint32_t filter, uint32_t mipmap_mode, const void* pixels);
+/* Host-only (no device needed): one level of the chain mpt_texture_upload_ex would build, for tests. out may be NULL (sizes only). */
+MPT_API mpt_status mpt_mip_level(const void* level0, uint32_t width, uint32_t height, uint32_t format, uint32_t level, void* out, uint64_t capacity_bytes,
+                                 uint32_t* level_width, uint32_t* level_height);
+/* Texels that are already in device memory — inside merian: the VkImage copied to an exportable VkBuffer and imported with
+ * mpt_import_external_memory_fd, which replaces the read-back of texture_manager.cpp:207-243 / scene.cpp:780-795 through the host.
+ * row_pitch_bytes: 0 = tightly packed. Device-to-device for MPT_MIPMAP_NONE; a mip chain is filtered on the host. */
+MPT_API mpt_status mpt_texture_upload_device(mpt_context* ctx, uint32_t texture_id, uint32_t width, uint32_t height, uint32_t format, uint32_t wrap_u,
+                                             uint32_t wrap_v, uint32_t filter, uint32_t mipmap_mode, const void* d_pixels, uint64_t row_pitch_bytes,
+                                             void* stream);
 
 /* Replaces LatLongEnvMap::write_to (env_map.hpp:112-118). `to_local` row-major 4x4; pixels RGBA32F,
  * repeat addressing, bilinear (scene.cpp:786-789). type MPT_ENV_EMPTY ignores the rest. The alias table of
@@ -258,6 +275,9 @@ MPT_API mpt_status mpt_texture_upload(mpt_context* ctx, uint32_t texture_id, uin
 MPT_API mpt_status mpt_env_set(mpt_context* ctx, uint32_t type, const float* to_local,
                                float intensity, uint32_t width, uint32_t height,
                                const float* rgba32f);
+/* The lat-long texels already in device memory (see mpt_texture_upload_device). */
+MPT_API mpt_status mpt_env_set_device(mpt_context* ctx, uint32_t type, const float* to_local, float intensity, uint32_t width, uint32_t height,
+                                      const void* d_rgba32f);
 
 /* Replaces the gbuffer_rt raygen for the hit texture (gbuffer_rt.slang:18-31, gbuffer.slang:40-61):
  * writes one PackedHitInfo (uint4) per pixel into d_tex1 (row-major, width*height*16 bytes). */

@@ -33,6 +33,7 @@ GLTF_TRANSMISSION, GLTF_VOLUME, GLTF_CLEARCOAT, GLTF_SHEEN, GLTF_IRIDESCENCE, GL
 TEX_RGBA8_UNORM, TEX_RGBA8_SRGB, TEX_RGBA32F = 0, 1, 2
 WRAP_REPEAT, WRAP_CLAMP_TO_EDGE, WRAP_MIRRORED_REPEAT = 0, 1, 2
 FILTER_NEAREST, FILTER_LINEAR = 0, 1
+MIPMAP_NONE, MIPMAP_NEAREST, MIPMAP_LINEAR = 0, 1, 2  # has a mip chain (cmd_generate_mipmaps) + VkSamplerMipmapMode
 TEXTURE_NONE = 0xFFFF
 
 ENV_EMPTY, ENV_LATLONG = 0, 1

@@ -55,8 +55,16 @@ class Context:
     def materials_set_hints(self, alpha_test_threshold=0.5, min_roughness=0.0316, clamp_normals=True):
         self._check(self.l.mpt_materials_set_hints(self.h, alpha_test_threshold, min_roughness, 1 if clamp_normals else 0))
 
-    def texture_upload(self, tid, w, h, fmt, wrap_u, wrap_v, filt, pixels):
-        self._check(self.l.mpt_texture_upload(self.h, tid, w, h, fmt, wrap_u, wrap_v, filt, _hp(pixels)))
+    def texture_upload(self, tid, w, h, fmt, wrap_u, wrap_v, filt, pixels, mipmap=abi.MIPMAP_NONE):
+        self._check(self.l.mpt_texture_upload_ex(self.h, tid, w, h, fmt, wrap_u, wrap_v, filt, mipmap, _hp(pixels)))
+
+    def texture_upload_device(self, tid, w, h, fmt, wrap_u, wrap_v, filt, d_pixels, mipmap=abi.MIPMAP_NONE, row_pitch=0):
+        """Texels already in device memory (a torch CUDA tensor): the Vulkan -> CUDA import leg (include/mpt.h)."""
+        self._check(self.l.mpt_texture_upload_device(self.h, tid, w, h, fmt, wrap_u, wrap_v, filt, mipmap, C.c_void_p(d_pixels.data_ptr()), row_pitch,
+                                                     self._stream()))
+
+    def env_set_device(self, typ, to_local, intensity, w, h, d_pixels):
+        self._check(self.l.mpt_env_set_device(self.h, typ, _hp(to_local), intensity, w, h, C.c_void_p(d_pixels.data_ptr())))
 
     def env_set(self, typ, to_local, intensity, w, h, pixels):
         self._check(self.l.mpt_env_set(self.h, typ, _hp(to_local), intensity, w, h, _hp(pixels)))

@@ -15,6 +15,7 @@
 #include "bvh8.h"
 #include "float_image_files.h"
 #include "scene_build.h"
+#include "texture_mips.h"
 #include "mpt_internal.h"
 #include "shading.cuh"
 #include "bvh8_traverse_pooled.cuh"
@@ -248,7 +249,11 @@ __global__ void __launch_bounds__(kThreads) k_gbuffer(const __grid_constant__ Sc
         p.geometry_index = uint16_t(__float_as_uint(__ldg(tp + 1).w));
         p.instance_index = uint16_t(hr.instance);
         p.bary = __floats2half2_rn(hr.u, hr.v);
-        surface_shading_point<FEAT>(S, o, d, hr, 1.0f, true, sp); // falls back to the environment for UseEnvMap geometry
+        f3 ox, oy, diff[2]; // r_x, r_y of gbuffer_rt.slang:36-37: the camera rays of the neighbouring pixels
+        float t0, t1;
+        camera_ray(cam, x + 1, y, w, h, ox, diff[0], t0, t1);
+        camera_ray(cam, x, y + 1, w, h, oy, diff[1], t0, t1);
+        surface_shading_point<FEAT>(S, o, d, hr, 1.0f, true, sp, diff); // falls back to the environment for UseEnvMap geometry
         surface = sp.has_material;
     }
     if (!surface) env_shading_point(S, o, d, sp);
@@ -1172,6 +1177,7 @@ struct DevBuf {
 
 struct TextureSlot {
     cudaArray_t array = nullptr;
+    cudaMipmappedArray_t mips = nullptr; // instead of `array` when the texture has a mip chain
     cudaTextureObject_t obj = 0;
 };
 
@@ -1572,6 +1578,7 @@ MPT_API void mpt_destroy(mpt_context* ctx) {
     for (auto& t : ctx->textures) {
         if (t.obj) cudaDestroyTextureObject(t.obj);
         if (t.array) cudaFreeArray(t.array);
+        if (t.mips) cudaFreeMipmappedArray(t.mips);
     }
     for (auto& f : ctx->in_flight) {
         if (f.copy) cudaStreamDestroy(f.copy);
@@ -1685,25 +1692,62 @@ MPT_API mpt_status mpt_materials_set_hints(mpt_context* ctx, float alpha_test_th
     return MPT_OK;
 }
 
-MPT_API mpt_status mpt_texture_upload(mpt_context* ctx, uint32_t texture_id, uint32_t width, uint32_t height, uint32_t format, uint32_t wrap_u,
-                                      uint32_t wrap_v, uint32_t filter, const void* pixels) {
+} // extern "C"
+namespace {
+// One material texture: CUDA array (or mipmapped array) + texture object. `pixels` is host memory unless `on_device`.
+mpt_status texture_upload_impl(mpt_context* ctx, uint32_t texture_id, uint32_t width, uint32_t height, uint32_t format, uint32_t wrap_u, uint32_t wrap_v,
+                               uint32_t filter, uint32_t mipmap_mode, const void* pixels, bool on_device, size_t src_pitch, cudaStream_t st) {
     if (!ctx || !pixels || width == 0 || height == 0) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "bad texture");
     if (texture_id >= 0xFFFFu) return fail(ctx, MPT_ERR_LIMIT, "TextureID is 16 bit");
+    if (format > MPT_TEX_RGBA32F || mipmap_mode > MPT_MIPMAP_LINEAR) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "unknown texture format or mipmap mode");
     CU(cudaSetDevice(ctx->device));
     CU(quiesce(ctx));
     if (ctx->textures.size() <= texture_id) ctx->textures.resize(texture_id + 1);
     TextureSlot& slot = ctx->textures[texture_id];
     if (slot.obj) { cudaDestroyTextureObject(slot.obj); slot.obj = 0; }
     if (slot.array) { cudaFreeArray(slot.array); slot.array = nullptr; }
+    if (slot.mips) { cudaFreeMipmappedArray(slot.mips); slot.mips = nullptr; }
     const bool f32 = format == MPT_TEX_RGBA32F;
     const cudaChannelFormatDesc cd = f32 ? cudaCreateChannelDesc<float4>() : cudaCreateChannelDesc<uchar4>();
-    CU(cudaMallocArray(&slot.array, &cd, width, height));
     const size_t pitch = size_t(width) * (f32 ? 16 : 4);
-    CU(cudaMemcpy2DToArray(slot.array, 0, 0, pixels, pitch, pitch, height, cudaMemcpyHostToDevice));
+    if (src_pitch == 0) src_pitch = pitch;
     cudaResourceDesc rd{};
-    rd.resType = cudaResourceTypeArray;
-    rd.res.array.array = slot.array;
     cudaTextureDesc td{};
+    if (mipmap_mode == MPT_MIPMAP_NONE) {
+        CU(cudaMallocArray(&slot.array, &cd, width, height));
+        if (on_device) {
+            CU(cudaMemcpy2DToArrayAsync(slot.array, 0, 0, pixels, src_pitch, pitch, height, cudaMemcpyDeviceToDevice, st));
+            CU(cudaStreamSynchronize(st));
+        } else {
+            CU(cudaMemcpy2DToArray(slot.array, 0, 0, pixels, src_pitch, pitch, height, cudaMemcpyHostToDevice));
+        }
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = slot.array;
+    } else {
+        // the whole chain, built on the host the way cmd_generate_mipmaps blits it (texture_mips.h)
+        std::vector<uint8_t> host;
+        const void* level0 = pixels;
+        if (on_device || src_pitch != pitch) {
+            host.resize(pitch * height);
+            CU(cudaMemcpy2D(host.data(), pitch, pixels, src_pitch, pitch, height, on_device ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost));
+            level0 = host.data();
+        }
+        std::vector<MipLevel> levels;
+        build_mip_chain(level0, width, height, f32, format == MPT_TEX_RGBA8_SRGB, levels);
+        CU(cudaMallocMipmappedArray(&slot.mips, &cd, make_cudaExtent(width, height, 0), uint32_t(levels.size())));
+        for (uint32_t l = 0; l < levels.size(); l++) {
+            cudaArray_t la = nullptr;
+            CU(cudaGetMipmappedArrayLevel(&la, slot.mips, l));
+            const size_t lp = size_t(levels[l].width) * (f32 ? 16 : 4);
+            CU(cudaMemcpy2DToArray(la, 0, 0, levels[l].bytes.data(), lp, lp, levels[l].height, cudaMemcpyHostToDevice));
+        }
+        rd.resType = cudaResourceTypeMipmappedArray;
+        rd.res.mipmap.mipmap = slot.mips;
+        td.mipmapFilterMode = mipmap_mode == MPT_MIPMAP_LINEAR ? cudaFilterModeLinear : cudaFilterModePoint;
+        td.minMipmapLevelClamp = 0.f;
+        td.maxMipmapLevelClamp = float(levels.size() - 1);
+        td.maxAnisotropy = 1; // anisotropy off (gltf_scene.cpp:298)
+    }
     auto am = [](uint32_t w) { return w == MPT_WRAP_CLAMP_TO_EDGE ? cudaAddressModeClamp : (w == MPT_WRAP_MIRRORED_REPEAT ? cudaAddressModeMirror : cudaAddressModeWrap); };
     td.addressMode[0] = am(wrap_u);
     td.addressMode[1] = am(wrap_v);
@@ -1719,16 +1763,77 @@ MPT_API mpt_status mpt_texture_upload(mpt_context* ctx, uint32_t texture_id, uin
     ctx->view.texture_count = uint32_t(table.size());
     return MPT_OK;
 }
+} // namespace
+extern "C" {
 
+MPT_API mpt_status mpt_mip_level(const void* level0, uint32_t width, uint32_t height, uint32_t format, uint32_t level, void* out, uint64_t capacity_bytes,
+                                 uint32_t* level_width, uint32_t* level_height) {
+    mpt_context* ctx = nullptr;
+    if (!level0 || !width || !height || format > MPT_TEX_RGBA32F) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "bad texture");
+    if (level >= mip_level_count(width, height)) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "level beyond the chain");
+    try {
+        std::vector<MipLevel> levels;
+        build_mip_chain(level0, width, height, format == MPT_TEX_RGBA32F, format == MPT_TEX_RGBA8_SRGB, levels);
+        const MipLevel& L = levels[level];
+        if (level_width) *level_width = L.width;
+        if (level_height) *level_height = L.height;
+        if (out) {
+            if (capacity_bytes < L.bytes.size()) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "output buffer too small");
+            std::memcpy(out, L.bytes.data(), L.bytes.size());
+        }
+    } catch (...) {
+        return fail(ctx, MPT_ERR_LIMIT, "out of host memory");
+    }
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_texture_upload(mpt_context* ctx, uint32_t texture_id, uint32_t width, uint32_t height, uint32_t format, uint32_t wrap_u,
+                                      uint32_t wrap_v, uint32_t filter, const void* pixels) {
+    return texture_upload_impl(ctx, texture_id, width, height, format, wrap_u, wrap_v, filter, MPT_MIPMAP_NONE, pixels, false, 0, nullptr);
+}
+
+MPT_API mpt_status mpt_texture_upload_ex(mpt_context* ctx, uint32_t texture_id, uint32_t width, uint32_t height, uint32_t format, uint32_t wrap_u,
+                                         uint32_t wrap_v, uint32_t filter, uint32_t mipmap_mode, const void* pixels) {
+    return texture_upload_impl(ctx, texture_id, width, height, format, wrap_u, wrap_v, filter, mipmap_mode, pixels, false, 0, nullptr);
+}
+
+MPT_API mpt_status mpt_texture_upload_device(mpt_context* ctx, uint32_t texture_id, uint32_t width, uint32_t height, uint32_t format, uint32_t wrap_u,
+                                             uint32_t wrap_v, uint32_t filter, uint32_t mipmap_mode, const void* d_pixels, uint64_t row_pitch_bytes,
+                                             void* stream) {
+    return texture_upload_impl(ctx, texture_id, width, height, format, wrap_u, wrap_v, filter, mipmap_mode, d_pixels, true, size_t(row_pitch_bytes),
+                               (cudaStream_t)stream);
+}
+
+} // extern "C"
+namespace {
+mpt_status env_set_impl(mpt_context* ctx, uint32_t type, const float* to_local, float intensity, uint32_t width, uint32_t height, const float* rgba32f,
+                        bool on_device);
+}
+extern "C" {
 MPT_API mpt_status mpt_env_set(mpt_context* ctx, uint32_t type, const float* to_local, float intensity, uint32_t width, uint32_t height,
                                const float* rgba32f) {
+    return env_set_impl(ctx, type, to_local, intensity, width, height, rgba32f, false);
+}
+MPT_API mpt_status mpt_env_set_device(mpt_context* ctx, uint32_t type, const float* to_local, float intensity, uint32_t width, uint32_t height,
+                                      const void* d_rgba32f) {
+    return env_set_impl(ctx, type, to_local, intensity, width, height, static_cast<const float*>(d_rgba32f), true);
+}
+} // extern "C"
+namespace {
+mpt_status env_set_impl(mpt_context* ctx, uint32_t type, const float* to_local, float intensity, uint32_t width, uint32_t height, const float* rgba32f,
+                        bool on_device) {
     if (!ctx) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL context");
     CU(cudaSetDevice(ctx->device));
     CU(quiesce(ctx));
     if (type == MPT_ENV_EMPTY) { ctx->view.env_type = 0; return MPT_OK; }
     if (type != MPT_ENV_LATLONG) return fail(ctx, MPT_ERR_UNSUPPORTED, "only Empty and LatLong environment maps are supported");
     if (!to_local || !rgba32f || !width || !height) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "bad env map");
-    CU(ctx->env_pixels.upload(rgba32f, size_t(width) * height * 16));
+    if (on_device) {
+        CU(ctx->env_pixels.ensure(size_t(width) * height * 16));
+        CU(cudaMemcpy(ctx->env_pixels.p, rgba32f, size_t(width) * height * 16, cudaMemcpyDeviceToDevice));
+    } else {
+        CU(ctx->env_pixels.upload(rgba32f, size_t(width) * height * 16));
+    }
     for (int r = 0; r < 3; r++)
         for (int c = 0; c < 3; c++) ctx->view.env_m[r * 3 + c] = to_local[r * 4 + c];
     {   // inverse of the 3x3 part (local -> world) for the light samples
@@ -1750,6 +1855,8 @@ MPT_API mpt_status mpt_env_set(mpt_context* ctx, uint32_t type, const float* to_
     ctx->view.env_type = 1;
     return MPT_OK;
 }
+} // namespace
+extern "C" {
 
 MPT_API mpt_status mpt_primary_visibility(mpt_context* ctx, const mpt_camera* camera, uint32_t width, uint32_t height, uint32_t instance_mask,
                                           void* d_tex1, void* stream) {

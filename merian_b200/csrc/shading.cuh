@@ -152,7 +152,18 @@ struct ShadingData { // shading-data.slang:27-58 (only the members the supported
     f3 face_normal;
     float ior;
     bool front_facing;
+    // the LODSampler2D the caller passes to get_material_sample: LOD0Sampler (pt: use_grad = false, a compile-time constant there) or
+    // GradLODSampler(ddx, ddy) (the GBuffer node, textures.slang:398-421)
+    bool use_grad;
+    f2 ddx, ddy;
 };
+MPT_DEV f4 sample_tex(const SceneView& S, uint32_t id, const ShadingData& sd) {
+    if (sd.use_grad) { // Sampler2D::SampleGrad; a texture without a mip chain has one level, so the gradients change nothing
+        const float4 t = tex2DGrad<float4>(S.textures[id].obj, sd.uv.x, sd.uv.y, make_float2(sd.ddx.x, sd.ddx.y), make_float2(sd.ddy.x, sd.ddy.y));
+        return mk4(t.x, t.y, t.z, t.w);
+    }
+    return sample_tex(S, id, sd.uv);
+}
 
 // Emission only: MaterialModel::get_emission (material.slang:40-47; gltf-material.slang:142-151; diffuse: 0).
 MPT_DEV f3 material_emission(const SceneView& S, uint32_t material_id, f2 uv) {
@@ -186,7 +197,7 @@ MPT_DEV void material_sample(const SceneView& S, uint32_t material_id, const Sha
         sp.frame = frame_apply_normal_map(sd.frame, mk3(0.f, 0.f, 1.f));
         f3 albedo = mk3(base.x, base.y, base.z);
         if (alpha_tex != kNoTexture) {
-            const f4 t = sample_tex(S, alpha_tex, sd.uv);
+            const f4 t = sample_tex(S, alpha_tex, sd);
             albedo = albedo * mk3(t.x, t.y, t.z);
         }
         b.gltf = 0u;
@@ -196,7 +207,7 @@ MPT_DEV void material_sample(const SceneView& S, uint32_t material_id, const Sha
     // ---- GltfMaterial::get_sample, gltf-material.slang:153-308; payload layout gltf_material.hpp:102-112
     const uint32_t feat = mt.y & FEAT;
     if (alpha_tex != kNoTexture) {
-        const f4 t = sample_tex(S, alpha_tex, sd.uv);
+        const f4 t = sample_tex(S, alpha_tex, sd);
         base = mk4(base.x * t.x, base.y * t.y, base.z * t.z, base.w * t.w);
     }
     f3 emission = mk3(wordf(p, 4), wordf(p, 5), wordf(p, 6));
@@ -206,13 +217,13 @@ MPT_DEV void material_sample(const SceneView& S, uint32_t material_id, const Sha
     const uint32_t t01 = __ldg(p + 12), t23 = __ldg(p + 13);
     const uint32_t mr_tex = lo16(t01), normal_tex = hi16(t01), em_tex = hi16(t23);
     if (mr_tex != kNoTexture) {
-        const f4 mr = sample_tex(S, mr_tex, sd.uv);
+        const f4 mr = sample_tex(S, mr_tex, sd);
         roughness *= mr.y;
         metallic *= mr.z;
     }
     Frame fr = sd.frame;
     if (normal_tex != kNoTexture) {
-        const f4 raw = sample_tex(S, normal_tex, sd.uv);
+        const f4 raw = sample_tex(S, normal_tex, sd);
         const float nx = (raw.x * 2.0f - 1.0f) * normal_scale, ny = (raw.y * 2.0f - 1.0f) * normal_scale;
         const float nz = sqrtf(fmaxf(0.0f, 1.0f - (nx * nx + ny * ny)));
         const Frame mapped = frame_apply_normal_map(sd.frame, mk3(nx, ny, nz));
@@ -220,7 +231,7 @@ MPT_DEV void material_sample(const SceneView& S, uint32_t material_id, const Sha
         fr = frame_from_tangent(cn, mapped.t, 1.0f);
     }
     if (em_tex != kNoTexture) {
-        const f4 t = sample_tex(S, em_tex, sd.uv);
+        const f4 t = sample_tex(S, em_tex, sd);
         emission = emission * mk3(t.x, t.y, t.z);
     }
     const float alpha = sq(fmaxf(roughness, S.min_roughness));
@@ -260,8 +271,8 @@ MPT_DEV void material_sample(const SceneView& S, uint32_t material_id, const Sha
                 b.coat_w = rdf(off);
                 float cr = rdf(off + 4);
                 const uint32_t ct = rd16(off + 8), crt = rd16(off + 10);
-                if (ct != kNoTexture) b.coat_w *= sample_tex(S, ct, sd.uv).x;
-                if (crt != kNoTexture) cr *= sample_tex(S, crt, sd.uv).y;
+                if (ct != kNoTexture) b.coat_w *= sample_tex(S, ct, sd).x;
+                if (crt != kNoTexture) cr *= sample_tex(S, crt, sd).y;
                 b.coat_alpha = sq(fmaxf(cr, S.min_roughness));
             }
             off += 12;
@@ -271,8 +282,8 @@ MPT_DEV void material_sample(const SceneView& S, uint32_t material_id, const Sha
                 f3 col = mk3(rdf(off), rdf(off + 4), rdf(off + 8));
                 float sr = rdf(off + 12);
                 const uint32_t sct = rd16(off + 16), srt = rd16(off + 18);
-                if (sct != kNoTexture) { const f4 t = sample_tex(S, sct, sd.uv); col = col * mk3(t.x, t.y, t.z); }
-                if (srt != kNoTexture) sr *= sample_tex(S, srt, sd.uv).w;
+                if (sct != kNoTexture) { const f4 t = sample_tex(S, sct, sd); col = col * mk3(t.x, t.y, t.z); }
+                if (srt != kNoTexture) sr *= sample_tex(S, srt, sd).w;
                 b.sheen_col = col;
                 b.sheen_alpha = sq(sr);
                 b.max_sheen = max3(col);
@@ -285,9 +296,9 @@ MPT_DEV void material_sample(const SceneView& S, uint32_t material_id, const Sha
                 b.iri_ior = rdf(off + 4);
                 const float tmin = rdf(off + 8), tmax = rdf(off + 12);
                 const uint32_t it = rd16(off + 16), itt = rd16(off + 18);
-                if (it != kNoTexture) b.iri *= sample_tex(S, it, sd.uv).x;
+                if (it != kNoTexture) b.iri *= sample_tex(S, it, sd).x;
                 float t = 1.0f;
-                if (itt != kNoTexture) t = sample_tex(S, itt, sd.uv).y;
+                if (itt != kNoTexture) t = sample_tex(S, itt, sd).y;
                 b.iri_thick = mix(tmin, tmax, t);
             }
             off += 20;
@@ -299,7 +310,7 @@ MPT_DEV void material_sample(const SceneView& S, uint32_t material_id, const Sha
                 const uint32_t at = rd16(off + 8);
                 float dx = cosf(rot), dy = sinf(rot);
                 if (at != kNoTexture) {
-                    const f4 a = sample_tex(S, at, sd.uv);
+                    const f4 a = sample_tex(S, at, sd);
                     float ex = a.x * 2.0f - 1.0f, ey = a.y * 2.0f - 1.0f;
                     const float l = sqrtf(ex * ex + ey * ey);
                     ex /= l;
@@ -344,7 +355,10 @@ MPT_DEV void env_shading_point(const SceneView& S, f3 ray_o, f3 ray_d, ShadingPo
 
 // scene.slang:418-469 with get_surface (:322-382) inlined. `hit.tri` must be valid.
 template <uint32_t FEAT>
-MPT_DEV void surface_shading_point(const SceneView& S, f3 ray_o, f3 ray_d, const HitRec& hit, float ctx_ior, bool with_material, ShadingPoint& sp) {
+// diff_dirs (GBuffer node only): the camera ray directions of the pixels to the right and below; the material is then sampled with the
+// screen-space UV gradients of the ray differential (gbuffer_rt.slang:41-50, ray-differential.slang) instead of at LOD 0.
+MPT_DEV void surface_shading_point(const SceneView& S, f3 ray_o, f3 ray_d, const HitRec& hit, float ctx_ior, bool with_material, ShadingPoint& sp,
+                                   const f3* diff_dirs = nullptr) {
     const float4* tp = S.accel.tris + size_t(hit.tri) * 3;
     const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
     const uint32_t geometry_index = __float_as_uint(tb.w);
@@ -416,6 +430,22 @@ MPT_DEV void surface_shading_point(const SceneView& S, f3 ray_o, f3 ray_d, const
         sd.face_normal = fn;
         sd.ior = ctx_ior;
         sd.front_facing = front_facing;
+        sd.use_grad = false;
+        sd.ddx = sd.ddy = mk2(0.f, 0.f);
+        if (diff_dirs) {
+            // RayDifferential::from_pinhole_camera + propagate (Igehy eq. 8, 10, 12) + compute_uv_gradients, ray-differential.slang:13-62
+            const float t = length(pos - ray_o);
+            f3 dOdx = t * (diff_dirs[0] - ray_d), dOdy = t * (diff_dirs[1] - ray_d);
+            const float rcp_dn = 1.0f / dot(ray_d, face_normal);
+            dOdx = dOdx + ray_d * (-dot(dOdx, face_normal) * rcp_dn);
+            dOdy = dOdy + ray_d * (-dot(dOdy, face_normal) * rcp_dn);
+            const f3 Nu = cross(e02, face_normal), Nv = cross(e01, face_normal);
+            const f3 Lu = Nu / dot(Nu, e01), Lv = Nv / dot(Nv, e02);
+            const f2 d1 = uv1 - uv0, d2 = uv2 - uv0;
+            sd.ddx = dot(Lu, dOdx) * d1 + dot(Lv, dOdx) * d2;
+            sd.ddy = dot(Lu, dOdy) * d1 + dot(Lv, dOdy) * d2;
+            sd.use_grad = true;
+        }
         material_sample<FEAT>(S, material_id, sd, sp);
     } else {
         sp.emission = material_emission(S, material_id, uv);

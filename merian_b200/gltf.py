@@ -185,15 +185,18 @@ def load_gltf(path, force_mipmaps_color: bool = False) -> SceneDescription:
         px = _decode_image(doc, src)
         if px is None or px.shape[0] <= 0 or px.shape[1] <= 0:
             return abi.TEXTURE_NONE
-        filt, wu, wv = abi.FILTER_LINEAR, abi.WRAP_REPEAT, abi.WRAP_REPEAT
+        filt, wu, wv, mip = abi.FILTER_LINEAR, abi.WRAP_REPEAT, abi.WRAP_REPEAT, abi.MIPMAP_NONE
         s = tex.get("sampler", -1)
         if 0 <= s < len(j.get("samplers", [])):
             sm = j["samplers"][s]
             if sm.get("magFilter", -1) == 9728:  # NEAREST (gltf_mag_filter_to_vk); libmpt has one filter per texture: mag wins
                 filt = abi.FILTER_NEAREST
+            # gltf_min_filter_to_vk (gltf_scene.cpp:212-248): the *_MIPMAP_* values ask for a chain, its second half is the mipmap mode.
+            # GLTFScene builds the chain for colour AND data textures when the sampler asks for it (gltf_scene.cpp:583-593).
+            mip = {9984: abi.MIPMAP_NEAREST, 9985: abi.MIPMAP_NEAREST, 9986: abi.MIPMAP_LINEAR, 9987: abi.MIPMAP_LINEAR}.get(sm.get("minFilter", -1), abi.MIPMAP_NONE)
             wu, wv = _WRAP.get(sm.get("wrapS", 10497), abi.WRAP_REPEAT), _WRAP.get(sm.get("wrapT", 10497), abi.WRAP_REPEAT)
         slots[key] = len(textures)
-        textures.append(Texture(px, srgb=not linear, wrap_u=wu, wrap_v=wv, filter=filt))
+        textures.append(Texture(px, srgb=not linear, wrap_u=wu, wrap_v=wv, filter=filt, mipmap=mip))
         return slots[key]
 
     def tex_index(obj, key):
@@ -414,7 +417,10 @@ def save_gltf(desc: SceneDescription, path, embed: bool = False):
                     f.write(png)
                 images.append({"uri": name})
             inv = {v: k for k, v in _WRAP.items()}
-            samplers.append({"magFilter": 9728 if t.filter == abi.FILTER_NEAREST else 9729, "minFilter": 9728 if t.filter == abi.FILTER_NEAREST else 9729,
+            nearest = t.filter == abi.FILTER_NEAREST
+            min_filter = {abi.MIPMAP_NONE: 9728 if nearest else 9729, abi.MIPMAP_NEAREST: 9984 if nearest else 9985,
+                          abi.MIPMAP_LINEAR: 9986 if nearest else 9987}[getattr(t, "mipmap", abi.MIPMAP_NONE)]
+            samplers.append({"magFilter": 9728 if nearest else 9729, "minFilter": min_filter,
                              "wrapS": inv[t.wrap_u], "wrapT": inv[t.wrap_v]})
             gtex.append({"source": len(images) - 1, "sampler": len(samplers) - 1})
             tex_of[tid] = len(gtex) - 1

@@ -246,6 +246,7 @@ class Texture:
     wrap_u: int = abi.WRAP_REPEAT
     wrap_v: int = abi.WRAP_REPEAT
     filter: int = abi.FILTER_LINEAR
+    mipmap: int = abi.MIPMAP_NONE  # a glTF sampler with a *_MIPMAP_* minFilter gets a mip chain (gltf_scene.cpp:212-248, 583-593)
 
 
 @dataclass
@@ -488,7 +489,7 @@ def upload_scene(backend, tables: SceneTables):
         else:
             px = px.astype(np.float32)
             fmt = abi.TEX_RGBA32F
-        backend.texture_upload(tid, px.shape[1], px.shape[0], fmt, t.wrap_u, t.wrap_v, t.filter, px)
+        backend.texture_upload(tid, px.shape[1], px.shape[0], fmt, t.wrap_u, t.wrap_v, t.filter, px, getattr(t, "mipmap", abi.MIPMAP_NONE))
     backend.materials_upload(tables.material_entries, tables.material_entry_size, len(d.materials),
                              tables.material_types_array(), len(tables.material_types))
     if d.env is not None:

@@ -171,14 +171,20 @@ inline bool intersect_triangle(const RayShear& rs, float3 org, float3 v0, float3
 // Scene tables
 struct Texture {
     uint32_t w = 0, h = 0, format = 0, wrap_u = 0, wrap_v = 0, filter = 1;
+    uint32_t mipmap_mode = MPT_MIPMAP_NONE; // VkSamplerMipmapMode of a texture that has a chain
     std::vector<uint8_t> rgba8;
     std::vector<float> rgba32f;
+    std::vector<Texture> mips; // levels 1 .. (level 0 is this texture)
     bool valid() const { return w > 0; }
+    const Texture& level(uint32_t l) const { return l == 0 ? *this : mips[l - 1]; }
+    uint32_t levels() const { return uint32_t(mips.size()) + 1; }
 };
 
 inline float srgb_to_linear(float c) { // Vulkan / Khronos data format spec sRGB EOTF
     return c <= 0.04045f ? c / 12.92f : std::pow((c + 0.055f) / 1.055f, 2.4f);
 }
+
+inline float linear_to_srgb(float l) { return l <= 0.0031308f ? 12.92f * l : 1.055f * std::pow(l, 1.0f / 2.4f) - 0.055f; }
 
 inline int wrap_coord(int i, int n, uint32_t mode) {
     if (mode == MPT_WRAP_CLAMP_TO_EDGE) return std::min(std::max(i, 0), n - 1);
@@ -212,6 +218,67 @@ inline float4 sample_texture(const Texture& t, float2 uv) {
     const int y0 = wrap_coord(j0, int(t.h), t.wrap_v), y1 = wrap_coord(j0 + 1, int(t.h), t.wrap_v);
     const float4 t00 = texel(t, x0, y0), t10 = texel(t, x1, y0), t01 = texel(t, x0, y1), t11 = texel(t, x1, y1);
     return ((1 - a) * (1 - b)) * t00 + (a * (1 - b)) * t10 + ((1 - a) * b) * t01 + (a * b) * t11;
+}
+
+// Mip chain of create_texture_from_rgba8 / _rgba32f(generate_mipmaps) (src/merian/vk/memory/resource_allocator.cpp:298-358):
+// floor(log2(max(w, h))) + 1 levels, level i = vkCmdBlitImage(level i - 1 -> max(1, dim >> i), VK_FILTER_LINEAR)
+// (include/merian/vk/utils/blits.hpp:101-168). Blits convert through the format: sRGB texels are filtered in linear space and re-encoded.
+inline void generate_mipmaps(Texture& t) {
+    t.mips.clear();
+    uint32_t n = 1;
+    for (uint32_t m = std::max(t.w, t.h); m > 1; m >>= 1) n++;
+    const Texture* src = &t;
+    t.mips.reserve(n);
+    for (uint32_t i = 1; i < n; i++) {
+        Texture d;
+        d.w = std::max(1u, t.w >> i); d.h = std::max(1u, t.h >> i);
+        d.format = t.format; d.wrap_u = t.wrap_u; d.wrap_v = t.wrap_v; d.filter = t.filter;
+        const bool f32 = t.format == MPT_TEX_RGBA32F;
+        if (f32) d.rgba32f.resize(size_t(d.w) * d.h * 4); else d.rgba8.resize(size_t(d.w) * d.h * 4);
+        const float sx = float(src->w) / float(d.w), sy = float(src->h) / float(d.h);
+        for (uint32_t y = 0; y < d.h; y++)
+            for (uint32_t x = 0; x < d.w; x++) {
+                const float u = (float(x) + 0.5f) * sx - 0.5f, v = (float(y) + 0.5f) * sy - 0.5f;
+                const float fu = std::floor(u), fv = std::floor(v), a = u - fu, b = v - fv;
+                auto at = [&](int xx, int yy) { // clamp to edge; texel() decodes sRGB
+                    return texel(*src, std::min(std::max(xx, 0), int(src->w) - 1), std::min(std::max(yy, 0), int(src->h) - 1));
+                };
+                const float4 r = ((1 - a) * (1 - b)) * at(int(fu), int(fv)) + (a * (1 - b)) * at(int(fu) + 1, int(fv)) +
+                                 ((1 - a) * b) * at(int(fu), int(fv) + 1) + (a * b) * at(int(fu) + 1, int(fv) + 1);
+                const size_t o = (size_t(y) * d.w + x) * 4;
+                if (f32) {
+                    d.rgba32f[o] = r.x; d.rgba32f[o + 1] = r.y; d.rgba32f[o + 2] = r.z; d.rgba32f[o + 3] = r.w;
+                } else {
+                    const bool srgb = t.format == MPT_TEX_RGBA8_SRGB;
+                    const float e[4] = {srgb ? linear_to_srgb(r.x) : r.x, srgb ? linear_to_srgb(r.y) : r.y, srgb ? linear_to_srgb(r.z) : r.z, r.w};
+                    for (int c = 0; c < 4; c++) d.rgba8[o + size_t(c)] = uint8_t(std::min(std::max(e[c] * 255.0f + 0.5f, 0.0f), 255.0f));
+                }
+            }
+        t.mips.push_back(std::move(d));
+        src = &t.mips.back();
+    }
+}
+
+// GradLODSampler::sample (textures.slang:398-421) = SampleGrad(uv, ddx, ddy): LOD from the gradients as the Vulkan specification defines
+// it for a sampler without anisotropy ("Scale Factor Operation", "LOD Operation", "Image Level(s) Selection"): rho = the longer of the two
+// gradient vectors in texel units, lambda = log2(rho); lambda <= 0 magnifies (level 0); otherwise the level nearest to lambda
+// (VK_SAMPLER_MIPMAP_MODE_NEAREST) or a blend of the two levels around it (LINEAR). The hardware may approximate rho and quantises
+// lambda to 8 fractional bits; tests compare with a tolerance.
+inline float4 sample_texture_grad(const Texture& t, float2 uv, float2 ddx, float2 ddy) {
+    if (t.mips.empty()) return sample_texture(t, uv);
+    const float rx = std::sqrt(ddx.x * float(t.w) * ddx.x * float(t.w) + ddx.y * float(t.h) * ddx.y * float(t.h));
+    const float ry = std::sqrt(ddy.x * float(t.w) * ddy.x * float(t.w) + ddy.y * float(t.h) * ddy.y * float(t.h));
+    const float rho = std::max(rx, ry);
+    const float q = float(t.levels() - 1);
+    if (!(rho > 1.0f)) return sample_texture(t, uv); // lambda <= 0 (or NaN gradients): magnification
+    const float lambda = std::min(std::log2(rho), q);
+    if (t.mipmap_mode == MPT_MIPMAP_NEAREST) {
+        const float d = std::min(std::max(std::ceil(lambda + 0.5f) - 1.0f, 0.0f), q);
+        return sample_texture(t.level(uint32_t(d)), uv);
+    }
+    const float dh = std::floor(lambda), delta = lambda - dh;
+    const uint32_t hi = uint32_t(dh), lo = std::min(hi + 1u, t.levels() - 1u);
+    return (1.0f - delta) * sample_texture(t.level(hi), uv) + delta * sample_texture(t.level(lo), uv);
 }
 
 struct Mesh {
@@ -278,6 +345,9 @@ struct ShadingData { // shading-data.slang:27-58
     uint16_t bounce;
     float ior;
     bool front_facing;
+    // the LODSampler2D handed to get_material_sample: LOD0Sampler (pt, textures.slang:338-366) or GradLODSampler(ddx, ddy) (GBuffer, :398-421)
+    bool use_grad = false;
+    float2 ddx{0, 0}, ddy{0, 0};
 };
 
 struct ShadingPoint { // hit.slang:105-147
@@ -339,6 +409,9 @@ struct Scene {
     static float rdf(const uint8_t* p) { float v; std::memcpy(&v, p, 4); return v; }
     static float3 rdf3(const uint8_t* p) { return float3(rdf(p), rdf(p + 4), rdf(p + 8)); }
     float4 tex(uint16_t id, float2 uv) const { return sample_texture(textures[id], uv); }
+    float4 tex(uint16_t id, const ShadingData& sd) const {
+        return sd.use_grad ? sample_texture_grad(textures[id], sd.uv, sd.ddx, sd.ddy) : sample_texture(textures[id], sd.uv);
+    }
 
     // material-system.slang:28-38
     bool alpha_test(uint32_t material_id, float2 uv) const {
@@ -362,7 +435,7 @@ struct Scene {
             if (emission_only) return s;
             out_frame = sd.frame.apply_normal_map(float3(0, 0, 1));
             float3 albedo = rdf3(p);
-            if (alpha_tex != MPT_TEXTURE_NONE) albedo = albedo * tex(alpha_tex, sd.uv).xyz();
+            if (alpha_tex != MPT_TEXTURE_NONE) albedo = albedo * tex(alpha_tex, sd).xyz();
             s.is_gltf = false;
             s.diffuse = LambertDiffuseBRDF(albedo);
             return s;
@@ -391,20 +464,20 @@ struct Scene {
         if (A) { an_s = rdf(q); an_rot = rdf(q + 4); an_tex = rd16(q + 8); q += 10; }
 
         float3 emission = emissive_factor;
-        if (emissive_tex != MPT_TEXTURE_NONE) emission = emission * tex(emissive_tex, sd.uv).xyz();
+        if (emissive_tex != MPT_TEXTURE_NONE) emission = emission * tex(emissive_tex, sd).xyz();
         out_emission = emission;
         if (emission_only) return s;
 
-        if (alpha_tex != MPT_TEXTURE_NONE) base = base * tex(alpha_tex, sd.uv);
+        if (alpha_tex != MPT_TEXTURE_NONE) base = base * tex(alpha_tex, sd);
         float metallic = metallic_factor, roughness = roughness_factor;
         if (mr_tex != MPT_TEXTURE_NONE) {
-            const float4 mr = tex(mr_tex, sd.uv);
+            const float4 mr = tex(mr_tex, sd);
             roughness *= mr.y;
             metallic *= mr.z;
         }
         Frame shading_frame = sd.frame;
         if (normal_tex != MPT_TEXTURE_NONE) {
-            const float4 raw = tex(normal_tex, sd.uv);
+            const float4 raw = tex(normal_tex, sd);
             const float2 nxy((raw.x * 2.0f - 1.0f) * normal_scale, (raw.y * 2.0f - 1.0f) * normal_scale);
             const float nz = std::sqrt(std::max(0.0f, 1.0f - dot(nxy, nxy)));
             const Frame mapped = sd.frame.apply_normal_map(float3(nxy.x, nxy.y, nz));
@@ -418,7 +491,7 @@ struct Scene {
             float strength = an_s;
             float2 dir(std::cos(an_rot), std::sin(an_rot));
             if (an_tex != MPT_TEXTURE_NONE) {
-                const float4 a = tex(an_tex, sd.uv);
+                const float4 a = tex(an_tex, sd);
                 const float2 d = normalize(float2(a.x * 2.0f - 1.0f, a.y * 2.0f - 1.0f));
                 dir = float2(dir.x * d.x - dir.y * d.y, dir.x * d.y + dir.y * d.x);
                 strength *= a.z;
@@ -435,10 +508,10 @@ struct Scene {
         float iridescence_factor = 0.f, iri_ior = 1.0f, iri_thickness = 0.f;
         if (I) {
             iridescence_factor = ir_f;
-            if (ir_tex != MPT_TEXTURE_NONE) iridescence_factor *= tex(ir_tex, sd.uv).x;
+            if (ir_tex != MPT_TEXTURE_NONE) iridescence_factor *= tex(ir_tex, sd).x;
             iri_ior = ir_ior;
             float t = 1.0f;
-            if (ir_ttex != MPT_TEXTURE_NONE) t = tex(ir_ttex, sd.uv).y;
+            if (ir_ttex != MPT_TEXTURE_NONE) t = tex(ir_ttex, sd).y;
             iri_thickness = lerp(ir_tmin, ir_tmax, t);
         }
         const float3 base_rgb = base.xyz();
@@ -454,9 +527,9 @@ struct Scene {
         float coat_weight = 0.f, coat_alpha = pow2(MIN_ROUGHNESS);
         if (C) {
             coat_weight = cc_w;
-            if (cc_tex != MPT_TEXTURE_NONE) coat_weight *= tex(cc_tex, sd.uv).x;
+            if (cc_tex != MPT_TEXTURE_NONE) coat_weight *= tex(cc_tex, sd).x;
             float coat_rough = cc_r;
-            if (cc_rtex != MPT_TEXTURE_NONE) coat_rough *= tex(cc_rtex, sd.uv).y;
+            if (cc_rtex != MPT_TEXTURE_NONE) coat_rough *= tex(cc_rtex, sd).y;
             coat_alpha = pow2(std::max(coat_rough, MIN_ROUGHNESS));
         }
         float3 absorb(0.f);
@@ -465,9 +538,9 @@ struct Scene {
         float sheen_rough = 0.f;
         if (S) {
             sheen_col = sh_col;
-            if (sh_ctex != MPT_TEXTURE_NONE) sheen_col = sheen_col * tex(sh_ctex, sd.uv).xyz();
+            if (sh_ctex != MPT_TEXTURE_NONE) sheen_col = sheen_col * tex(sh_ctex, sd).xyz();
             sheen_rough = sh_r;
-            if (sh_rtex != MPT_TEXTURE_NONE) sheen_rough *= tex(sh_rtex, sd.uv).w;
+            if (sh_rtex != MPT_TEXTURE_NONE) sheen_rough *= tex(sh_rtex, sd).w;
         }
         const float sheen_alpha = pow2(sheen_rough);
         const float max_sheen = std::max(sheen_col.x, std::max(sheen_col.y, sheen_col.z));
@@ -772,6 +845,22 @@ struct Scene {
                     if (!front_facing) { frame.flip_normal(); face_normal = -face_normal; }
                 }
                 ShadingData sd{-ray.d, surface.pos, surface.uv, frame, face_normal, 0, 1.0f, front_facing};
+                {   // screen-space UV gradients for the mip selection, gbuffer_rt.slang:41-50 + ray-differential.slang:13-62
+                    // (RayDifferential::from_pinhole_camera, propagate: Igehy eq. 8, 10, 12; compute_uv_gradients)
+                    const float3 e01 = to_world_vector(gd, hit.instance_index, vpos(m.vertices[ib]) - vpos(m.vertices[ia]));
+                    const float3 e02 = to_world_vector(gd, hit.instance_index, vpos(m.vertices[ic]) - vpos(m.vertices[ia]));
+                    const float3 N = surface.face_normal;
+                    float3 dOdx = linear_z * (r_x - ray.d), dOdy = linear_z * (r_y - ray.d);
+                    const float rcpDN = 1.0f / dot(ray.d, N);
+                    dOdx = dOdx + ray.d * (-dot(dOdx, N) * rcpDN);
+                    dOdy = dOdy + ray.d * (-dot(dOdy, N) * rcpDN);
+                    const float3 Nu = cross(e02, N), Nv = cross(e01, N);
+                    const float3 Lu = Nu / dot(Nu, e01), Lv = Nv / dot(Nv, e02);
+                    const float2 d1 = vertex_uv(m.vertices[ib]) - vertex_uv(m.vertices[ia]), d2 = vertex_uv(m.vertices[ic]) - vertex_uv(m.vertices[ia]);
+                    sd.ddx = dot(Lu, dOdx) * d1 + dot(Lv, dOdx) * d2;
+                    sd.ddy = dot(Lu, dOdy) * d1 + dot(Lv, dOdy) * d2;
+                    sd.use_grad = true;
+                }
                 Frame mat_frame;
                 float3 mat_emission;
                 const MaterialSample mat = get_material_sample(surface.material_id, sd, mat_emission, mat_frame);
@@ -1033,15 +1122,32 @@ int oracle_materials_set_hints(oracle_context* c, float alpha_test_threshold, fl
     return 0;
 }
 
-int oracle_texture_upload(oracle_context* c, uint32_t id, uint32_t w, uint32_t h, uint32_t format, uint32_t wrap_u, uint32_t wrap_v,
-                          uint32_t filter, const void* pixels) {
+int oracle_texture_upload_ex(oracle_context* c, uint32_t id, uint32_t w, uint32_t h, uint32_t format, uint32_t wrap_u, uint32_t wrap_v,
+                             uint32_t filter, uint32_t mipmap_mode, const void* pixels) {
     Scene& s = c->scene;
     if (s.textures.size() <= id) s.textures.resize(id + 1);
     Texture& t = s.textures[id];
-    t.w = w; t.h = h; t.format = format; t.wrap_u = wrap_u; t.wrap_v = wrap_v; t.filter = filter;
+    t = Texture();
+    t.w = w; t.h = h; t.format = format; t.wrap_u = wrap_u; t.wrap_v = wrap_v; t.filter = filter; t.mipmap_mode = mipmap_mode;
     if (format == MPT_TEX_RGBA32F) t.rgba32f.assign((const float*)pixels, (const float*)pixels + size_t(w) * h * 4);
     else t.rgba8.assign((const uint8_t*)pixels, (const uint8_t*)pixels + size_t(w) * h * 4);
+    if (mipmap_mode != MPT_MIPMAP_NONE) generate_mipmaps(t);
     return 0;
+}
+int oracle_texture_upload(oracle_context* c, uint32_t id, uint32_t w, uint32_t h, uint32_t format, uint32_t wrap_u, uint32_t wrap_v,
+                          uint32_t filter, const void* pixels) {
+    return oracle_texture_upload_ex(c, id, w, h, format, wrap_u, wrap_v, filter, MPT_MIPMAP_NONE, pixels);
+}
+// one texel of one mip level, decoded (test hook for the mip chain)
+void oracle_texture_level_texel(oracle_context* c, uint32_t id, uint32_t level, uint32_t x, uint32_t y, float* out4, uint32_t* dims2) {
+    const Texture& t = c->scene.textures[id].level(level);
+    const float4 v = texel(t, int(x), int(y));
+    out4[0] = v.x; out4[1] = v.y; out4[2] = v.z; out4[3] = v.w;
+    if (dims2) { dims2[0] = t.w; dims2[1] = t.h; }
+}
+void oracle_sample_texture_grad(oracle_context* c, uint32_t id, float u, float v, const float* ddx, const float* ddy, float* out) {
+    const float4 t = sample_texture_grad(c->scene.textures[id], float2(u, v), float2(ddx[0], ddx[1]), float2(ddy[0], ddy[1]));
+    out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
 }
 
 int oracle_env_set(oracle_context* c, uint32_t type, const float* to_local, float intensity, uint32_t w, uint32_t h, const float* rgba32f) {

@@ -74,9 +74,21 @@ class OracleContext:
     def materials_set_hints(self, alpha_test_threshold=0.5, min_roughness=0.0316, clamp_normals=True):
         assert self.l.oracle_materials_set_hints(self.h, C.c_float(alpha_test_threshold), C.c_float(min_roughness), C.c_uint32(1 if clamp_normals else 0)) == 0
 
-    def texture_upload(self, tid, w, h, fmt, wrap_u, wrap_v, filt, pixels):
-        assert self.l.oracle_texture_upload(self.h, C.c_uint32(tid), C.c_uint32(w), C.c_uint32(h), C.c_uint32(fmt), C.c_uint32(wrap_u),
-                                            C.c_uint32(wrap_v), C.c_uint32(filt), _p(pixels)) == 0
+    def texture_upload(self, tid, w, h, fmt, wrap_u, wrap_v, filt, pixels, mipmap=abi.MIPMAP_NONE):
+        assert self.l.oracle_texture_upload_ex(self.h, C.c_uint32(tid), C.c_uint32(w), C.c_uint32(h), C.c_uint32(fmt), C.c_uint32(wrap_u),
+                                               C.c_uint32(wrap_v), C.c_uint32(filt), C.c_uint32(mipmap), _p(pixels)) == 0
+
+    def texture_level_texel(self, tid, level, x, y):
+        """(decoded texel, (width, height)) of one mip level (test hook)."""
+        out, dims = np.zeros(4, np.float32), np.zeros(2, np.uint32)
+        self.l.oracle_texture_level_texel(self.h, C.c_uint32(tid), C.c_uint32(level), C.c_uint32(x), C.c_uint32(y), _p(out), _p(dims))
+        return out, (int(dims[0]), int(dims[1]))
+
+    def sample_texture_grad(self, tid, u, v, ddx, ddy):
+        out = np.zeros(4, np.float32)
+        dx, dy = np.ascontiguousarray(ddx, np.float32), np.ascontiguousarray(ddy, np.float32)  # kept alive across the call
+        self.l.oracle_sample_texture_grad(self.h, C.c_uint32(tid), C.c_float(u), C.c_float(v), _p(dx), _p(dy), _p(out))
+        return out
 
     def env_set(self, typ, to_local, intensity, w, h, pixels):
         assert self.l.oracle_env_set(self.h, C.c_uint32(typ), _p(to_local), C.c_float(intensity), C.c_uint32(w), C.c_uint32(h), _p(pixels)) == 0

@@ -203,3 +203,114 @@ def test_gbuffer_feeds_pt_with_demodulation(gpu_ctx):
     demod = gpu_ctx.render_device(cam, render_params(w, h, 16, flags=abi.RENDER_EMISSION_ON_PRIMARY | abi.RENDER_DEMODULATE_ALBEDO), tex1=g["tex1"], albedo=g["tex3"])
     back = demod[..., :3] * torch.clamp(g["tex3"][..., :3], min=1e-2)
     assert torch.allclose(back, plain[..., :3], rtol=1e-4, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------- mip chains + ray differentials
+def _minified_floor_scene(mipmap):
+    """A large floor under a low camera with a high-frequency base-colour texture tiled 24x: towards the horizon a pixel covers many
+    texels, which is what GradLODSampler + the mip chain exist for (gbuffer_rt.slang:41-66)."""
+    from merian_b200 import abi
+    from merian_b200.scene import Texture
+    s = 20.0
+    p = np.array([[-s, 0, -s], [s, 0, -s], [s, 0, s], [-s, 0, s]], np.float32)
+    n = np.tile(np.array([[0, 1, 0]], np.float32), (4, 1))
+    uv = np.array([[0, 0], [24, 0], [24, 24], [0, 24]], np.float32)
+    floor = Mesh(positions=p, normals=n, uvs=uv, indices=np.array([[0, 2, 1], [0, 3, 2]], np.uint16), material_id=0, flags=MESH_IS_OPAQUE)
+    rng = np.random.default_rng(11)
+    px = rng.integers(0, 256, (64, 64, 4), dtype=np.uint8)
+    px[..., 3] = 255
+    tex = Texture(px, srgb=True, filter=abi.FILTER_LINEAR, mipmap=mipmap)
+    mats = [GltfMaterial(base_color_factor=(1, 1, 1, 1), metallic_factor=0.0, roughness_factor=1.0, base_color_texture=0)]
+    env = synthetic.sky_env(64, 32, sun_peak=10.0, sun_sigma_deg=10.0)
+    return SceneDescription(meshes=[floor], nodes=[Node([0])], materials=mats, textures=[tex], env=env,
+                            camera=CameraDesc(position=(0.0, 1.0, 12.0), target=(0.0, 0.0, 0.0), yfov_deg=50.0, aspect=1.5, near=0.01, far=200.0))
+
+
+def test_oracle_gbuffer_selects_coarser_levels_towards_the_horizon(oracle_lib):
+    from merian_b200 import abi
+    w, h = 150, 100
+    res = {}
+    for mode in (abi.MIPMAP_NONE, abi.MIPMAP_LINEAR):
+        t = SceneTables(_minified_floor_scene(mode))
+        o = make_oracle(t)
+        g = o.gbuffer(t.desc.camera.to_abi(0), w, h)
+        res[mode] = g
+    hit = res[abi.MIPMAP_NONE]["tex1"]["instance_id"] != MISS
+    far = hit & (res[abi.MIPMAP_NONE]["tex2"][..., 2] > 15.0)   # strongly minified
+    assert far.sum() > 200
+    a0, a1 = res[abi.MIPMAP_NONE]["tex3"][..., :3], res[abi.MIPMAP_LINEAR]["tex3"][..., :3]
+    # LOD 0 aliases (texel noise: large pixel-to-pixel variance); the mip chain converges to the texture's mean
+    assert a1[far].std(axis=0).mean() < 0.35 * a0[far].std(axis=0).mean()
+    assert np.abs(a1[far].mean(axis=0) - a0[hit].mean(axis=0)).max() < 0.05
+    # (magnification selecting level 0 is pinned on the sampler itself: tests/test_texture_mips.py)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["nearest", "linear"])
+def test_cuda_gbuffer_with_mip_chain_matches_oracle(gpu_ctx, mode):
+    """tex2DGrad on a mip-mapped CUDA array against the oracle's SampleGrad (Vulkan LOD rules in fp32). The hardware quantises the LOD to 8
+    fractional bits, the bilinear weights to 8, and may approximate the gradient length, so texels agree to a few percent; a kernel that
+    ignored the gradients (round 1: LOD 0 only) would be far outside (asserted against the chain-less render below)."""
+    from merian_b200 import abi
+    m = abi.MIPMAP_NEAREST if mode == "nearest" else abi.MIPMAP_LINEAR
+    t = SceneTables(_minified_floor_scene(m))
+    upload_scene(gpu_ctx, t)
+    o = make_oracle(t)
+    cam = t.desc.camera.to_abi(0)
+    w, h = 150, 100
+    got, ref = gpu_ctx.gbuffer(cam, w, h), o.gbuffer(cam, w, h)
+    mism, bary_err, _ = compare_hits(got["tex1"], ref["tex1"])
+    assert mism == 0.0 and bary_err == 0.0
+    hit = ref["tex1"]["instance_id"] != MISS
+    d = np.abs(got["tex3"][..., :3] - ref["tex3"][..., :3])[hit]
+    print(f"mip {mode}: albedo |diff| mean {d.mean():.4f} p99 {np.quantile(d, 0.99):.4f} max {d.max():.4f}")
+    if m == abi.MIPMAP_LINEAR:
+        assert d.mean() < 0.01 and np.quantile(d, 0.99) < 0.06
+    else:
+        assert d.mean() < 0.03  # nearest level: a rounding difference in lambda switches the level for a pixel
+    # and the chain is really used: the LOD-0 image of the same scene is far away from both
+    t0 = SceneTables(_minified_floor_scene(abi.MIPMAP_NONE))
+    upload_scene(gpu_ctx, t0)
+    lod0 = gpu_ctx.gbuffer(cam, w, h)
+    far = hit & (ref["tex2"][..., 2] > 15.0)
+    assert np.abs(lod0["tex3"][..., :3] - ref["tex3"][..., :3])[far].mean() > 5 * np.abs(got["tex3"][..., :3] - ref["tex3"][..., :3])[far].mean()
+    # pt reads LOD 0 whatever the texture has (LOD0Sampler): the irradiance of the chained and the chain-less scene is the same image
+    from helpers import render_params
+    P = render_params(w, h, 4)
+    upload_scene(gpu_ctx, t)
+    a = gpu_ctx.render(cam, P)
+    upload_scene(gpu_ctx, t0)
+    b = gpu_ctx.render(cam, P)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.gpu
+def test_texture_and_env_upload_from_device_memory(gpu_ctx):
+    """mpt_texture_upload_device / mpt_env_set_device (the Vulkan -> CUDA import leg: texels that already live in device memory, e.g. an
+    imported VkBuffer): same renders as the host uploads, with and without a row pitch."""
+    import torch
+    from merian_b200 import abi
+    from helpers import render_params
+    t = SceneTables(_minified_floor_scene(abi.MIPMAP_LINEAR))
+    upload_scene(gpu_ctx, t)
+    cam = t.desc.camera.to_abi(0)
+    w, h = 120, 80
+    want_g = gpu_ctx.gbuffer(cam, w, h)
+    want = gpu_ctx.render(cam, render_params(w, h, 4))
+    tex = t.desc.textures[0]
+    px = np.ascontiguousarray(tex.pixels)
+    H, W = px.shape[:2]
+    padded = np.zeros((H, W + 16, 4), np.uint8)  # row pitch = (W + 16) * 4 bytes
+    padded[:, :W] = px
+    d_px = torch.from_numpy(padded).cuda()
+    gpu_ctx.texture_upload_device(0, W, H, abi.TEX_RGBA8_SRGB, tex.wrap_u, tex.wrap_v, tex.filter, d_px, mipmap=abi.MIPMAP_LINEAR, row_pitch=(W + 16) * 4)
+    env = t.desc.env
+    d_env = torch.from_numpy(np.ascontiguousarray(env.pixels, np.float32)).cuda()
+    gpu_ctx.env_set_device(abi.ENV_LATLONG, np.ascontiguousarray(env.to_local, np.float32), env.intensity, env.pixels.shape[1], env.pixels.shape[0], d_env)
+    got_g = gpu_ctx.gbuffer(cam, w, h)
+    assert np.array_equal(got_g["tex3"], want_g["tex3"]) and np.array_equal(got_g["emission"], want_g["emission"])
+    assert np.array_equal(gpu_ctx.render(cam, render_params(w, h, 4)), want)
+    # device-to-device path (no chain), tightly packed
+    gpu_ctx.texture_upload_device(0, W, H, abi.TEX_RGBA8_SRGB, tex.wrap_u, tex.wrap_v, tex.filter, torch.from_numpy(px).cuda())
+    gpu_ctx.texture_upload(1, W, H, abi.TEX_RGBA8_SRGB, tex.wrap_u, tex.wrap_v, tex.filter, px)
+    assert np.array_equal(gpu_ctx.render(cam, render_params(w, h, 4)), want)  # pt reads level 0 either way
