@@ -508,7 +508,8 @@ MPT_API void mpt_host_accel_free(mpt_host_accel* accel);
 /* Test hook for the BSDF property suite (tests/test_bsdf.cpp of the reference restated): runs
  * sample_eval / eval / pdf of one BSDF on the device. See merian_b200/csrc/bsdf_check.cu. */
 typedef struct mpt_bsdf_check_params {
-    uint32_t bsdf;        /* 0 Lambert, 1 GGX, 2 GGX aniso, 3 FresnelMix<GGX, Lambert>, 4 IridescentFresnelMix, 5 IridescentRoughDielectric,
+    uint32_t bsdf;        /* 0 Lambert, 1 GGX, 2 GGX aniso, 3 FresnelMix<GGX, Lambert> (= the clearcoat construction: ior_f0 must be 0.04),
+                           * 4 IridescentFresnelMix, 5 IridescentRoughDielectric,
                            * 6 SheenBRDF alone (oracle only: on the device the sheen lobe exists only inside SheenLayer, MPT_ERR_UNSUPPORTED),
                            * 7 the whole GltfBSDF nest (metallic 0.5, clearcoat 0.5, sheen 0.5 * albedo, iridescence as given, no transmission),
                            * 8 Conductor, 9 SheenLayer<dielectric> with sheen colour = albedo */

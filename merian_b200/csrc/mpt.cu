@@ -1071,8 +1071,9 @@ template <uint32_t FEAT> __global__ void k_bsdf_check(mpt_bsdf_check_params P, f
     case 4: b.iri = P.iridescence; break;                                          // IridescentFresnelMix<GGX, Lambert>, eta 1/1.5
     case 5: b.tw = 1.f; b.f0 = 0.04f; b.iri = P.iridescence; break;                // IridescentRoughDielectric
     case 8: b.metallic = 1.f; b.base = mk3(P.f0[0], P.f0[1], P.f0[2]); break;      // Conductor: Schlick(f0) * GGX
-    case 3: break;                                                                 // FresnelMix<GGX, Lambert>: the kernel is instantiated without
-                                                                                   // the iridescence feature (gltf-material.slang:64-90 prunes it)
+    case 3:                                                                        // FresnelMix<GGX, Lambert> is the clearcoat construction of the nest
+        b.coat_w = 1.f; b.coat_alpha = P.alpha; b.eta = 1.0f;                      // (GltfCoated, f0 = 0.04): full coat over a dielectric whose own
+        break;                                                                     // Fresnel term is 0 (eta = 1), i.e. over plain Lambert
     case 9:                                                                        // SheenLayer<dielectric>: sheen colour = albedo over the same base
         b.sheen_col = b.base; b.sheen_alpha = P.alpha; b.max_sheen = fmaxf(b.base.x, fmaxf(b.base.y, b.base.z));
         break;
@@ -2344,8 +2345,9 @@ MPT_API mpt_status mpt_bsdf_check(mpt_context* ctx, const mpt_bsdf_check_params*
     CU(cudaSetDevice(ctx->device));
     DevBuf o;
     CU(o.ensure(64));
-    if (p->bsdf == 3) k_bsdf_check<0u><<<1, 1>>>(*p, o.as<float>());
-    else k_bsdf_check<0x3Fu><<<1, 1>>>(*p, o.as<float>());
+    if (p->bsdf == 3 && std::fabs(p->ior_f0 - 0.04f) > 1e-6f)
+        return fail(ctx, MPT_ERR_UNSUPPORTED, "FresnelMix is reachable as the clearcoat layer only, whose f0 is 0.04 (GLTF_DIELECTRIC_IOR_F0, gltf-material.slang:29)");
+    k_bsdf_check<0x3Fu><<<1, 1>>>(*p, o.as<float>());
     CU(cudaGetLastError());
     CU(cudaMemcpy(out16, o.p, 64, cudaMemcpyDeviceToHost));
     return MPT_OK;
