@@ -156,7 +156,7 @@ typedef struct mpt_camera {
     float near_plane;
     float far_plane;
     float aspect_ratio;
-    float aperture_radius; /* must be 0 (pinhole); thin lens is out of scope */
+    float aperture_radius; /* 0 = pinhole; > 0 = thin lens (camera.slang:73-92; the hint merian_hint_enable_thin_lens follows it, scene.cpp:2019-2021) */
     float jitter[2];
 } mpt_camera;
 
@@ -278,6 +278,11 @@ MPT_API mpt_status mpt_env_set(mpt_context* ctx, uint32_t type, const float* to_
 /* The lat-long texels already in device memory (see mpt_texture_upload_device). */
 MPT_API mpt_status mpt_env_set_device(mpt_context* ctx, uint32_t type, const float* to_local, float intensity, uint32_t width, uint32_t height,
                                       const void* d_rgba32f);
+
+/* Scene::frame (scene.slang:48) for the entry points that take no mpt_render_params (mpt_primary_visibility, mpt_gbuffer): a thin-lens
+ * camera draws its lens sample from (pixel, frame) (Scene::generate_camera_ray, scene.slang:91-101), so every pass of one iteration must
+ * see the same frame number. mpt_render* set it from params->frame. Pinhole cameras do not read it. */
+MPT_API mpt_status mpt_set_scene_frame(mpt_context* ctx, uint32_t frame);
 
 /* Replaces the gbuffer_rt raygen for the hit texture (gbuffer_rt.slang:18-31, gbuffer.slang:40-61):
  * writes one PackedHitInfo (uint4) per pixel into d_tex1 (row-major, width*height*16 bytes). */

@@ -1186,6 +1186,7 @@ struct TextureSlot {
 
 struct mpt_context {
     int device = 0;
+    uint32_t scene_frame = 0;     // Scene::frame for the entry points without mpt_render_params (mpt_set_scene_frame)
     int sm_count = 148;
     uint32_t extend_blocks_per_sm = 7;       // resident blocks of the persistent kernels in general
     uint32_t extend_plain_blocks_per_sm = 8; // ... of the plain k_extend variant
@@ -1263,8 +1264,10 @@ cudaError_t quiesce(mpt_context* ctx) {
     return cudaDeviceSynchronize(); // renders issued on caller-provided streams
 }
 
-CameraParams to_device_camera(const mpt_camera& c) {
+CameraParams to_device_camera(const mpt_camera& c, uint32_t frame) {
     CameraParams p;
+    p.aperture_radius = c.aperture_radius;
+    p.frame = frame;
     p.position = {c.position[0], c.position[1], c.position[2]};
     p.U = {c.U[0], c.U[1], c.U[2]};
     p.V = {c.V[0], c.V[1], c.V[2]};
@@ -1863,13 +1866,12 @@ MPT_API mpt_status mpt_primary_visibility(mpt_context* ctx, const mpt_camera* ca
                                           void* d_tex1, void* stream) {
     if (!ctx || !camera || !d_tex1 || !width || !height) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!ctx->scene_ready || !ctx->materials_ready) return fail(ctx, MPT_ERR_NOT_READY, "scene or materials not uploaded");
-    if (camera->aperture_radius > 0.f) return fail(ctx, MPT_ERR_UNSUPPORTED, "thin-lens camera is out of scope (pinhole only)");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     if (!ctx->counters.p) { CU(ctx->counters.ensure(sizeof(Counters))); CU(cudaMemset(ctx->counters.p, 0, sizeof(Counters))); }
     const uint32_t tiles = ((width + 7) / 8) * ((height + 3) / 4);
     const uint32_t blocks = (tiles * 32 + kThreads - 1) / kThreads;
-    const CameraParams cam = to_device_camera(*camera);
+    const CameraParams cam = to_device_camera(*camera, ctx->scene_frame);
     const bool cnt = ctx->profile_flags & 1u, tl = ctx->view.accel.two_level != 0;
     const uint32_t persistent_blocks = uint32_t(ctx->sm_count) * ctx->extend_blocks_per_sm;
     if (blocks > persistent_blocks && !getenv("MPT_TRACE_ONE_SHOT")) { // enough pixels to fill the machine: per-lane dynamic fetch
@@ -1899,12 +1901,11 @@ MPT_API mpt_status mpt_gbuffer(mpt_context* ctx, const mpt_camera* camera, const
                                uint32_t instance_mask, const mpt_gbuffer_images* images, void* stream) {
     if (!ctx || !camera || !images || !width || !height) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!ctx->scene_ready || !ctx->materials_ready) return fail(ctx, MPT_ERR_NOT_READY, "scene or materials not uploaded");
-    if (camera->aperture_radius > 0.f) return fail(ctx, MPT_ERR_UNSUPPORTED, "thin-lens camera is out of scope (pinhole only)");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t tiles = ((width + 7) / 8) * ((height + 3) / 4);
     const uint32_t blocks = (tiles * 32 + kThreads - 1) / kThreads;
-    const CameraParams cam = to_device_camera(*camera), prev = to_device_camera(prev_camera ? *prev_camera : *camera);
+    const CameraParams cam = to_device_camera(*camera, ctx->scene_frame), prev = to_device_camera(prev_camera ? *prev_camera : *camera, ctx->scene_frame);
     const GBufferOut out{(uint2*)images->d_tex0, (PackedHitInfo*)images->d_tex1, (float4*)images->d_tex2, (float4*)images->d_tex3, (float4*)images->d_emission};
     const bool tl = ctx->view.accel.two_level != 0;
 #define MPT_LAUNCH_GBUFFER(F) do { if (tl) k_gbuffer<F, true><<<blocks, kThreads, 0, st>>>(ctx->view, cam, prev, width, height, instance_mask, out); \
@@ -1960,7 +1961,6 @@ mpt_status render_impl(mpt_context* ctx, const mpt_camera* camera, const mpt_ren
     if (!ctx->scene_ready || !ctx->materials_ready) return fail(ctx, MPT_ERR_NOT_READY, "scene or materials not uploaded");
     if (!P->width || !P->height || P->spp < 0 || P->max_path_length < 1 || P->sample_stride == 0) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "bad render parameters");
     if (P->max_path_length > kMaxBounces) return fail(ctx, MPT_ERR_LIMIT, "max_path_length above 64 (per-bounce queue counters)");
-    if (camera->aperture_radius > 0.f) return fail(ctx, MPT_ERR_UNSUPPORTED, "thin-lens camera is out of scope (pinhole only)");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t npix = size_t(P->width) * P->height;
@@ -1980,13 +1980,14 @@ mpt_status render_impl(mpt_context* ctx, const mpt_camera* camera, const mpt_ren
         if (es != MPT_OK) return es;
     }
     const PackedHitInfo* tex1 = (const PackedHitInfo*)d_tex1;
+    ctx->scene_frame = P->frame; // Scene::frame of this iteration: what the lens sample of a thin-lens camera is keyed on
     if (!tex1) {
         CU(ctx->tex1_internal.ensure(npix * sizeof(PackedHitInfo)));
         const mpt_status s = mpt_primary_visibility(ctx, camera, P->width, P->height, P->instance_mask, ctx->tex1_internal.p, stream);
         if (s != MPT_OK) return s;
         tex1 = ctx->tex1_internal.as<PackedHitInfo>();
     }
-    const CameraParams cam = to_device_camera(*camera);
+    const CameraParams cam = to_device_camera(*camera, P->frame);
     if (P->spp == 0) {
         CU(cudaMemsetAsync(d_irradiance, 0, npix * 16, st));
         if (acc.enabled) k_accumulate<<<uint32_t((npix + kThreads - 1) / kThreads), kThreads, 0, st>>>(acc, (const float4*)d_irradiance, uint32_t(npix));
@@ -2213,6 +2214,12 @@ MPT_API mpt_status mpt_render_host_end(mpt_context* ctx, uint32_t in_flight_inde
     CU(cudaSetDevice(ctx->device));
     CU(cudaEventSynchronize(f.d2h));
     f.pending = false; // only once the copies are known to be complete
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_set_scene_frame(mpt_context* ctx, uint32_t frame) {
+    if (!ctx) return MPT_ERR_INVALID_ARGUMENT;
+    ctx->scene_frame = frame;
     return MPT_OK;
 }
 

@@ -475,6 +475,8 @@ struct CameraParams {
     f3 position, U, V, W;
     float near_plane, far_plane;
     float jitter_x, jitter_y;
+    float aperture_radius; // > 0: thin lens (camera.slang:73-92), the hint merian_hint_enable_thin_lens follows the camera (scene.cpp:2019-2021)
+    uint32_t frame;        // Scene::frame: the lens sample depends on (pixel, frame) only (scene.slang:91-101)
 };
 // camera.slang:58-70
 MPT_DEV f2 project_pinhole(const CameraParams& c, f3 world_pos, uint32_t w, uint32_t h) {
@@ -490,14 +492,43 @@ MPT_DEV f3 normalize_rn(f3 v) {
     const float l = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)), __fmul_rn(v.z, v.z)));
     return mk3(__fdiv_rn(v.x, l), __fdiv_rn(v.y, l), __fdiv_rn(v.z, l));
 }
+// xxhash32(uint2), hash.slang:68-77
+MPT_DEV uint32_t xxhash32_2(uint32_t px, uint32_t py) {
+    const uint32_t P2 = 2246822519u, P3 = 3266489917u, P4 = 668265263u, P5 = 374761393u;
+    uint32_t h = py + P5 + px * P3;
+    h = P4 * ((h << 17) | (h >> 15));
+    h = P2 * (h ^ (h >> 15));
+    h = P3 * (h ^ (h >> 13));
+    return h ^ (h >> 16);
+}
+// Scene::generate_camera_ray (scene.slang:94-101): pinhole (camera.slang:45-56) or, with aperture_radius > 0, thin lens
+// (camera.slang:73-92) whose lens sample is the R2 sequence over frames (pseudorandom.slang:35-38) rotated per pixel by PCG(xxhash32(pixel)).
+// The pinhole path is evaluated with individually rounded operations (see normalize_rn); the lens sample goes through sin / cos, whose
+// last bits differ between libraries, so thin-lens rays agree with a host evaluation to a few ulp only.
 MPT_DEV void camera_ray(const CameraParams& c, uint32_t px, uint32_t py, uint32_t w, uint32_t h, f3& o, f3& d, float& tmin, float& tmax) {
     const float pxn = __fdiv_rn(__fadd_rn(__fadd_rn(float(px), 0.5f), c.jitter_x), float(w));
     const float pyn = __fdiv_rn(__fadd_rn(__fadd_rn(float(py), 0.5f), c.jitter_y), float(h));
     const float nx = __fadd_rn(__fmul_rn(2.f, pxn), -1.f), ny = __fadd_rn(__fmul_rn(-2.f, pyn), 1.f);
     o = c.position;
-    d = normalize_rn(mk3(__fadd_rn(__fadd_rn(__fmul_rn(nx, c.U.x), __fmul_rn(ny, c.V.x)), c.W.x),
-                         __fadd_rn(__fadd_rn(__fmul_rn(nx, c.U.y), __fmul_rn(ny, c.V.y)), c.W.y),
-                         __fadd_rn(__fadd_rn(__fmul_rn(nx, c.U.z), __fmul_rn(ny, c.V.z)), c.W.z)));
+    f3 dv = mk3(__fadd_rn(__fadd_rn(__fmul_rn(nx, c.U.x), __fmul_rn(ny, c.V.x)), c.W.x),
+                __fadd_rn(__fadd_rn(__fmul_rn(nx, c.U.y), __fmul_rn(ny, c.V.y)), c.W.y),
+                __fadd_rn(__fadd_rn(__fmul_rn(nx, c.U.z), __fmul_rn(ny, c.V.z)), c.W.z));
+    if (c.aperture_radius > 0.f) {
+        Rng rng = make_pcg(xxhash32_2(px, py));
+        const float fn = float(c.frame);
+        const float r2x = __fadd_rn(0.5f, __fmul_rn(0.7548776662466927f, fn)), r2y = __fadd_rn(0.5f, __fmul_rn(0.5698402909980532f, fn));
+        const float sx = __fadd_rn(r2x - floorf(r2x), rng.next_float()), sy = __fadd_rn(r2y - floorf(r2y), rng.next_float());
+        const float rx = sx - floorf(sx), ry = sy - floorf(sy);
+        const float angle = __fmul_rn(kTwoPi, rx), rad = __fsqrt_rn(ry);
+        const float dx = __fmul_rn(cosf(angle), rad), dy = __fmul_rn(sinf(angle), rad); // sample_disk, sampling.slang:39-42
+        const f3 un = normalize_rn(c.U), vn = normalize_rn(c.V);
+        const f3 off = mk3(__fmul_rn(c.aperture_radius, __fadd_rn(__fmul_rn(dx, un.x), __fmul_rn(dy, vn.x))),
+                           __fmul_rn(c.aperture_radius, __fadd_rn(__fmul_rn(dx, un.y), __fmul_rn(dy, vn.y))),
+                           __fmul_rn(c.aperture_radius, __fadd_rn(__fmul_rn(dx, un.z), __fmul_rn(dy, vn.z))));
+        o = mk3(__fadd_rn(c.position.x, off.x), __fadd_rn(c.position.y, off.y), __fadd_rn(c.position.z, off.z));
+        dv = mk3(__fsub_rn(dv.x, off.x), __fsub_rn(dv.y, off.y), __fsub_rn(dv.z, off.z));
+    }
+    d = normalize_rn(dv);
     const f3 wn = normalize_rn(c.W);
     const float inv_cos = __fdiv_rn(1.f, __fadd_rn(__fadd_rn(__fmul_rn(wn.x, d.x), __fmul_rn(wn.y, d.y)), __fmul_rn(wn.z, d.z)));
     tmin = __fmul_rn(c.near_plane, inv_cos);

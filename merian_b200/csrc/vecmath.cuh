@@ -64,7 +64,20 @@ MPT_DEV f3 mix(f3 a, f3 b, float s) { return a * (1.0f - s) + b * s; }
 MPT_DEV float sgn(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
 MPT_DEV bool all_below(f3 a, float b) { return a.x < b && a.y < b && a.z < b; }
 MPT_DEV bool finite3(f3 a) { return isfinite(a.x) && isfinite(a.y) && isfinite(a.z); }
-MPT_DEV float comp(f3 v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+// Component i of v as two SELs. Written in PTX because the ternary form `i == 0 ? v.x : (i == 1 ? v.y : v.z)` came out of nvcc 12.9 as a
+// divergent branch per call (BSSY / BRA / BSYNC, 7-8 instructions each): the nine selections of the watertight triangle test were 72 of
+// its 135 SASS instructions (cuobjdump of k_extend_pooled, round 2 session M).
+MPT_DEV float comp(f3 v, int i) {
+#if defined(__CUDA_ARCH__) && !defined(MPT_COMP_TERNARY)
+    float r;
+    asm("{\n\t.reg .pred p0, p1;\n\t.reg .f32 t;\n\tsetp.eq.s32 p0, %4, 0;\n\tsetp.eq.s32 p1, %4, 1;\n\tselp.f32 t, %2, %3, p1;\n\tselp.f32 %0, %1, t, p0;\n\t}"
+        : "=f"(r)
+        : "f"(v.x), "f"(v.y), "f"(v.z), "r"(i));
+    return r;
+#else
+    return i == 0 ? v.x : (i == 1 ? v.y : v.z);
+#endif
+}
 
 // ---- hash.slang:138-146
 MPT_DEV uint32_t pcg4d16(uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
