@@ -81,6 +81,10 @@ class Context:
         self._check(self.l.mpt_image_write(self.h, os.fsencode(path), C.c_void_p(image.data_ptr()), w, h, self._stream()))
 
     # ------------------------------------------------------------------ device entry points (torch tensors)
+    def set_scene_frame(self, frame):
+        """Scene::frame for primary_visibility / gbuffer (thin-lens cameras key their lens sample on it); render() takes it from its params."""
+        self._check(self.l.mpt_set_scene_frame(self.h, C.c_uint32(int(frame))))
+
     def primary_visibility_device(self, cam, w, h, mask=0xFF, out=None):
         if out is None:
             out = torch.empty((h, w, 4), dtype=torch.int32, device=self.torch_device)

@@ -50,6 +50,8 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
     float best_t;
     uint32_t ray_mask;
     int sp, psp, pbase;    // node stack pointer; primitive stack pointer and its floor inside the current instance
+    uint32_t ptop_h;       // single-level scenes: the node-stack height the TOP parked group was uncovered at (each parked entry's w lane
+                           // keeps the value for the entry below it), so that section 3 needs no local-memory read to decide
     uint2 G;               // current node group: x = first inner child, y = hits << 24 | imask
     uint2 Gt;              // pending primitive group: x = first primitive record of its node, y = hit primitives (slot-space bits)
     uint32_t Gv;           //   ... and the node's leaf_bits: the primitive at bit b is record Gt.x + popc(Gv & ((1 << b) - 1)). Kept in a
@@ -74,6 +76,7 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
         const uint4 p = pst[--psp];
         Gt = make_uint2(p.x, p.y & 0x00FFFFFFu);
         Gv = p.z;
+        if (!TWO_LEVEL) ptop_h = p.w;
     }
     MPT_DEV uint2 top() const { return (SS > 0 && sp - 1 < SS) ? sst[(sp - 1) * STRIDE] : lst[sp - 1 - SS]; }
 
@@ -103,6 +106,7 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
         sp = 0;
         psp = 0;
         pbase = 0;
+        ptop_h = 0u;
         in_blas = !TWO_LEVEL;
         cur_instance = 0;
         cull = 0;
@@ -130,7 +134,10 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
             uint2 pl; // first primitive record, leaf_bits
             bvh8_node_test<true>(A, ni, o, idir, perm, 0.f, best_t, G, leaf, &pl);
             if (leaf) {
-                if (Gt.y) pst[psp++] = make_uint4(pl.x, leaf | (uint32_t(sp) << 24), pl.y, 0u); // one group is already pending: park the new one
+                if (Gt.y) { // one group is already pending: park the new one
+                    pst[psp++] = make_uint4(pl.x, leaf | (uint32_t(sp) << 24), pl.y, TWO_LEVEL ? 0u : ptop_h);
+                    if (!TWO_LEVEL) ptop_h = uint32_t(sp);
+                }
                 else { Gt = make_uint2(pl.x, leaf); Gv = pl.y; }
             }
         }
@@ -211,6 +218,22 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
         // group while ANY primitive is pending" brings the counts down to the oracle's immediate-test traversal (11.03 nodes, 3.57
         // triangles per ray) but costs 2-4 % time on every scene tried (C1, C3, C5: profiles/r02h_drain_first.jsonl): lanes idle through
         // node sections while they drain.
+#ifndef MPT_POP_LOOP
+        if (!TWO_LEVEL) {
+            // Single-level scenes: the node stack holds node groups only and section 2 never pushes, so the loop below runs at most once
+            // and its stack top is pre_top. Written out flat (predicated moves instead of the loop's nest of divergent branches, which
+            // was ~45 instructions at 5-9 of 32 lanes, profiles/r02d_extend_summary.txt).
+            if (Gt.y == 0u && psp > 0) unpark();
+            if ((G.y & 0xFF000000u) == 0u) {
+                if (sp == 0) return Gt.y == 0u; // nothing left to visit: finished once the pending primitives are done
+                if (!(psp > 0 && ptop_h >= uint32_t(sp))) {
+                    G = pre_top;
+                    --sp;
+                }
+            }
+            return false;
+        }
+#endif
         if (Gt.y == 0u && psp > pbase) unpark();
         bool first_pop = true;
         while ((G.y & 0xFF000000u) == 0u) {

@@ -251,8 +251,10 @@ __global__ void __launch_bounds__(kThreads) k_gbuffer(const __grid_constant__ Sc
         p.bary = __floats2half2_rn(hr.u, hr.v);
         f3 ox, oy, diff[2]; // r_x, r_y of gbuffer_rt.slang:36-37: the camera rays of the neighbouring pixels
         float t0, t1;
-        camera_ray(cam, x + 1, y, w, h, ox, diff[0], t0, t1);
-        camera_ray(cam, x, y + 1, w, h, oy, diff[1], t0, t1);
+        CameraParams pin = cam; // get_pinhole_direction (camera.slang:34-37), whatever the aperture
+        pin.aperture_radius = 0.f;
+        camera_ray(pin, x + 1, y, w, h, ox, diff[0], t0, t1);
+        camera_ray(pin, x, y + 1, w, h, oy, diff[1], t0, t1);
         surface_shading_point<FEAT>(S, o, d, hr, 1.0f, true, sp, diff); // falls back to the environment for UseEnvMap geometry
         surface = sp.has_material;
     }
@@ -265,8 +267,10 @@ __global__ void __launch_bounds__(kThreads) k_gbuffer(const __grid_constant__ Sc
     if (surface) {
         f3 ox, rx, oy, ry;
         float t0, t1;
-        camera_ray(cam, x + 1, y, w, h, ox, rx, t0, t1);
-        camera_ray(cam, x, y + 1, w, h, oy, ry, t0, t1);
+        CameraParams pin = cam;
+        pin.aperture_radius = 0.f;
+        camera_ray(pin, x + 1, y, w, h, ox, rx, t0, t1);
+        camera_ray(pin, x, y + 1, w, h, oy, ry, t0, t1);
         const float n_dot_oo = dot(sp.geo_normal, sp.pos - o); // Surface::compute_grad_z, hit.slang:99-103
         grad_z = mk2(n_dot_oo / dot(sp.geo_normal, rx) - linear_z, n_dot_oo / dot(sp.geo_normal, ry) - linear_z);
         delta_z = length(sp.pos - prev_cam.position) - linear_z;

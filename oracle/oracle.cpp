@@ -778,14 +778,37 @@ struct Scene {
         return r;
     }
 
-    // camera.slang:29-56
-    static Ray generate_camera_ray(const mpt_camera& c, uint32_t px, uint32_t py, uint32_t w, uint32_t h) {
+    // Scene::generate_camera_ray, scene.slang:91-101: pinhole (camera.slang:45-56) or thin lens (camera.slang:73-92) when the camera has an
+    // aperture (merian_hint_enable_thin_lens follows the active camera, scene.cpp:2019-2021). frame = Scene::frame (scene.slang:48).
+    static uint32_t xxhash32(uint32_t px, uint32_t py) { // hash.slang:68-77
+        const uint32_t P2 = 2246822519u, P3 = 3266489917u, P4 = 668265263u, P5 = 374761393u;
+        uint32_t h = py + P5 + px * P3;
+        h = P4 * ((h << 17) | (h >> 15));
+        h = P2 * (h ^ (h >> 15));
+        h = P3 * (h ^ (h >> 13));
+        return h ^ (h >> 16);
+    }
+    static float2 r2_sequence(uint32_t n) { // pseudorandom.slang:35-38
+        return float2(frac(0.5f + 0.7548776662466927f * float(n)), frac(0.5f + 0.5698402909980532f * float(n)));
+    }
+    static Ray generate_camera_ray(const mpt_camera& c, uint32_t px, uint32_t py, uint32_t w, uint32_t h, uint32_t frame = 0) {
         const float2 p((float(px) + 0.5f + c.jitter[0]) / float(w), (float(py) + 0.5f + c.jitter[1]) / float(h));
         const float2 ndc(2.f * p.x + -1.f, -2.f * p.y + 1.f);
         const float3 U(c.U[0], c.U[1], c.U[2]), V(c.V[0], c.V[1], c.V[2]), W(c.W[0], c.W[1], c.W[2]);
         Ray r;
         r.o = float3(c.position[0], c.position[1], c.position[2]);
-        r.d = normalize(ndc.x * U + ndc.y * V + W);
+        float3 dir = ndc.x * U + ndc.y * V + W;
+        if (c.aperture_radius > 0.f) {
+            Rng rng = Rng::pcg(xxhash32(px, py));
+            const float2 r2 = r2_sequence(frame), xi = rng.next_float2();
+            const float2 random(frac(r2.x + xi.x), frac(r2.y + xi.y));
+            const float angle = 6.28318530717958647692f * random.x, rad = std::sqrt(random.y); // sample_disk, sampling.slang:39-42
+            const float2 a(std::cos(angle) * rad, std::sin(angle) * rad);
+            const float3 aperture_offset = c.aperture_radius * (a.x * normalize(U) + a.y * normalize(V));
+            r.o = r.o + aperture_offset;
+            dir = dir - aperture_offset;
+        }
+        r.d = normalize(dir);
         const float inv_cos = 1.f / dot(normalize(W), r.d);
         r.tmin = c.near_plane * inv_cos;
         r.tmax = c.far_plane * inv_cos;
@@ -812,9 +835,10 @@ struct Scene {
         Hit hit; // packed into tex1 by the caller (gbuffer.slang:167-169)
         float tex2[4], tex3[4], emission[4];
     };
+    uint32_t frame = 0; // Scene::frame (scene.slang:48) for the passes without render params (oracle_set_scene_frame)
     GBufferTexel gbuffer_pixel(const mpt_camera& cam, const mpt_camera& prev_cam, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint32_t mask) const {
         GBufferTexel g;
-        const Ray ray = generate_camera_ray(cam, x, y, w, h);
+        const Ray ray = generate_camera_ray(cam, x, y, w, h, frame);
         const Hit hit = trace_ray(ray, mask);
         g.hit = hit;
         float3 normal, albedo, emission;
@@ -831,7 +855,9 @@ struct Scene {
                 const Surface surface = get_surface(hit, gd, m.vertices[ia], m.vertices[ib], m.vertices[ic]);
                 const float3 prev_pos = surface.pos;
                 linear_z = length(surface.pos - ray.o);
-                const float3 r_x = generate_camera_ray(cam, x + 1, y, w, h).d, r_y = generate_camera_ray(cam, x, y + 1, w, h).d;
+                mpt_camera pin = cam; // get_pinhole_direction (camera.slang:34-37), whatever the aperture
+                pin.aperture_radius = 0.f;
+                const float3 r_x = generate_camera_ray(pin, x + 1, y, w, h).d, r_y = generate_camera_ray(pin, x, y + 1, w, h).d;
                 const float n_dot_oo = dot(surface.face_normal, surface.pos - ray.o);                          // hit.slang:99-103
                 grad_z = float2(n_dot_oo / dot(surface.face_normal, r_x) - linear_z, n_dot_oo / dot(surface.face_normal, r_y) - linear_z);
                 delta_z = length(prev_pos - float3(prev_cam.position[0], prev_cam.position[1], prev_cam.position[2])) - linear_z;
@@ -1171,7 +1197,7 @@ int oracle_primary_visibility(oracle_context* c, const mpt_camera* cam, uint32_t
 #pragma omp parallel for schedule(dynamic, 4)
     for (int y = 0; y < int(h); y++)
         for (uint32_t x = 0; x < w; x++) {
-            const Ray r = Scene::generate_camera_ray(*cam, x, uint32_t(y), w, h);
+            const Ray r = Scene::generate_camera_ray(*cam, x, uint32_t(y), w, h, s.frame);
             out[size_t(y) * w + x] = pack_hit(s.trace_ray(r, mask));
         }
     return 0;
@@ -1222,7 +1248,7 @@ int oracle_render(oracle_context* c, const mpt_camera* cam, const mpt_render_par
         uint64_t rays = 0;
         for (uint32_t x = 0; x < w; x++) {
             const size_t pix = size_t(y) * w + x;
-            const Ray primary_ray = Scene::generate_camera_ray(*cam, x, uint32_t(y), w, h);
+            const Ray primary_ray = Scene::generate_camera_ray(*cam, x, uint32_t(y), w, h, P->frame);
             Hit primary_hit;
             if (tex1) primary_hit = unpack_hit(((const PackedHitInfo*)tex1)[pix]);
             else { primary_hit = unpack_hit(pack_hit(s.trace_ray(primary_ray, P->instance_mask))); rays++; }
@@ -1387,6 +1413,11 @@ float oracle_half_to_float(uint16_t h) { return half_to_float(h); }
 void oracle_offset_ray_origin(const float* p, const float* n, float* out) {
     const float3 o = offset_ray_origin(float3(p[0], p[1], p[2]), float3(n[0], n[1], n[2]));
     out[0] = o.x; out[1] = o.y; out[2] = o.z;
+}
+void oracle_set_scene_frame(oracle_context* c, uint32_t frame) { c->scene.frame = frame; }
+void oracle_camera_ray_frame(const mpt_camera* cam, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint32_t frame, mpt_ray* out) {
+    const Ray r = Scene::generate_camera_ray(*cam, x, y, w, h, frame);
+    *out = {{r.o.x, r.o.y, r.o.z}, r.tmin, {r.d.x, r.d.y, r.d.z}, r.tmax};
 }
 void oracle_camera_ray(const mpt_camera* cam, uint32_t x, uint32_t y, uint32_t w, uint32_t h, mpt_ray* out) {
     const Ray r = Scene::generate_camera_ray(*cam, x, y, w, h);

@@ -35,6 +35,8 @@ def lib():
         _lib.oracle_create.restype = C.c_void_p
         _lib.oracle_last_error.restype = C.c_char_p
         _lib.oracle_half_to_float.restype = C.c_float
+        _lib.oracle_set_scene_frame.argtypes = [C.c_void_p, C.c_uint32]
+        _lib.oracle_set_scene_frame.restype = None
         _lib.oracle_half_to_float.argtypes = [C.c_uint16]
         _lib.oracle_float_to_half.restype = C.c_uint16
         _lib.oracle_float_to_half.argtypes = [C.c_float]
@@ -92,6 +94,9 @@ class OracleContext:
 
     def env_set(self, typ, to_local, intensity, w, h, pixels):
         assert self.l.oracle_env_set(self.h, C.c_uint32(typ), _p(to_local), C.c_float(intensity), C.c_uint32(w), C.c_uint32(h), _p(pixels)) == 0
+
+    def set_scene_frame(self, frame):
+        self.l.oracle_set_scene_frame(self.h, C.c_uint32(int(frame)))
 
     def primary_visibility(self, cam, w, h, mask=0xFF):
         out = np.zeros((h, w), abi.PACKED_HIT_DTYPE)

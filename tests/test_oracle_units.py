@@ -125,6 +125,56 @@ def test_camera_ray_matches_numpy(oracle_lib):
         assert tuple(r.origin[:]) == (1.0, 2.0, 3.0)
 
 
+# ------------------------------------------------------------------------------------------------- camera.slang:73-92, scene.slang:91-101
+def test_thin_lens_ray_matches_numpy(oracle_lib):
+    """Thin lens: origin on the aperture disk spanned by normalize(U), normalize(V); the ray passes through the pixel's point on the plane
+    of perfect focus (position + ndc.x U + ndc.y V + W); lens sample = frac(R2(frame) + PCG(xxhash32(pixel)).next_float2())."""
+    cam = CameraDesc(position=(1, 2, 3), target=(0, 0.5, -1), yfov_deg=50.0, aspect=16 / 9, near=0.1, far=1000.0).to_abi(0)
+    cam.aperture_radius = 0.25
+    w, h = 64, 36
+    U, V, W, P = (np.array(v[:], np.float64) for v in (cam.U, cam.V, cam.W, cam.position))
+
+    def xxhash32(px, py):
+        M = 0xFFFFFFFF
+        P2, P3, P4, P5 = 2246822519, 3266489917, 668265263, 374761393
+        h32 = (py + P5 + px * P3) & M
+        h32 = (P4 * (((h32 << 17) | (h32 >> 15)) & M)) & M
+        h32 = (P2 * (h32 ^ (h32 >> 15))) & M
+        h32 = (P3 * (h32 ^ (h32 >> 13))) & M
+        return h32 ^ (h32 >> 16)
+
+    def pcg_floats(seed, n):
+        u = np.zeros(n, np.uint32)
+        f = np.zeros(n, np.float32)
+        oracle_lib.oracle_pcg_stream(C.c_uint32(seed), C.c_uint32(n), C.c_void_p(u.ctypes.data), C.c_void_p(f.ctypes.data))
+        return f
+
+    seen = set()
+    for frame in (0, 1, 5):
+        for (x, y) in [(0, 0), (63, 35), (31, 17)]:
+            r = abi.Ray()
+            oracle_lib.oracle_camera_ray_frame(C.byref(cam), C.c_uint32(x), C.c_uint32(y), C.c_uint32(w), C.c_uint32(h), C.c_uint32(frame), C.byref(r))
+            o, d = np.array(r.origin[:], np.float64), np.array(r.direction[:], np.float64)
+            xi = pcg_floats(xxhash32(x, y), 2).astype(np.float64)
+            r2 = np.array([(0.5 + np.float32(0.7548776662466927) * frame) % 1.0, (0.5 + np.float32(0.5698402909980532) * frame) % 1.0])
+            rnd = (r2 + xi) % 1.0
+            disk = np.array([np.cos(2 * np.pi * rnd[0]), np.sin(2 * np.pi * rnd[0])]) * np.sqrt(rnd[1])
+            off = 0.25 * (disk[0] * U / np.linalg.norm(U) + disk[1] * V / np.linalg.norm(V))
+            assert np.abs(o - (P + off)).max() < 1e-5
+            ndc = (2 * ((x + 0.5) / w) - 1, -2 * ((y + 0.5) / h) + 1)
+            focus = P + ndc[0] * U + ndc[1] * V + W
+            want = (focus - o) / np.linalg.norm(focus - o)
+            assert np.abs(d - want).max() < 1e-5
+            seen.add((frame, x, y, round(float(o[0]), 6)))
+    assert len({s[3] for s in seen}) == len(seen)  # a different lens point for every (pixel, frame)
+    # aperture 0 = the pinhole ray, whatever the frame
+    cam.aperture_radius = 0.0
+    a, b = abi.Ray(), abi.Ray()
+    oracle_lib.oracle_camera_ray_frame(C.byref(cam), C.c_uint32(3), C.c_uint32(4), C.c_uint32(w), C.c_uint32(h), C.c_uint32(9), C.byref(a))
+    oracle_lib.oracle_camera_ray(C.byref(cam), C.c_uint32(3), C.c_uint32(4), C.c_uint32(w), C.c_uint32(h), C.byref(b))
+    assert bytes(a) == bytes(b)
+
+
 def test_r2_jitter_sequence():
     cam = CameraDesc(position=(0, 0, 1), target=(0, 0, 0), jitter_sequence="R2")
     assert cam.jitter(0) == (0.0, 0.0)  # frame 0 => no jitter (camera.cpp:325-330)
