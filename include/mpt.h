@@ -405,6 +405,12 @@ MPT_API mpt_status mpt_reset_stats(mpt_context* ctx);
  * *count = rays in that queue; at most `capacity` are copied. SURVEY.md §8(d): the oracle counts nodes / triangles per ray on these rays. */
 MPT_API mpt_status mpt_debug_ray_queue(mpt_context* ctx, uint32_t bounce, mpt_ray* h_rays, uint32_t* h_leaves, uint64_t capacity, uint64_t* count);
 
+/* Test hook: the per-ray setup of the traversal for n directions (3 floats each). h_shear: Sx, Sy, Sz of the watertight triangle test
+ * (IEEE quotients d[kx]/d[kz], d[ky]/d[kz], 1/d[kz]: the device computes them with one shared reciprocal and must match a host division bit
+ * for bit); h_k_perm: kx | ky << 2 | kz << 4, then the child visiting-order word; h_idir: the inverse direction as the single-level path
+ * computes it (IEEE) followed by the 1-ulp form used when a ray enters an instance (6 floats per ray). */
+MPT_API mpt_status mpt_debug_ray_setup(mpt_context* ctx, const float* h_dirs, uint64_t n, float* h_shear, uint32_t* h_k_perm, float* h_idir);
+
 /* Introspection used by tests and DESIGN.md figures. */
 typedef struct mpt_bvh_info {
     uint64_t node_count;     /* 80-byte BVH8 nodes over all BLAS + TLAS */

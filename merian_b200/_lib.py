@@ -14,7 +14,7 @@ _lib = None
 EXPORTS = ["mpt_abi_version", "mpt_create", "mpt_destroy", "mpt_last_error", "mpt_scene_upload", "mpt_materials_upload",
            "mpt_materials_set_hints", "mpt_texture_upload", "mpt_texture_upload_ex", "mpt_texture_upload_device", "mpt_mip_level", "mpt_env_set", "mpt_env_set_device", "mpt_set_scene_frame", "mpt_primary_visibility", "mpt_gbuffer", "mpt_trace", "mpt_render", "mpt_render_host", "mpt_render_host_begin", "mpt_render_host_end",
            "mpt_accumulate", "mpt_render_accumulate", "mpt_pfm_info", "mpt_pfm_load", "mpt_pfm_save", "mpt_hdr_load", "mpt_env_load", "mpt_image_write",
-           "mpt_set_profiling", "mpt_get_stats", "mpt_reset_stats", "mpt_debug_ray_queue", "mpt_bvh_get_info", "mpt_bvh8_build_info", "mpt_bsdf_check",
+           "mpt_set_profiling", "mpt_get_stats", "mpt_reset_stats", "mpt_debug_ray_queue", "mpt_debug_ray_setup", "mpt_bvh_get_info", "mpt_bvh8_build_info", "mpt_bsdf_check",
            "mpt_host_accel_build", "mpt_host_accel_get", "mpt_host_accel_free",
            "mpt_comm_unique_id", "mpt_comm_create", "mpt_comm_adopt", "mpt_comm_destroy", "mpt_comm_last_error", "mpt_comm_info",
            "mpt_reduce_begin", "mpt_reduce_end", "mpt_reduce_wait",
@@ -78,6 +78,7 @@ def lib():
         l.mpt_set_profiling.argtypes = [C.c_void_p, C.c_uint32]
         l.mpt_get_stats.argtypes = [C.c_void_p, C.POINTER(abi.Stats)]
         l.mpt_reset_stats.argtypes = [C.c_void_p]
+        l.mpt_debug_ray_setup.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         l.mpt_debug_ray_queue.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         l.mpt_bvh_get_info.argtypes = [C.c_void_p, C.POINTER(abi.BvhInfo)]
         l.mpt_bvh8_build_info.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.BvhInfo), C.c_void_p]

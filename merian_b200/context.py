@@ -195,6 +195,14 @@ class Context:
             self._check(self.l.mpt_debug_ray_queue(self.h, bounce, _hp(rays), _hp(leaves), m, C.byref(n)))
         return rays, leaves
 
+    def debug_ray_setup(self, dirs):
+        """Per-ray traversal setup of n directions (n, 3) float32: (shear (n, 3), k bits (n,), perm (n,), idir IEEE (n, 3), idir 1-ulp (n, 3))."""
+        dirs = np.ascontiguousarray(dirs, np.float32)
+        n = len(dirs)
+        shear, kp, idir = np.zeros((n, 3), np.float32), np.zeros((n, 2), np.uint32), np.zeros((n, 6), np.float32)
+        self._check(self.l.mpt_debug_ray_setup(self.h, _hp(dirs), C.c_uint64(n), _hp(shear), _hp(kp), _hp(idir)))
+        return shear, kp[:, 0], kp[:, 1], idir[:, :3], idir[:, 3:]
+
     def bvh_info(self) -> abi.BvhInfo:
         b = abi.BvhInfo()
         self._check(self.l.mpt_bvh_get_info(self.h, C.byref(b)))

@@ -50,8 +50,8 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
     float best_t;
     uint32_t ray_mask;
     int sp, psp, pbase;    // node stack pointer; primitive stack pointer and its floor inside the current instance
-    uint32_t ptop_h;       // single-level scenes: the node-stack height the TOP parked group was uncovered at (each parked entry's w lane
-                           // keeps the value for the entry below it), so that section 3 needs no local-memory read to decide
+    uint32_t ptop_h;       // the node-stack height the TOP parked group was uncovered at (each parked entry's w lane keeps the value for
+                           // the entry below it), so that section 3 needs no local-memory read to decide
     uint2 G;               // current node group: x = first inner child, y = hits << 24 | imask
     uint2 Gt;              // pending primitive group: x = first primitive record of its node, y = hit primitives (slot-space bits)
     uint32_t Gv;           //   ... and the node's leaf_bits: the primitive at bit b is record Gt.x + popc(Gv & ((1 << b) - 1)). Kept in a
@@ -76,7 +76,7 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
         const uint4 p = pst[--psp];
         Gt = make_uint2(p.x, p.y & 0x00FFFFFFu);
         Gv = p.z;
-        if (!TWO_LEVEL) ptop_h = p.w;
+        ptop_h = p.w;
     }
     MPT_DEV uint2 top() const { return (SS > 0 && sp - 1 < SS) ? sst[(sp - 1) * STRIDE] : lst[sp - 1 - SS]; }
 
@@ -135,8 +135,8 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
             bvh8_node_test<true>(A, ni, o, idir, perm, 0.f, best_t, G, leaf, &pl);
             if (leaf) {
                 if (Gt.y) { // one group is already pending: park the new one
-                    pst[psp++] = make_uint4(pl.x, leaf | (uint32_t(sp) << 24), pl.y, TWO_LEVEL ? 0u : ptop_h);
-                    if (!TWO_LEVEL) ptop_h = uint32_t(sp);
+                    pst[psp++] = make_uint4(pl.x, leaf | (uint32_t(sp) << 24), pl.y, ptop_h);
+                    ptop_h = uint32_t(sp);
                 }
                 else { Gt = make_uint2(pl.x, leaf); Gv = pl.y; }
             }
@@ -188,7 +188,10 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
                     if (((meta.z & 0xFFu) & ray_mask) == 0) continue;
                     const float4 r0 = __ldg(&ip->inv0), r1 = __ldg(&ip->inv1), r2 = __ldg(&ip->inv2);
                     if (G.y & 0xFF000000u) push(G);
-                    if (Gt.y) pst[psp++] = make_uint4(Gt.x, Gt.y | (uint32_t(sp) << 24), Gv, 0u);
+                    if (Gt.y) {
+                        pst[psp++] = make_uint4(Gt.x, Gt.y | (uint32_t(sp) << 24), Gv, ptop_h);
+                        ptop_h = uint32_t(sp);
+                    }
                     push(make_uint2(uint32_t(pbase), 0u)); // sentinel: leave the instance (x = the TLAS level's primitive-stack floor)
                     pbase = psp;
                     const float4 wa = ent->a, wd = ent->d;
@@ -198,7 +201,7 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
                     const f3 oo = mk3(affine_rn(r0, org_w, r0.w), affine_rn(r1, org_w, r1.w), affine_rn(r2, org_w, r2.w));
                     const f3 od = mk3(linear_rn(r0, dir_w), linear_rn(r1, dir_w), linear_rn(r2, dir_w));
                     RaySetup R;
-                    setup_ray(R, oo, od);
+                    setup_ray<true>(R, oo, od);
                     o = R.o; idir = R.idir; perm = R.perm; shear = R.shear;
                     cur_instance = inst;
                     const uint32_t fl = meta.z >> 8;
@@ -219,10 +222,10 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
         // triangles per ray) but costs 2-4 % time on every scene tried (C1, C3, C5: profiles/r02h_drain_first.jsonl): lanes idle through
         // node sections while they drain.
 #ifndef MPT_POP_LOOP
+        // Written out flat (predicated moves instead of a loop with a nest of divergent branches, which was ~45 instructions at 5-9 of 32
+        // lanes on C3 and 18 % of the instructions at 2-15 lanes on C5: profiles/r02d_extend_summary.txt, r02p_c5_extend_summary.txt).
         if (!TWO_LEVEL) {
-            // Single-level scenes: the node stack holds node groups only and section 2 never pushes, so the loop below runs at most once
-            // and its stack top is pre_top. Written out flat (predicated moves instead of the loop's nest of divergent branches, which
-            // was ~45 instructions at 5-9 of 32 lanes, profiles/r02d_extend_summary.txt).
+            // Single-level scenes: the node stack holds node groups only and section 2 never pushes: the stack top is pre_top.
             if (Gt.y == 0u && psp > 0) unpark();
             if ((G.y & 0xFF000000u) == 0u) {
                 if (sp == 0) return Gt.y == 0u; // nothing left to visit: finished once the pending primitives are done
@@ -231,6 +234,28 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
                     --sp;
                 }
             }
+            return false;
+        } else {
+            // Two-level scenes: the top is a node group, or the sentinel that ends the instance (then the next entry, if any, is a node
+            // group of the TLAS: instances do not nest). The same decisions as the loop below, at most one instance exit per step.
+            if (Gt.y == 0u && psp > pbase) unpark();
+            if ((G.y & 0xFF000000u) != 0u) return false;
+            if (sp == 0) return Gt.y == 0u;
+            if (psp > pbase && ptop_h >= uint32_t(sp)) return false;
+            uint2 t = top();
+            if ((t.y & 0xFF000000u) == 0u) { // the sentinel
+                if (Gt.y) return false;      // the instance's pending primitives go first
+                --sp;                        // back to the TLAS with the world-space ray of the record
+                pbase = int(t.x);
+                load_world_setup();
+                in_blas = false;
+                if (psp > pbase) unpark();
+                if (sp == 0) return Gt.y == 0u;
+                if (psp > pbase && ptop_h >= uint32_t(sp)) return false;
+                t = top();
+            }
+            G = t;
+            --sp;
             return false;
         }
 #endif

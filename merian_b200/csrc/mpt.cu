@@ -1054,6 +1054,23 @@ __global__ void __launch_bounds__(kThreads) k_resolve(RenderConst rc, PathBuffer
     else out[pix] = make_float4(irr.x, irr.y, irr.z, m2);
 }
 
+// --------------------------------------------------------------------------------------- ray setup, for tests
+// setup_ray of one direction per thread: the shear constants of the watertight test (which must be IEEE quotients: they define the
+// barycentrics bit for bit), kx | ky << 2 | kz << 4, the visiting-order word and the two forms of the inverse direction.
+__global__ void k_debug_ray_setup(const float* __restrict__ dirs, uint64_t n, float* __restrict__ shear, uint32_t* __restrict__ k_perm, float* __restrict__ idir) {
+    const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const f3 d = mk3(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]);
+    RaySetup R, A;
+    setup_ray<false>(R, mk3(0.f), d);
+    setup_ray<true>(A, mk3(0.f), d);
+    shear[3 * i] = R.shear.Sx; shear[3 * i + 1] = R.shear.Sy; shear[3 * i + 2] = R.shear.Sz;
+    k_perm[2 * i] = uint32_t(R.shear.kx) | (uint32_t(R.shear.ky) << 2) | (uint32_t(R.shear.kz) << 4);
+    k_perm[2 * i + 1] = R.perm;
+    idir[6 * i] = R.idir.x; idir[6 * i + 1] = R.idir.y; idir[6 * i + 2] = R.idir.z;
+    idir[6 * i + 3] = A.idir.x; idir[6 * i + 4] = A.idir.y; idir[6 * i + 5] = A.idir.z;
+}
+
 // --------------------------------------------------------------------------------------- BSDF property suite on the device
 // tests/bsdf/bsdf-checks.slang:30-135 restated: one thread, XorShift32 stream, Welford means, 256x512 quadrature.
 template <uint32_t FEAT> MPT_DEV bool check_sample(const Bsdf& b, f3 wi, Rng& rng, f3& wo, float& pdf, f3& w) {
@@ -2286,6 +2303,23 @@ MPT_API mpt_status mpt_debug_ray_queue(mpt_context* ctx, uint32_t bounce, mpt_ra
     } catch (...) {
         return fail(ctx, MPT_ERR_LIMIT, "out of host memory");
     }
+    return MPT_OK;
+}
+
+MPT_API mpt_status mpt_debug_ray_setup(mpt_context* ctx, const float* h_dirs, uint64_t n, float* h_shear, uint32_t* h_k_perm, float* h_idir) {
+    if (!ctx || !h_dirs || !h_shear || !h_k_perm || !h_idir || n == 0) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    DevBuf d, s, k, r;
+    CU(d.ensure(n * 12));
+    CU(s.ensure(n * 12));
+    CU(k.ensure(n * 8));
+    CU(r.ensure(n * 24));
+    CU(cudaMemcpy(d.p, h_dirs, n * 12, cudaMemcpyHostToDevice));
+    k_debug_ray_setup<<<uint32_t((n + 255) / 256), 256>>>(d.as<float>(), n, s.as<float>(), k.as<uint32_t>(), r.as<float>());
+    CU(cudaGetLastError());
+    CU(cudaMemcpy(h_shear, s.p, n * 12, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h_k_perm, k.p, n * 8, cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(h_idir, r.p, n * 24, cudaMemcpyDeviceToHost));
     return MPT_OK;
 }
 

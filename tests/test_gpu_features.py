@@ -222,6 +222,46 @@ def test_reference_bsdf_suite_on_device(gpu_ctx, name, params, checks, extra):
     assert abs(r.mean_cos - ro.mean_cos) <= 6 * (r.se_cos + ro.se_cos) + 2e-3
 
 
+# ------------------------------------------------------------------------------------------------- per-ray setup
+def test_ray_setup_matches_ieee(gpu_ctx):
+    """The shear constants of the watertight test define the barycentrics bit for bit; the device computes the three quotients with one shared
+    reciprocal (bvh8_traverse.cuh shear_quotients) and must agree with IEEE float32 divisions, including directions with tiny, zero and
+    huge components. The 1-ulp inverse direction used when a ray enters an instance stays within 2 ulp of the IEEE one."""
+    rng = np.random.default_rng(11)
+    n = 1 << 20
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    # stress cases: axis-aligned, tiny / zero minor components, very long and very short vectors, exact ties between components
+    d[:1000, 1] = 0.0
+    d[1000:2000, 0] *= np.float32(1e-30)
+    d[2000:3000] *= np.float32(1e-25)
+    d[3000:4000] *= np.float32(1e20)
+    d[4000:5000, 1] = d[4000:5000, 0]
+    d[5000:6000, 2] = -d[5000:6000, 0]
+    d[6000:7000, 0] = np.float32(1e-45)  # a denormal
+    d[7000:7003] = np.eye(3, dtype=np.float32)
+    d[7003:7006] = -np.eye(3, dtype=np.float32)
+    shear, k, perm, idir, idir_a = gpu_ctx.debug_ray_setup(d)
+    ax, ay, az = np.abs(d[:, 0]), np.abs(d[:, 1]), np.abs(d[:, 2])
+    kz = np.where(ax > ay, np.where(ax > az, 0, 2), np.where(ay > az, 1, 2))
+    kx, ky = (kz + 1) % 3, (kz + 2) % 3
+    idx = np.arange(n)
+    dz = d[idx, kz]
+    swap = dz < 0
+    kx, ky = np.where(swap, ky, kx), np.where(swap, kx, ky)
+    assert np.array_equal(k, (kx | (ky << 2) | (kz << 4)).astype(np.uint32))
+    with np.errstate(all="ignore"):
+        want = np.stack([d[idx, kx] / dz, d[idx, ky] / dz, np.float32(1.0) / dz], axis=1).astype(np.float32)
+    assert np.array_equal(shear.view(np.uint32), want.view(np.uint32)), int((shear.view(np.uint32) != want.view(np.uint32)).any(axis=1).sum())
+    octant = (d[:, 0] < 0).astype(np.uint32) | ((d[:, 1] < 0).astype(np.uint32) << 1) | ((d[:, 2] < 0).astype(np.uint32) << 2)
+    c = 7 - octant
+    want_perm = np.where(c & 1, 0x55, 0) | np.where(c & 2, 0x3300, 0) | np.where(c & 4, 0x0F0000, 0) | (c << 24)
+    assert np.array_equal(perm, want_perm.astype(np.uint32))
+    ok = np.abs(d) > 1e-20  # away from the clamp of safe_rcp
+    rel = np.abs(idir_a[ok].astype(np.float64) - idir[ok].astype(np.float64)) / np.abs(idir[ok].astype(np.float64))
+    assert rel.max() < 2.5e-7, rel.max()
+
+
 # ------------------------------------------------------------------------------------------------- thin-lens camera
 def test_thin_lens_camera_matches_oracle(gpu_ctx):
     """camera.slang:73-92 through Scene::generate_camera_ray (scene.slang:91-101): lens sample = R2(frame) rotated per pixel. The lens sample
