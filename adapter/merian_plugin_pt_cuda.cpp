@@ -35,6 +35,8 @@
 
 #include <nlohmann/json.hpp>
 
+#include <unistd.h>
+
 #include <array>
 #include <cmath>
 #include <cstring>
@@ -76,7 +78,7 @@ class ExportedBuffer {
         const int fd = device.getMemoryFdKHR(vk::MemoryGetFdInfoKHR{memory, vk::ExternalMemoryHandleTypeFlagBits::eOpaqueFd});
         // a successful import owns the descriptor (include/mpt.h); a failed one leaves it with us
         if (mpt_import_external_memory_fd(mpt, fd, req.size, MPT_EXTERNAL_MEMORY_OPAQUE_FD, MPT_EXTERNAL_MEMORY_DEDICATED, &imported, &d_ptr) != MPT_OK) {
-            ::close_fd(fd);
+            ::close(fd);
             destroy_vulkan();
             throw graph_errors::node_error{mpt_last_error(mpt)};
         }
@@ -98,8 +100,6 @@ class ExportedBuffer {
         buffer = nullptr;
         memory = nullptr;
     }
-    static void close_fd(int fd);
-
     vk::Device device;
     mpt_context* mpt;
     vk::DeviceSize size;
@@ -516,11 +516,11 @@ class RenderPTCuda : public Node {
             to_src.push_back(image->barrier2(vk::ImageLayout::eTransferSrcOptimal));
             back.push_back(image->barrier2(old_layout)); // the barriers are recorded in this order below, so the tracked state matches
         }
-        cmd->barrier({}, {}, to_src);
+        cmd->barrier(to_src);
         for (const Item& it : items)
             cmd->get_command_buffer().copyImageToBuffer(it.texture->get_image()->get_image(), vk::ImageLayout::eTransferSrcOptimal, staging.buffer,
                                                         whole_image(it.texture->get_image()->get_extent(), it.offset));
-        cmd->barrier({}, {}, back);
+        cmd->barrier(back);
         const uint64_t n = ++timeline_value;
         submission.submit();
         vk_done->queue_signal(submission.get_queue(), n);
@@ -568,9 +568,6 @@ class RenderPTCuda : public Node {
 };
 
 } // namespace merian
-
-#include <unistd.h>
-void merian::ExportedBuffer::close_fd(int fd) { ::close(fd); }
 
 extern "C" {
 
