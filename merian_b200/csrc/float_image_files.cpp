@@ -8,6 +8,10 @@
 #include <memory>
 
 namespace mpt {
+// Headers are not trusted: a width * height beyond this (2^28 texels = 4 GiB of RGBA32F, 16x the largest env map of the configs) is
+// reported as a malformed file instead of being handed to std::vector.
+constexpr uint64_t kMaxImagePixels = uint64_t(1) << 28;
+
 namespace {
 
 struct FileCloser {
@@ -25,6 +29,7 @@ std::string parse_header(FILE* f, const char* path, PfmInfo& info) {
     else return std::string("image_io: bad PFM magic in ") + path;
     if (fscanf(f, "%d %d %f", &info.width, &info.height, &scale) != 3 || info.width <= 0 || info.height <= 0)
         return std::string("image_io: malformed PFM header in ") + path;
+    if (uint64_t(info.width) * uint64_t(info.height) > kMaxImagePixels) return std::string("image_io: implausible image size in the header of ") + path;
     if (fgetc(f) == EOF) return std::string("image_io: malformed PFM header in ") + path;
     info.little_endian = scale < 0.f;
     return {};
@@ -111,6 +116,7 @@ std::string hdr_load(const char* path, int desired_channels, int& width, int& he
     if (!format_ok) return std::string("image_io: unsupported HDR format in ") + path;
     if (!line(l) || std::sscanf(l.c_str(), "-Y %d +X %d", &height, &width) != 2 || width <= 0 || height <= 0)
         return std::string("image_io: unsupported HDR data layout in ") + path;
+    if (uint64_t(width) * uint64_t(height) > kMaxImagePixels) return std::string("image_io: implausible image size in the header of ") + path;
     const size_t w = size_t(width), h = size_t(height);
     out.assign(w * h * size_t(desired_channels), 0.f);
     std::vector<unsigned char> scan(w * 4);

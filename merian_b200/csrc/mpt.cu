@@ -1546,7 +1546,7 @@ MPT_API uint32_t mpt_abi_version(void) { return MPT_ABI_VERSION; }
 
 MPT_API const char* mpt_last_error(const mpt_context* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
 
-MPT_API mpt_status mpt_create(int device, mpt_context** out_ctx) {
+MPT_API mpt_status mpt_create(int device, mpt_context** out_ctx) try {
     mpt_context* ctx = nullptr;
     if (!out_ctx) return fail(nullptr, MPT_ERR_INVALID_ARGUMENT, "out_ctx is NULL");
     *out_ctx = nullptr;
@@ -1594,6 +1594,12 @@ MPT_API mpt_status mpt_create(int device, mpt_context** out_ctx) {
     ctx->shade_blocks_cap = std::max(1u, env_u32("MPT_SHADE_BLOCKS_PER_SM", ctx->shade_blocks_cap));
     *out_ctx = ctx;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_LIMIT, "mpt_create: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_INVALID_ARGUMENT, std::string("mpt_create: ") + e.what());
+} catch (...) {
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_INVALID_ARGUMENT, "mpt_create: unknown exception");
 }
 
 MPT_API void mpt_destroy(mpt_context* ctx) {
@@ -1616,7 +1622,7 @@ MPT_API void mpt_destroy(mpt_context* ctx) {
     delete ctx;
 }
 
-MPT_API mpt_status mpt_scene_upload(mpt_context* ctx, const mpt_scene_desc* d) {
+MPT_API mpt_status mpt_scene_upload(mpt_context* ctx, const mpt_scene_desc* d) try {
     if (!ctx || !d) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     CU(cudaSetDevice(ctx->device));
     ctx->scene_ready = false;
@@ -1677,10 +1683,16 @@ MPT_API mpt_status mpt_scene_upload(mpt_context* ctx, const mpt_scene_desc* d) {
     ctx->bvh_info.build_ms = H.build_ms;
     ctx->scene_ready = true;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_scene_upload: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_scene_upload: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_scene_upload: unknown exception");
 }
 
 MPT_API mpt_status mpt_materials_upload(mpt_context* ctx, const void* entries, uint32_t entry_size, uint32_t material_count,
-                                        const mpt_material_type* types, uint32_t type_count) {
+                                        const mpt_material_type* types, uint32_t type_count) try {
     if (!ctx || (!entries && material_count) || !types) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     if (entry_size % 4 != 0 || entry_size < 20) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "material entry size must be a multiple of 4 and hold header + base colour");
     CU(cudaSetDevice(ctx->device));
@@ -1705,9 +1717,15 @@ MPT_API mpt_status mpt_materials_upload(mpt_context* ctx, const void* entries, u
     ctx->view.material_types = ctx->material_types.as<uint2>();
     ctx->materials_ready = true;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_materials_upload: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_materials_upload: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_materials_upload: unknown exception");
 }
 
-MPT_API mpt_status mpt_materials_set_hints(mpt_context* ctx, float alpha_test_threshold, float min_roughness, uint32_t clamp_normals) {
+MPT_API mpt_status mpt_materials_set_hints(mpt_context* ctx, float alpha_test_threshold, float min_roughness, uint32_t clamp_normals) try {
     if (!ctx) return MPT_ERR_INVALID_ARGUMENT;
     if (!(alpha_test_threshold >= 0.f && alpha_test_threshold <= 1.f) || !(min_roughness >= 0.f && min_roughness <= 1.f))
         return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "hints out of range");
@@ -1715,6 +1733,12 @@ MPT_API mpt_status mpt_materials_set_hints(mpt_context* ctx, float alpha_test_th
     ctx->view.min_roughness = min_roughness;
     ctx->view.clamp_normals = clamp_normals ? 1u : 0u;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_materials_set_hints: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_materials_set_hints: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_materials_set_hints: unknown exception");
 }
 
 } // extern "C"
@@ -1792,7 +1816,7 @@ mpt_status texture_upload_impl(mpt_context* ctx, uint32_t texture_id, uint32_t w
 extern "C" {
 
 MPT_API mpt_status mpt_mip_level(const void* level0, uint32_t width, uint32_t height, uint32_t format, uint32_t level, void* out, uint64_t capacity_bytes,
-                                 uint32_t* level_width, uint32_t* level_height) {
+                                 uint32_t* level_width, uint32_t* level_height) try {
     mpt_context* ctx = nullptr;
     if (!level0 || !width || !height || format > MPT_TEX_RGBA32F) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "bad texture");
     if (level >= mip_level_count(width, height)) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "level beyond the chain");
@@ -1810,23 +1834,47 @@ MPT_API mpt_status mpt_mip_level(const void* level0, uint32_t width, uint32_t he
         return fail(ctx, MPT_ERR_LIMIT, "out of host memory");
     }
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_LIMIT, "mpt_mip_level: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_INVALID_ARGUMENT, std::string("mpt_mip_level: ") + e.what());
+} catch (...) {
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_INVALID_ARGUMENT, "mpt_mip_level: unknown exception");
 }
 
 MPT_API mpt_status mpt_texture_upload(mpt_context* ctx, uint32_t texture_id, uint32_t width, uint32_t height, uint32_t format, uint32_t wrap_u,
-                                      uint32_t wrap_v, uint32_t filter, const void* pixels) {
+                                      uint32_t wrap_v, uint32_t filter, const void* pixels) try {
     return texture_upload_impl(ctx, texture_id, width, height, format, wrap_u, wrap_v, filter, MPT_MIPMAP_NONE, pixels, false, 0, nullptr);
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_texture_upload: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_texture_upload: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_texture_upload: unknown exception");
 }
 
 MPT_API mpt_status mpt_texture_upload_ex(mpt_context* ctx, uint32_t texture_id, uint32_t width, uint32_t height, uint32_t format, uint32_t wrap_u,
-                                         uint32_t wrap_v, uint32_t filter, uint32_t mipmap_mode, const void* pixels) {
+                                         uint32_t wrap_v, uint32_t filter, uint32_t mipmap_mode, const void* pixels) try {
     return texture_upload_impl(ctx, texture_id, width, height, format, wrap_u, wrap_v, filter, mipmap_mode, pixels, false, 0, nullptr);
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_texture_upload_ex: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_texture_upload_ex: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_texture_upload_ex: unknown exception");
 }
 
 MPT_API mpt_status mpt_texture_upload_device(mpt_context* ctx, uint32_t texture_id, uint32_t width, uint32_t height, uint32_t format, uint32_t wrap_u,
                                              uint32_t wrap_v, uint32_t filter, uint32_t mipmap_mode, const void* d_pixels, uint64_t row_pitch_bytes,
-                                             void* stream) {
+                                             void* stream) try {
     return texture_upload_impl(ctx, texture_id, width, height, format, wrap_u, wrap_v, filter, mipmap_mode, d_pixels, true, size_t(row_pitch_bytes),
                                (cudaStream_t)stream);
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_texture_upload_device: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_texture_upload_device: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_texture_upload_device: unknown exception");
 }
 
 } // extern "C"
@@ -1836,12 +1884,24 @@ mpt_status env_set_impl(mpt_context* ctx, uint32_t type, const float* to_local, 
 }
 extern "C" {
 MPT_API mpt_status mpt_env_set(mpt_context* ctx, uint32_t type, const float* to_local, float intensity, uint32_t width, uint32_t height,
-                               const float* rgba32f) {
+                               const float* rgba32f) try {
     return env_set_impl(ctx, type, to_local, intensity, width, height, rgba32f, false);
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_env_set: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_env_set: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_env_set: unknown exception");
 }
 MPT_API mpt_status mpt_env_set_device(mpt_context* ctx, uint32_t type, const float* to_local, float intensity, uint32_t width, uint32_t height,
-                                      const void* d_rgba32f) {
+                                      const void* d_rgba32f) try {
     return env_set_impl(ctx, type, to_local, intensity, width, height, static_cast<const float*>(d_rgba32f), true);
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_env_set_device: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_env_set_device: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_env_set_device: unknown exception");
 }
 } // extern "C"
 namespace {
@@ -1884,7 +1944,7 @@ mpt_status env_set_impl(mpt_context* ctx, uint32_t type, const float* to_local, 
 extern "C" {
 
 MPT_API mpt_status mpt_primary_visibility(mpt_context* ctx, const mpt_camera* camera, uint32_t width, uint32_t height, uint32_t instance_mask,
-                                          void* d_tex1, void* stream) {
+                                          void* d_tex1, void* stream) try {
     if (!ctx || !camera || !d_tex1 || !width || !height) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!ctx->scene_ready || !ctx->materials_ready) return fail(ctx, MPT_ERR_NOT_READY, "scene or materials not uploaded");
     CU(cudaSetDevice(ctx->device));
@@ -1916,10 +1976,16 @@ MPT_API mpt_status mpt_primary_visibility(mpt_context* ctx, const mpt_camera* ca
     ctx->stats.kernel_launches++;
     ctx->stats.rays_primary += uint64_t(width) * height;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_primary_visibility: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_primary_visibility: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_primary_visibility: unknown exception");
 }
 
 MPT_API mpt_status mpt_gbuffer(mpt_context* ctx, const mpt_camera* camera, const mpt_camera* prev_camera, uint32_t width, uint32_t height,
-                               uint32_t instance_mask, const mpt_gbuffer_images* images, void* stream) {
+                               uint32_t instance_mask, const mpt_gbuffer_images* images, void* stream) try {
     if (!ctx || !camera || !images || !width || !height) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!ctx->scene_ready || !ctx->materials_ready) return fail(ctx, MPT_ERR_NOT_READY, "scene or materials not uploaded");
     CU(cudaSetDevice(ctx->device));
@@ -1939,9 +2005,15 @@ MPT_API mpt_status mpt_gbuffer(mpt_context* ctx, const mpt_camera* camera, const
     ctx->stats.kernel_launches++;
     ctx->stats.rays_primary += uint64_t(width) * height;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_gbuffer: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_gbuffer: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_gbuffer: unknown exception");
 }
 
-MPT_API mpt_status mpt_trace(mpt_context* ctx, const void* d_rays, uint64_t n, uint32_t instance_mask, void* d_hits, void* stream) {
+MPT_API mpt_status mpt_trace(mpt_context* ctx, const void* d_rays, uint64_t n, uint32_t instance_mask, void* d_hits, void* stream) try {
     if (!ctx || (!d_rays && n) || (!d_hits && n)) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!ctx->scene_ready || !ctx->materials_ready) return fail(ctx, MPT_ERR_NOT_READY, "scene or materials not uploaded");
     if (n == 0) return MPT_OK;
@@ -1972,6 +2044,12 @@ MPT_API mpt_status mpt_trace(mpt_context* ctx, const void* d_rays, uint64_t n, u
     ctx->stats.kernel_launches++;
     ctx->stats.rays_continuation += n;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_trace: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_trace: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_trace: unknown exception");
 }
 
 } // extern "C"
@@ -2047,12 +2125,18 @@ mpt_status make_accum_args(mpt_context* ctx, const mpt_accumulate_params* A, con
 extern "C" {
 
 MPT_API mpt_status mpt_render(mpt_context* ctx, const mpt_camera* camera, const mpt_render_params* P, const void* d_tex1, const void* d_albedo,
-                              void* d_irradiance, void* stream) {
+                              void* d_irradiance, void* stream) try {
     if (!d_irradiance) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     return render_impl(ctx, camera, P, d_tex1, d_albedo, d_irradiance, AccumArgs{}, stream);
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_render: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_render: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_render: unknown exception");
 }
 
-MPT_API mpt_status mpt_accumulate(mpt_context* ctx, const mpt_accumulate_params* A, const void* d_src, const mpt_accumulate_buffers* B, void* stream) {
+MPT_API mpt_status mpt_accumulate(mpt_context* ctx, const mpt_accumulate_params* A, const void* d_src, const mpt_accumulate_buffers* B, void* stream) try {
     if (!ctx || !d_src) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     AccumArgs a{};
     const mpt_status s = make_accum_args(ctx, A, B, a);
@@ -2064,10 +2148,16 @@ MPT_API mpt_status mpt_accumulate(mpt_context* ctx, const mpt_accumulate_params*
     CU(cudaGetLastError());
     ctx->stats.kernel_launches++;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_accumulate: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_accumulate: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_accumulate: unknown exception");
 }
 
 MPT_API mpt_status mpt_render_accumulate(mpt_context* ctx, const mpt_camera* camera, const mpt_render_params* P, const void* d_tex1,
-                                         const void* d_albedo, const mpt_accumulate_params* A, const mpt_accumulate_buffers* B, void* stream) {
+                                         const void* d_albedo, const mpt_accumulate_params* A, const mpt_accumulate_buffers* B, void* stream) try {
     if (!ctx || !P) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     AccumArgs a{};
     const mpt_status s = make_accum_args(ctx, A, B, a);
@@ -2078,10 +2168,16 @@ MPT_API mpt_status mpt_render_accumulate(mpt_context* ctx, const mpt_camera* cam
     // the running sums of a multi-pass call (and the spp = 0 image) live in a scratch image; with one pass it is never touched
     CU(ctx->stage_out.ensure(size_t(P->width) * P->height * 16));
     return render_impl(ctx, camera, P, d_tex1, d_albedo, ctx->stage_out.p, a, stream);
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_render_accumulate: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_render_accumulate: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_render_accumulate: unknown exception");
 }
 
 MPT_API mpt_status mpt_render_host(mpt_context* ctx, const mpt_camera* camera, const mpt_render_params* P, const void* h_tex1, const void* h_albedo,
-                                   void* h_irradiance, void* stream) {
+                                   void* h_irradiance, void* stream) try {
     if (!ctx || !P || !h_irradiance) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
@@ -2104,10 +2200,16 @@ MPT_API mpt_status mpt_render_host(mpt_context* ctx, const mpt_camera* camera, c
     CU(cudaMemcpyAsync(h_irradiance, ctx->stage_out.p, npix * 16, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_render_host: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_render_host: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_render_host: unknown exception");
 }
 
 // ---- wire formats at either end of the path
-MPT_API mpt_status mpt_pfm_info(const char* path, uint32_t* width, uint32_t* height, uint32_t* channels) {
+MPT_API mpt_status mpt_pfm_info(const char* path, uint32_t* width, uint32_t* height, uint32_t* channels) try {
     mpt_context* ctx = nullptr;
     if (!path || !width || !height || !channels) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     PfmInfo info;
@@ -2115,9 +2217,15 @@ MPT_API mpt_status mpt_pfm_info(const char* path, uint32_t* width, uint32_t* hei
     if (!err.empty()) return fail(ctx, MPT_ERR_IO, err);
     *width = uint32_t(info.width); *height = uint32_t(info.height); *channels = uint32_t(info.channels);
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_LIMIT, "mpt_pfm_info: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_INVALID_ARGUMENT, std::string("mpt_pfm_info: ") + e.what());
+} catch (...) {
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_INVALID_ARGUMENT, "mpt_pfm_info: unknown exception");
 }
 
-MPT_API mpt_status mpt_pfm_load(const char* path, uint32_t desired_channels, float* out, uint64_t capacity_floats) {
+MPT_API mpt_status mpt_pfm_load(const char* path, uint32_t desired_channels, float* out, uint64_t capacity_floats) try {
     mpt_context* ctx = nullptr;
     if (!path || !out) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     PfmInfo info;
@@ -2127,17 +2235,29 @@ MPT_API mpt_status mpt_pfm_load(const char* path, uint32_t desired_channels, flo
     if (px.size() > capacity_floats) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "output buffer too small for the image");
     std::memcpy(out, px.data(), px.size() * sizeof(float));
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_LIMIT, "mpt_pfm_load: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_INVALID_ARGUMENT, std::string("mpt_pfm_load: ") + e.what());
+} catch (...) {
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_INVALID_ARGUMENT, "mpt_pfm_load: unknown exception");
 }
 
-MPT_API mpt_status mpt_pfm_save(const char* path, const float* data, uint32_t width, uint32_t height, uint32_t channels) {
+MPT_API mpt_status mpt_pfm_save(const char* path, const float* data, uint32_t width, uint32_t height, uint32_t channels) try {
     mpt_context* ctx = nullptr;
     if (!path || !data) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     const std::string err = pfm_save(path, data, int(width), int(height), int(channels));
     if (!err.empty()) return fail(ctx, err.find("supports only") != std::string::npos || err.find("empty") != std::string::npos ? MPT_ERR_INVALID_ARGUMENT : MPT_ERR_IO, err);
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_LIMIT, "mpt_pfm_save: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_INVALID_ARGUMENT, std::string("mpt_pfm_save: ") + e.what());
+} catch (...) {
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_INVALID_ARGUMENT, "mpt_pfm_save: unknown exception");
 }
 
-MPT_API mpt_status mpt_hdr_load(const char* path, uint32_t desired_channels, uint32_t* width, uint32_t* height, float* out, uint64_t capacity_floats) {
+MPT_API mpt_status mpt_hdr_load(const char* path, uint32_t desired_channels, uint32_t* width, uint32_t* height, float* out, uint64_t capacity_floats) try {
     mpt_context* ctx = nullptr;
     if (!path || !width || !height) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     int w = 0, h = 0;
@@ -2150,9 +2270,15 @@ MPT_API mpt_status mpt_hdr_load(const char* path, uint32_t desired_channels, uin
     if (px.size() > capacity_floats) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "output buffer too small for the image");
     std::memcpy(out, px.data(), px.size() * sizeof(float));
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_LIMIT, "mpt_hdr_load: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_INVALID_ARGUMENT, std::string("mpt_hdr_load: ") + e.what());
+} catch (...) {
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_INVALID_ARGUMENT, "mpt_hdr_load: unknown exception");
 }
 
-MPT_API mpt_status mpt_env_load(mpt_context* ctx, const char* path, const float* to_local, float intensity) {
+MPT_API mpt_status mpt_env_load(mpt_context* ctx, const char* path, const float* to_local, float intensity) try {
     if (!ctx || !path || !to_local) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     const size_t n = std::strlen(path);
     auto ends = [&](const char* e) { std::string t(n >= 4 ? path + n - 4 : ""); for (char& c : t) c = char(std::tolower((unsigned char)c)); return t == e; };
@@ -2171,9 +2297,15 @@ MPT_API mpt_status mpt_env_load(mpt_context* ctx, const char* path, const float*
     }
     if (!err.empty()) return fail(ctx, MPT_ERR_IO, err);
     return mpt_env_set(ctx, MPT_ENV_LATLONG, to_local, intensity, uint32_t(w), uint32_t(h), px.data());
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_env_load: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_env_load: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_env_load: unknown exception");
 }
 
-MPT_API mpt_status mpt_image_write(mpt_context* ctx, const char* path, const void* d_rgba32f, uint32_t width, uint32_t height, void* stream) {
+MPT_API mpt_status mpt_image_write(mpt_context* ctx, const char* path, const void* d_rgba32f, uint32_t width, uint32_t height, void* stream) try {
     if (!ctx || !path || !d_rgba32f || !width || !height) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     CU(cudaSetDevice(ctx->device));
     std::vector<float> host(size_t(width) * height * 4);
@@ -2182,13 +2314,19 @@ MPT_API mpt_status mpt_image_write(mpt_context* ctx, const char* path, const voi
     const std::string err = pfm_save(path, host.data(), int(width), int(height), 4);
     if (!err.empty()) return fail(ctx, MPT_ERR_IO, err);
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_image_write: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_image_write: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_image_write: unknown exception");
 }
 
 // Several iterations in flight (merian's graph keeps 2 by default, examples/gltf.json:39): the host->device copy of iteration i+1 and
 // the device->host copy of iteration i-1 run on per-slot copy streams while iteration i renders on the context's compute stream (the
 // path pool is shared, so renders are serialised among themselves).
 MPT_API mpt_status mpt_render_host_begin(mpt_context* ctx, const mpt_camera* camera, const mpt_render_params* P, const void* h_tex1, const void* h_albedo,
-                                         void* h_irradiance, uint32_t in_flight_index) {
+                                         void* h_irradiance, uint32_t in_flight_index) try {
     if (!ctx || !camera || !P || !h_irradiance) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     if (in_flight_index >= mpt_context::kMaxInFlight) return fail(ctx, MPT_ERR_LIMIT, "in_flight_index must be < 4");
     CU(cudaSetDevice(ctx->device));
@@ -2225,9 +2363,15 @@ MPT_API mpt_status mpt_render_host_begin(mpt_context* ctx, const mpt_camera* cam
     CU(cudaEventRecord(f.d2h, f.copy));
     f.pending = true;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_render_host_begin: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_render_host_begin: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_render_host_begin: unknown exception");
 }
 
-MPT_API mpt_status mpt_render_host_end(mpt_context* ctx, uint32_t in_flight_index) {
+MPT_API mpt_status mpt_render_host_end(mpt_context* ctx, uint32_t in_flight_index) try {
     if (!ctx) return MPT_ERR_INVALID_ARGUMENT;
     if (in_flight_index >= mpt_context::kMaxInFlight) return fail(ctx, MPT_ERR_LIMIT, "in_flight_index must be < 4");
     mpt_context::InFlight& f = ctx->in_flight[in_flight_index];
@@ -2236,21 +2380,39 @@ MPT_API mpt_status mpt_render_host_end(mpt_context* ctx, uint32_t in_flight_inde
     CU(cudaEventSynchronize(f.d2h));
     f.pending = false; // only once the copies are known to be complete
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_render_host_end: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_render_host_end: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_render_host_end: unknown exception");
 }
 
-MPT_API mpt_status mpt_set_scene_frame(mpt_context* ctx, uint32_t frame) {
+MPT_API mpt_status mpt_set_scene_frame(mpt_context* ctx, uint32_t frame) try {
     if (!ctx) return MPT_ERR_INVALID_ARGUMENT;
     ctx->scene_frame = frame;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_set_scene_frame: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_set_scene_frame: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_set_scene_frame: unknown exception");
 }
 
-MPT_API mpt_status mpt_set_profiling(mpt_context* ctx, uint32_t profile_flags) {
+MPT_API mpt_status mpt_set_profiling(mpt_context* ctx, uint32_t profile_flags) try {
     if (!ctx) return MPT_ERR_INVALID_ARGUMENT;
     ctx->profile_flags = profile_flags;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_set_profiling: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_set_profiling: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_set_profiling: unknown exception");
 }
 
-MPT_API mpt_status mpt_get_stats(mpt_context* ctx, mpt_stats* out) {
+MPT_API mpt_status mpt_get_stats(mpt_context* ctx, mpt_stats* out) try {
     if (!ctx || !out) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     CU(cudaSetDevice(ctx->device));
     CU(cudaDeviceSynchronize());
@@ -2266,9 +2428,15 @@ MPT_API mpt_status mpt_get_stats(mpt_context* ctx, mpt_stats* out) {
         out->tris_tested += c.tris_tested;
     }
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_get_stats: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_get_stats: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_get_stats: unknown exception");
 }
 
-MPT_API mpt_status mpt_reset_stats(mpt_context* ctx) {
+MPT_API mpt_status mpt_reset_stats(mpt_context* ctx) try {
     if (!ctx) return MPT_ERR_INVALID_ARGUMENT;
     CU(cudaSetDevice(ctx->device));
     CU(cudaDeviceSynchronize());
@@ -2276,9 +2444,15 @@ MPT_API mpt_status mpt_reset_stats(mpt_context* ctx) {
     ctx->stats = mpt_stats{};
     if (ctx->counters.p) CU(cudaMemset(ctx->counters.p, 0, sizeof(Counters)));
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_reset_stats: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_reset_stats: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_reset_stats: unknown exception");
 }
 
-MPT_API mpt_status mpt_debug_ray_queue(mpt_context* ctx, uint32_t bounce, mpt_ray* h_rays, uint32_t* h_leaves, uint64_t capacity, uint64_t* count) {
+MPT_API mpt_status mpt_debug_ray_queue(mpt_context* ctx, uint32_t bounce, mpt_ray* h_rays, uint32_t* h_leaves, uint64_t capacity, uint64_t* count) try {
     if (!ctx || !count) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     if (bounce < 1 || bounce > uint32_t(kMaxBounces) || !ctx->counters.p || !ctx->pool_slots) return fail(ctx, MPT_ERR_NOT_READY, "no frame has been rendered");
     CU(cudaSetDevice(ctx->device));
@@ -2304,9 +2478,15 @@ MPT_API mpt_status mpt_debug_ray_queue(mpt_context* ctx, uint32_t bounce, mpt_ra
         return fail(ctx, MPT_ERR_LIMIT, "out of host memory");
     }
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_debug_ray_queue: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_debug_ray_queue: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_debug_ray_queue: unknown exception");
 }
 
-MPT_API mpt_status mpt_debug_ray_setup(mpt_context* ctx, const float* h_dirs, uint64_t n, float* h_shear, uint32_t* h_k_perm, float* h_idir) {
+MPT_API mpt_status mpt_debug_ray_setup(mpt_context* ctx, const float* h_dirs, uint64_t n, float* h_shear, uint32_t* h_k_perm, float* h_idir) try {
     if (!ctx || !h_dirs || !h_shear || !h_k_perm || !h_idir || n == 0) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     CU(cudaSetDevice(ctx->device));
     DevBuf d, s, k, r;
@@ -2321,20 +2501,32 @@ MPT_API mpt_status mpt_debug_ray_setup(mpt_context* ctx, const float* h_dirs, ui
     CU(cudaMemcpy(h_k_perm, k.p, n * 8, cudaMemcpyDeviceToHost));
     CU(cudaMemcpy(h_idir, r.p, n * 24, cudaMemcpyDeviceToHost));
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_debug_ray_setup: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_debug_ray_setup: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_debug_ray_setup: unknown exception");
 }
 
-MPT_API mpt_status mpt_bvh_get_info(mpt_context* ctx, mpt_bvh_info* out) {
+MPT_API mpt_status mpt_bvh_get_info(mpt_context* ctx, mpt_bvh_info* out) try {
     if (!ctx || !out) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!ctx->scene_ready) return fail(ctx, MPT_ERR_NOT_READY, "scene not uploaded");
     *out = ctx->bvh_info;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_bvh_get_info: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_bvh_get_info: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_bvh_get_info: unknown exception");
 }
 
 struct mpt_host_accel {
     HostAccel a;
 };
 
-MPT_API mpt_status mpt_host_accel_build(const mpt_scene_desc* scene, mpt_host_accel** out) {
+MPT_API mpt_status mpt_host_accel_build(const mpt_scene_desc* scene, mpt_host_accel** out) try {
     if (!scene || !out) return fail(nullptr, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     *out = nullptr;
     mpt_host_accel* h = nullptr;
@@ -2349,9 +2541,15 @@ MPT_API mpt_status mpt_host_accel_build(const mpt_scene_desc* scene, mpt_host_ac
     }
     *out = h;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_LIMIT, "mpt_host_accel_build: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_INVALID_ARGUMENT, std::string("mpt_host_accel_build: ") + e.what());
+} catch (...) {
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_INVALID_ARGUMENT, "mpt_host_accel_build: unknown exception");
 }
 
-MPT_API mpt_status mpt_host_accel_get(const mpt_host_accel* h, mpt_host_accel_view* v) {
+MPT_API mpt_status mpt_host_accel_get(const mpt_host_accel* h, mpt_host_accel_view* v) try {
     if (!h || !v) return fail(nullptr, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     const HostAccel& a = h->a;
     v->nodes = a.nodes.data(); v->node_count = a.nodes.size();
@@ -2362,11 +2560,17 @@ MPT_API mpt_status mpt_host_accel_get(const mpt_host_accel* h, mpt_host_accel_vi
     v->root = a.root; v->two_level = a.two_level; v->max_blas_depth = a.max_blas_depth; v->tlas_depth = a.tlas_depth;
     v->build_ms = a.build_ms;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_LIMIT, "mpt_host_accel_get: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_INVALID_ARGUMENT, std::string("mpt_host_accel_get: ") + e.what());
+} catch (...) {
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_INVALID_ARGUMENT, "mpt_host_accel_get: unknown exception");
 }
 
 MPT_API void mpt_host_accel_free(mpt_host_accel* h) { delete h; }
 
-MPT_API mpt_status mpt_bvh8_build_info(const float* boxes, uint32_t n, mpt_bvh_info* out, uint32_t* prim_order) {
+MPT_API mpt_status mpt_bvh8_build_info(const float* boxes, uint32_t n, mpt_bvh_info* out, uint32_t* prim_order) try {
     mpt_context* ctx = nullptr;
     if ((!boxes && n) || !out) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     const auto t0 = std::chrono::steady_clock::now();
@@ -2381,9 +2585,15 @@ MPT_API mpt_status mpt_bvh8_build_info(const float* boxes, uint32_t n, mpt_bvh_i
     out->build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     if (prim_order) std::memcpy(prim_order, bvh.prim_order.data(), bvh.prim_order.size() * 4);
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_LIMIT, "mpt_bvh8_build_info: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_INVALID_ARGUMENT, std::string("mpt_bvh8_build_info: ") + e.what());
+} catch (...) {
+    return fail(static_cast<mpt_context*>(nullptr), MPT_ERR_INVALID_ARGUMENT, "mpt_bvh8_build_info: unknown exception");
 }
 
-MPT_API mpt_status mpt_bsdf_check(mpt_context* ctx, const mpt_bsdf_check_params* p, float* out16) {
+MPT_API mpt_status mpt_bsdf_check(mpt_context* ctx, const mpt_bsdf_check_params* p, float* out16) try {
     if (!ctx || !p || !out16) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     if (p->bsdf == 6 || p->bsdf > 9)
         return fail(ctx, MPT_ERR_UNSUPPORTED, "not a sub-tree of GltfBSDF that can be isolated (SheenBRDF alone: use 9, SheenLayer over the dielectric)");
@@ -2396,6 +2606,12 @@ MPT_API mpt_status mpt_bsdf_check(mpt_context* ctx, const mpt_bsdf_check_params*
     CU(cudaGetLastError());
     CU(cudaMemcpy(out16, o.p, 64, cudaMemcpyDeviceToHost));
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_bsdf_check: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_bsdf_check: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_bsdf_check: unknown exception");
 }
 
 } // extern "C"

@@ -165,11 +165,17 @@ mpt_status nfail(mptn_node* n, mpt_status s, const std::string& msg) {
 
 extern "C" {
 
-MPT_API mpt_status mptn_create(mpt_context* ctx, mptn_node** out_node) {
+MPT_API mpt_status mptn_create(mpt_context* ctx, mptn_node** out_node) try {
     if (!out_node) return MPT_ERR_INVALID_ARGUMENT; // ctx may be NULL: a node that only loads / dumps its configuration
     *out_node = new mptn_node();
     (*out_node)->ctx = ctx;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return MPT_ERR_LIMIT;
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return MPT_ERR_INVALID_ARGUMENT;
+} catch (...) {
+    return MPT_ERR_INVALID_ARGUMENT;
 }
 
 MPT_API void mptn_destroy(mptn_node* node) {
@@ -180,7 +186,7 @@ MPT_API void mptn_destroy(mptn_node* node) {
 
 MPT_API const char* mptn_last_error(const mptn_node* node) { return node ? node->error.c_str() : "NULL node"; }
 
-MPT_API mpt_status mptn_load_config(mptn_node* node, const char* json, uint32_t* out_status) {
+MPT_API mpt_status mptn_load_config(mptn_node* node, const char* json, uint32_t* out_status) try {
     if (!node || !json) return nfail(node, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     if (out_status) *out_status = 0;
     std::map<std::string, JValue> o;
@@ -191,7 +197,9 @@ MPT_API mpt_status mptn_load_config(mptn_node* node, const char* json, uint32_t*
     auto want_int = [&](const char* key, int32_t& dst, std::string& e) {
         if (const JValue* v = find(key)) {
             if (v->kind != JValue::Number) { e = std::string("property '") + key + "' must be a number"; return; }
-            dst = int32_t(v->num); // nlohmann::json::get<int32_t> truncates a float
+            // nlohmann::json::get<int32_t> truncates a float; out-of-range / NaN values would be undefined behaviour in the cast
+            if (!(v->num >= -2147483648.0 && v->num <= 2147483647.0)) { e = std::string("property '") + key + "' is out of the int32 range"; return; }
+            dst = int32_t(v->num);
         }
     };
     auto want_bool = [&](const char* key, bool& dst, std::string& e) {
@@ -223,6 +231,10 @@ MPT_API mpt_status mptn_load_config(mptn_node* node, const char* json, uint32_t*
         }
     }
     if (!e.empty()) return nfail(node, MPT_ERR_INVALID_ARGUMENT, e);
+    // UI min / max are not applied on load (properties_json_load.cpp:126-133), but values no frame can be rendered with are refused here
+    // instead of failing later in process()
+    if (t.spp < 0) return nfail(node, MPT_ERR_INVALID_ARGUMENT, "property 'samples per pixel' must not be negative");
+    if (t.max_path_length < 1) return nfail(node, MPT_ERR_INVALID_ARGUMENT, "property 'max path length' must be at least 1");
     const bool reconnect = t.irradiance_format != node->irradiance_format;
     t.d_scratch = node->d_scratch;
     t.scratch_bytes = node->scratch_bytes;
@@ -230,9 +242,15 @@ MPT_API mpt_status mptn_load_config(mptn_node* node, const char* json, uint32_t*
     *node = t;
     if (out_status && reconnect) *out_status |= MPTN_NEEDS_RECONNECT;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return nfail(node, MPT_ERR_LIMIT, "mptn_load_config: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return nfail(node, MPT_ERR_INVALID_ARGUMENT, std::string("mptn_load_config: ") + e.what());
+} catch (...) {
+    return nfail(node, MPT_ERR_INVALID_ARGUMENT, "mptn_load_config: unknown exception");
 }
 
-MPT_API mpt_status mptn_dump_config(mptn_node* node, char* buf, size_t capacity, size_t* out_len) {
+MPT_API mpt_status mptn_dump_config(mptn_node* node, char* buf, size_t capacity, size_t* out_len) try {
     if (!node) return MPT_ERR_INVALID_ARGUMENT;
     std::string s = "{";
     for (int bit = 0; bit < 8; bit++) s += "\"" + std::to_string(bit) + "\": " + (node->mask_enabled[size_t(bit)] ? "true" : "false") + ", ";
@@ -251,9 +269,15 @@ MPT_API mpt_status mptn_dump_config(mptn_node* node, char* buf, size_t capacity,
         if (n < s.size()) return nfail(node, MPT_ERR_LIMIT, "buffer too small for the configuration");
     }
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return nfail(node, MPT_ERR_LIMIT, "mptn_dump_config: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return nfail(node, MPT_ERR_INVALID_ARGUMENT, std::string("mptn_dump_config: ") + e.what());
+} catch (...) {
+    return nfail(node, MPT_ERR_INVALID_ARGUMENT, "mptn_dump_config: unknown exception");
 }
 
-MPT_API mpt_status mptn_describe_outputs(mptn_node* node, uint32_t gw, uint32_t gh, uint32_t* out_vk_format, uint32_t* out_w, uint32_t* out_h) {
+MPT_API mpt_status mptn_describe_outputs(mptn_node* node, uint32_t gw, uint32_t gh, uint32_t* out_vk_format, uint32_t* out_w, uint32_t* out_h) try {
     if (!node || !gw || !gh) return nfail(node, MPT_ERR_INVALID_ARGUMENT, "describe_outputs: the gbuffer extent must be non-zero");
     node->width = gw;
     node->height = gh;
@@ -261,17 +285,29 @@ MPT_API mpt_status mptn_describe_outputs(mptn_node* node, uint32_t gw, uint32_t 
     if (out_w) *out_w = gw;
     if (out_h) *out_h = gh;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return nfail(node, MPT_ERR_LIMIT, "mptn_describe_outputs: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return nfail(node, MPT_ERR_INVALID_ARGUMENT, std::string("mptn_describe_outputs: ") + e.what());
+} catch (...) {
+    return nfail(node, MPT_ERR_INVALID_ARGUMENT, "mptn_describe_outputs: unknown exception");
 }
 
-MPT_API mpt_status mptn_set_shard(mptn_node* node, uint32_t rank, uint32_t world) {
+MPT_API mpt_status mptn_set_shard(mptn_node* node, uint32_t rank, uint32_t world) try {
     if (!node || world == 0 || rank >= world) return nfail(node, MPT_ERR_INVALID_ARGUMENT, "set_shard: need rank < world");
     node->rank = rank;
     node->world = world;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return nfail(node, MPT_ERR_LIMIT, "mptn_set_shard: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return nfail(node, MPT_ERR_INVALID_ARGUMENT, std::string("mptn_set_shard: ") + e.what());
+} catch (...) {
+    return nfail(node, MPT_ERR_INVALID_ARGUMENT, "mptn_set_shard: unknown exception");
 }
 
 MPT_API mpt_status mptn_process(mptn_node* node, const mpt_camera* camera, uint32_t frame, const void* d_tex1, const void* d_albedo,
-                                void* d_irradiance, void* stream, uint32_t* out_events) {
+                                void* d_irradiance, void* stream, uint32_t* out_events) try {
     if (!node || !camera || !d_irradiance) return nfail(node, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!node->ctx) return nfail(node, MPT_ERR_NOT_READY, "the node was created without a device context (initialize)");
     if (out_events) *out_events = 0;
@@ -304,6 +340,10 @@ MPT_API mpt_status mptn_process(mptn_node* node, const mpt_camera* camera, uint3
     }
     void* target = d_irradiance;
     const size_t npix = size_t(node->width) * node->height;
+    // a shard writes SUMS over its samples (and of luminance^2 in .w): they leave the fp16 range (65504) long before the reduce has
+    // normalised them, so partial sums stay fp32 whatever the configured output format is; the host converts after the reduce
+    if (node->world > 1 && node->irradiance_format == MPTN_FORMAT_R16G16B16A16_SFLOAT)
+        return nfail(node, MPT_ERR_UNSUPPORTED, "a sample shard (mptn_set_shard, world > 1) writes fp32 partial sums: set \"irradiance format\" to R32G32B32A32Sfloat and convert after the reduce");
     if (node->irradiance_format == MPTN_FORMAT_R16G16B16A16_SFLOAT) {
         if (node->scratch_bytes < npix * 16) {
             if (node->d_scratch) cudaFree(node->d_scratch);
@@ -322,6 +362,12 @@ MPT_API mpt_status mptn_process(mptn_node* node, const mpt_camera* camera, uint3
         if (cudaGetLastError() != cudaSuccess) return nfail(node, MPT_ERR_CUDA, "rgba16f pack kernel launch failed");
     }
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return nfail(node, MPT_ERR_LIMIT, "mptn_process: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return nfail(node, MPT_ERR_INVALID_ARGUMENT, std::string("mptn_process: ") + e.what());
+} catch (...) {
+    return nfail(node, MPT_ERR_INVALID_ARGUMENT, "mptn_process: unknown exception");
 }
 
 } // extern "C"
@@ -405,16 +451,22 @@ mpt_status copy_out(const std::string& s, char* buf, size_t capacity, size_t* ou
 
 extern "C" {
 
-MPT_API mpt_status mptn_gbuffer_create(mpt_context* ctx, mptn_gbuffer** out_node) {
+MPT_API mpt_status mptn_gbuffer_create(mpt_context* ctx, mptn_gbuffer** out_node) try {
     if (!out_node) return MPT_ERR_INVALID_ARGUMENT;
     *out_node = new mptn_gbuffer();
     (*out_node)->ctx = ctx;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return MPT_ERR_LIMIT;
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return MPT_ERR_INVALID_ARGUMENT;
+} catch (...) {
+    return MPT_ERR_INVALID_ARGUMENT;
 }
 MPT_API void mptn_gbuffer_destroy(mptn_gbuffer* node) { delete node; }
 MPT_API const char* mptn_gbuffer_last_error(const mptn_gbuffer* node) { return node ? node->error.c_str() : "NULL node"; }
 
-MPT_API mpt_status mptn_gbuffer_load_config(mptn_gbuffer* node, const char* json, uint32_t* out_status) {
+MPT_API mpt_status mptn_gbuffer_load_config(mptn_gbuffer* node, const char* json, uint32_t* out_status) try {
     if (!node || !json) return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     if (out_status) *out_status = 0;
     PropReader r;
@@ -436,9 +488,15 @@ MPT_API mpt_status mptn_gbuffer_load_config(mptn_gbuffer* node, const char* json
     *node = t;
     if (out_status && reconnect) *out_status |= MPTN_NEEDS_RECONNECT;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return nfail2(node, MPT_ERR_LIMIT, "mptn_gbuffer_load_config: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return nfail2(node, MPT_ERR_INVALID_ARGUMENT, std::string("mptn_gbuffer_load_config: ") + e.what());
+} catch (...) {
+    return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "mptn_gbuffer_load_config: unknown exception");
 }
 
-MPT_API mpt_status mptn_gbuffer_dump_config(mptn_gbuffer* node, char* buf, size_t capacity, size_t* out_len) {
+MPT_API mpt_status mptn_gbuffer_dump_config(mptn_gbuffer* node, char* buf, size_t capacity, size_t* out_len) try {
     if (!node) return MPT_ERR_INVALID_ARGUMENT;
     std::string s = "{";
     for (int bit = 0; bit < 8; bit++) s += "\"" + std::to_string(bit) + "\": " + (node->mask_enabled[size_t(bit)] ? "true" : "false") + ", ";
@@ -446,26 +504,44 @@ MPT_API mpt_status mptn_gbuffer_dump_config(mptn_gbuffer* node, char* buf, size_
     s += "\"height\": " + std::to_string(node->height) + ", \"width\": " + std::to_string(node->width) + "}";
     const mpt_status st = copy_out(s, buf, capacity, out_len);
     return st == MPT_OK ? st : nfail2(node, st, "buffer too small for the configuration");
+} catch (const std::bad_alloc&) {
+    return nfail2(node, MPT_ERR_LIMIT, "mptn_gbuffer_dump_config: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return nfail2(node, MPT_ERR_INVALID_ARGUMENT, std::string("mptn_gbuffer_dump_config: ") + e.what());
+} catch (...) {
+    return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "mptn_gbuffer_dump_config: unknown exception");
 }
 
-MPT_API mpt_status mptn_gbuffer_set_resolution(mptn_gbuffer* node, uint32_t width, uint32_t height, uint32_t* out_status) {
+MPT_API mpt_status mptn_gbuffer_set_resolution(mptn_gbuffer* node, uint32_t width, uint32_t height, uint32_t* out_status) try {
     if (!node || !width || !height) return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "resolution must be non-zero");
     if (out_status) *out_status = (width != node->width || height != node->height) ? MPTN_NEEDS_RECONNECT : 0u; // pre_process, gbuffer.cpp:104-115
     node->width = width;
     node->height = height;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return nfail2(node, MPT_ERR_LIMIT, "mptn_gbuffer_set_resolution: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return nfail2(node, MPT_ERR_INVALID_ARGUMENT, std::string("mptn_gbuffer_set_resolution: ") + e.what());
+} catch (...) {
+    return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "mptn_gbuffer_set_resolution: unknown exception");
 }
 
-MPT_API mpt_status mptn_gbuffer_describe_outputs(mptn_gbuffer* node, uint32_t* out_width, uint32_t* out_height, uint32_t* out_emission_vk_format) {
+MPT_API mpt_status mptn_gbuffer_describe_outputs(mptn_gbuffer* node, uint32_t* out_width, uint32_t* out_height, uint32_t* out_emission_vk_format) try {
     if (!node) return MPT_ERR_INVALID_ARGUMENT;
     if (out_width) *out_width = node->width;
     if (out_height) *out_height = node->height;
     if (out_emission_vk_format) *out_emission_vk_format = node->emission_format;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return nfail2(node, MPT_ERR_LIMIT, "mptn_gbuffer_describe_outputs: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return nfail2(node, MPT_ERR_INVALID_ARGUMENT, std::string("mptn_gbuffer_describe_outputs: ") + e.what());
+} catch (...) {
+    return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "mptn_gbuffer_describe_outputs: unknown exception");
 }
 
 MPT_API mpt_status mptn_gbuffer_process(mptn_gbuffer* node, const mpt_camera* camera, const mpt_camera* prev_camera, const mpt_gbuffer_images* images,
-                                        void* stream) {
+                                        void* stream) try {
     if (!node || !camera || !images) return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!node->ctx) return nfail2(node, MPT_ERR_NOT_READY, "the node was created without a device context (initialize)");
     uint32_t mask = 0; // gbuffer.cpp:129-134
@@ -475,18 +551,30 @@ MPT_API mpt_status mptn_gbuffer_process(mptn_gbuffer* node, const mpt_camera* ca
     if (s == MPT_ERR_NOT_READY) return MPT_OK; // `if (scene->is_ready())`, gbuffer.cpp:136
     if (s != MPT_OK) return nfail2(node, s, mpt_last_error(node->ctx));
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return nfail2(node, MPT_ERR_LIMIT, "mptn_gbuffer_process: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return nfail2(node, MPT_ERR_INVALID_ARGUMENT, std::string("mptn_gbuffer_process: ") + e.what());
+} catch (...) {
+    return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "mptn_gbuffer_process: unknown exception");
 }
 
-MPT_API mpt_status mptn_accumulate_create(mpt_context* ctx, mptn_accumulate** out_node) {
+MPT_API mpt_status mptn_accumulate_create(mpt_context* ctx, mptn_accumulate** out_node) try {
     if (!out_node) return MPT_ERR_INVALID_ARGUMENT;
     *out_node = new mptn_accumulate();
     (*out_node)->ctx = ctx;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return MPT_ERR_LIMIT;
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return MPT_ERR_INVALID_ARGUMENT;
+} catch (...) {
+    return MPT_ERR_INVALID_ARGUMENT;
 }
 MPT_API void mptn_accumulate_destroy(mptn_accumulate* node) { delete node; }
 MPT_API const char* mptn_accumulate_last_error(const mptn_accumulate* node) { return node ? node->error.c_str() : "NULL node"; }
 
-MPT_API mpt_status mptn_accumulate_load_config(mptn_accumulate* node, const char* json, uint32_t* out_status) {
+MPT_API mpt_status mptn_accumulate_load_config(mptn_accumulate* node, const char* json, uint32_t* out_status) try {
     if (!node || !json) return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     if (out_status) *out_status = 0;
     PropReader r;
@@ -525,9 +613,15 @@ MPT_API mpt_status mptn_accumulate_load_config(mptn_accumulate* node, const char
     *node = t;
     if (out_status && rebuild) *out_status |= MPTN_NEEDS_RECONNECT;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return nfail2(node, MPT_ERR_LIMIT, "mptn_accumulate_load_config: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return nfail2(node, MPT_ERR_INVALID_ARGUMENT, std::string("mptn_accumulate_load_config: ") + e.what());
+} catch (...) {
+    return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "mptn_accumulate_load_config: unknown exception");
 }
 
-MPT_API mpt_status mptn_accumulate_dump_config(mptn_accumulate* node, char* buf, size_t capacity, size_t* out_len) {
+MPT_API mpt_status mptn_accumulate_dump_config(mptn_accumulate* node, char* buf, size_t capacity, size_t* out_len) try {
     if (!node) return MPT_ERR_INVALID_ARGUMENT;
     static const char* modes[3] = {"always", "only if moving", "never"};
     auto b = [](bool v) { return v ? "true" : "false"; };
@@ -541,12 +635,24 @@ MPT_API mpt_status mptn_accumulate_dump_config(mptn_accumulate* node, char* buf,
     s += "\"normal threshold\": " + jnum(std::acos(node->normal_reject_cos)) + ", \"use motion vectors\": " + b(node->use_motion_vectors) + "}";
     const mpt_status st = copy_out(s, buf, capacity, out_len);
     return st == MPT_OK ? st : nfail2(node, st, "buffer too small for the configuration");
+} catch (const std::bad_alloc&) {
+    return nfail2(node, MPT_ERR_LIMIT, "mptn_accumulate_dump_config: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return nfail2(node, MPT_ERR_INVALID_ARGUMENT, std::string("mptn_accumulate_dump_config: ") + e.what());
+} catch (...) {
+    return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "mptn_accumulate_dump_config: unknown exception");
 }
 
-MPT_API mpt_status mptn_accumulate_request_clear(mptn_accumulate* node) { // Accumulate::request_clear, accumulate.cpp:255-257
+MPT_API mpt_status mptn_accumulate_request_clear(mptn_accumulate* node) try { // Accumulate::request_clear, accumulate.cpp:255-257
     if (!node) return MPT_ERR_INVALID_ARGUMENT;
     node->clear = true;
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return nfail2(node, MPT_ERR_LIMIT, "mptn_accumulate_request_clear: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return nfail2(node, MPT_ERR_INVALID_ARGUMENT, std::string("mptn_accumulate_request_clear: ") + e.what());
+} catch (...) {
+    return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "mptn_accumulate_request_clear: unknown exception");
 }
 
 namespace {
@@ -568,7 +674,7 @@ mpt_status accumulate_params(mptn_accumulate* node, uint64_t iteration, uint32_t
 } // namespace
 
 MPT_API mpt_status mptn_accumulate_process(mptn_accumulate* node, uint64_t iteration, uint32_t width, uint32_t height, const void* d_src,
-                                           const mpt_accumulate_buffers* buffers, void* stream, uint32_t* out_events) {
+                                           const mpt_accumulate_buffers* buffers, void* stream, uint32_t* out_events) try {
     if (!node || !d_src || !buffers) return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!node->ctx) return nfail2(node, MPT_ERR_NOT_READY, "the node was created without a device context (initialize)");
     mpt_accumulate_params A;
@@ -577,11 +683,17 @@ MPT_API mpt_status mptn_accumulate_process(mptn_accumulate* node, uint64_t itera
     const mpt_status s = mpt_accumulate(node->ctx, &A, d_src, buffers, stream);
     if (s != MPT_OK) return nfail2(node, s, mpt_last_error(node->ctx));
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return nfail2(node, MPT_ERR_LIMIT, "mptn_accumulate_process: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return nfail2(node, MPT_ERR_INVALID_ARGUMENT, std::string("mptn_accumulate_process: ") + e.what());
+} catch (...) {
+    return nfail2(node, MPT_ERR_INVALID_ARGUMENT, "mptn_accumulate_process: unknown exception");
 }
 
 MPT_API mpt_status mptn_process_accumulate(mptn_node* pt, mptn_accumulate* acc, const mpt_camera* camera, uint32_t frame, uint64_t iteration,
                                            const void* d_tex1, const void* d_albedo, const mpt_accumulate_buffers* buffers, void* stream,
-                                           uint32_t* out_events) {
+                                           uint32_t* out_events) try {
     if (!pt || !acc || !camera || !buffers) return nfail2(acc, MPT_ERR_INVALID_ARGUMENT, "NULL argument");
     if (!pt->ctx || pt->ctx != acc->ctx) return nfail2(acc, MPT_ERR_INVALID_ARGUMENT, "both nodes must live on the same device context");
     if (pt->world > 1) return nfail2(acc, MPT_ERR_INVALID_ARGUMENT, "a sharded pt node writes partial sums: reduce first, then mptn_accumulate_process");
@@ -605,6 +717,12 @@ MPT_API mpt_status mptn_process_accumulate(mptn_node* pt, mptn_accumulate* acc, 
     if (s == MPT_ERR_NOT_READY) return MPT_OK;
     if (s != MPT_OK) return nfail2(acc, s, mpt_last_error(pt->ctx));
     return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return nfail(pt, MPT_ERR_LIMIT, "mptn_process_accumulate: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return nfail(pt, MPT_ERR_INVALID_ARGUMENT, std::string("mptn_process_accumulate: ") + e.what());
+} catch (...) {
+    return nfail(pt, MPT_ERR_INVALID_ARGUMENT, "mptn_process_accumulate: unknown exception");
 }
 
 } // extern "C"

@@ -83,6 +83,14 @@ def test_errors(tmp_path):
     neg.write_bytes(b"PF\n-4 4\n-1\n")
     with pytest.raises(MptError, match="malformed"):
         image_io.load_pfm(neg)
+    huge = tmp_path / "huge.pfm"  # a header that would ask std::vector for 16 EB: reported, not thrown across the C ABI
+    huge.write_bytes(b"PF\n2000000000 2000000000\n-1\n" + bytes(16))
+    with pytest.raises(MptError, match="implausible"):
+        image_io.load_pfm(huge)
+    hdr = tmp_path / "huge.hdr"
+    hdr.write_bytes(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y 2000000000 +X 2000000000\n" + bytes(16))
+    with pytest.raises(MptError, match="implausible"):
+        image_io.load_hdr(hdr)
     with pytest.raises(MptError, match="1, 3 or 4"):
         image_io.save_pfm(tmp_path / "two.pfm", np.zeros((2, 2, 2), np.float32))
 

@@ -62,6 +62,12 @@ def test_load_semantics():
         n.load_config({"irradiance format": "B10G11R11UfloatPack32"})
     assert e.value.status == abi.MPT_ERR_UNSUPPORTED
     assert n.dump_config() == before
+    # values no frame can be rendered with, and numbers an int32 cannot hold, are refused at load time (not later in process())
+    for bad in ({"samples per pixel": -1}, {"max path length": 0}, {"samples per pixel": 1e12}, {"max path length": -3e9}):
+        with pytest.raises(MptError) as e:
+            n.load_config(bad)
+        assert e.value.status == abi.MPT_ERR_INVALID_ARGUMENT
+    assert n.dump_config() == before
     # round trip
     m = nodes.RenderPT()
     m.load_config(n.dump_config())
