@@ -17,6 +17,11 @@
 #include <new>
 #include <numeric>
 
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#define MPT_BVH_SSE 1
+#endif
+
 namespace mpt {
 namespace {
 
@@ -122,7 +127,7 @@ struct Builder {
     void build(uint32_t n) {
         const auto t0 = std::chrono::steady_clock::now();
         const size_t nn = size_t(n) * 2 + 1;
-        if (!idx.alloc(n) || !cent.alloc(size_t(n) * 3) || !nodes.alloc(nn) || !cost.alloc(nn * 7) || !dec.alloc(nn * 7) || !dist8.alloc(nn))
+        if (!idx.alloc(n) || !cent.alloc(size_t(n) * 3 + 1) || !nodes.alloc(nn) || !cost.alloc(nn * 7) || !dec.alloc(nn * 7) || !dist8.alloc(nn))
             throw std::bad_alloc();
         B3 box, cbox;
 #pragma omp parallel
@@ -155,6 +160,48 @@ struct Builder {
         const Box* boxes = V.boxes;
         const float* cent = V.cent;
         const uint32_t* idx = V.idx;
+#ifdef MPT_BVH_SSE
+        // The same arithmetic four lanes at a time: a box and a centroid are one vector each (lane 3 is padding and never read back), so a
+        // bin update is four min / max instead of twelve scalar ones. Bin index: the scalar form's subtract, multiply and truncation, with
+        // the clamp to [0, NBINS - 1] applied before the conversion (same result: truncation is towards zero). Centroids are read 16 bytes
+        // at a time from a 12-byte stride, hence the one float of padding behind every centroid array.
+        struct alignas(16) VB { __m128 blo, bhi, clo, chi; };
+        VB vb[3][NBINS];
+        const __m128 big = _mm_set1_ps(FLT_MAX), small = _mm_set1_ps(-FLT_MAX);
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < NBINS; b++) vb[a][b] = VB{big, small, big, small};
+        const __m128 cmin = _mm_setr_ps(j.cbox.lo[0], j.cbox.lo[1], j.cbox.lo[2], 0.f), kk = _mm_setr_ps(k[0], k[1], k[2], 0.f);
+        const __m128 zero = _mm_setzero_ps(), top = _mm_set1_ps(float(NBINS) - 0.5f);
+        for (uint32_t i = first; i < last; i++) {
+            const uint32_t p = idx[i];
+            const __m128 c = _mm_loadu_ps(&cent[size_t(p) * 3]);
+            const __m128 lo = _mm_loadu_ps(&boxes[p].lo[0]);             // lo.x lo.y lo.z hi.x
+            const __m128 t = _mm_loadu_ps(&boxes[p].lo[2]);              // lo.z hi.x hi.y hi.z
+            const __m128 hi = _mm_shuffle_ps(t, t, _MM_SHUFFLE(3, 3, 2, 1)); // hi.x hi.y hi.z hi.z
+            const __m128 f = _mm_min_ps(_mm_max_ps(_mm_mul_ps(_mm_sub_ps(c, cmin), kk), zero), top); // max(NaN, 0) = 0, as int(NaN) clamps
+            alignas(16) int bi[4];
+            _mm_store_si128(reinterpret_cast<__m128i*>(bi), _mm_cvttps_epi32(f));
+            for (int a = 0; a < 3; a++) {
+                if (!axis_ok[a]) continue;
+                VB& v = vb[a][bi[a]];
+                B.bc[a][bi[a]]++;
+                v.blo = _mm_min_ps(v.blo, lo);
+                v.bhi = _mm_max_ps(v.bhi, hi);
+                v.clo = _mm_min_ps(v.clo, c);
+                v.chi = _mm_max_ps(v.chi, c);
+            }
+        }
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < NBINS; b++) {
+                if (!B.bc[a][b]) continue;
+                alignas(16) float q[4][4];
+                _mm_store_ps(q[0], vb[a][b].blo); _mm_store_ps(q[1], vb[a][b].bhi); _mm_store_ps(q[2], vb[a][b].clo); _mm_store_ps(q[3], vb[a][b].chi);
+                for (int d = 0; d < 3; d++) {
+                    B.bb[a][b].lo[d] = q[0][d]; B.bb[a][b].hi[d] = q[1][d];
+                    B.cb[a][b].lo[d] = q[2][d]; B.cb[a][b].hi[d] = q[3][d];
+                }
+            }
+#else
         for (uint32_t i = first; i < last; i++) {
             const uint32_t p = idx[i];
             const float* c = &cent[size_t(p) * 3];
@@ -167,6 +214,7 @@ struct Builder {
                 B.cb[a][b].grow_pt(c);
             }
         }
+#endif
     }
 
     // the dynamic program for one node whose children are done
@@ -269,7 +317,7 @@ struct Builder {
         if (V.first0 == 0 && V.idx == idx.data() && j.count <= kLocalSubtree && j.count > kSmallNode) {
             // small enough for L2: build this subtree from private contiguous copies, then write the resulting order back
             std::vector<Box> lb(j.count);
-            std::vector<float> lc(size_t(j.count) * 3);
+            std::vector<float> lc(size_t(j.count) * 3 + 1); // + 1: bin_range reads centroids 16 bytes at a time
             std::vector<uint32_t> li(j.count), lg(j.count);
             for (uint32_t i = 0; i < j.count; i++) {
                 const uint32_t p = idx[j.first + i];
