@@ -369,23 +369,37 @@ def run_ours(args):
     # (examples/gltf.json:39). One GPU: mpt_render_host_begin / _end (the C-ABI's host-buffer entry points). Several GPUs: the same
     # copies around mpt_render + mpt_reduce_begin(h_out); a step is complete when rank 0 holds the normalised frame in host memory.
     h_tex1 = tex1.cpu().pin_memory()
-    h_outs = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    F = max(1, min(int(args.in_flight), 4))  # iterations in flight (mpt_render_host_begin: in_flight_index < 4; merian's ring size is a graph setting)
+    h_outs = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(max(F, 2))]
     e2e_steps = max(2, args.steps)
-    if world == 1:
-        ctx.render_host(cam, params(0), h_tex1=h_tex1, h_out=h_outs[0])  # warm (allocates the staging buffers)
-        for s_ in range(2):
+    e2e_two = None
+
+    def pipelined(f, first_frame):
+        """e2e_steps iterations through mpt_render_host_begin / _end with f iterations in flight; wall time from the first begin to the
+        last frame's pixels in host memory."""
+        for s_ in range(f):
             ctx.render_host_begin(cam, params(s_), h_outs[s_], s_, h_tex1=h_tex1)
-        for s_ in range(2):
+        for s_ in range(f):
             ctx.render_host_end(s_)
         barrier()
         t0 = time.perf_counter()
         for i in range(e2e_steps):
-            if i >= 2:
-                ctx.render_host_end(i % 2)
-            ctx.render_host_begin(cam, params(args.warmup + i), h_outs[i % 2], i % 2, h_tex1=h_tex1)
-        for i in range(max(e2e_steps - 2, 0), e2e_steps):
-            ctx.render_host_end(i % 2)
-        e2e_dt = time.perf_counter() - t0
+            if i >= f:
+                ctx.render_host_end(i % f)
+            ctx.render_host_begin(cam, params(first_frame + i), h_outs[i % f], i % f, h_tex1=h_tex1)
+        for i in range(max(e2e_steps - f, 0), e2e_steps):
+            ctx.render_host_end(i % f)
+        return time.perf_counter() - t0
+
+    if world == 1:
+        ctx.render_host(cam, params(0), h_tex1=h_tex1, h_out=h_outs[0])  # warm (allocates the staging buffers)
+        # The host thread of a pipelined loop stalls now and then for 60-110 ms inside a CUDA call (scripts/e2e_probe.py,
+        # profiles/r02s_e2e_probe.json: 2-3 times in 20 steps on the GPU boxes, the same driver-lock contention as the NVML start-up
+        # described above). Two iterations in flight hold one frame (35 ms) of queued work, so every such stall idles the GPU; four hold
+        # three. Both are measured; `e2e.value` is the configured depth.
+        if F != 2:
+            e2e_two = npix * spp_total * e2e_steps / pipelined(2, args.warmup + 1000) / 1e6
+        e2e_dt = pipelined(F, args.warmup)
     else:
         d_tex1s = [torch.empty_like(tex1) for _ in range(2)]
         for i in range(2):
@@ -462,7 +476,7 @@ def run_ours(args):
                          "shade_share_of_step": st.shade_ms * timed_share / ms if ms > 0 else None},
             "cpu_baseline": base,
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": npix * 16 * world, "d2h_bytes_per_step": npix * 16,
-                    "iterations_in_flight": 2, "steps": e2e_steps, "synchronous_call_value": e2e_sync_value,
+                    "iterations_in_flight": (F if world == 1 else 2), "two_in_flight_value": e2e_two, "steps": e2e_steps, "synchronous_call_value": e2e_sync_value,
                     "includes_reduce": world > 1},
             "gpu_launches": int(rays[2].item()),
             "clocks": clocks,
@@ -508,6 +522,7 @@ def main():
     ap.add_argument("--width", type=int, default=WIDTH)
     ap.add_argument("--height", type=int, default=HEIGHT)
     ap.add_argument("--spp", type=int, default=SPP)
+    ap.add_argument("--in-flight", type=int, default=4, help="iterations in flight of the end-to-end (host buffer) measurement on one GPU, 1..4")
     ap.add_argument("--small", action="store_true", help="tiny scene (harness test only; not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],

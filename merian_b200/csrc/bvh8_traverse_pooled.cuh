@@ -159,7 +159,7 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
                     if (TWO_LEVEL || rec != hit.tri) {
                         if (COUNT) n_tris++;
                         const float4* tp = A.tris + size_t(rec) * 3;
-                        const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                        const float4 a = ld_tri(tp), b = ld_tri(tp + 1), c = ld_tri(tp + 2);
                         Shear s;
                         if (TWO_LEVEL) {
                             s = shear;
