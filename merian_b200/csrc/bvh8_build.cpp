@@ -16,6 +16,8 @@
 #include <cstring>
 #include <new>
 #include <numeric>
+#include <omp.h>
+#include <vector>
 
 #if defined(__SSE2__)
 #include <emmintrin.h>
@@ -75,7 +77,7 @@ template <class T> struct RawArray { // uninitialised storage for trivially cons
 constexpr int NBINS = 16;
 constexpr uint32_t kSmallNode = 8;              // at most this many primitives: exact sweep over sorted centroids instead of binning
 constexpr uint32_t kTaskGrain = 4096;           // subtrees below this size are built by the thread that reaches them
-constexpr uint32_t kParallelBinning = 1u << 17; // nodes above this size bin their primitives with several tasks
+constexpr uint32_t kParallelBinning = 1u << 17; // nodes of at least this size are split by all threads together (Builder::split_top)
 constexpr uint32_t kLocalSubtree = 16384;       // subtrees of at most this many primitives are built from private contiguous copies
 constexpr uint32_t kMaxRecursion = 256;         // SAH levels before the builder switches to median splits (bounds the recursion depth)
 
@@ -104,6 +106,22 @@ struct Builder {
     float balance = 0.f; // SAH candidates must leave at least this fraction of the primitives on the smaller side (0 = plain SAH)
     float c_prim = 0.5f, c_node = 1.0f;
 
+    // Node ids are handed out in blocks of kIdBlock per thread: with one shared counter the nodes that neighbour each other in the arrays
+    // (44 B of Node2, 28 B of costs, 7 + 1 B of decisions per node) were being written by different threads at the same time, and the
+    // cache lines they share bounced between the cores (8 threads: 2.3x over one thread; profiles/r02_bvh_build.md).
+    static constexpr uint32_t kIdBlock = 256;
+    struct alignas(64) IdBlock { uint32_t next = 0, end = 0; };
+    std::vector<IdBlock> id_blocks;
+    uint32_t alloc_pair() {
+        IdBlock& b = id_blocks[size_t(omp_get_thread_num())];
+        if (b.next + 2 > b.end) {
+            b.next = next_node.fetch_add(kIdBlock);
+            b.end = b.next + kIdBlock;
+        }
+        const uint32_t l = b.next;
+        b.next += 2;
+        return l;
+    }
     struct Job { uint32_t node, first, count, depth; B3 box, cbox; };
     // The arrays a subtree is built from: the global ones, or — once a subtree is small enough to live in L2 — private contiguous copies
     // of its primitives' boxes and centroids (the global index array is a random permutation by then, and every level of the tree would
@@ -126,7 +144,8 @@ struct Builder {
 
     void build(uint32_t n) {
         const auto t0 = std::chrono::steady_clock::now();
-        const size_t nn = size_t(n) * 2 + 1;
+        id_blocks.assign(size_t(std::max(1, omp_get_max_threads())), IdBlock());
+        const size_t nn = size_t(n) * 2 + 1 + id_blocks.size() * kIdBlock;
         if (!idx.alloc(n) || !cent.alloc(size_t(n) * 3 + 1) || !nodes.alloc(nn) || !cost.alloc(nn * 7) || !dec.alloc(nn * 7) || !dist8.alloc(nn))
             throw std::bad_alloc();
         B3 box, cbox;
@@ -150,10 +169,136 @@ struct Builder {
         if (std::getenv("MPT_BUILD_TIMING"))
             std::fprintf(stderr, "[bvh8_build] alloc + centroids %.1f ms; ", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
         const View global{boxes, cent.data(), idx.data(), 0u};
+        // The top of the tree (nodes of >= kParallelBinning primitives: 7 nodes for 1 M primitives) is split breadth-first with every
+        // thread working on ONE node at a time (parallel binning, parallel stable partition). As tasks, these nodes were the critical
+        // path: a thread waiting for its binning tasks picks up a whole subtree task in the meantime and returns to the split of the
+        // large node only when that is built (the 500 k-primitive node took 227 ms to bin, profiles/r02_bvh_build.md). The subtrees
+        // below become tasks; the dynamic program of the top nodes runs afterwards, children before parents.
+        std::vector<Job> work{Job{0, 0, n, 0, box, cbox}}, subtrees;
+        std::vector<uint32_t> top_nodes;
+        for (size_t head = 0; head < work.size(); head++) {
+            const Job j = work[head];
+            Job lj, rj;
+            if (j.count >= kParallelBinning && j.depth < sah_depth_limit && split_top(j, global, lj, rj)) {
+                top_nodes.push_back(j.node);
+                work.push_back(lj);
+                work.push_back(rj);
+            } else {
+                subtrees.push_back(j);
+            }
+        }
+        if (std::getenv("MPT_BUILD_TIMING"))
+            std::fprintf(stderr, "top %zu nodes done at %.1f ms; ", top_nodes.size(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
 #pragma omp parallel
 #pragma omp single
-        build_node(Job{0, 0, n, 0, box, cbox}, global);
+        for (size_t i = 0; i < subtrees.size(); i++) {
+            const Job sj = subtrees[i];
+#pragma omp task default(shared) firstprivate(sj)
+            build_node(sj, global);
+        }
+        for (size_t i = top_nodes.size(); i-- > 0;) collapse_cost(top_nodes[i]);
         node_count = next_node.load();
+    }
+
+    // The binned SAH split of build_subtree for one LARGE node, all threads on it. Returns false when the bins do not separate the
+    // primitives (the caller then hands the node to build_subtree, which knows the fallbacks).
+    bool split_top(const Job& j, const View& V, Job& lj, Job& rj) {
+        float k[3];
+        bool axis_ok[3];
+        for (int a = 0; a < 3; a++) {
+            axis_ok[a] = j.cbox.hi[a] > j.cbox.lo[a];
+            k[a] = axis_ok[a] ? float(NBINS) * (1.0f - 1e-6f) / (j.cbox.hi[a] - j.cbox.lo[a]) : 0.f;
+        }
+        constexpr int kParts = 64; // fixed: the result does not depend on the number of threads
+        std::vector<Bins> part(kParts);
+        auto part_first = [&](int t) { return j.first + uint32_t(uint64_t(j.count) * uint64_t(t) / kParts); };
+#pragma omp parallel for schedule(dynamic, 1)
+        for (int t = 0; t < kParts; t++) bin_range(j, V, part_first(t), part_first(t + 1), k, axis_ok, part[size_t(t)]);
+        Bins B;
+        for (int t = 0; t < kParts; t++) B.merge(part[size_t(t)]);
+        int best_axis = -1, best_bin = -1;
+        best_split(j, B, axis_ok, best_axis, best_bin);
+        if (best_axis < 0) return false;
+        const int a = best_axis;
+        const float cmin = j.cbox.lo[a], ka = k[a];
+        const float* cent = V.cent;
+        uint32_t* const idx = V.idx;
+        auto goes_left = [&](uint32_t p) {
+            int b = int((cent[size_t(p) * 3 + a] - cmin) * ka);
+            b = std::min(std::max(b, 0), NBINS - 1);
+            return b <= best_bin;
+        };
+        // stable partition in kParts chunks: count, prefix sum, scatter into a scratch array, copy back
+        uint32_t nl[kParts + 1];
+        nl[kParts] = 0;
+#pragma omp parallel for schedule(static)
+        for (int t = 0; t < kParts; t++) {
+            uint32_t c = 0;
+            for (uint32_t i = part_first(t); i < part_first(t + 1); i++) c += goes_left(idx[i]) ? 1u : 0u;
+            nl[t] = c;
+        }
+        uint32_t lbase[kParts], rbase[kParts], mid = 0;
+        for (int t = 0; t < kParts; t++) { lbase[t] = mid; mid += nl[t]; }
+        if (mid == 0 || mid == j.count) return false;
+        uint32_t rcur = mid;
+        for (int t = 0; t < kParts; t++) { rbase[t] = rcur; rcur += (part_first(t + 1) - part_first(t)) - nl[t]; }
+        RawArray<uint32_t> tmp;
+        if (!tmp.alloc(j.count)) throw std::bad_alloc();
+#pragma omp parallel for schedule(static)
+        for (int t = 0; t < kParts; t++) {
+            uint32_t l = lbase[t], r = rbase[t];
+            for (uint32_t i = part_first(t); i < part_first(t + 1); i++) {
+                const uint32_t p = idx[i];
+                if (goes_left(p)) tmp[l++] = p; else tmp[r++] = p;
+            }
+        }
+#pragma omp parallel for schedule(static)
+        for (int64_t i = 0; i < int64_t(j.count); i++) idx[j.first + size_t(i)] = tmp[size_t(i)];
+
+        Node2& nd = nodes[j.node];
+        set_box(nd, j.box);
+        nd.rfirst = V.first0 + j.first;
+        nd.rcount = j.count;
+        nd.count = 0;
+        const uint32_t l = alloc_pair();
+        nd.left = l;
+        nd.right = l + 1;
+        lj = Job{l, j.first, mid, j.depth + 1, B3(), B3()};
+        rj = Job{l + 1, j.first + mid, j.count - mid, j.depth + 1, B3(), B3()};
+        for (int b = 0; b < NBINS; b++) { // the children's boxes are unions of the bins on either side of the split
+            Job& t = b <= best_bin ? lj : rj;
+            t.box.grow(B.bb[a][b]);
+            t.cbox.grow(B.cb[a][b]);
+        }
+        return true;
+    }
+
+    // the cheapest bin boundary over the three axes (SAH: area x count on either side); best_axis stays -1 if no boundary separates
+    void best_split(const Job& j, const Bins& B, const bool* axis_ok, int& best_axis, int& best_bin) const {
+        float best_cost = FLT_MAX;
+        for (int a = 0; a < 3; a++) {
+            if (!axis_ok[a]) continue;
+            float ra[NBINS];
+            uint32_t rc[NBINS];
+            B3 acc;
+            uint32_t cnt = 0;
+            for (int b = NBINS - 1; b > 0; b--) {
+                acc.grow(B.bb[a][b]);
+                cnt += B.bc[a][b];
+                ra[b] = acc.half_area();
+                rc[b] = cnt;
+            }
+            acc = B3();
+            cnt = 0;
+            for (int b = 0; b < NBINS - 1; b++) {
+                acc.grow(B.bb[a][b]);
+                cnt += B.bc[a][b];
+                if (cnt == 0 || rc[b + 1] == 0) continue;
+                if (float(std::min(cnt, rc[b + 1])) < balance * float(j.count)) continue;
+                const float c = acc.half_area() * float(cnt) + ra[b + 1] * float(rc[b + 1]);
+                if (c < best_cost) { best_cost = c; best_axis = a; best_bin = b; }
+            }
+        }
     }
 
     void bin_range(const Job& j, const View& V, uint32_t first, uint32_t last, const float* k, const bool* axis_ok, Bins& B) const {
@@ -372,45 +517,9 @@ struct Builder {
                 k[a] = axis_ok[a] ? float(NBINS) * (1.0f - 1e-6f) / (j.cbox.hi[a] - j.cbox.lo[a]) : 0.f;
             }
             Bins B;
-            if (j.count >= kParallelBinning) {
-                constexpr int kParts = 16;
-                std::vector<Bins> part(kParts);
-                for (int t = 0; t < kParts; t++) {
-                    const uint32_t f = j.first + uint32_t(uint64_t(j.count) * t / kParts), l = j.first + uint32_t(uint64_t(j.count) * (t + 1) / kParts);
-                    Bins* dst = &part[t];
-#pragma omp task default(shared) firstprivate(f, l, dst)
-                    bin_range(j, V, f, l, k, axis_ok, *dst);
-                }
-#pragma omp taskwait
-                for (int t = 0; t < kParts; t++) B.merge(part[t]); // fixed order: deterministic
-            } else {
-                bin_range(j, V, j.first, j.first + j.count, k, axis_ok, B);
-            }
-            float best_cost = FLT_MAX;
+            bin_range(j, V, j.first, j.first + j.count, k, axis_ok, B);
             int best_axis = -1, best_bin = -1;
-            for (int a = 0; a < 3; a++) {
-                if (!axis_ok[a]) continue;
-                float ra[NBINS];
-                uint32_t rc[NBINS];
-                B3 acc;
-                uint32_t cnt = 0;
-                for (int b = NBINS - 1; b > 0; b--) {
-                    acc.grow(B.bb[a][b]);
-                    cnt += B.bc[a][b];
-                    ra[b] = acc.half_area();
-                    rc[b] = cnt;
-                }
-                acc = B3();
-                cnt = 0;
-                for (int b = 0; b < NBINS - 1; b++) {
-                    acc.grow(B.bb[a][b]);
-                    cnt += B.bc[a][b];
-                    if (cnt == 0 || rc[b + 1] == 0) continue;
-                    if (float(std::min(cnt, rc[b + 1])) < balance * float(j.count)) continue;
-                    const float c = acc.half_area() * float(cnt) + ra[b + 1] * float(rc[b + 1]);
-                    if (c < best_cost) { best_cost = c; best_axis = a; best_bin = b; }
-                }
-            }
+            best_split(j, B, axis_ok, best_axis, best_bin);
             if (best_axis >= 0) {
                 const int a = best_axis;
                 const float cmin = j.cbox.lo[a], ka = k[a];
@@ -433,7 +542,7 @@ struct Builder {
             mid = j.count / 2;
             have_child_boxes = false;
         }
-        const uint32_t l = next_node.fetch_add(2);
+        const uint32_t l = alloc_pair();
         nd.left = l;
         nd.right = l + 1;
         nd.count = 0;

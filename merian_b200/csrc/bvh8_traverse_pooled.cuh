@@ -35,6 +35,9 @@ struct alignas(16) PoolEntry {
 // kernel's instructions, at 8.6 of 32 lanes) — and the shear constants of the watertight test are read from the ray record when a
 // triangle is tested (single-level scenes) instead of occupying registers through the node tests.
 // SS = node-stack entries kept in shared memory (per lane, stride STRIDE uint2); 0 = all in local memory (measured best, see k_extend_pooled).
+#ifndef MPT_TLAS_GATE
+#define MPT_TLAS_GATE 1
+#endif
 constexpr int kPrimStackSize = 24; // parked primitive groups: at most one per node test while another group is pending
 
 template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struct TraversalP {
@@ -121,7 +124,8 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
         Gv = 0u;
     }
 
-    MPT_DEV bool step() {
+    // tick: the caller's loop counter (the same in every lane of a warp), see MPT_TLAS_GATE
+    MPT_DEV bool step(uint32_t tick = 0u) {
         // ---------------------------------------------------------------- 1. one node test
         if (G.y & 0xFF000000u) {
             const uint32_t bit = 31u - uint32_t(__clz(G.y));
@@ -148,7 +152,13 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
         if (pre_valid) pre_top = top();
         // ---------------------------------------------------------------- 2. one primitive of the pending group
         // (all of it when the primitive stack is nearly full, so that parking can never overflow)
-        if (Gt.y) {
+        // MPT_TLAS_GATE = m > 0 (two-level scenes): a lane at the TLAS level enters an instance only in the loop iterations with
+        // (tick & m) == 0 and goes on with the node tests of the TLAS in between: entering an instance is ~190 instructions that ran at
+        // 5 of 32 lanes when every lane entered the moment it uncovered an instance (profiles/r02p_c5_extend_summary.txt); the counter
+        // is the same in all lanes, so the entries of a warp fall into the same iterations.
+        // Measured on C5 (profiles/r02v_ab.md): m = 1: +0.9 %, m = 3: -0.9 % (a lane that has nothing else to do idles until its turn).
+        const bool gated = TWO_LEVEL && MPT_TLAS_GATE > 0 && !in_blas && (tick & uint32_t(MPT_TLAS_GATE)) != 0u && psp <= kPrimStackSize - 4;
+        if (Gt.y && !gated) {
             do {
                 const uint32_t i = 31u - uint32_t(__clz(Gt.y));
                 Gt.y &= ~(1u << i);

@@ -507,16 +507,26 @@ __global__ void __launch_bounds__(kThreads, (!COUNT && !MEDIUM && !TWO_LEVEL && 
 // from the queue when the ray retires) were slower than 64-byte ones: the converged phase then chains two dependent DRAM latencies.
 // Postponing the primitive section to every 2nd / 4th loop iteration: +7 % / +34 % (the hit distance lags, rays take more iterations).
 #ifndef MPT_POOL_READY
-#define MPT_POOL_READY 16 // READY records per warp on top of the 32 a warp can be traversing
+#define MPT_POOL_READY 32 // READY records per warp on top of the 32 a warp can be traversing
 #endif
 #ifndef MPT_POOL_SMEM_STACK
 #define MPT_POOL_SMEM_STACK 0 // traversal-stack entries per lane kept in shared memory (the rest: local memory, i.e. L1)
+#endif
+// MPT_POOL_TRIGGER = T > 0: the warp re-converges as soon as T records are DONE (polled once per step) instead of waiting until the READY
+// list is empty and the busy lanes have dwindled below tune.refill: the converged phase then always finds (a multiple of) 32 records
+// to retire and refill — it runs at full width — and a finishing lane (almost) always finds a READY record, so the traversal loop
+// does not ramp down between refills. Needs T <= MPT_POOL_READY (otherwise lanes could starve below the trigger). 0 = the ramp-down form.
+// Measured (profiles/r02v_ab.md): READY 32 / trigger 32 against the ramp-down form with READY 16: C3 +0.7 %, C5 +3.0 %; trigger 16 (half-empty
+// converged rounds) -4 %, READY 24 / trigger 24 +-0.
+#ifndef MPT_POOL_TRIGGER
+#define MPT_POOL_TRIGGER 32
 #endif
 template <bool COUNT, bool MEDIUM, bool TWO_LEVEL, bool NEE>
 __global__ void __launch_bounds__(kThreads, (!COUNT && !MEDIUM && !TWO_LEVEL && !NEE) ? MPT_EXTEND_PLAIN_MIN_BLOCKS : MPT_EXTEND_MIN_BLOCKS)
 k_extend_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ q_o, const float4* __restrict__ q_d, PathBuffers pb, uint32_t bounce, uint32_t mask,
                 ExtendTune tune, Counters* ctr) {
-    constexpr int NE = 32 + MPT_POOL_READY, SS = MPT_POOL_SMEM_STACK, kWarps = kThreads / 32;
+    constexpr int NE = 32 + MPT_POOL_READY, SS = MPT_POOL_SMEM_STACK, kWarps = kThreads / 32, TRIG = MPT_POOL_TRIGGER;
+    static_assert(TRIG >= 0 && TRIG <= MPT_POOL_READY && MPT_POOL_READY <= 32, "MPT_POOL_TRIGGER <= MPT_POOL_READY <= 32");
     using Trav = TraversalP<COUNT, TWO_LEVEL, MaterialAlphaTest, SS, kThreads>;
     using Entry = PoolEntry;
     struct Pool {
@@ -551,13 +561,22 @@ k_extend_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ 
     int ready_n = 0;
     while (true) {
         // ======================================================= converged: retire DONE records, refill them, hand READY records to idle lanes
-        const int nd = P.done_n;
+        const int nd_all = P.done_n;
+        // trigger form: whole rounds of 32 only (what is left over stays DONE for the next phase), unless the queue is used up
+        const int nd = (TRIG > 0 && !exhausted && nd_all > 32) ? (nd_all & ~31) : nd_all;
         uint32_t base = 0;
         if (!exhausted && nd > 0) {
             if (lane == 0) base = atomicAdd(&ctr->fetch[bounce], uint32_t(nd));
             base = __shfl_sync(0xFFFFFFFFu, base, 0);
         }
         int nready = 0;
+        if (TRIG > 0) { // READY records nobody has taken yet move to the front of the list
+            const int rh = min(P.ready_head, ready_n), left = ready_n - rh;
+            const uint8_t v = int(lane) < left ? P.ready[rh + int(lane)] : uint8_t(0);
+            __syncwarp();
+            if (int(lane) < left) P.ready[lane] = v;
+            nready = left;
+        }
 #pragma unroll 1
         for (int r = 0; r * 32 < nd; r++) {
             const int i = r * 32 + int(lane);
@@ -650,17 +669,27 @@ k_extend_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ 
             T.start(&P.e[my], mask, scene_flags, !NEE);
             active = true;
         }
+        const int rem = nd_all - nd; // < 32
+        if (TRIG > 0 && rem > 0) {
+            const uint8_t v = int(lane) < rem ? P.done[nd + int(lane)] : uint8_t(0);
+            __syncwarp();
+            if (int(lane) < rem) P.done[lane] = v;
+        }
         if (lane == 0) {
-            P.done_n = 0;
+            P.done_n = rem;
             P.ready_n = nready;
             P.ready_head = min(__popc(idle), nready);
         }
         ready_n = nready;
         __syncwarp();
-        if (!__any_sync(0xFFFFFFFFu, active)) break;
+        if (!__any_sync(0xFFFFFFFFu, active)) {
+            if (rem == 0) break;
+            continue; // the queue ran out in this phase: the next one retires the rest
+        }
         // ======================================================= divergent: traverse; a finished lane swaps its record for a READY one
+        uint32_t tick = 0u; // the same in every lane of the warp (TraversalP::step, MPT_TLAS_GATE); unused and compiled out for single-level scenes
         while (active) {
-            if (T.step()) {
+            if (T.step(TWO_LEVEL ? tick++ : 0u)) {
                 Entry& E = P.e[my];
                 const bool f = T.found();
                 E.b = make_float4(__uint_as_float(f ? T.hit.tri : kMiss), __uint_as_float(T.hit.instance), T.hit.u, T.hit.v);
@@ -676,7 +705,9 @@ k_extend_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ 
             }
             // re-converge for a refill when the READY list is used up and too few lanes are left (never once the queue is exhausted:
             // the remaining rays just run to completion)
-            if (!exhausted && uint32_t(__popc(__activemask())) < tune.refill && *(volatile int*)&P.ready_head >= ready_n) break;
+            if (TRIG > 0) {
+                if (!exhausted && *(volatile int*)&P.done_n >= TRIG) break;
+            } else if (!exhausted && uint32_t(__popc(__activemask())) < tune.refill && *(volatile int*)&P.ready_head >= ready_n) break;
         }
         __syncwarp();
     }

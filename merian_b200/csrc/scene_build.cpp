@@ -60,8 +60,8 @@ mpt_status build_host_accel(const mpt_scene_desc* d, HostAccel& out, uint32_t st
             total += d->meshes[bd.meshes[g]].primitive_count;
         }
         if (total > 0xFFFFFFF0ull || out.tris.size() / 3 + total > 0xFFFFFFF0ull) { err = "more than 2^32 triangle records"; return MPT_ERR_LIMIT; }
-        std::vector<Ref> refs(total);
-        std::vector<Box> boxes(total);
+        RawVector<Ref> refs(total);
+        RawVector<Box> boxes(total);
         bool bad_index = false;
         for (uint32_t g = 0; g < bd.mesh_count; g++) {
             const mpt_mesh_desc& m = d->meshes[bd.meshes[g]];
