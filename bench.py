@@ -369,6 +369,10 @@ def run_ours(args):
     # (examples/gltf.json:39). One GPU: mpt_render_host_begin / _end (the C-ABI's host-buffer entry points). Several GPUs: the same
     # copies around mpt_render + mpt_reduce_begin(h_out); a step is complete when rank 0 holds the normalised frame in host memory.
     h_tex1 = tex1.cpu().pin_memory()
+    import gc
+    gc.collect()
+    gc.freeze()   # the host loop below is what a C++ graph runtime would run: keep CPython's cycle collector (a full pass over torch's
+    gc.disable()  # module graph takes tens of ms) out of the timed region
     F = max(1, min(int(args.in_flight), 4))  # iterations in flight (mpt_render_host_begin: in_flight_index < 4; merian's ring size is a graph setting)
     h_outs = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(max(F, 2))]
     e2e_steps = max(2, args.steps)

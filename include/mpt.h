@@ -284,6 +284,14 @@ MPT_API mpt_status mpt_env_set_device(mpt_context* ctx, uint32_t type, const flo
  * see the same frame number. mpt_render* set it from params->frame. Pinhole cameras do not read it. */
 MPT_API mpt_status mpt_set_scene_frame(mpt_context* ctx, uint32_t frame);
 
+/* Scene::prev_instance_transforms (scene.slang:38, 136-139): the object -> world matrices of the PREVIOUS frame, instance_count x 16
+ * floats in the layout of mpt_scene_desc::instance_transforms (row-major 4x4). Read by mpt_gbuffer for geometry flagged
+ * MPT_GEOM_IS_ANIMATED and not MPT_GEOM_PRETRANSFORMED (Scene::to_prev_world_position, scene.slang:261-270): motion vector and
+ * delta_z then follow the moving instance. NULL = drop them (every instance static, the state after mpt_scene_upload).
+ * instance_count must equal the uploaded scene's. Previous-frame VERTICES (MPT_GEOM_HAS_PREV_VERTICES: morphed / skinned meshes,
+ * transform_prev_vertex.slang) are not supported: mpt_scene_upload refuses that flag. */
+MPT_API mpt_status mpt_scene_set_prev_transforms(mpt_context* ctx, const float* prev_instance_transforms, uint32_t instance_count);
+
 /* Replaces the gbuffer_rt raygen for the hit texture (gbuffer_rt.slang:18-31, gbuffer.slang:40-61):
  * writes one PackedHitInfo (uint4) per pixel into d_tex1 (row-major, width*height*16 bytes). */
 MPT_API mpt_status mpt_primary_visibility(mpt_context* ctx, const mpt_camera* camera, uint32_t width,
@@ -293,7 +301,8 @@ MPT_API mpt_status mpt_primary_visibility(mpt_context* ctx, const mpt_camera* ca
 /* The whole `GBuffer (Raytraced)` node: replaces the gbuffer_rt raygen
  * (include/merian-graph/nodes/gbuffer_rt/gbuffer_rt.slang:18-94) with the texel layouts of include/merian-shaders/gbuffer.slang:63-82,152-172.
  * Any image may be NULL (not written). prev_camera NULL = camera (static view: motion vector = -jitter, delta_z = 0).
- * Static scenes only (prev_pos = pos); material textures are read at LOD 0 (no mip chains in libmpt). */
+ * Moving instances: mpt_scene_set_prev_transforms. Material textures are sampled with the ray-differential UV gradients over the
+ * mip chains of mpt_texture_upload_ex (textures uploaded without a chain: LOD 0). */
 typedef struct mpt_gbuffer_images {
     void* d_tex0;     /* uint2:  .x = encode_normal(material shading normal), .y = half2 grad_z          */
     void* d_tex1;     /* uint4:  PackedHitInfo (same as mpt_primary_visibility)                           */

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", f"libmpt_{_VARIANT}.so" if _VARIANT else 
 _lib = None
 
 EXPORTS = ["mpt_abi_version", "mpt_create", "mpt_destroy", "mpt_last_error", "mpt_scene_upload", "mpt_materials_upload",
-           "mpt_materials_set_hints", "mpt_texture_upload", "mpt_texture_upload_ex", "mpt_texture_upload_device", "mpt_mip_level", "mpt_env_set", "mpt_env_set_device", "mpt_set_scene_frame", "mpt_primary_visibility", "mpt_gbuffer", "mpt_trace", "mpt_render", "mpt_render_host", "mpt_render_host_begin", "mpt_render_host_end",
+           "mpt_materials_set_hints", "mpt_texture_upload", "mpt_texture_upload_ex", "mpt_texture_upload_device", "mpt_mip_level", "mpt_env_set", "mpt_env_set_device", "mpt_set_scene_frame", "mpt_scene_set_prev_transforms", "mpt_primary_visibility", "mpt_gbuffer", "mpt_trace", "mpt_render", "mpt_render_host", "mpt_render_host_begin", "mpt_render_host_end",
            "mpt_accumulate", "mpt_render_accumulate", "mpt_pfm_info", "mpt_pfm_load", "mpt_pfm_save", "mpt_hdr_load", "mpt_env_load", "mpt_image_write",
            "mpt_set_profiling", "mpt_get_stats", "mpt_reset_stats", "mpt_debug_ray_queue", "mpt_debug_ray_setup", "mpt_bvh_get_info", "mpt_bvh8_build_info", "mpt_bsdf_check",
            "mpt_host_accel_build", "mpt_host_accel_get", "mpt_host_accel_free",
@@ -58,6 +58,7 @@ def lib():
         l.mpt_env_set_device.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_float, C.c_uint32, C.c_uint32, C.c_void_p]
         l.mpt_env_set.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_float, C.c_uint32, C.c_uint32, C.c_void_p]
         l.mpt_set_scene_frame.argtypes = [C.c_void_p, C.c_uint32]
+        l.mpt_scene_set_prev_transforms.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         l.mpt_primary_visibility.argtypes = [C.c_void_p, C.POINTER(abi.Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         l.mpt_gbuffer.argtypes = [C.c_void_p, C.POINTER(abi.Camera), C.POINTER(abi.Camera), C.c_uint32, C.c_uint32, C.c_uint32,
                                   C.POINTER(abi.GBufferImages), C.c_void_p]

@@ -85,6 +85,14 @@ class Context:
         """Scene::frame for primary_visibility / gbuffer (thin-lens cameras key their lens sample on it); render() takes it from its params."""
         self._check(self.l.mpt_set_scene_frame(self.h, C.c_uint32(int(frame))))
 
+    def set_prev_transforms(self, transforms):
+        """Scene::prev_instance_transforms for the GBuffer's motion vectors: (instance_count, 4, 4) float32 row-major, None = static scene."""
+        if transforms is None:
+            self._check(self.l.mpt_scene_set_prev_transforms(self.h, None, 0))
+            return
+        t = np.ascontiguousarray(transforms, np.float32).reshape(-1, 16)
+        self._check(self.l.mpt_scene_set_prev_transforms(self.h, C.c_void_p(t.ctypes.data), C.c_uint32(len(t))))
+
     def primary_visibility_device(self, cam, w, h, mask=0xFF, out=None):
         if out is None:
             out = torch.empty((h, w, 4), dtype=torch.int32, device=self.torch_device)

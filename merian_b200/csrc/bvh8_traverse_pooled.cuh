@@ -36,7 +36,7 @@ struct alignas(16) PoolEntry {
 // triangle is tested (single-level scenes) instead of occupying registers through the node tests.
 // SS = node-stack entries kept in shared memory (per lane, stride STRIDE uint2); 0 = all in local memory (measured best, see k_extend_pooled).
 #ifndef MPT_TLAS_GATE
-#define MPT_TLAS_GATE 1
+#define MPT_TLAS_GATE 0 // see step(): measured, no gain with the trigger form of the pool
 #endif
 constexpr int kPrimStackSize = 24; // parked primitive groups: at most one per node test while another group is pending
 
@@ -156,7 +156,8 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
         // (tick & m) == 0 and goes on with the node tests of the TLAS in between: entering an instance is ~190 instructions that ran at
         // 5 of 32 lanes when every lane entered the moment it uncovered an instance (profiles/r02p_c5_extend_summary.txt); the counter
         // is the same in all lanes, so the entries of a warp fall into the same iterations.
-        // Measured on C5 (profiles/r02v_ab.md): m = 1: +0.9 %, m = 3: -0.9 % (a lane that has nothing else to do idles until its turn).
+        // Measured on C5 (profiles/r02v_ab.md): with the ramp-down pool m = 1: +0.9 %, m = 3: -0.9 % (a lane that has nothing else to do idles
+        // until its turn); with the trigger pool m = 1: +-0 (1929 vs 1930 Msamples/s). Off by default.
         const bool gated = TWO_LEVEL && MPT_TLAS_GATE > 0 && !in_blas && (tick & uint32_t(MPT_TLAS_GATE)) != 0u && psp <= kPrimStackSize - 4;
         if (Gt.y && !gated) {
             do {

@@ -212,8 +212,9 @@ __global__ void __launch_bounds__(kThreads) k_primary(const __grid_constant__ Sc
 // --------------------------------------------------------------------------------------- GBuffer (Raytraced) node
 // gbuffer_rt.slang:18-94 with the stores of gbuffer.slang:152-172: primary hit, material shading normal, linear depth and its
 // screen-space gradient, depth change and motion vector against the previous camera, directional albedo, emission.
-// Static scene (prev_pos = pos); material textures are read at LOD 0 (libmpt holds no mip chains), so the ray-differential
-// UV gradients of gbuffer_rt.slang:41-50 have no consumer here.
+// prev_pos: the hit point carried by the previous frame's instance transform for animated geometry (Scene::get_prev_world_position,
+// scene.slang:392-401, to_prev_world_position :261-270), else the hit point itself. Material textures are sampled with the
+// ray-differential UV gradients of gbuffer_rt.slang:41-50.
 struct GBufferOut {
     uint2* tex0;           // enc_normal | half2 grad_z
     PackedHitInfo* tex1;
@@ -264,6 +265,7 @@ __global__ void __launch_bounds__(kThreads) k_gbuffer(const __grid_constant__ Sc
     f2 grad_z = mk2(0.f, 0.f);
     float delta_z = 0.f;
     f3 albedo = sp.emission; // miss: store_albedo(Albedo(sp.emission)), gbuffer_rt.slang:90
+    f3 prev_pos = sp.pos;
     if (surface) {
         f3 ox, rx, oy, ry;
         float t0, t1;
@@ -273,10 +275,19 @@ __global__ void __launch_bounds__(kThreads) k_gbuffer(const __grid_constant__ Sc
         camera_ray(pin, x, y + 1, w, h, oy, ry, t0, t1);
         const float n_dot_oo = dot(sp.geo_normal, sp.pos - o); // Surface::compute_grad_z, hit.slang:99-103
         grad_z = mk2(n_dot_oo / dot(sp.geo_normal, rx) - linear_z, n_dot_oo / dot(sp.geo_normal, ry) - linear_z);
-        delta_z = length(sp.pos - prev_cam.position) - linear_z;
+        if (S.inst_xform_prev) {
+            const float4* tp = S.accel.tris + size_t(hr.tri) * 3;
+            const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
+            const uint32_t gflags = __ldg(S.geometries + S.accel.instances[hr.instance].custom_index + __float_as_uint(tb.w)).x >> 16;
+            if ((gflags & G_IS_ANIMATED) && !(gflags & G_PRETRANSFORMED)) {
+                const f3 p_obj = (1.0f - hr.u - hr.v) * xyz(ta) + hr.u * xyz(tb) + hr.v * xyz(tc); // TriangleHit::get_position, as surface_shading_point
+                prev_pos = xf_point(S.inst_xform_prev + size_t(hr.instance) * 4, p_obj);
+            }
+        }
+        delta_z = length(prev_pos - prev_cam.position) - linear_z;
         albedo = bsdf_albedo<FEAT>(sp.bsdf, sp.frame.to_local(-d));
     }
-    const f2 pp = project_pinhole(prev_cam, sp.pos, w, h); // Scene::compute_motion_vector, scene.slang:404-414
+    const f2 pp = project_pinhole(prev_cam, prev_pos, w, h); // Scene::compute_motion_vector, scene.slang:404-414
     const f2 mv = mk2(pp.x - float(x) - cam.jitter_x, pp.y - float(y) - cam.jitter_y);
     if (out.tex0) {
         const __half2 g = __floats2half2_rn(grad_z.x, grad_z.y);
@@ -1256,7 +1267,8 @@ struct mpt_context {
     DevBuf accel_mem; // BVH8 nodes, then (256-byte aligned) the triangle records
     size_t accel_bytes = 0;
     size_t l2_window_bytes = 0; // > 0: persisting-L2 access-policy window over accel_mem while a frame's kernels run (MPT_L2_PERSIST)
-    DevBuf tri_attr, geometries, prim_to_tri, instances, tlas_prims, xform, xform_it;
+    DevBuf tri_attr, geometries, prim_to_tri, instances, tlas_prims, xform, xform_it, xform_prev;
+    uint32_t instance_count = 0; // of the uploaded scene
     DevBuf materials, material_types, texture_table, env_pixels, env_alias, env_pmf;
     bool env_sampling_ready = false;
     std::vector<TextureSlot> textures;
@@ -1705,6 +1717,8 @@ MPT_API mpt_status mpt_scene_upload(mpt_context* ctx, const mpt_scene_desc* d) t
     v.prim_to_tri = ctx->prim_to_tri.as<uint32_t>();
     v.inst_xform = ctx->xform.as<float4>();
     v.inst_xform_it = ctx->xform_it.as<float4>();
+    v.inst_xform_prev = nullptr; // a new scene starts static
+    ctx->instance_count = d->instance_count;
 
     ctx->bvh_info.node_count = nodes.size();
     ctx->bvh_info.triangle_count = tris.size() / 3;
@@ -2429,6 +2443,26 @@ MPT_API mpt_status mpt_set_scene_frame(mpt_context* ctx, uint32_t frame) try {
     return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_set_scene_frame: ") + e.what());
 } catch (...) {
     return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_set_scene_frame: unknown exception");
+}
+
+MPT_API mpt_status mpt_scene_set_prev_transforms(mpt_context* ctx, const float* prev_instance_transforms, uint32_t instance_count) try {
+    if (!ctx) return MPT_ERR_INVALID_ARGUMENT;
+    if (!ctx->scene_ready) return fail(ctx, MPT_ERR_NOT_READY, "mpt_scene_set_prev_transforms: no scene uploaded");
+    CU(quiesce(ctx)); // a frame in flight may be reading the old matrices
+    if (!prev_instance_transforms) {
+        ctx->view.inst_xform_prev = nullptr;
+        return MPT_OK;
+    }
+    if (instance_count != ctx->instance_count) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_scene_set_prev_transforms: instance_count differs from the uploaded scene's");
+    CU(ctx->xform_prev.upload(prev_instance_transforms, size_t(instance_count) * 64));
+    ctx->view.inst_xform_prev = ctx->xform_prev.as<float4>();
+    return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return fail(ctx, MPT_ERR_LIMIT, "mpt_scene_set_prev_transforms: out of host memory");
+} catch (const std::exception& e) { // no C++ exception crosses the C ABI
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, std::string("mpt_scene_set_prev_transforms: ") + e.what());
+} catch (...) {
+    return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "mpt_scene_set_prev_transforms: unknown exception");
 }
 
 MPT_API mpt_status mpt_set_profiling(mpt_context* ctx, uint32_t profile_flags) try {

@@ -204,6 +204,11 @@ mpt_status build_host_accel(const mpt_scene_desc* d, HostAccel& out, uint32_t st
     // ---- geometry table
     out.geoms.resize(d->geometry_count);
     for (uint32_t g = 0; g < d->geometry_count; g++)
+        if (d->geometries[g].flags & MPT_GEOM_HAS_PREV_VERTICES) {
+            err = "MPT_GEOM_HAS_PREV_VERTICES (previous-frame vertices of morphed / skinned meshes, transform_prev_vertex.slang) is not supported";
+            return MPT_ERR_UNSUPPORTED;
+        }
+    for (uint32_t g = 0; g < d->geometry_count; g++)
         out.geoms[g] = HostUVec4{uint32_t(d->geometries[g].material_id) | (uint32_t(d->geometries[g].flags) << 16), d->geometries[g].primitive_count, 0u, 0u};
     for (uint32_t i = 0; i < d->instance_count; i++) {
         const mpt_instance_desc& in = d->instances[i];

@@ -20,7 +20,7 @@
 namespace mpt {
 
 enum : uint32_t { // GeometryDataFlags, scene-data.slangh:15-42
-    G_PRETRANSFORMED = 0x1, G_FLIP_FACING = 0x8, G_FLAT_SHADING = 0x80, G_HAS_TANGENTS = 0x100, G_USE_ENV_MAP = 0x200, G_TWO_SIDED = 0x400
+    G_PRETRANSFORMED = 0x1, G_IS_ANIMATED = 0x4, G_FLIP_FACING = 0x8, G_FLAT_SHADING = 0x80, G_HAS_TANGENTS = 0x100, G_USE_ENV_MAP = 0x200, G_TWO_SIDED = 0x400
 };
 
 struct TextureRec {
@@ -36,6 +36,7 @@ struct SceneView {
     const uint32_t* __restrict__ prim_to_tri;
     const float4* __restrict__ inst_xform;    // 4 float4 per instance: rows of object->world
     const float4* __restrict__ inst_xform_it; // rows of the inverse transpose
+    const float4* __restrict__ inst_xform_prev; // object->world of the previous frame (mpt_scene_set_prev_transforms), nullptr = static scene
     const uint32_t* __restrict__ materials;   // material buffer as words
     uint32_t material_stride_words;
     const uint2* __restrict__ material_types; // (model, features)

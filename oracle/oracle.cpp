@@ -384,6 +384,7 @@ struct Scene {
     std::vector<mpt_geometry_desc> geometries;
     std::vector<mpt_instance_desc> instances;
     std::vector<float> instance_transforms, inv_t_instance_transforms;
+    std::vector<float> prev_instance_transforms; // Scene::prev_instance_transforms (scene.slang:38); empty = static scene
     std::vector<AABB> instance_bounds;
     std::vector<std::array<float, 12>> instance_inverse; // world -> object
     Bvh2 tlas;
@@ -828,8 +829,7 @@ struct Scene {
 
     // One pixel of the GBuffer (Raytraced) node: gbuffer_rt.slang:18-94, stores of gbuffer.slang:152-172.
     // Textures are sampled at LOD 0 (mpt_texture_upload takes no mip chain), so the ray-differential UV gradients of
-    // gbuffer_rt.slang:41-50 have no consumer and are not evaluated. Static scene: prev_pos = pos (scene.slang:392-401
-    // without HasPrevVertices / IsAnimated).
+    // gbuffer_rt.slang:41-50 have no consumer and are not evaluated. prev_pos: scene.slang:392-401 without HasPrevVertices.
     struct GBufferTexel {
         uint32_t tex0[2];
         Hit hit; // packed into tex1 by the caller (gbuffer.slang:167-169)
@@ -853,7 +853,14 @@ struct Scene {
                 uint32_t ia, ib, ic;
                 m.tri(hit.primitive_id, ia, ib, ic);
                 const Surface surface = get_surface(hit, gd, m.vertices[ia], m.vertices[ib], m.vertices[ic]);
-                const float3 prev_pos = surface.pos;
+                // Scene::get_prev_world_position (scene.slang:392-401) without HasPrevVertices: the object-space hit point carried by the
+                // previous frame's instance transform for animated geometry (to_prev_world_position, :261-270)
+                float3 prev_pos = surface.pos;
+                if (!prev_instance_transforms.empty() && (gd.flags & MPT_GEOM_IS_ANIMATED) && !(gd.flags & MPT_GEOM_PRETRANSFORMED)) {
+                    const float3 bary = hit.bary3();
+                    const float3 p_obj = bary.x * vpos(m.vertices[ia]) + bary.y * vpos(m.vertices[ib]) + bary.z * vpos(m.vertices[ic]);
+                    prev_pos = mul_point(&prev_instance_transforms[size_t(hit.instance_index) * 16], p_obj);
+                }
                 linear_z = length(surface.pos - ray.o);
                 mpt_camera pin = cam; // get_pinhole_direction (camera.slang:34-37), whatever the aperture
                 pin.aperture_radius = 0.f;
@@ -1415,6 +1422,11 @@ void oracle_offset_ray_origin(const float* p, const float* n, float* out) {
     out[0] = o.x; out[1] = o.y; out[2] = o.z;
 }
 void oracle_set_scene_frame(oracle_context* c, uint32_t frame) { c->scene.frame = frame; }
+// Scene::prev_instance_transforms (scene.slang:38): instance_count x 16 floats, NULL = static scene
+void oracle_scene_set_prev_transforms(oracle_context* c, const float* t, uint32_t instance_count) {
+    c->scene.prev_instance_transforms.clear();
+    if (t) c->scene.prev_instance_transforms.assign(t, t + size_t(instance_count) * 16);
+}
 void oracle_camera_ray_frame(const mpt_camera* cam, uint32_t x, uint32_t y, uint32_t w, uint32_t h, uint32_t frame, mpt_ray* out) {
     const Ray r = Scene::generate_camera_ray(*cam, x, y, w, h, frame);
     *out = {{r.o.x, r.o.y, r.o.z}, r.tmin, {r.d.x, r.d.y, r.d.z}, r.tmax};

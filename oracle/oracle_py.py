@@ -37,6 +37,8 @@ def lib():
         _lib.oracle_half_to_float.restype = C.c_float
         _lib.oracle_set_scene_frame.argtypes = [C.c_void_p, C.c_uint32]
         _lib.oracle_set_scene_frame.restype = None
+        _lib.oracle_scene_set_prev_transforms.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        _lib.oracle_scene_set_prev_transforms.restype = None
         _lib.oracle_half_to_float.argtypes = [C.c_uint16]
         _lib.oracle_float_to_half.restype = C.c_uint16
         _lib.oracle_float_to_half.argtypes = [C.c_float]
@@ -97,6 +99,14 @@ class OracleContext:
 
     def set_scene_frame(self, frame):
         self.l.oracle_set_scene_frame(self.h, C.c_uint32(int(frame)))
+
+    def set_prev_transforms(self, transforms):
+        """Scene::prev_instance_transforms: (instance_count, 4, 4) float32 row-major, None = static scene."""
+        if transforms is None:
+            self.l.oracle_scene_set_prev_transforms(self.h, None, 0)
+            return
+        t = np.ascontiguousarray(transforms, np.float32).reshape(-1, 16)
+        self.l.oracle_scene_set_prev_transforms(self.h, C.c_void_p(t.ctypes.data), C.c_uint32(len(t)))
 
     def primary_visibility(self, cam, w, h, mask=0xFF):
         out = np.zeros((h, w), abi.PACKED_HIT_DTYPE)

@@ -205,6 +205,105 @@ def test_gbuffer_feeds_pt_with_demodulation(gpu_ctx):
     assert torch.allclose(back, plain[..., :3], rtol=1e-4, atol=1e-6)
 
 
+# ------------------------------------------------------------------------------------------------- moving instances
+def _moving_instances_scene():
+    """One quad instanced twice (an instanced mesh group keeps its node transforms: scene.cpp:1023-1105); the geometry of the SECOND
+    instance is flagged IsAnimated, the way Scene::update marks the geometries of animated nodes."""
+    from merian_b200 import abi
+    s = 0.6
+    p = np.array([[-s, -s, 0], [s, -s, 0], [s, s, 0.2], [-s, s, 0.2]], np.float32)
+    n = np.tile(np.array([[0, -0.316228, 0.948683]], np.float32), (4, 1))
+    quad = Mesh(positions=p, normals=n, uvs=np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float32), indices=np.array([[0, 1, 2], [0, 2, 3]], np.uint16),
+                material_id=0, flags=MESH_IS_OPAQUE)
+
+    def xf(tx, ty, tz, angle):
+        c, si = np.cos(angle), np.sin(angle)
+        return np.array([[c, -si, 0, tx], [si, c, 0, ty], [0, 0, 1, tz], [0, 0, 0, 1]], np.float32)
+    desc = SceneDescription(meshes=[quad], nodes=[Node([0], xf(-0.8, 0.0, 0.0, 0.2)), Node([0], xf(0.8, 0.1, -0.2, -0.3))],
+                            materials=[DiffuseMaterial((0.6, 0.5, 0.4, 1.0))], env=synthetic.sky_env(64, 32, sun_peak=10.0, sun_sigma_deg=10.0),
+                            camera=CameraDesc(position=(0.0, 0.1, 3.0), target=(0.0, 0.0, 0.0), yfov_deg=55.0, aspect=1.5, near=0.01, far=100.0))
+    t = SceneTables(desc)
+    assert len(t.instances) == 2 and len(t.geometries) == 2
+    assert not (t.geometries[1][2] & abi.GEOM_PRETRANSFORMED)
+    mesh_id, mat, flags, prims = t.geometries[1]
+    t.geometries[1] = (mesh_id, mat, flags | abi.GEOM_IS_ANIMATED, prims)
+    prev = t.instance_transforms.copy()
+    prev[0] = xf(-0.5, 0.3, 0.1, 0.0)    # not animated: must be ignored
+    prev[1] = xf(0.65, 0.02, -0.25, -0.1)
+    return t, prev
+
+
+def test_oracle_gbuffer_moving_instance(oracle_lib):
+    """Scene::to_prev_world_position (scene.slang:261-270): the motion vector and delta_z of an animated instance follow the previous
+    frame's instance transform; geometry without IsAnimated ignores it."""
+    t, prev_xf = _moving_instances_scene()
+    o = make_oracle(t)
+    w, h = 150, 100
+    cam = t.desc.camera.to_abi(0)
+    static = o.gbuffer(cam, w, h)
+    o.set_prev_transforms(prev_xf)
+    g = o.gbuffer(cam, w, h)
+    for k in ("tex0", "tex3", "emission"):
+        assert np.array_equal(g[k], static[k])
+    assert np.array_equal(g["tex1"], static["tex1"]) and np.array_equal(g["tex2"][..., 2], static["tex2"][..., 2])
+    inst = g["tex1"]["instance_index"]
+    hit = g["tex1"]["instance_id"] != MISS
+    a, b = hit & (inst == 0), hit & (inst == 1)
+    assert a.sum() > 500 and b.sum() > 500
+    assert np.array_equal(g["tex2"][a], static["tex2"][a]) and np.array_equal(g["tex2"][~hit], static["tex2"][~hit])
+    # instance 1: world position -> object space with the current matrix -> world space of the previous frame, in float64
+    d = _primary_dirs(cam, w, h)
+    z = g["tex2"][..., 2]
+    pos = np.array(cam.position[:], np.float64) + d.astype(np.float64) * z[..., None]
+    M, Mp = t.instance_transforms[1].astype(np.float64), prev_xf[1].astype(np.float64)
+    obj = (np.concatenate([pos[b], np.ones((int(b.sum()), 1))], -1) @ np.linalg.inv(M).T)
+    prev_pos = (obj @ Mp.T)[:, :3]
+    px, py = np.meshgrid(np.arange(w), np.arange(h))
+    mv_ref = _project(cam, prev_pos, w, h) - np.stack([px, py], -1)[b]
+    assert np.abs(mv_ref).max() > 3.0                                            # the instance moved by several pixels
+    assert np.abs(g["tex2"][..., :2][b] - mv_ref).max() < 5e-3
+    dz_ref = np.linalg.norm(prev_pos - np.array(cam.position[:], np.float64), axis=-1) - z[b]
+    assert np.abs(g["tex2"][..., 3][b] - dz_ref).max() < 1e-4
+    o.set_prev_transforms(None)
+    assert np.array_equal(o.gbuffer(cam, w, h)["tex2"], static["tex2"])
+
+
+@pytest.mark.gpu
+def test_cuda_gbuffer_moving_instance_matches_oracle(gpu_ctx):
+    t, prev_xf = _moving_instances_scene()
+    upload_scene(gpu_ctx, t)
+    o = make_oracle(t)
+    w, h = 150, 100
+    cam = t.desc.camera.to_abi(1)
+    cd = t.desc.camera
+    prev = CameraDesc(position=tuple(np.array(cd.position) + [0.04, -0.02, 0.03]), target=cd.target, up=cd.up, yfov_deg=cd.yfov_deg, aspect=cd.aspect,
+                      near=cd.near, far=cd.far).to_abi(0)
+    static = gpu_ctx.gbuffer(cam, w, h, prev_cam=prev)
+    gpu_ctx.set_prev_transforms(prev_xf)
+    o.set_prev_transforms(prev_xf)
+    got, ref = gpu_ctx.gbuffer(cam, w, h, prev_cam=prev), o.gbuffer(cam, w, h, prev_cam=prev)
+    _compare_gbuffers(got, ref)
+    b = (got["tex1"]["instance_id"] != MISS) & (got["tex1"]["instance_index"] == 1)
+    assert np.abs(got["tex2"][..., :2][b] - static["tex2"][..., :2][b]).max() > 3.0
+    assert np.array_equal(got["tex2"][~b], static["tex2"][~b])
+    with pytest.raises(Exception):
+        gpu_ctx.set_prev_transforms(prev_xf[:1])                                  # instance count must match the scene's
+    gpu_ctx.set_prev_transforms(None)
+    assert np.array_equal(gpu_ctx.gbuffer(cam, w, h, prev_cam=prev)["tex2"], static["tex2"])
+
+
+def test_prev_vertices_are_refused(oracle_lib):
+    """MPT_GEOM_HAS_PREV_VERTICES (morphed / skinned meshes) is outside the built scope: the host-side scene build says so."""
+    from merian_b200 import abi
+    from merian_b200.host_accel import HostAccel
+    from merian_b200._lib import MptError
+    t, _ = _moving_instances_scene()
+    mesh_id, mat, flags, prims = t.geometries[0]
+    t.geometries[0] = (mesh_id, mat, flags | abi.GEOM_HAS_PREV_VERTICES, prims)
+    with pytest.raises(MptError):
+        HostAccel(t)
+
+
 # ------------------------------------------------------------------------------------------------- mip chains + ray differentials
 def _minified_floor_scene(mipmap):
     """A large floor under a low camera with a high-frequency base-colour texture tiled 24x: towards the horizon a pixel covers many
