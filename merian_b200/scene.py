@@ -481,15 +481,21 @@ class SceneTables:
 def upload_scene(backend, tables: SceneTables):
     """Push tables, materials, textures and env through a backend exposing the mpt_* entry points
     (merian_b200.Context for the product; oracle_py.OracleContext in tests)."""
+    import time
     d = tables.desc
+    timing = {"generate_s": 0.0, "texture_upload_s": 0.0, "scene_upload_s": 0.0}  # harness-side texel synthesis vs the library's share
     for tid, t in enumerate(d.textures):
+        t0 = time.perf_counter()
         px = np.ascontiguousarray(t.pixels() if callable(t.pixels) else t.pixels)  # callables defer large synthetic textures
         if px.dtype == np.uint8:
             fmt = abi.TEX_RGBA8_SRGB if t.srgb else abi.TEX_RGBA8_UNORM
         else:
             px = px.astype(np.float32)
             fmt = abi.TEX_RGBA32F
+        t1 = time.perf_counter()
         backend.texture_upload(tid, px.shape[1], px.shape[0], fmt, t.wrap_u, t.wrap_v, t.filter, px, getattr(t, "mipmap", abi.MIPMAP_NONE))
+        timing["generate_s"] += t1 - t0
+        timing["texture_upload_s"] += time.perf_counter() - t1
     backend.materials_upload(tables.material_entries, tables.material_entry_size, len(d.materials),
                              tables.material_types_array(), len(tables.material_types))
     if d.env is not None:
@@ -498,4 +504,7 @@ def upload_scene(backend, tables: SceneTables):
                         px.shape[0], px)
     else:
         backend.env_set(abi.ENV_EMPTY, None, 1.0, 0, 0, None)
+    t0 = time.perf_counter()
     backend.scene_upload(tables.scene_desc())
+    timing["scene_upload_s"] = time.perf_counter() - t0
+    tables.upload_timing = timing

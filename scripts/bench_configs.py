@@ -111,7 +111,7 @@ def render_config(name, tables, W, H, spp, L, rank, world, dev, steps, warmup, e
             "msamples_per_s": W * H * spp * world / (ms * 1e-3) / 1e6,
             "mrays_per_s": float(rays.item()) / total_steps / (ms * 1e-3) / 1e6,
             "bvh_nodes": bvh.node_count, "bvh_mb": (bvh.node_bytes + 2 * bvh.triangle_bytes) / 1e6, "bvh_build_ms": bvh.build_ms,
-            "upload_s": upload_s, "work": work, "checks": checks, "mean_luminance": float((out[..., :3] * torch.tensor([0.299, 0.587, 0.114], device=dev)).sum(-1).mean()) if rank == 0 else None}
+            "upload_s": upload_s, "upload_split_s": getattr(tables, "upload_timing", None), "work": work, "checks": checks, "mean_luminance": float((out[..., :3] * torch.tensor([0.299, 0.587, 0.114], device=dev)).sum(-1).mean()) if rank == 0 else None}
     line["generator"] = synthetic.GENERATOR_VERSION
     line["seed"] = tables.desc.seed
     line.update(extra)
