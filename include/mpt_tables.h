@@ -1,0 +1,73 @@
+/* mpt_tables.h — the host logic of merian::Scene that defines what `pt` sees, for hosts that are not
+ * merian: source meshes + scene-graph nodes in, the flat mpt_scene_desc of mpt.h out (host-only, no CUDA call).
+ *
+ * Inside merian the plugin reads these tables from merian::Scene; a standalone C or C++ host has no Scene, so libmpt
+ * restates the part of it the renderer depends on:
+ *   vertex packing          src/merian-shaders/scene/gltf_scene.cpp:107-118, src/merian/utils/normal_encoding.cpp:9-25 (host encode)
+ *   the device pre-transform src/merian-shaders/scene/transform_vertex.slang:12-40 (decode, transform, re-encode; runs even with identity)
+ *   mesh grouping -> BLAS    src/merian-shaders/scene/scene.cpp:1023-1105 (split by FlipFacing / TwoSided and instance mask; meshes with
+ *                            one instance form pre-transformed static groups, meshes with several share a group per instance set)
+ *   GeometryData order       src/merian-shaders/scene/scene.cpp:1236-1291
+ *   TLAS instances / ids     src/merian-shaders/scene/scene.cpp:1808-1857
+ * Same names and meaning as the Python mirror merian_b200/scene.py (SceneTables, pack_vertices); tests/test_tables_cabi.py compares the two. */
+#ifndef MPT_TABLES_H
+#define MPT_TABLES_H
+
+#include "mpt.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* merian::Scene::MeshFlags, include/merian-shaders/scene/scene.hpp:39-58 */
+enum {
+    MPT_MESH_IS_MORPHED = 0x1,
+    MPT_MESH_HAS_VARIABLE_TOPOLOGY = 0x2,
+    MPT_MESH_IS_OPAQUE = 0x4,
+    MPT_MESH_FLIP_FACING = 0x8,
+    MPT_MESH_TWO_SIDED = 0x10,
+    MPT_MESH_HAS_TANGENTS = 0x20,
+    MPT_MESH_FLAT_SHADING = 0x40,
+    MPT_MESH_USE_ENV_MAP = 0x80
+};
+
+/* One source mesh as a loader hands it to Scene::add_mesh (gltf_scene.cpp:88-160): float attributes, optional indices. */
+typedef struct mpt_src_mesh {
+    const float* positions; /* vertex_count x 3 */
+    const float* normals;   /* vertex_count x 3 */
+    const float* uvs;       /* vertex_count x 2, or NULL (zeros) */
+    const float* tangents;  /* vertex_count x 4 (xyz + handedness), or NULL */
+    uint32_t vertex_count;
+    const void* indices;    /* index triples, or NULL: sequential (vertex_count / 3 primitives) */
+    uint32_t primitive_count;
+    uint32_t index_size;    /* bytes per index: 1, 2 or 4 (ignored without indices) */
+    uint32_t material_id;
+    uint32_t flags;         /* MPT_MESH_* */
+    uint32_t instance_mask; /* 8 bit */
+} mpt_src_mesh;
+
+/* One scene-graph node with its GLOBAL transform and the meshes it instantiates (Scene::Node, scene.hpp:300-330). */
+typedef struct mpt_src_node {
+    float transform[16]; /* row-major 4x4 object -> world */
+    const uint32_t* meshes;
+    uint32_t mesh_count;
+} mpt_src_node;
+
+typedef struct mpt_tables mpt_tables;
+
+/* Builds the tables. Morphed / variable-topology meshes (animated vertex data) are refused with MPT_ERR_UNSUPPORTED.
+ * The source arrays may be released after the call (indices are copied). Errors: mpt_last_error(NULL). */
+MPT_API mpt_status mptt_build(const mpt_src_mesh* meshes, uint32_t mesh_count, const mpt_src_node* nodes, uint32_t node_count, mpt_tables** out);
+/* The result, valid until mptt_free: pass it to mpt_scene_upload / mpt_host_accel_build. */
+MPT_API const mpt_scene_desc* mptt_scene_desc(const mpt_tables* t);
+MPT_API void mptt_free(mpt_tables* t);
+
+/* The vertex path alone (A13): host packing followed by the device transform pass with `transform` (row-major 4x4, NULL = identity).
+ * uvs / tangents may be NULL. Writes vertex_count records. */
+MPT_API mpt_status mptt_pack_vertices(const float* positions, const float* normals, const float* uvs, const float* tangents, uint32_t vertex_count,
+                                      const float* transform, mpt_packed_vertex* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

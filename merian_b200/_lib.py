@@ -26,7 +26,9 @@ EXPORTS = ["mpt_abi_version", "mpt_create", "mpt_destroy", "mpt_last_error", "mp
            "mptn_gbuffer_create", "mptn_gbuffer_destroy", "mptn_gbuffer_last_error", "mptn_gbuffer_load_config", "mptn_gbuffer_dump_config",
            "mptn_gbuffer_set_resolution", "mptn_gbuffer_describe_outputs", "mptn_gbuffer_process",
            "mptn_accumulate_create", "mptn_accumulate_destroy", "mptn_accumulate_last_error", "mptn_accumulate_load_config",
-           "mptn_accumulate_dump_config", "mptn_accumulate_request_clear", "mptn_accumulate_process", "mptn_process_accumulate"]
+           "mptn_accumulate_dump_config", "mptn_accumulate_request_clear", "mptn_accumulate_process", "mptn_process_accumulate",
+           # include/mpt_tables.h
+           "mptt_build", "mptt_scene_desc", "mptt_free", "mptt_pack_vertices"]
 
 
 class MptError(RuntimeError):
@@ -57,6 +59,12 @@ def lib():
         l.mpt_mip_level.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         l.mpt_env_set_device.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_float, C.c_uint32, C.c_uint32, C.c_void_p]
         l.mpt_env_set.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_float, C.c_uint32, C.c_uint32, C.c_void_p]
+        l.mptt_build.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p)]
+        l.mptt_scene_desc.argtypes = [C.c_void_p]
+        l.mptt_scene_desc.restype = C.POINTER(abi.SceneDesc)
+        l.mptt_free.argtypes = [C.c_void_p]
+        l.mptt_free.restype = None
+        l.mptt_pack_vertices.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         l.mpt_set_scene_frame.argtypes = [C.c_void_p, C.c_uint32]
         l.mpt_scene_set_prev_transforms.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         l.mpt_primary_visibility.argtypes = [C.c_void_p, C.POINTER(abi.Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]

@@ -82,6 +82,16 @@ class SceneDesc(C.Structure):
                 ("instance_transforms", C.c_void_p), ("inverse_transposed_instance_transforms", C.c_void_p)]
 
 
+class SrcMesh(C.Structure):  # mpt_src_mesh, include/mpt_tables.h
+    _fields_ = [("positions", C.c_void_p), ("normals", C.c_void_p), ("uvs", C.c_void_p), ("tangents", C.c_void_p), ("vertex_count", C.c_uint32),
+                ("indices", C.c_void_p), ("primitive_count", C.c_uint32), ("index_size", C.c_uint32), ("material_id", C.c_uint32),
+                ("flags", C.c_uint32), ("instance_mask", C.c_uint32)]
+
+
+class SrcNode(C.Structure):  # mpt_src_node
+    _fields_ = [("transform", C.c_float * 16), ("meshes", C.c_void_p), ("mesh_count", C.c_uint32)]
+
+
 class MaterialType(C.Structure):
     _fields_ = [("model", C.c_uint32), ("features", C.c_uint32)]
 

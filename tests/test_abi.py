@@ -13,12 +13,12 @@ from merian_b200._lib import EXPORTS, LIB_PATH
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "mpt.h")
-HEADERS = [HEADER, os.path.join(ROOT, "include", "mpt_node.h")]
+HEADERS = [HEADER, os.path.join(ROOT, "include", "mpt_node.h"), os.path.join(ROOT, "include", "mpt_tables.h")]
 
 
 def _declared():
     src = "".join(open(h).read() for h in HEADERS)
-    return sorted(set(re.findall(r"MPT_API\s+[\w\s\*]+?\b(mptn?_\w+)\s*\(", src)))
+    return sorted(set(re.findall(r"MPT_API\s+[\w\s\*]+?\b(mpt[nt]?_\w+)\s*\(", src)))
 
 
 @pytest.fixture(scope="module")
@@ -43,8 +43,8 @@ def test_library_exports_every_declared_symbol(libmpt):
 def test_only_mpt_symbols_are_exported():
     out = subprocess.check_output(["nm", "-D", "--defined-only", LIB_PATH], text=True)
     syms = [l.split()[-1] for l in out.splitlines() if " T " in l]
-    assert sorted(s for s in syms if s.startswith(("mpt_", "mptn_"))) == sorted(EXPORTS)
-    assert not [s for s in syms if not s.startswith(("mpt_", "mptn_")) and not s.startswith("_")], syms
+    assert sorted(s for s in syms if s.startswith(("mpt_", "mptn_", "mptt_"))) == sorted(EXPORTS)
+    assert not [s for s in syms if not s.startswith(("mpt_", "mptn_", "mptt_")) and not s.startswith("_")], syms
 
 
 def test_no_gpu_fails_loudly(libmpt):

@@ -1,0 +1,151 @@
+"""include/mpt_tables.h (mptt_*): libmpt's C++ restatement of the merian::Scene host logic against the numpy
+restatement in merian_b200/scene.py — two independent implementations of scene.cpp:1023-1105 / 1236-1291 / 1808-1857 and of the vertex
+path gltf_scene.cpp:107-118 + transform_vertex.slang:12-40. Ids, flags, groups and instance records must be identical; vertex words are
+identical up to the rounding of the matrix products (numpy's matmul does not promise an order of summation)."""
+import numpy as np
+import pytest
+
+from merian_b200 import abi, synthetic
+from merian_b200.scene import (MESH_FLIP_FACING, MESH_HAS_TANGENTS, MESH_IS_MORPHED, MESH_IS_OPAQUE, MESH_TWO_SIDED, DiffuseMaterial, Mesh, Node,
+                               SceneDescription, SceneTables, pack_vertices)
+from merian_b200.tables_cabi import CTables, pack_vertices as c_pack_vertices
+
+
+def _snorm_delta(a, b):
+    lo = np.abs((a & 0xFFFF).astype(np.uint16).view(np.int16).astype(np.int32) - (b & 0xFFFF).astype(np.uint16).view(np.int16).astype(np.int32))
+    hi = np.abs((a >> 16).astype(np.uint16).view(np.int16).astype(np.int32) - (b >> 16).astype(np.uint16).view(np.int16).astype(np.int32))
+    return np.maximum(lo, hi)
+
+
+def _compare_vertices(c, p, exact):
+    assert len(c) == len(p)
+    assert np.array_equal(c["uv"], p["uv"])                                                    # float -> half, round to nearest even
+    if exact:
+        assert np.array_equal(c["position"], p["position"])
+        assert np.array_equal(c["encoded_normal"], p["encoded_normal"]) and np.array_equal(c["encoded_tangent"], p["encoded_tangent"])
+    else:
+        np.testing.assert_allclose(c["position"], p["position"], rtol=3e-7, atol=4e-6)   # an ulp of the largest term of the row product
+        assert _snorm_delta(c["encoded_normal"], p["encoded_normal"]).max() <= 1
+        assert (c["encoded_tangent"] & 1 == p["encoded_tangent"] & 1).all()
+        assert _snorm_delta(c["encoded_tangent"] & 0xFFFFFFFE, p["encoded_tangent"] & 0xFFFFFFFE).max() <= 2
+
+
+def _compare_tables(desc, exact_vertices):
+    p, c = SceneTables(desc), CTables(desc)
+    assert c.groups == [g["meshes"] for g in p.groups]
+    assert c.geometries == [tuple(int(v) for v in g) for g in p.geometries]
+    assert len(c.instances) == len(p.instances)
+    for (ct, cid, cmask, cfl, cgid), (pt, pid, pmask, pfl, pgid) in zip(c.instances, p.instances):
+        assert np.array_equal(ct, pt) and (cid, cmask, cfl, cgid) == (pid, pmask, pfl, pgid)
+    assert np.array_equal(c.instance_transforms, p.instance_transforms)
+    np.testing.assert_allclose(c.inv_t_instance_transforms, p.inv_t_instance_transforms, rtol=2e-7, atol=1e-9)
+    md = c.mesh_descs()
+    for i, mesh in enumerate(desc.meshes):
+        pv = p.mesh_vertices[i]
+        if pv is None:
+            assert md[i].vertex_count == 0 and not md[i].vertices
+            continue
+        assert md[i].index_flag == p.mesh_index_flag[i] and md[i].opaque == (1 if mesh.flags & MESH_IS_OPAQUE else 0)
+        assert md[i].primitive_count == (len(mesh.indices) if mesh.indices is not None else len(mesh.positions) // 3)
+        _compare_vertices(c.mesh_vertices(i), pv, exact_vertices)
+        if mesh.indices is not None:
+            n = md[i].primitive_count * 3
+            got = np.frombuffer((__import__("ctypes").c_char * (n * mesh.indices.dtype.itemsize)).from_address(md[i].indices), dtype=mesh.indices.dtype, count=n)
+            assert np.array_equal(got, np.ascontiguousarray(mesh.indices).reshape(-1))
+    return p, c
+
+
+@pytest.mark.parametrize("name", ["cornell", "terrain", "instanced_rocks"])
+def test_tables_match_the_numpy_restatement_on_the_synthetic_scenes(name):
+    desc = {"cornell": lambda: synthetic.cornell(), "terrain": lambda: synthetic.terrain(nx=60, ny=30, env_size=(64, 32)),
+            "instanced_rocks": lambda: synthetic.instanced_rocks(n_instances=12, rock_res=9, seed=5, env_size=(64, 32))}[name]()
+    # static scenes bake identity node transforms: every operation is exact; the rocks are instanced (identity pre-transform) as well
+    _compare_tables(desc, exact_vertices=True)
+
+
+def _quad(cx, flags, mask=0xFF, tangents=False, idx_dtype=np.uint16, mat=0):
+    p = np.array([[cx - 0.4, -0.4, 0], [cx + 0.4, -0.4, 0], [cx + 0.4, 0.4, 0.2], [cx - 0.4, 0.4, 0.2]], np.float32)
+    rng = np.random.default_rng(int(cx * 10) + 100)
+    n = rng.normal(size=(4, 3)).astype(np.float32)
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    t = None
+    if tangents:
+        t = np.concatenate([rng.normal(size=(4, 3)), np.array([[1], [-1], [1], [-1]])], 1).astype(np.float32)
+    idx = None if idx_dtype is None else np.array([[0, 1, 2], [0, 2, 3]], idx_dtype)
+    if idx is None:
+        p, n = p[[0, 1, 2, 0, 2, 3]], n[[0, 1, 2, 0, 2, 3]]
+        t = None if t is None else t[[0, 1, 2, 0, 2, 3]]
+    uv = rng.random((len(p), 2)).astype(np.float32) * 3 - 1
+    return Mesh(positions=p, normals=n, uvs=uv, tangents=t, indices=idx, material_id=mat, flags=flags | (MESH_HAS_TANGENTS if tangents else 0), instance_mask=mask)
+
+
+def _xf(tx, ty, tz, angle, s=1.0):
+    c, si = np.cos(angle) * s, np.sin(angle) * s
+    return np.array([[c, -si, 0, tx], [si, c, 0, ty], [0, 0, s, tz], [0, 0, 0, 1]], np.float32)
+
+
+def test_grouping_ids_and_flags_on_a_mixed_scene():
+    """Static groups split by FlipFacing / TwoSided and by instance mask, instanced groups keyed by their instance set, an unreferenced
+    mesh, a non-opaque mesh, every index width, identity and non-identity nodes."""
+    meshes = [_quad(-2.0, MESH_IS_OPAQUE), _quad(-1.0, MESH_IS_OPAQUE | MESH_TWO_SIDED, tangents=True, idx_dtype=np.uint32),
+              _quad(0.0, MESH_FLIP_FACING, idx_dtype=np.uint8, mat=1), _quad(1.0, MESH_IS_OPAQUE, mask=0x0F, idx_dtype=None),
+              _quad(2.0, MESH_IS_OPAQUE, tangents=True), _quad(3.0, MESH_IS_OPAQUE | MESH_TWO_SIDED), _quad(4.0, MESH_IS_OPAQUE),
+              _quad(5.0, MESH_IS_OPAQUE, mat=1)]
+    nodes = [Node([0, 1], _xf(0.1, 0.2, 0.3, 0.4)), Node([2]), Node([3], _xf(0, 1, 0, -0.7, 1.5)),
+             Node([4, 5], _xf(1, 0, 0, 0.2)), Node([4, 5], _xf(-1, 0, 2, 1.1, 0.5)), Node([4]), Node([7], _xf(0, 0, -1, 0.0))]   # mesh 6: unreferenced
+    desc = SceneDescription(meshes=meshes, nodes=nodes, materials=[DiffuseMaterial(), DiffuseMaterial((0.5, 0.5, 0.5, 1))])
+    p, c = _compare_tables(desc, exact_vertices=False)
+    assert len(c.groups) >= 5 and any(len(g) > 1 for g in c.groups)
+    flags = [g[2] for g in c.geometries]
+    assert any(f & abi.GEOM_PRETRANSFORMED for f in flags) and any(not (f & abi.GEOM_PRETRANSFORMED) for f in flags)
+    assert sum(1 for (_t, _i, _m, fl, _g) in c.instances if not (fl & abi.INSTANCE_FORCE_OPAQUE)) == 1   # the group of the non-opaque mesh 2
+    c.close()
+
+
+def test_pack_vertices_matches_numpy():
+    rng = np.random.default_rng(3)
+    n = 5000
+    pos = (rng.random((n, 3)) * 20 - 10).astype(np.float32)
+    nrm = rng.normal(size=(n, 3)).astype(np.float32)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    nrm[:8] = [[0, 0, 1], [0, 0, -1], [1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0.70710678, 0, -0.70710678], [0, -0.6, -0.8]]
+    uv = np.concatenate([rng.random((n - 6, 2)) * 8 - 4, [[0, 0], [1, 1], [65504, -65504], [1e-8, 6e-8], [0.33325195, 2049.0], [1e5, -1e-5]]]).astype(np.float32)
+    tan = np.concatenate([rng.normal(size=(n, 3)), np.where(rng.random((n, 1)) < 0.5, -1.0, 1.0)], 1).astype(np.float32)
+    tan[0, :3] = 0                                                                # degenerate tangent -> (0, 0, 1)
+    _compare_vertices(c_pack_vertices(pos, nrm, uv, tan), pack_vertices(pos, nrm, uv, tan), exact=True)
+    _compare_vertices(c_pack_vertices(pos, nrm), pack_vertices(pos, nrm), exact=True)
+    M = _xf(0.3, -2.0, 5.0, 0.9, 1.7)
+    M[2, 0], M[0, 2] = 0.2, -0.1
+    _compare_vertices(c_pack_vertices(pos, nrm, uv, tan, M), pack_vertices(pos, nrm, uv, tan, M), exact=False)
+
+
+def test_errors_are_reported_not_thrown():
+    from merian_b200._lib import MptError
+    bad = SceneDescription(meshes=[_quad(0.0, MESH_IS_OPAQUE | MESH_IS_MORPHED)], nodes=[Node([0])], materials=[DiffuseMaterial()])
+    with pytest.raises(MptError):
+        CTables(bad)
+    out_of_range = SceneDescription(meshes=[_quad(0.0, MESH_IS_OPAQUE)], nodes=[Node([3])], materials=[DiffuseMaterial()])
+    with pytest.raises(MptError):
+        CTables(out_of_range)
+    with pytest.raises(MptError):
+        c_pack_vertices(np.zeros((3, 3), np.float32), np.ones((3, 3), np.float32), transform=np.zeros((4, 4), np.float32))   # singular
+
+
+def test_c_tables_feed_the_host_accel_build():
+    """The mpt_scene_desc of mptt_build goes straight into mpt_host_accel_build (what mpt_scene_upload runs on the host) and gives the
+    acceleration structure the numpy tables give."""
+    import ctypes as C
+    from merian_b200._lib import lib
+    from merian_b200.host_accel import HostAccel
+    desc = synthetic.instanced_rocks(n_instances=12, rock_res=9, seed=5, env_size=(64, 32))
+    ref = HostAccel(SceneTables(desc))
+    c = CTables(desc)
+    h = C.c_void_p()
+    assert lib().mpt_host_accel_build(C.byref(c.scene_desc()), C.byref(h)) == abi.MPT_OK
+    view = abi.HostAccelView()
+    assert lib().mpt_host_accel_get(h, C.byref(view)) == abi.MPT_OK
+    assert (view.node_count, view.triangle_count, view.prim_count) == (ref.view.node_count, ref.view.triangle_count, ref.view.prim_count)
+    got = np.frombuffer((C.c_char * (view.node_count * 80)).from_address(view.nodes), dtype=np.uint8)
+    assert np.array_equal(got, ref.nodes.view(np.uint8).reshape(-1))
+    lib().mpt_host_accel_free(h)
+    c.close()
