@@ -66,7 +66,11 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.lines, self.proc = index, [], None
+        self.index, self.lines, self.proc, self.first = index, [], None, 0
+
+    def mark(self):
+        """The timed region starts here: earlier samples (warm-up load) only serve as a fallback for a region shorter than one period."""
+        self.first = len(self.lines)
 
     def start(self):
         try:
@@ -84,7 +88,10 @@ class ClockSampler:
         self.thread.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for l in self.lines:
+        window, note = self.lines[self.first:], None
+        if not window and self.first > 0:  # e.g. 8-GPU strong scaling: 20 steps of 5 ms end before the next 100 ms sample
+            window, note = self.lines[self.first - 1:self.first], "timed region shorter than the sampling period: last sample of the warm-up load"
+        for l in window:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 6:
                 continue
@@ -96,8 +103,11 @@ class ClockSampler:
             for n, v in zip(names, f[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        out = {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+               "samples": len(sm)}
+        if note:
+            out["note"] = note
+        return out
 
 
 def build_scene(small=False):
@@ -332,7 +342,7 @@ def run_ours(args):
     barrier()
     ctx.reset_stats()
     if rank == 0:
-        sampler.lines.clear()  # keep only the samples of the timed region
+        sampler.mark()  # only the samples of the timed region count
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     # One more untimed step goes in front of the timed ones, behind the barrier: right after a synchronize the GPU's queue is empty, and a
