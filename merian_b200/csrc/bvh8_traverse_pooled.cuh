@@ -40,9 +40,7 @@ struct alignas(16) PoolEntry {
 #endif
 constexpr int kPrimStackSize = 24; // parked primitive groups: at most one per node test while another group is pending
 
-// FIXED >= 0 (single-level scenes): the instance flags of the scene's only instance are known when the kernel is chosen — bits 0-1 = cull
-// mode, bit 2 = force-opaque — and the per-ray copies (two registers, the cull-mode selects and the alpha-test call) compile away.
-template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE, int FIXED = -1> struct TraversalP {
+template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struct TraversalP {
     const AccelView& A;
     const AlphaTest& alpha_test;
     uint2* sst;            // shared-memory part of the node stack: entry i at sst[i * STRIDE]
@@ -116,7 +114,7 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE, int F
         cur_instance = 0;
         cull = 0;
         force_opaque = true;
-        if (!TWO_LEVEL && FIXED < 0) {
+        if (!TWO_LEVEL) {
             const uint32_t fl = scene_flags >> 8;
             cull = (fl & 1u) ? 2 : ((fl & 2u) ? 1 : 0);
             force_opaque = (fl & 4u) != 0;
@@ -183,10 +181,8 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE, int F
                             s.kx = int(kk & 3u); s.ky = int((kk >> 2) & 3u); s.kz = int((kk >> 4) & 3u);
                         }
                         float t, u, v;
-                        const int cull_mode = FIXED >= 0 ? (FIXED & 3) : cull;
-                        const bool opaque = FIXED >= 0 ? (FIXED & 4) != 0 : force_opaque;
-                        if (intersect_triangle(s, o, xyz(a), xyz(b), xyz(c), cull_mode, 0.f, best_t, t, u, v)) {
-                            if (opaque || !(__float_as_uint(c.w) & kTriNonOpaque) || !alpha_test(rec, cur_instance, u, v)) {
+                        if (intersect_triangle(s, o, xyz(a), xyz(b), xyz(c), cull, 0.f, best_t, t, u, v)) {
+                            if (force_opaque || !(__float_as_uint(c.w) & kTriNonOpaque) || !alpha_test(rec, cur_instance, u, v)) {
                                 best_t = t;
                                 hit.tri = rec;
                                 hit.instance = cur_instance;

@@ -532,21 +532,13 @@ __global__ void __launch_bounds__(kThreads, (!COUNT && !MEDIUM && !TWO_LEVEL && 
 #ifndef MPT_POOL_TRIGGER
 #define MPT_POOL_TRIGGER 32
 #endif
-// MPT_FIXED_FLAGS: the plain variant also exists with the scene's instance flags as a template constant (FIXED = 4: cull back faces,
-// force-opaque — every single-level scene whose meshes are one-sided and opaque, C3 among them); TraversalP explains what that removes.
-#ifndef MPT_FIXED_FLAGS
-#define MPT_FIXED_FLAGS 0
-#endif
-#ifndef MPT_POLL_EARLY
-#define MPT_POLL_EARLY 0
-#endif
-template <bool COUNT, bool MEDIUM, bool TWO_LEVEL, bool NEE, int FIXED = -1>
+template <bool COUNT, bool MEDIUM, bool TWO_LEVEL, bool NEE>
 __global__ void __launch_bounds__(kThreads, (!COUNT && !MEDIUM && !TWO_LEVEL && !NEE) ? MPT_EXTEND_PLAIN_MIN_BLOCKS : MPT_EXTEND_MIN_BLOCKS)
 k_extend_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ q_o, const float4* __restrict__ q_d, PathBuffers pb, uint32_t bounce, uint32_t mask,
                 ExtendTune tune, Counters* ctr) {
     constexpr int NE = 32 + MPT_POOL_READY, SS = MPT_POOL_SMEM_STACK, kWarps = kThreads / 32, TRIG = MPT_POOL_TRIGGER;
     static_assert(TRIG >= 0 && TRIG <= MPT_POOL_READY && MPT_POOL_READY <= 32, "MPT_POOL_TRIGGER <= MPT_POOL_READY <= 32");
-    using Trav = TraversalP<COUNT, TWO_LEVEL, MaterialAlphaTest, SS, kThreads, FIXED>;
+    using Trav = TraversalP<COUNT, TWO_LEVEL, MaterialAlphaTest, SS, kThreads>;
     using Entry = PoolEntry;
     struct Pool {
         Entry e[NE];
@@ -708,10 +700,6 @@ k_extend_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ 
         // ======================================================= divergent: traverse; a finished lane swaps its record for a READY one
         uint32_t tick = 0u; // the same in every lane of the warp (TraversalP::step, MPT_TLAS_GATE); unused and compiled out for single-level scenes
         while (active) {
-#if MPT_POLL_EARLY
-            // the DONE count for the re-convergence test below, read BEFORE the step so that the shared-memory latency hides behind it
-            const int done_seen = *(volatile int*)&P.done_n;
-#endif
             if (T.step(TWO_LEVEL ? tick++ : 0u)) {
                 Entry& E = P.e[my];
                 const bool f = T.found();
@@ -729,11 +717,7 @@ k_extend_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ 
             // re-converge for a refill when the READY list is used up and too few lanes are left (never once the queue is exhausted:
             // the remaining rays just run to completion)
             if (TRIG > 0) {
-#if MPT_POLL_EARLY
-                if (!exhausted && done_seen >= TRIG) break;
-#else
                 if (!exhausted && *(volatile int*)&P.done_n >= TRIG) break;
-#endif
             } else if (!exhausted && uint32_t(__popc(__activemask())) < tune.refill && *(volatile int*)&P.ready_head >= ready_n) break;
         }
         __syncwarp();
@@ -1285,7 +1269,6 @@ struct mpt_context {
     size_t l2_window_bytes = 0; // > 0: persisting-L2 access-policy window over accel_mem while a frame's kernels run (MPT_L2_PERSIST)
     DevBuf tri_attr, geometries, prim_to_tri, instances, tlas_prims, xform, xform_it, xform_prev;
     uint32_t instance_count = 0; // of the uploaded scene
-    bool scene_flags_fixed4 = false; // single-level scene whose only instance culls back faces and is force-opaque (k_extend_pooled<..., 4>)
     DevBuf materials, material_types, texture_table, env_pixels, env_alias, env_pmf;
     bool env_sampling_ready = false;
     std::vector<TextureSlot> textures;
@@ -1569,9 +1552,7 @@ mpt_status run_passes(mpt_context* ctx, const CameraParams& cam, const mpt_rende
                                                                                      : (plain ? ctx->extend_plain_blocks_per_sm : ctx->extend_blocks_per_sm));
 #define MPT_LAUNCH_EXTEND(C, TL)                                                                                                                          \
     do {                                                                                                                                                \
-        if (ctx->extend_pooled && MPT_FIXED_FLAGS && plain && ctx->scene_flags_fixed4)                                                                        \
-            k_extend_pooled<false, false, false, false, 4><<<grid, kThreads, 0, st>>>(ctx->view, pb.q_o[in], pb.q_d[in], pb, uint32_t(b), P.instance_mask, ctx->tune_pooled, ctr); \
-        else if (ctx->extend_pooled) k_extend_pooled<C, MED, TL, NEE><<<grid, kThreads, 0, st>>>(ctx->view, pb.q_o[in], pb.q_d[in], pb, uint32_t(b), P.instance_mask, ctx->tune_pooled, ctr); \
+        if (ctx->extend_pooled) k_extend_pooled<C, MED, TL, NEE><<<grid, kThreads, 0, st>>>(ctx->view, pb.q_o[in], pb.q_d[in], pb, uint32_t(b), P.instance_mask, ctx->tune_pooled, ctr); \
         else k_extend<C, MED, TL, NEE><<<grid, kThreads, 0, st>>>(ctx->view, pb.q_o[in], pb.q_d[in], pb, uint32_t(b), P.instance_mask, ctx->tune, ctr);              \
     } while (0)
                 if (count) { if (tl) MPT_LAUNCH_EXTEND(true, true); else MPT_LAUNCH_EXTEND(true, false); }
@@ -1737,7 +1718,6 @@ MPT_API mpt_status mpt_scene_upload(mpt_context* ctx, const mpt_scene_desc* d) t
     v.inst_xform = ctx->xform.as<float4>();
     v.inst_xform_it = ctx->xform_it.as<float4>();
     v.inst_xform_prev = nullptr; // a new scene starts static
-    ctx->scene_flags_fixed4 = !H.two_level && !H.instances.empty() && ((H.instances[0].mask_flags >> 8) & 7u) == 4u;
     ctx->instance_count = d->instance_count;
 
     ctx->bvh_info.node_count = nodes.size();
