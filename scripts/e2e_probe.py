@@ -39,10 +39,13 @@ def main():
     torch.cuda.synchronize()
     device_ms = e0.elapsed_time(e1) / steps
     h_tex1 = tex1.cpu().pin_memory()
-    h_outs = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    h_outs = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(4)]
+    if os.environ.get("PROBE_GC_OFF"):
+        import gc
+        gc.collect(); gc.freeze(); gc.disable()
     ctx.render_host(cam, P(0), h_tex1=h_tex1, h_out=h_outs[0])
     res = {"device_ms_per_step": device_ms}
-    for name, in_flight in (("two_in_flight", 2), ("one_in_flight", 1)):
+    for name, in_flight in (("two_in_flight", 2), ("four_in_flight", 4), ("one_in_flight", 1)):
         for s_ in range(in_flight):
             ctx.render_host_begin(cam, P(s_), h_outs[s_], s_, h_tex1=h_tex1)
         for s_ in range(in_flight):
@@ -62,7 +65,7 @@ def main():
         for i in range(max(steps - in_flight, 0), steps):
             ctx.render_host_end(i % in_flight)
         total = (time.perf_counter() - t0) * 1e3
-        res[name] = {"ms_per_step": total / steps, "total_ms": total, "begin_ms_max": max(begin_ms), "begin_ms_mean": sum(begin_ms) / len(begin_ms),
+        res[name] = {"ms_per_step": total / steps, "total_ms": total, "begin_ms_max": max(begin_ms), "begin_ms_mean": sum(begin_ms) / len(begin_ms), "begin_ms": [round(x, 2) for x in begin_ms],
                      "end_ms": [round(x, 2) for x in end_ms], "loop_stamps_ms": [round(x, 1) for x in stamps]}
     # the same pipelined loop, copies only (no render): what the PCIe legs cost by themselves
     d = torch.empty_like(tex1)
