@@ -86,3 +86,31 @@ def test_degenerate_geometry_renders_like_the_oracle(gpu_ctx):
     mism, bary, _ = compare_hits(got, ref)
     assert (ref["instance_id"] != 0xFFFFFFFF).mean() > 0.02
     assert mism < 1e-4 and bary == 0.0
+
+
+def test_tree_does_not_depend_on_the_thread_count():
+    """The parallel builder (top of the tree split by all threads in fixed chunks, subtrees as tasks, node ids in per-thread blocks) must
+    emit the same BVH8 whatever the number of threads: 150 k boxes (above the 131 072 threshold of Builder::split_top) built with 1, 3 and
+    8 OpenMP threads in fresh processes."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    prog = (
+        "import sys, hashlib, ctypes as C, numpy as np\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "from merian_b200 import abi\n"
+        "from merian_b200._lib import lib\n"
+        "rng = np.random.default_rng(7)\n"
+        "c = rng.random((150000, 3)) * [200, 20, 100]\n"
+        "r = (rng.random((150000, 1)) ** 4) * 3 + 1e-3\n"
+        "boxes = np.ascontiguousarray(np.concatenate([c - r, c + r], -1), np.float32)\n"
+        "info = abi.BvhInfo(); order = np.zeros(len(boxes), np.uint32)\n"
+        "assert lib().mpt_bvh8_build_info(C.c_void_p(boxes.ctypes.data), len(boxes), C.byref(info), C.c_void_p(order.ctypes.data)) == abi.MPT_OK\n"
+        "print(info.node_count, info.max_depth, hashlib.sha256(order.tobytes()).hexdigest())\n")
+    outs = []
+    for threads in ("1", "3", "8"):
+        env = dict(os.environ, OMP_NUM_THREADS=threads)
+        outs.append(subprocess.check_output([sys.executable, "-c", prog], env=env, text=True).strip())
+    assert outs[0] == outs[1] == outs[2], outs
