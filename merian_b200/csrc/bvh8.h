@@ -46,6 +46,9 @@ struct Bvh8 {
 constexpr uint32_t kMaxBvh8Depth = 14;
 
 // max_leaf: primitives per leaf child (<= 3). Deterministic (no threads inside).
-void build_bvh8(const Box* boxes, uint32_t n, Bvh8& out, int max_leaf = 3);
+// c_prim: cost of testing one primitive relative to one node test in the dynamic program of the wide collapse; < 0 = the default for
+// triangles (0.5, MPT_BVH_CPRIM). The TLAS passes a larger value: "testing" an instance means transforming the ray, a ray setup and at
+// least one node test of its BLAS.
+void build_bvh8(const Box* boxes, uint32_t n, Bvh8& out, int max_leaf = 3, float c_prim = -1.f);
 
 } // namespace mpt

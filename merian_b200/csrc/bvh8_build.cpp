@@ -589,7 +589,7 @@ struct Wide {
 
 } // namespace
 
-static void build_bvh8_once(const Box* boxes, uint32_t n, Bvh8& out, uint32_t sah_depth_limit) {
+static void build_bvh8_once(const Box* boxes, uint32_t n, Bvh8& out, uint32_t sah_depth_limit, float c_prim) {
     out.nodes.clear();
     out.prim_order.clear();
     out.depth = 1;
@@ -605,7 +605,7 @@ static void build_bvh8_once(const Box* boxes, uint32_t n, Bvh8& out, uint32_t sa
     b2.boxes = boxes;
     b2.sah_depth_limit = std::min(sah_depth_limit, kMaxRecursion);
     b2.balance = env_float("MPT_BVH_BALANCE", 0.f);
-    b2.c_prim = env_float("MPT_BVH_CPRIM", 0.5f); // measured optimum on C3 (0.15 ... 2.0 within 0.6 %)
+    b2.c_prim = c_prim >= 0.f ? c_prim : env_float("MPT_BVH_CPRIM", 0.5f); // triangles: measured optimum on C3 (0.15 ... 2.0 within 0.6 %)
     const bool timing = std::getenv("MPT_BUILD_TIMING") != nullptr;
     auto now = [] { return std::chrono::steady_clock::now(); };
     auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
@@ -753,13 +753,13 @@ static void build_bvh8_once(const Box* boxes, uint32_t n, Bvh8& out, uint32_t sa
 // real scenes are 8-10 wide levels deep (1 M-triangle terrain: 8); a degenerate input (primitives of geometrically growing size on a
 // line) makes SAH peel one primitive per level. When that happens the tree is rebuilt with SAH only for the top levels and object-median
 // splits below, which bounds the depth by about log8(n) + the SAH levels.
-void build_bvh8(const Box* boxes, uint32_t n, Bvh8& out, int /*max_leaf*/) {
+void build_bvh8(const Box* boxes, uint32_t n, Bvh8& out, int /*max_leaf*/, float c_prim) {
     if (std::getenv("MPT_BVH_SAH_DEPTH")) { // tuning sessions: SAH for the top levels only, object-median splits below
-        build_bvh8_once(boxes, n, out, uint32_t(env_float("MPT_BVH_SAH_DEPTH", 64.f)));
+        build_bvh8_once(boxes, n, out, uint32_t(env_float("MPT_BVH_SAH_DEPTH", 64.f)), c_prim);
         if (out.depth <= kMaxBvh8Depth) return;
     }
     for (uint32_t limit : {0xFFFFFFFFu, 16u, 8u, 0u}) {
-        build_bvh8_once(boxes, n, out, limit);
+        build_bvh8_once(boxes, n, out, limit, c_prim);
         if (out.depth <= kMaxBvh8Depth) return;
     }
 }

@@ -36,6 +36,11 @@ inline void fetch_indices(const mpt_mesh_desc& m, uint32_t p, uint32_t ix[3]) {
 
 } // namespace
 
+// Cost of one instance in a TLAS leaf slot relative to a node test, for the collapse's dynamic program. With the triangles' 0.5 a quarter of
+// C5's instances shared a slot with a neighbour, and a ray that hits the slot's box enters both: 1 / 2 / 4 -> +2.9 % on C5 (1929 -> 1984
+// Msamples/s, profiles/r02z_c5_tlas.jsonl), every instance in a slot of its own. MPT_BVH_CPRIM_TLAS overrides (tuning sessions).
+constexpr float kTlasPrimCost = 2.0f;
+
 mpt_status build_host_accel(const mpt_scene_desc* d, HostAccel& out, uint32_t stack_entries, std::string& err) {
     if (d->instance_count == 0 || d->blas_count == 0) { err = "scene has no instances"; return MPT_ERR_INVALID_ARGUMENT; }
     if (d->instance_count > 0xFFFFu) { err = "more than 65535 TLAS instances (PackedHitInfo.instance_index is 16 bit, gbuffer.slang:44)"; return MPT_ERR_LIMIT; }
@@ -184,7 +189,11 @@ mpt_status build_host_accel(const mpt_scene_desc* d, HostAccel& out, uint32_t st
     out.root = blas_root[d->instances[0].blas];
     if (!identity_single) {
         Bvh8 tl;
-        build_bvh8(ibox.data(), d->instance_count, tl);
+        // an instance in a leaf slot is entered whenever the slot's box is hit (ray transform + ray setup + at least one BLAS node test,
+        // ~450 instructions in k_extend_pooled against ~150 for a triangle): the collapse prices it accordingly, which keeps instances in
+        // slots of their own instead of three to a slot
+        const char* ev = std::getenv("MPT_BVH_CPRIM_TLAS");
+        build_bvh8(ibox.data(), d->instance_count, tl, 3, ev ? float(std::atof(ev)) : kTlasPrimCost);
         const uint32_t node_off = uint32_t(out.nodes.size());
         out.root = node_off;
         for (Bvh8Node nd : tl.nodes) {

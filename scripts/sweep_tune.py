@@ -15,7 +15,7 @@ from merian_b200 import abi  # noqa: E402
 from merian_b200.context import Context  # noqa: E402
 from merian_b200.scene import upload_scene  # noqa: E402
 
-KNOBS = ("MPT_EXTEND_LEGACY", "MPT_POOLED_REFILL_THRESHOLD", "MPT_POOLED_DRAIN_FIRST", "MPT_L2_PERSIST", "MPT_L2_PERSIST_MB", "MPT_TRI_VOTE", "MPT_PREFETCH", "MPT_REFILL_THRESHOLD", "MPT_POOL_MSLOTS", "MPT_EXTEND_BLOCKS_PER_SM", "MPT_BVH_MAX_LEAF", "MPT_BVH_TRAV_COST", "MPT_BVH_COLLAPSE", "MPT_BVH_CPRIM", "MPT_SHADE_BLOCKS_PER_SM")
+KNOBS = ("MPT_EXTEND_LEGACY", "MPT_POOLED_REFILL_THRESHOLD", "MPT_POOLED_DRAIN_FIRST", "MPT_L2_PERSIST", "MPT_L2_PERSIST_MB", "MPT_TRI_VOTE", "MPT_PREFETCH", "MPT_REFILL_THRESHOLD", "MPT_POOL_MSLOTS", "MPT_EXTEND_BLOCKS_PER_SM", "MPT_BVH_MAX_LEAF", "MPT_BVH_TRAV_COST", "MPT_BVH_COLLAPSE", "MPT_BVH_CPRIM", "MPT_BVH_CPRIM_TLAS", "MPT_SHADE_BLOCKS_PER_SM")
 
 
 def main():
