@@ -35,6 +35,9 @@ struct alignas(16) PoolEntry {
 // kernel's instructions, at 8.6 of 32 lanes) — and the shear constants of the watertight test are read from the ray record when a
 // triangle is tested (single-level scenes) instead of occupying registers through the node tests.
 // SS = node-stack entries kept in shared memory (per lane, stride STRIDE uint2); 0 = all in local memory (measured best, see k_extend_pooled).
+#ifndef MPT_TLAS_BOX_RECHECK
+#define MPT_TLAS_BOX_RECHECK 1 // instance_box_missed() before an instance is entered (bvh8_traverse.cuh)
+#endif
 #ifndef MPT_TLAS_GATE
 #define MPT_TLAS_GATE 0 // see step(): measured, no gain with the trigger form of the pool
 #endif
@@ -193,6 +196,9 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
                     }
                 } else {
                     // TLAS leaf: enter the instance
+#if MPT_TLAS_BOX_RECHECK
+                    if (instance_box_missed(__ldg(A.tlas_boxes + 2 * rec), __ldg(A.tlas_boxes + 2 * rec + 1), o, idir, best_t)) continue; // (o, idir): the world-space ray at the TLAS level
+#endif
                     const uint32_t inst = __ldg(A.tlas_prims + rec);
                     const InstanceRec* ip = A.instances + inst;
                     const uint4 meta = __ldg(reinterpret_cast<const uint4*>(ip) + 3);

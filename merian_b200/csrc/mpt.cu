@@ -1267,7 +1267,7 @@ struct mpt_context {
     DevBuf accel_mem; // BVH8 nodes, then (256-byte aligned) the triangle records
     size_t accel_bytes = 0;
     size_t l2_window_bytes = 0; // > 0: persisting-L2 access-policy window over accel_mem while a frame's kernels run (MPT_L2_PERSIST)
-    DevBuf tri_attr, geometries, prim_to_tri, instances, tlas_prims, xform, xform_it, xform_prev;
+    DevBuf tri_attr, geometries, prim_to_tri, instances, tlas_prims, tlas_boxes, xform, xform_it, xform_prev;
     uint32_t instance_count = 0; // of the uploaded scene
     DevBuf materials, material_types, texture_table, env_pixels, env_alias, env_pmf;
     bool env_sampling_ready = false;
@@ -1698,6 +1698,7 @@ MPT_API mpt_status mpt_scene_upload(mpt_context* ctx, const mpt_scene_desc* d) t
     CU(ctx->prim_to_tri.upload(prim_to_tri.data(), prim_to_tri.size() * 4));
     CU(ctx->instances.upload(inst.data(), inst.size() * sizeof(HostInstanceRec)));
     CU(ctx->tlas_prims.upload(tlas_prims.data(), tlas_prims.size() * 4));
+    CU(ctx->tlas_boxes.upload(H.tlas_boxes.data(), H.tlas_boxes.size() * sizeof(HostVec4)));
     CU(ctx->geometries.upload(geoms.data(), geoms.size() * sizeof(HostUVec4)));
     std::vector<float> ident(size_t(d->instance_count) * 16, 0.f);
     for (uint32_t i = 0; i < d->instance_count; i++) ident[i * 16] = ident[i * 16 + 5] = ident[i * 16 + 10] = ident[i * 16 + 15] = 1.f;
@@ -1709,6 +1710,7 @@ MPT_API mpt_status mpt_scene_upload(mpt_context* ctx, const mpt_scene_desc* d) t
     v.accel.tris = reinterpret_cast<const float4*>(ctx->accel_mem.as<char>() + node_bytes);
     v.accel.instances = ctx->instances.as<InstanceRec>();
     v.accel.tlas_prims = ctx->tlas_prims.as<uint32_t>();
+    v.accel.tlas_boxes = ctx->tlas_boxes.as<float4>();
     v.accel.root = root;
     v.accel.two_level = identity_single ? 0u : 1u;
     v.accel.prmt_bias = 0x47000000u;

@@ -201,6 +201,14 @@ mpt_status build_host_accel(const mpt_scene_desc* d, HostAccel& out, uint32_t st
             out.nodes.push_back(nd); // prim_base indexes tlas_prims directly
         }
         out.tlas_prims = tl.prim_order;
+        // the exact world box of every TLAS leaf record's instance, in record order: a leaf slot's quantised box and the hit distance at
+        // the time of the node test only say "maybe" (instance_box_missed, bvh8_traverse.cuh)
+        out.tlas_boxes.resize(tl.prim_order.size() * 2);
+        for (size_t k = 0; k < tl.prim_order.size(); k++) {
+            const Box& b = ibox[tl.prim_order[k]];
+            out.tlas_boxes[2 * k] = HostVec4{b.lo[0], b.lo[1], b.lo[2], 0.f};
+            out.tlas_boxes[2 * k + 1] = HostVec4{b.hi[0], b.hi[1], b.hi[2], 0.f};
+        }
         out.tlas_depth = tl.depth;
     }
     out.two_level = identity_single ? 0u : 1u;

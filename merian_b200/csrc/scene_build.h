@@ -47,6 +47,7 @@ struct HostAccel {
     RawVector<uint32_t> prim_to_tri;
     std::vector<HostInstanceRec> instances;
     std::vector<uint32_t> tlas_prims;
+    std::vector<HostVec4> tlas_boxes; // 2 per TLAS primitive record: lo, hi of the instance's world box (unquantised), two-level scenes only
     std::vector<HostUVec4> geoms;
     uint32_t root = 0;
     uint32_t two_level = 0;
