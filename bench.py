@@ -254,8 +254,10 @@ def run_ours(args):
     cam = desc.camera.to_abi(0)
     tex1 = ctx.primary_visibility_device(cam, W, H)  # the GBuffer node's product (gbuffer_rt.slang), resident in HBM
     # two frames in flight: frame i's partial sums are being reduced on the library's side stream while frame i + 1 renders
-    sums = [torch.empty((H, W, 4), dtype=torch.float32, device=dev) for _ in range(2)]
-    outs = [torch.empty((H, W, 4), dtype=torch.float32, device=dev) for _ in range(2)] if (world > 1 and rank == 0) else [None, None]
+    NS = 4  # frame slots (sum buffer + reduce slot of the library, mpt_reduce_begin takes up to 4): the device-timed loop never blocks the
+    #         host; the end-to-end loop blocks on the frame that used the slot NS frames ago, i.e. NS - 1 frames stay queued on the GPU
+    sums = [torch.empty((H, W, 4), dtype=torch.float32, device=dev) for _ in range(NS)]
+    outs = [torch.empty((H, W, 4), dtype=torch.float32, device=dev) for _ in range(NS)] if (world > 1 and rank == 0) else [None] * NS
     comm = None
     if world > 1:
         def exchange(raw):  # rank 0's NCCL unique id -> every rank (out of band: torch.distributed is only plumbing here)
@@ -265,15 +267,15 @@ def run_ours(args):
             dist.broadcast(t, src=0)
             return bytes(t.cpu().numpy().tobytes())
         comm = sharding.ShardComm(local_rank, rank, world, exchange)  # mpt_comm_create: NCCL inside libmpt.so
-    pending = [False, False]  # a reduce is in flight in slot b (reading sums[b], writing outs[b] / the host buffer)
+    pending = [False] * NS  # a reduce is in flight in slot b (reading sums[b], writing outs[b] / the host buffer)
 
     def step(i, h_out=None, h_tex1=None, d_tex1=tex1):
-        """One frame. Multi-GPU: render this rank's samples into sums[i % 2], then mpt_reduce_begin(slot i % 2): reduce -> normalise ->
+        """One frame. Multi-GPU: render this rank's samples into sums[i % NS], then mpt_reduce_begin(slot i % NS): reduce -> normalise ->
         optional copy to the host buffer, on the library's side stream, overlapping the next frame's render. The host never blocks on the
         previous frame (that would leave a single frame queued on the GPU, and every host hiccup would stall it): before a sum buffer is
         rendered into again, the render STREAM waits for the reduce that read it (mpt_reduce_end), or — when the frames land in host
-        buffers, which the host reuses — the host waits for that two-frames-old reduce (mpt_reduce_wait)."""
-        b = i % 2
+        buffers, which the host reuses — the host waits for the reduce that used the slot NS frames ago (mpt_reduce_wait)."""
+        b = i % NS
         if world > 1 and pending[b]:
             if h_out is not None:
                 comm.reduce_wait(slot=b)
@@ -291,7 +293,7 @@ def run_ours(args):
         pending[b] = True
 
     def drain(on_stream=False):
-        for b in range(2):
+        for b in range(NS):
             if world > 1 and pending[b]:
                 if on_stream:
                     comm.reduce_end(slot=b)
@@ -335,7 +337,7 @@ def run_ours(args):
     ctx.set_profiling(2)  # CUDA-event timing of every extend / shade launch; on during the warm-up so that libmpt's event pool is
     #                       fully created before the timed region (no cudaEventCreate inside it)
     for i in range(max(6, args.steps + 1)):  # clocks and caches up before the W warm-up steps the caller asked for
-        ctx.render_device(cam, params(20_000 + i), tex1=tex1, out=sums[i % 2])
+        ctx.render_device(cam, params(20_000 + i), tex1=tex1, out=sums[i % NS])
     ctx.reset_stats()
     for i in range(args.warmup):
         step(i)
@@ -384,7 +386,7 @@ def run_ours(args):
     gc.freeze()   # the host loop below is what a C++ graph runtime would run: keep CPython's cycle collector (a full pass over torch's
     gc.disable()  # module graph takes tens of ms) out of the timed region
     F = max(1, min(int(args.in_flight), 4))  # iterations in flight (mpt_render_host_begin: in_flight_index < 4; merian's ring size is a graph setting)
-    h_outs = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(max(F, 2))]
+    h_outs = [torch.empty((H, W, 4), dtype=torch.float32).pin_memory() for _ in range(max(F, NS))]
     e2e_steps = max(2, args.steps)
     e2e_two = None
 
@@ -415,13 +417,13 @@ def run_ours(args):
             e2e_two = npix * spp_total * e2e_steps / pipelined(2, args.warmup + 1000) / 1e6
         e2e_dt = pipelined(F, args.warmup)
     else:
-        d_tex1s = [torch.empty_like(tex1) for _ in range(2)]
-        for i in range(2):
-            step(i, h_out=h_outs[i % 2], h_tex1=h_tex1, d_tex1=d_tex1s[i % 2])
+        d_tex1s = [torch.empty_like(tex1) for _ in range(NS)]
+        for i in range(NS):
+            step(i, h_out=h_outs[i % NS], h_tex1=h_tex1, d_tex1=d_tex1s[i % NS])
         barrier()
         t0 = time.perf_counter()
         for i in range(e2e_steps):
-            step(args.warmup + i, h_out=h_outs[i % 2], h_tex1=h_tex1, d_tex1=d_tex1s[i % 2])
+            step(args.warmup + i, h_out=h_outs[i % NS], h_tex1=h_tex1, d_tex1=d_tex1s[i % NS])
         drain()  # rank 0: the last frame is in host memory; other ranks: their last contribution has been sent
         torch.cuda.synchronize()
         e2e_dt = time.perf_counter() - t0
@@ -490,7 +492,7 @@ def run_ours(args):
                          "shade_share_of_step": st.shade_ms * timed_share / ms if ms > 0 else None},
             "cpu_baseline": base,
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": npix * 16 * world, "d2h_bytes_per_step": npix * 16,
-                    "iterations_in_flight": (F if world == 1 else 2), "two_in_flight_value": e2e_two, "steps": e2e_steps, "synchronous_call_value": e2e_sync_value,
+                    "iterations_in_flight": (F if world == 1 else NS), "two_in_flight_value": e2e_two, "steps": e2e_steps, "synchronous_call_value": e2e_sync_value,
                     "includes_reduce": world > 1},
             "gpu_launches": int(rays[2].item()),
             "clocks": clocks,

@@ -187,12 +187,14 @@ MPT_API mpt_status mptt_build(const mpt_src_mesh* meshes, uint32_t mesh_count, c
     *out = nullptr;
     // ---- instances of every mesh: SmallSet<NodeID> = ascending, unique (small_set.hpp:13)
     std::vector<std::vector<uint32_t>> instances_of(mesh_count);
-    for (uint32_t nid = 0; nid < node_count; nid++)
+    for (uint32_t nid = 0; nid < node_count; nid++) {
+        if (nodes[nid].mesh_count && !nodes[nid].meshes) return tables_fail(MPT_ERR_INVALID_ARGUMENT, "mptt_build: node with a mesh count but no mesh list");
         for (uint32_t k = 0; k < nodes[nid].mesh_count; k++) {
             const uint32_t m = nodes[nid].meshes[k];
             if (m >= mesh_count) return tables_fail(MPT_ERR_INVALID_ARGUMENT, "mptt_build: node references a mesh out of range");
             if (instances_of[m].empty() || instances_of[m].back() != nid) instances_of[m].push_back(nid); // nid ascends
         }
+    }
     // ---- grouping, scene.cpp:1023-1105
     std::vector<Group> groups;
     std::map<uint32_t, uint32_t> groups_static;
