@@ -1289,6 +1289,10 @@ struct mpt_context {
     static constexpr uint32_t kMaxInFlight = 4;
     InFlight in_flight[kMaxInFlight];
     cudaStream_t compute = nullptr;
+    // pageable host -> CUDA array uploads go through two pinned chunks on their own stream (staged_upload_to_array)
+    cudaStream_t upload_stream = nullptr;
+    void* upload_pinned[2] = {nullptr, nullptr};
+    cudaEvent_t upload_done[2] = {nullptr, nullptr};
     // fetch cursors of the persistent mpt_trace / mpt_primary_visibility kernels: their own words (a ring of 64, one per launch), so
     // that a launch on a caller's stream never shares a cursor with a frame rendering on ctx->compute (whose passes clear `counters`)
     DevBuf cursors;
@@ -1660,6 +1664,11 @@ MPT_API void mpt_destroy(mpt_context* ctx) {
             if (e) cudaEventDestroy(e);
     }
     if (ctx->compute) cudaStreamDestroy(ctx->compute);
+    if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
+    for (int k = 0; k < 2; k++) {
+        if (ctx->upload_pinned[k]) cudaFreeHost(ctx->upload_pinned[k]);
+        if (ctx->upload_done[k]) cudaEventDestroy(ctx->upload_done[k]);
+    }
     for (auto* pool : {&ctx->ev_extend, &ctx->ev_shade})
         for (auto& p : *pool) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     delete ctx;
@@ -1791,6 +1800,38 @@ MPT_API mpt_status mpt_materials_set_hints(mpt_context* ctx, float alpha_test_th
 } // extern "C"
 namespace {
 // One material texture: CUDA array (or mipmapped array) + texture object. `pixels` is host memory unless `on_device`.
+// Rows of a pageable host image into a CUDA array through two pinned chunks: the CPU copies chunk k + 1 into pinned memory while the copy
+// engine moves chunk k. cudaMemcpy2DToArray from pageable memory ran at 1.6 GB/s (C4: 10.8 s for 256 textures of 4096^2 RGBA8).
+constexpr size_t kUploadChunkBytes = size_t(8) << 20;
+mpt_status staged_upload_to_array(mpt_context* ctx, cudaArray_t array, const void* pixels, size_t src_pitch, size_t row_bytes, size_t height) {
+    if (!ctx->upload_stream) {
+        CU(cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; k++) {
+            CU(cudaHostAlloc(&ctx->upload_pinned[k], kUploadChunkBytes, cudaHostAllocDefault));
+            CU(cudaEventCreateWithFlags(&ctx->upload_done[k], cudaEventDisableTiming));
+        }
+    }
+    const size_t rows_per_chunk = std::max<size_t>(1, kUploadChunkBytes / row_bytes);
+    static const bool direct = std::getenv("MPT_UPLOAD_DIRECT") != nullptr; // A/B knob: the driver's own pageable path
+    if (direct || row_bytes > kUploadChunkBytes) { // (a single row larger than a chunk is not worth a special path)
+        CU(cudaMemcpy2DToArray(array, 0, 0, pixels, src_pitch, row_bytes, height, cudaMemcpyHostToDevice));
+        return MPT_OK;
+    }
+    int k = 0;
+    for (size_t row = 0; row < height; row += rows_per_chunk, k ^= 1) {
+        const size_t rows = std::min(rows_per_chunk, height - row);
+        CU(cudaEventSynchronize(ctx->upload_done[k])); // the copy that last read this chunk (a fresh event counts as complete)
+        const char* src = static_cast<const char*>(pixels) + row * src_pitch;
+        char* dst = static_cast<char*>(ctx->upload_pinned[k]);
+        if (src_pitch == row_bytes) std::memcpy(dst, src, rows * row_bytes);
+        else for (size_t r = 0; r < rows; r++) std::memcpy(dst + r * row_bytes, src + r * src_pitch, row_bytes);
+        CU(cudaMemcpy2DToArrayAsync(array, 0, row, dst, row_bytes, row_bytes, rows, cudaMemcpyHostToDevice, ctx->upload_stream));
+        CU(cudaEventRecord(ctx->upload_done[k], ctx->upload_stream));
+    }
+    CU(cudaStreamSynchronize(ctx->upload_stream));
+    return MPT_OK;
+}
+
 mpt_status texture_upload_impl(mpt_context* ctx, uint32_t texture_id, uint32_t width, uint32_t height, uint32_t format, uint32_t wrap_u, uint32_t wrap_v,
                                uint32_t filter, uint32_t mipmap_mode, const void* pixels, bool on_device, size_t src_pitch, cudaStream_t st) {
     if (!ctx || !pixels || width == 0 || height == 0) return fail(ctx, MPT_ERR_INVALID_ARGUMENT, "bad texture");
@@ -1815,7 +1856,8 @@ mpt_status texture_upload_impl(mpt_context* ctx, uint32_t texture_id, uint32_t w
             CU(cudaMemcpy2DToArrayAsync(slot.array, 0, 0, pixels, src_pitch, pitch, height, cudaMemcpyDeviceToDevice, st));
             CU(cudaStreamSynchronize(st));
         } else {
-            CU(cudaMemcpy2DToArray(slot.array, 0, 0, pixels, src_pitch, pitch, height, cudaMemcpyHostToDevice));
+            const mpt_status us = staged_upload_to_array(ctx, slot.array, pixels, src_pitch, pitch, height);
+            if (us != MPT_OK) return us;
         }
         rd.resType = cudaResourceTypeArray;
         rd.res.array.array = slot.array;
@@ -1835,7 +1877,8 @@ mpt_status texture_upload_impl(mpt_context* ctx, uint32_t texture_id, uint32_t w
             cudaArray_t la = nullptr;
             CU(cudaGetMipmappedArrayLevel(&la, slot.mips, l));
             const size_t lp = size_t(levels[l].width) * (f32 ? 16 : 4);
-            CU(cudaMemcpy2DToArray(la, 0, 0, levels[l].bytes.data(), lp, lp, levels[l].height, cudaMemcpyHostToDevice));
+            const mpt_status us = staged_upload_to_array(ctx, la, levels[l].bytes.data(), lp, lp, levels[l].height);
+            if (us != MPT_OK) return us;
         }
         rd.resType = cudaResourceTypeMipmappedArray;
         rd.res.mipmap.mipmap = slot.mips;
