@@ -43,7 +43,9 @@ struct alignas(16) PoolEntry {
 #endif
 constexpr int kPrimStackSize = 24; // parked primitive groups: at most one per node test while another group is pending
 
-template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struct TraversalP {
+// TMIN_ZERO = true: continuation rays (tmin 0, tmax SCENE_RAY_TMAX). false: rays with their own interval (mpt_trace, primary visibility):
+// the record's b.w lane holds tmin and its d.w lane tmax instead of the origin triangle / the BSDF pdf.
+template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE, bool TMIN_ZERO = true> struct TraversalP {
     const AccelView& A;
     const AlphaTest& alpha_test;
     uint2* sst;            // shared-memory part of the node stack: entry i at sst[i * STRIDE]
@@ -54,6 +56,7 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
     uint32_t perm;         // make_perm(octant) of the current-space ray
     Shear shear;           // TWO_LEVEL only (registers); single-level scenes read the record's shear when a triangle is tested
     float best_t;
+    float tmin;            // !TMIN_ZERO only
     uint32_t ray_mask;
     int sp, psp, pbase;    // node stack pointer; primitive stack pointer and its floor inside the current instance
     uint32_t ptop_h;       // the node-stack height the TOP parked group was uncovered at (each parked entry's w lane keeps the value for
@@ -104,9 +107,14 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
     MPT_DEV void start(const PoolEntry* e, uint32_t mask, uint32_t scene_flags, bool use_skip) {
         ent = e;
         const uint32_t leaves = load_world_setup();
-        best_t = 1e7f; // SCENE_RAY_TMAX, hit.slang:8 (continuation rays: tmin 0)
+        if (TMIN_ZERO) {
+            best_t = 1e7f; // SCENE_RAY_TMAX, hit.slang:8 (continuation rays: tmin 0)
+        } else {
+            tmin = __uint_as_float(leaves);
+            best_t = e->d.w;
+        }
         ray_mask = mask;
-        hit.tri = (TWO_LEVEL || !use_skip) ? kMiss : leaves;
+        hit.tri = (TWO_LEVEL || !use_skip || !TMIN_ZERO) ? kMiss : leaves;
         hit.instance = kMiss;
         hit.u = hit.v = 0.f;
         sp = 0;
@@ -139,7 +147,7 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
             if (COUNT) n_nodes++;
             uint32_t leaf;
             uint2 pl; // first primitive record, leaf_bits
-            bvh8_node_test<true>(A, ni, o, idir, perm, 0.f, best_t, G, leaf, &pl);
+            bvh8_node_test<TMIN_ZERO>(A, ni, o, idir, perm, TMIN_ZERO ? 0.f : tmin, best_t, G, leaf, &pl);
             if (leaf) {
                 if (Gt.y) { // one group is already pending: park the new one
                     pst[psp++] = make_uint4(pl.x, leaf | (uint32_t(sp) << 24), pl.y, ptop_h);
@@ -184,7 +192,7 @@ template <bool COUNT, bool TWO_LEVEL, class AlphaTest, int SS, int STRIDE> struc
                             s.kx = int(kk & 3u); s.ky = int((kk >> 2) & 3u); s.kz = int((kk >> 4) & 3u);
                         }
                         float t, u, v;
-                        if (intersect_triangle(s, o, xyz(a), xyz(b), xyz(c), cull, 0.f, best_t, t, u, v)) {
+                        if (intersect_triangle(s, o, xyz(a), xyz(b), xyz(c), cull, TMIN_ZERO ? 0.f : tmin, best_t, t, u, v)) {
                             if (force_opaque || !(__float_as_uint(c.w) & kTriNonOpaque) || !alpha_test(rec, cur_instance, u, v)) {
                                 best_t = t;
                                 hit.tri = rec;

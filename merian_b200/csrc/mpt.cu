@@ -916,6 +916,201 @@ __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_primary_per
     }
 }
 
+// --------------------------------------------------------------------------------------- closest-hit queries, pooled form
+// mpt_trace (PRIMARY = false: the caller's ray array, results at the ray's own index) and mpt_primary_visibility (PRIMARY = true: camera rays
+// in 8x4-pixel tile order, PackedHitInfo per pixel) through the per-warp ray pool of k_extend_pooled: converged retire / refill / ray setup
+// at full width, a finishing lane swaps its record for a READY one, re-convergence on 32 DONE records. The records carry the ray's own
+// interval (TraversalP<..., TMIN_ZERO = false>): b.w = tmin, d.w = tmax, a.w = the ray index / pixel index.
+template <bool COUNT, bool TWO_LEVEL, bool PRIMARY>
+__global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS)
+k_query_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ rays, CameraParams cam, uint32_t w, uint32_t h, uint32_t n, uint32_t mask,
+               void* __restrict__ out, Counters* ctr, uint32_t* fetch) {
+    constexpr int NE = 32 + MPT_POOL_READY, kWarps = kThreads / 32, TRIG = MPT_POOL_TRIGGER > 0 ? MPT_POOL_TRIGGER : MPT_POOL_READY;
+    using Trav = TraversalP<COUNT, TWO_LEVEL, MaterialAlphaTest, 0, kThreads, false>;
+    using Entry = PoolEntry;
+    struct Pool {
+        Entry e[NE];
+        uint8_t ready[NE], done[NE];
+        int ready_head, ready_n, done_n, pad;
+    };
+    __shared__ Pool s_pool[kWarps];
+    __shared__ uint2 s_stack[1];
+    const uint32_t lane = lane_id();
+    const uint32_t lt = (1u << lane) - 1u;
+    Pool& P = s_pool[threadIdx.x >> 5];
+    uint2 lstack[kStackSize];
+    uint4 pstack[kPrimStackSize];
+    MaterialAlphaTest at{&S};
+    Trav T(S.accel, at, s_stack, lstack, pstack);
+    const uint32_t scene_flags = TWO_LEVEL ? 0u : S.accel.instances[0].mask_flags;
+    const bool scene_masked = !TWO_LEVEL && ((scene_flags & 0xFFu) & mask) == 0u; // the only instance is masked out: every ray misses
+    constexpr uint32_t kNoRay = 0xFFFFFFFFu;
+    const uint32_t tiles_x = (w + 7) / 8;
+
+    // the result of one ray: hits6 of mpt_trace (include/mpt.h) or the PackedHitInfo of gbuffer.slang:40-61
+    auto store = [&](uint32_t tag, uint32_t tri, uint32_t instance, float u, float v) {
+        uint32_t custom = kMiss, prim = kMiss, geom = kMiss;
+        if (tri != kMiss) {
+            const float4* tp = S.accel.tris + size_t(tri) * 3;
+            custom = S.accel.instances[instance].custom_index;
+            prim = __float_as_uint(__ldg(tp).w);
+            geom = __float_as_uint(__ldg(tp + 1).w);
+        }
+        if (PRIMARY) {
+            PackedHitInfo p;
+            p.instance_id = custom; p.primitive_id = prim;
+            p.geometry_index = uint16_t(tri != kMiss ? geom : 0xFFFFu);
+            p.instance_index = uint16_t(tri != kMiss ? instance : 0xFFFFu);
+            p.bary = tri != kMiss ? __floats2half2_rn(u, v) : __floats2half2_rn(0.f, 0.f);
+            static_cast<PackedHitInfo*>(out)[tag] = p;
+        } else {
+            uint32_t* o = static_cast<uint32_t*>(out) + 6 * size_t(tag);
+            o[0] = custom; o[1] = tri != kMiss ? instance : kMiss; o[2] = prim; o[3] = geom;
+            o[4] = tri != kMiss ? __float_as_uint(u) : 0u;
+            o[5] = tri != kMiss ? __float_as_uint(v) : 0u;
+        }
+    };
+
+    for (int i = int(lane); i < NE; i += 32) {
+        P.e[i].a.w = __uint_as_float(kNoRay);
+        P.done[i] = uint8_t(i);
+    }
+    if (lane == 0) { P.done_n = NE; P.ready_head = 0; P.ready_n = 0; }
+    __syncwarp();
+
+    bool active = false, exhausted = false;
+    uint32_t my = 0;
+    int ready_n = 0;
+    while (true) {
+        // ======================================================= converged: retire DONE records, refill them, hand READY records to idle lanes
+        const int nd_all = P.done_n;
+        const int nd = (!exhausted && nd_all > 32) ? (nd_all & ~31) : nd_all; // whole rounds of 32 (the rest stays DONE) unless the rays ran out
+        uint32_t base = 0;
+        if (!exhausted && nd > 0) {
+            if (lane == 0) base = atomicAdd(fetch, uint32_t(nd));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        }
+        int nready = 0;
+        {   // READY records nobody has taken yet move to the front of the list
+            const int rh = min(P.ready_head, ready_n), left = ready_n - rh;
+            const uint8_t v = int(lane) < left ? P.ready[rh + int(lane)] : uint8_t(0);
+            __syncwarp();
+            if (int(lane) < left) P.ready[lane] = v;
+            nready = left;
+        }
+        int nrq = 0; // records whose ray needed no traversal (padding pixel of a partial tile, masked-out scene): straight back onto the DONE list
+#pragma unroll 1
+        for (int r = 0; r * 32 < nd; r++) {
+            const int i = r * 32 + int(lane);
+            const bool have = i < nd;
+            const uint32_t e = have ? uint32_t(P.done[i]) : 0u;
+            Entry& E = P.e[e];
+            const uint32_t tag = have ? __float_as_uint(E.a.w) : kNoRay;
+            if (tag != kNoRay) {
+                const float4 hb = E.b;
+                store(tag, __float_as_uint(hb.x), __float_as_uint(hb.y), hb.z, hb.w);
+            }
+            bool filled = false, consumed = false;
+            if (have) {
+                const uint32_t jn = base + uint32_t(i);
+                if (!exhausted && jn < n) {
+                    consumed = true;
+                    float4 ro, rd;
+                    uint32_t rtag = jn;
+                    bool valid = true;
+                    if (PRIMARY) {
+                        const uint32_t tile = jn >> 5, in = jn & 31u;
+                        const uint32_t x = (tile % tiles_x) * 8 + (in & 7u), y = (tile / tiles_x) * 4 + (in >> 3);
+                        valid = x < w && y < h; // else: padding of a partial tile
+                        rtag = y * w + x;
+                        f3 o = mk3(0.f), d = mk3(0.f, 0.f, 1.f);
+                        float tmin = 0.f, tmax = 0.f;
+                        if (valid) camera_ray(cam, x, y, w, h, o, d, tmin, tmax);
+                        ro = make_float4(o.x, o.y, o.z, tmin);
+                        rd = make_float4(d.x, d.y, d.z, tmax);
+                    } else {
+                        ro = __ldg(rays + 2 * size_t(jn));
+                        rd = __ldg(rays + 2 * size_t(jn) + 1);
+                    }
+                    if (valid && scene_masked) {
+                        store(rtag, kMiss, kMiss, 0.f, 0.f);
+                    } else if (valid) {
+                        RaySetup R;
+                        setup_ray(R, xyz(ro), xyz(rd));
+                        const uint32_t oct = 7u - (R.perm >> 24);
+                        E.a = make_float4(ro.x, ro.y, ro.z, __uint_as_float(rtag));
+                        E.b = make_float4(R.idir.x, R.idir.y, R.idir.z, ro.w); // tmin
+                        E.c = make_float4(R.shear.Sx, R.shear.Sy, R.shear.Sz,
+                                          __uint_as_float(uint32_t(R.shear.kx) | (uint32_t(R.shear.ky) << 2) | (uint32_t(R.shear.kz) << 4) | (oct << 8)));
+                        E.d = rd;                                               // direction | tmax
+                        filled = true;
+                    }
+                }
+                if (!filled) E.a.w = __uint_as_float(kNoRay);
+            }
+            const uint32_t fm = __ballot_sync(0xFFFFFFFFu, filled);
+            if (filled) P.ready[nready + __popc(fm & lt)] = uint8_t(e);
+            nready += __popc(fm);
+            // a record that consumed a ray without being filled goes round again (positions below the ones this and later rounds read)
+            const bool rq = consumed && !filled;
+            const uint32_t qm = __ballot_sync(0xFFFFFFFFu, rq);
+            if (rq) P.done[nrq + __popc(qm & lt)] = uint8_t(e);
+            nrq += __popc(qm);
+        }
+        if (!exhausted && nd > 0 && base + uint32_t(nd) >= n) exhausted = true;
+        __syncwarp();
+        const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
+        const int k = __popc(idle & lt);
+        if (!active && k < nready) {
+            my = P.ready[k];
+            T.start(&P.e[my], mask, scene_flags, false);
+            active = true;
+        }
+        const int rem = nd_all - nd; // < 32: DONE records beyond the whole rounds, kept for the next phase behind the re-queued ones
+        {
+            const uint8_t v = int(lane) < rem ? P.done[nd + int(lane)] : uint8_t(0);
+            __syncwarp();
+            if (int(lane) < rem) P.done[nrq + int(lane)] = v;
+        }
+        if (lane == 0) {
+            P.done_n = nrq + rem;
+            P.ready_n = nready;
+            P.ready_head = min(__popc(idle), nready);
+        }
+        ready_n = nready;
+        __syncwarp();
+        if (!__any_sync(0xFFFFFFFFu, active)) {
+            if (exhausted && nrq + rem == 0) break; // the rays have run out and every record is retired
+            continue;
+        }
+        // ======================================================= divergent: traverse; a finished lane swaps its record for a READY one
+        uint32_t tick = 0u;
+        while (active) {
+            if (T.step(TWO_LEVEL ? tick++ : 0u)) {
+                Entry& E = P.e[my];
+                const bool f = T.found();
+                E.b = make_float4(__uint_as_float(f ? T.hit.tri : kMiss), __uint_as_float(T.hit.instance), T.hit.u, T.hit.v);
+                P.done[atomicAdd(&P.done_n, 1)] = uint8_t(my);
+                const int kk = atomicAdd(&P.ready_head, 1);
+                if (kk < ready_n) {
+                    my = P.ready[kk];
+                    T.start(&P.e[my], mask, scene_flags, false);
+                } else {
+                    active = false;
+                    break;
+                }
+            }
+            if (!exhausted && *(volatile int*)&P.done_n >= TRIG) break;
+        }
+        __syncwarp();
+    }
+    if (COUNT) {
+        atomicAdd(&ctr->nodes_visited, (unsigned long long)T.n_nodes);
+        atomicAdd(&ctr->tris_tested, (unsigned long long)T.n_tris);
+    }
+}
+
+
 // --------------------------------------------------------------------------------------- wavefront: shade after extend
 template <uint32_t FEAT, bool NEE>
 __global__ void __launch_bounds__(kThreads, FEAT == 0u ? MPT_SHADE_MIN_BLOCKS : 1) k_shade_bounce(const __grid_constant__ SceneView S, RenderConst rc, PathBuffers pb, uint32_t bounce, Counters* ctr) {
@@ -1269,6 +1464,9 @@ struct mpt_context {
     size_t l2_window_bytes = 0; // > 0: persisting-L2 access-policy window over accel_mem while a frame's kernels run (MPT_L2_PERSIST)
     DevBuf tri_attr, geometries, prim_to_tri, instances, tlas_prims, tlas_boxes, xform, xform_it, xform_prev;
     uint32_t instance_count = 0; // of the uploaded scene
+    uint32_t single_instance_mask = 0xFFu; // single-level scenes: the 8-bit mask of the one instance (a masked-out scene takes the legacy extend kernel)
+    uint32_t query_blocks_per_sm = 0;      // resident blocks of k_query_pooled (0 = not asked yet)
+    bool query_pooled = true;              // MPT_QUERY_LEGACY=1: the per-lane-fetch forms of mpt_trace / mpt_primary_visibility (A/B runs)
     DevBuf materials, material_types, texture_table, env_pixels, env_alias, env_pmf;
     bool env_sampling_ready = false;
     std::vector<TextureSlot> textures;
@@ -1406,6 +1604,15 @@ mpt_status ensure_pool(mpt_context* ctx, size_t slots, bool need_medium, bool ne
         CU(cudaMemset(ctx->counters.p, 0, sizeof(Counters)));
     }
     return MPT_OK;
+}
+
+uint32_t query_blocks_per_sm(mpt_context* ctx) {
+    if (!ctx->query_blocks_per_sm) {
+        int occ = 0;
+        ctx->query_blocks_per_sm = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_query_pooled<false, false, false>, kThreads, 0) == cudaSuccess && occ > 0)
+                                       ? uint32_t(occ) : 7u;
+    }
+    return ctx->query_blocks_per_sm;
 }
 
 mpt_status next_cursor(mpt_context* ctx, cudaStream_t st, uint32_t** out) {
@@ -1552,11 +1759,14 @@ mpt_status run_passes(mpt_context* ctx, const CameraParams& cam, const mpt_rende
                 constexpr bool MED = (FEAT & F_TRANSMISSION) != 0;
                 const bool tl = ctx->view.accel.two_level != 0;
                 const bool plain = !count && !MED && !tl && !NEE;
-                const uint32_t grid = uint32_t(ctx->sm_count) * (ctx->extend_pooled ? (plain ? ctx->pooled_plain_blocks_per_sm : ctx->pooled_blocks_per_sm)
+                const uint32_t grid = uint32_t(ctx->sm_count) * ((ctx->extend_pooled && (tl || (ctx->single_instance_mask & P.instance_mask & 0xFFu) != 0u)) ? (plain ? ctx->pooled_plain_blocks_per_sm : ctx->pooled_blocks_per_sm)
                                                                                      : (plain ? ctx->extend_plain_blocks_per_sm : ctx->extend_blocks_per_sm));
+                // (a single-level scene whose only instance the ray mask excludes: the pooled kernel's records would drop out of circulation
+                // after the first rays of every warp — every ray is a miss that needs no record — so the per-lane-fetch kernel shades them)
+                const bool use_pooled = ctx->extend_pooled && (tl || (ctx->single_instance_mask & P.instance_mask & 0xFFu) != 0u);
 #define MPT_LAUNCH_EXTEND(C, TL)                                                                                                                          \
     do {                                                                                                                                                \
-        if (ctx->extend_pooled) k_extend_pooled<C, MED, TL, NEE><<<grid, kThreads, 0, st>>>(ctx->view, pb.q_o[in], pb.q_d[in], pb, uint32_t(b), P.instance_mask, ctx->tune_pooled, ctr); \
+        if (use_pooled) k_extend_pooled<C, MED, TL, NEE><<<grid, kThreads, 0, st>>>(ctx->view, pb.q_o[in], pb.q_d[in], pb, uint32_t(b), P.instance_mask, ctx->tune_pooled, ctr); \
         else k_extend<C, MED, TL, NEE><<<grid, kThreads, 0, st>>>(ctx->view, pb.q_o[in], pb.q_d[in], pb, uint32_t(b), P.instance_mask, ctx->tune, ctr);              \
     } while (0)
                 if (count) { if (tl) MPT_LAUNCH_EXTEND(true, true); else MPT_LAUNCH_EXTEND(true, false); }
@@ -1620,6 +1830,7 @@ MPT_API mpt_status mpt_create(int device, mpt_context** out_ctx) try {
     auto env_u32 = [](const char* name, uint32_t def) { const char* v = getenv(name); return v ? uint32_t(strtoul(v, nullptr, 10)) : def; };
     ctx->tune.refill = env_u32("MPT_REFILL_THRESHOLD", ctx->tune.refill);
     ctx->tune_pooled.refill = env_u32("MPT_POOLED_REFILL_THRESHOLD", ctx->tune_pooled.refill);
+    ctx->query_pooled = !getenv("MPT_QUERY_LEGACY");
     ctx->extend_pooled = env_u32("MPT_EXTEND_LEGACY", 0u) == 0u;
     if (env_u32("MPT_L2_PERSIST", 0u)) {
         // B200: 126 MB L2. Reserve a persisting carve-out and remember the largest window the device accepts.
@@ -1729,6 +1940,7 @@ MPT_API mpt_status mpt_scene_upload(mpt_context* ctx, const mpt_scene_desc* d) t
     v.inst_xform = ctx->xform.as<float4>();
     v.inst_xform_it = ctx->xform_it.as<float4>();
     v.inst_xform_prev = nullptr; // a new scene starts static
+    ctx->single_instance_mask = (!H.two_level && !H.instances.empty()) ? (H.instances[0].mask_flags & 0xFFu) : 0xFFu;
     ctx->instance_count = d->instance_count;
 
     ctx->bvh_info.node_count = nodes.size();
@@ -2049,7 +2261,12 @@ MPT_API mpt_status mpt_primary_visibility(mpt_context* ctx, const mpt_camera* ca
         Counters* ctr = ctx->counters.as<Counters>();
         uint32_t* cursor = nullptr;
         { const mpt_status cs = next_cursor(ctx, st, &cursor); if (cs != MPT_OK) return cs; }
-#define MPT_LAUNCH_PRIMARY_P(C, TL) k_primary_persistent<C, TL><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, cam, width, height, instance_mask, (PackedHitInfo*)d_tex1, ctx->tune, ctr, cursor)
+        const uint32_t query_blocks = uint32_t(ctx->sm_count) * query_blocks_per_sm(ctx);
+#define MPT_LAUNCH_PRIMARY_P(C, TL)                                                                                                                     \
+    do {                                                                                                                                              \
+        if (ctx->query_pooled) k_query_pooled<C, TL, true><<<query_blocks, kThreads, 0, st>>>(ctx->view, nullptr, cam, width, height, tiles * 32u, instance_mask, d_tex1, ctr, cursor); \
+        else k_primary_persistent<C, TL><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, cam, width, height, instance_mask, (PackedHitInfo*)d_tex1, ctx->tune, ctr, cursor); \
+    } while (0)
         if (cnt) { if (tl) MPT_LAUNCH_PRIMARY_P(true, true); else MPT_LAUNCH_PRIMARY_P(true, false); }
         else { if (tl) MPT_LAUNCH_PRIMARY_P(false, true); else MPT_LAUNCH_PRIMARY_P(false, false); }
 #undef MPT_LAUNCH_PRIMARY_P
@@ -2117,7 +2334,12 @@ MPT_API mpt_status mpt_trace(mpt_context* ctx, const void* d_rays, uint64_t n, u
         Counters* ctr = ctx->counters.as<Counters>();
         uint32_t* cursor = nullptr;
         { const mpt_status cs = next_cursor(ctx, st, &cursor); if (cs != MPT_OK) return cs; }
-#define MPT_LAUNCH_TRACE_P(C, TL) k_trace_persistent<C, TL><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, (const float4*)d_rays, uint32_t(n), instance_mask, (uint32_t*)d_hits, ctx->tune, ctr, cursor)
+        const uint32_t query_blocks = uint32_t(ctx->sm_count) * query_blocks_per_sm(ctx);
+#define MPT_LAUNCH_TRACE_P(C, TL)                                                                                                                       \
+    do {                                                                                                                                              \
+        if (ctx->query_pooled) k_query_pooled<C, TL, false><<<query_blocks, kThreads, 0, st>>>(ctx->view, (const float4*)d_rays, CameraParams{}, 0u, 0u, uint32_t(n), instance_mask, d_hits, ctr, cursor); \
+        else k_trace_persistent<C, TL><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, (const float4*)d_rays, uint32_t(n), instance_mask, (uint32_t*)d_hits, ctx->tune, ctr, cursor); \
+    } while (0)
         if (cnt) { if (tl) MPT_LAUNCH_TRACE_P(true, true); else MPT_LAUNCH_TRACE_P(true, false); }
         else { if (tl) MPT_LAUNCH_TRACE_P(false, true); else MPT_LAUNCH_TRACE_P(false, false); }
 #undef MPT_LAUNCH_TRACE_P
