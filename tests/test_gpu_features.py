@@ -446,3 +446,29 @@ def test_material_system_hints(gpu_ctx):
         assert (ref["instance_id"] + ref["geometry_index"] != base["instance_id"] + base["geometry_index"]).any()  # threshold moved the holes
     finally:
         gpu_ctx.materials_set_hints()
+
+
+@pytest.mark.gpu
+def test_masked_out_scene_shades_every_continuation_ray(gpu_ctx):
+    """The GBuffer hit texture is made with one instance mask and the path tracer runs with another that excludes the scene's only
+    instance (both are independent node properties, render_pt.cpp:147-187 / gbuffer.cpp): every continuation ray is a miss that still
+    has to collect the environment. 2 M samples — far more rays than the pooled extend kernel has records, which is what went wrong:
+    records that needed no traversal dropped out of circulation and the rest of the queue was never shaded."""
+    from helpers import make_oracle, render_params
+    t = tables("terrain", nx=120, ny=60, env_size=(128, 64))
+    upload_scene(gpu_ctx, t)
+    cam = t.desc.camera.to_abi(0)
+    w, h, spp = 512, 256, 16
+    tex1 = gpu_ctx.primary_visibility(cam, w, h, mask=0xFF)
+    P = render_params(w, h, spp, mask=0x00)
+    got = gpu_ctx.render(cam, P, tex1=tex1)
+    o = make_oracle(t)
+    ref = o.render(cam, P, tex1=np.ascontiguousarray(tex1))
+    assert np.isfinite(got).all()
+    hit = tex1["instance_id"] != 0xFFFFFFFF
+    assert hit.mean() > 0.3
+    lg, lr = luminance(got)[hit].mean(), luminance(ref)[hit].mean()
+    assert lr > 0 and abs(lg - lr) / lr < 0.02, (lg, lr)
+    # every path of a hit pixel ends at the sky after one bounce: rows of the image are not left dark towards the end of the queue
+    rows = luminance(got).reshape(h, -1).mean(1), luminance(ref).reshape(h, -1).mean(1)
+    assert np.abs(rows[0] - rows[1]).max() < 0.15 * rows[1].mean()
