@@ -450,18 +450,23 @@ def run_ours(args):
         for i in range(2):
             ctx.render_device(cam, params(30_000 + i, abi.RENDER_EMISSION_ON_PRIMARY | abi.RENDER_NEE), tex1=tex1, out=sums[0])
         torch.cuda.synchronize()
-        ctx.reset_stats()
         n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # an untimed lead-in frame in front of n0, as in the main loop: the timed frames are enqueued while it runs, so a host thread that is
+        # held up for tens of ms (profiles/r02y_e2e_probe.json) does not leave the GPU idle inside the timed region (two frames timed from
+        # an idle GPU read 89-95 ms where four frames behind a lead-in frame read 69.6 ms: profiles/r02z_nee_live.jsonl)
+        NN = 4
+        ctx.render_device(cam, params(30_002, abi.RENDER_EMISSION_ON_PRIMARY | abi.RENDER_NEE), tex1=tex1, out=sums[0])
+        ctx.reset_stats()
         n0.record()
-        for i in range(2):
-            ctx.render_device(cam, params(30_002 + i, abi.RENDER_EMISSION_ON_PRIMARY | abi.RENDER_NEE), tex1=tex1, out=sums[0])
+        for i in range(NN):
+            ctx.render_device(cam, params(30_003 + i, abi.RENDER_EMISSION_ON_PRIMARY | abi.RENDER_NEE), tex1=tex1, out=sums[0])
         n1.record()
         torch.cuda.synchronize()
-        nms = n0.elapsed_time(n1) / 2
+        nms = n0.elapsed_time(n1) / NN
         ns = ctx.stats()
         nee = {"msamples_per_s": npix * spp_total / (nms * 1e-3) / 1e6, "ms_per_step": nms,
-               "mrays_closest_hit_per_s": ns.rays_continuation / 2 / (nms * 1e-3) / 1e6, "mrays_occlusion_per_s": ns.rays_shadow / 2 / (nms * 1e-3) / 1e6,
-               "mrays_total_per_s": (ns.rays_continuation + ns.rays_shadow) / 2 / (nms * 1e-3) / 1e6}
+               "mrays_closest_hit_per_s": ns.rays_continuation / NN / (nms * 1e-3) / 1e6, "mrays_occlusion_per_s": ns.rays_shadow / NN / (nms * 1e-3) / 1e6,
+               "mrays_total_per_s": (ns.rays_continuation + ns.rays_shadow) / NN / (nms * 1e-3) / 1e6}
 
     if rank == 0:
         peak, peak_src = load_peak()
