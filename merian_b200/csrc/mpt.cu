@@ -917,16 +917,22 @@ __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_primary_per
 }
 
 // --------------------------------------------------------------------------------------- closest-hit queries, pooled form
-// mpt_trace (PRIMARY = false: the caller's ray array, results at the ray's own index) and mpt_primary_visibility (PRIMARY = true: camera rays
-// in 8x4-pixel tile order, PackedHitInfo per pixel) through the per-warp ray pool of k_extend_pooled: converged retire / refill / ray setup
-// at full width, a finishing lane swaps its record for a READY one, re-convergence on 32 DONE records. The records carry the ray's own
-// interval (TraversalP<..., TMIN_ZERO = false>): b.w = tmin, d.w = tmax, a.w = the ray index / pixel index.
-template <bool COUNT, bool TWO_LEVEL, bool PRIMARY>
+// mpt_trace (MODE 0: the caller's ray array, results at the ray's own index), mpt_primary_visibility (MODE 1: camera rays in 8x4-pixel
+// tile order, PackedHitInfo per pixel) and the shadow rays of MPT_RENDER_NEE (MODE 2: the shadow queue of the bounce, a ray ends at the
+// first accepted hit, an unoccluded one adds its contribution to the path) through the per-warp ray pool of k_extend_pooled: converged
+// retire / refill / ray setup at full width, a finishing lane swaps its record for a READY one, re-convergence on 32 DONE records.
+// Modes 0 and 1: the records carry the ray's own interval (TraversalP<..., TMIN_ZERO = false>): b.w = tmin, d.w = tmax, a.w = the ray /
+// pixel index. Mode 2: continuation-ray records (b.w = the triangle the ray leaves, a.w = the shadow-queue index).
+constexpr int kQueryTrace = 0, kQueryPrimary = 1, kQueryShadow = 2;
+template <bool COUNT, bool TWO_LEVEL, int MODE>
 __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS)
-k_query_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ rays, CameraParams cam, uint32_t w, uint32_t h, uint32_t n, uint32_t mask,
-               void* __restrict__ out, Counters* ctr, uint32_t* fetch) {
+k_query_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ rays, const float4* __restrict__ rays_d, const float4* __restrict__ contrib,
+               CameraParams cam, uint32_t w, uint32_t h, uint32_t n_host, const uint32_t* __restrict__ n_dev, uint32_t mask, void* __restrict__ out, Counters* ctr,
+               uint32_t* fetch) {
+    constexpr bool PRIMARY = MODE == kQueryPrimary, SHADOW = MODE == kQueryShadow;
+    const uint32_t n = n_dev ? *n_dev : n_host; // the shadow queue's length only exists on the device
     constexpr int NE = 32 + MPT_POOL_READY, kWarps = kThreads / 32, TRIG = MPT_POOL_TRIGGER > 0 ? MPT_POOL_TRIGGER : MPT_POOL_READY;
-    using Trav = TraversalP<COUNT, TWO_LEVEL, MaterialAlphaTest, 0, kThreads, false>;
+    using Trav = TraversalP<COUNT, TWO_LEVEL, MaterialAlphaTest, 0, kThreads, SHADOW>;
     using Entry = PoolEntry;
     struct Pool {
         Entry e[NE];
@@ -949,6 +955,19 @@ k_query_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ r
 
     // the result of one ray: hits6 of mpt_trace (include/mpt.h) or the PackedHitInfo of gbuffer.slang:40-61
     auto store = [&](uint32_t tag, uint32_t tri, uint32_t instance, float u, float v) {
+        if (SHADOW) { // unoccluded: the MIS-weighted light sample reaches the path (one shadow ray per slot and bounce: no race)
+            if (tri == kMiss) {
+                const float4 c = ldq(contrib + tag);
+                float4* rad = static_cast<float4*>(out);
+                const uint32_t slot = __float_as_uint(c.w);
+                float4 ra = rad[slot];
+                ra.x += c.x;
+                ra.y += c.y;
+                ra.z += c.z;
+                rad[slot] = ra;
+            }
+            return;
+        }
         uint32_t custom = kMiss, prim = kMiss, geom = kMiss;
         if (tri != kMiss) {
             const float4* tp = S.accel.tris + size_t(tri) * 3;
@@ -1028,6 +1047,9 @@ k_query_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ r
                         if (valid) camera_ray(cam, x, y, w, h, o, d, tmin, tmax);
                         ro = make_float4(o.x, o.y, o.z, tmin);
                         rd = make_float4(d.x, d.y, d.z, tmax);
+                    } else if (SHADOW) {
+                        ro = ldq(rays + jn);
+                        rd = ldq(rays_d + jn);
                     } else {
                         ro = __ldg(rays + 2 * size_t(jn));
                         rd = __ldg(rays + 2 * size_t(jn) + 1);
@@ -1039,7 +1061,7 @@ k_query_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ r
                         setup_ray(R, xyz(ro), xyz(rd));
                         const uint32_t oct = 7u - (R.perm >> 24);
                         E.a = make_float4(ro.x, ro.y, ro.z, __uint_as_float(rtag));
-                        E.b = make_float4(R.idir.x, R.idir.y, R.idir.z, ro.w); // tmin
+                        E.b = make_float4(R.idir.x, R.idir.y, R.idir.z, SHADOW ? rd.w : ro.w); // the triangle the shadow ray leaves | tmin
                         E.c = make_float4(R.shear.Sx, R.shear.Sy, R.shear.Sz,
                                           __uint_as_float(uint32_t(R.shear.kx) | (uint32_t(R.shear.ky) << 2) | (uint32_t(R.shear.kz) << 4) | (oct << 8)));
                         E.d = rd;                                               // direction | tmax
@@ -1063,7 +1085,7 @@ k_query_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ r
         const int k = __popc(idle & lt);
         if (!active && k < nready) {
             my = P.ready[k];
-            T.start(&P.e[my], mask, scene_flags, false);
+            T.start(&P.e[my], mask, scene_flags, SHADOW);
             active = true;
         }
         const int rem = nd_all - nd; // < 32: DONE records beyond the whole rounds, kept for the next phase behind the re-queued ones
@@ -1086,7 +1108,7 @@ k_query_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ r
         // ======================================================= divergent: traverse; a finished lane swaps its record for a READY one
         uint32_t tick = 0u;
         while (active) {
-            if (T.step(TWO_LEVEL ? tick++ : 0u)) {
+            if (T.step(TWO_LEVEL ? tick++ : 0u) || (SHADOW && T.found())) { // a shadow ray ends at the first accepted hit
                 Entry& E = P.e[my];
                 const bool f = T.found();
                 E.b = make_float4(__uint_as_float(f ? T.hit.tri : kMiss), __uint_as_float(T.hit.instance), T.hit.u, T.hit.v);
@@ -1094,7 +1116,7 @@ k_query_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ r
                 const int kk = atomicAdd(&P.ready_head, 1);
                 if (kk < ready_n) {
                     my = P.ready[kk];
-                    T.start(&P.e[my], mask, scene_flags, false);
+                    T.start(&P.e[my], mask, scene_flags, SHADOW);
                 } else {
                     active = false;
                     break;
@@ -1609,7 +1631,7 @@ mpt_status ensure_pool(mpt_context* ctx, size_t slots, bool need_medium, bool ne
 uint32_t query_blocks_per_sm(mpt_context* ctx) {
     if (!ctx->query_blocks_per_sm) {
         int occ = 0;
-        ctx->query_blocks_per_sm = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_query_pooled<false, false, false>, kThreads, 0) == cudaSuccess && occ > 0)
+        ctx->query_blocks_per_sm = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_query_pooled<false, false, kQueryTrace>, kThreads, 0) == cudaSuccess && occ > 0)
                                        ? uint32_t(occ) : 7u;
     }
     return ctx->query_blocks_per_sm;
@@ -1751,7 +1773,12 @@ mpt_status run_passes(mpt_context* ctx, const CameraParams& cam, const mpt_rende
         for (int b = 1; b < L; b++) {
             const uint32_t in = uint32_t(b - 1) & 1u;
             if (NEE) { // shadow rays of the vertex shaded last: before the extend so that both add to rad[] in stream order
-                if (ctx->view.accel.two_level) k_shadow<true><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, pb, uint32_t(b), P.instance_mask, ctx->tune, ctr);
+                const bool tl_s = ctx->view.accel.two_level != 0;
+                if (ctx->query_pooled && (tl_s || (ctx->single_instance_mask & P.instance_mask & 0xFFu) != 0u)) { // (masked-out scene: see the extend launch)
+                    const uint32_t qb = uint32_t(ctx->sm_count) * query_blocks_per_sm(ctx);
+                    if (tl_s) k_query_pooled<false, true, kQueryShadow><<<qb, kThreads, 0, st>>>(ctx->view, pb.sq_o, pb.sq_d, pb.sq_c, CameraParams{}, 0u, 0u, 0u, &ctr->scount[b], P.instance_mask, pb.rad, ctr, &ctr->sfetch[b]);
+                    else k_query_pooled<false, false, kQueryShadow><<<qb, kThreads, 0, st>>>(ctx->view, pb.sq_o, pb.sq_d, pb.sq_c, CameraParams{}, 0u, 0u, 0u, &ctr->scount[b], P.instance_mask, pb.rad, ctr, &ctr->sfetch[b]);
+                } else if (tl_s) k_shadow<true><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, pb, uint32_t(b), P.instance_mask, ctx->tune, ctr);
                 else k_shadow<false><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, pb, uint32_t(b), P.instance_mask, ctx->tune, ctr);
                 ctx->stats.kernel_launches++;
             }
@@ -2264,7 +2291,7 @@ MPT_API mpt_status mpt_primary_visibility(mpt_context* ctx, const mpt_camera* ca
         const uint32_t query_blocks = uint32_t(ctx->sm_count) * query_blocks_per_sm(ctx);
 #define MPT_LAUNCH_PRIMARY_P(C, TL)                                                                                                                     \
     do {                                                                                                                                              \
-        if (ctx->query_pooled) k_query_pooled<C, TL, true><<<query_blocks, kThreads, 0, st>>>(ctx->view, nullptr, cam, width, height, tiles * 32u, instance_mask, d_tex1, ctr, cursor); \
+        if (ctx->query_pooled) k_query_pooled<C, TL, kQueryPrimary><<<query_blocks, kThreads, 0, st>>>(ctx->view, nullptr, nullptr, nullptr, cam, width, height, tiles * 32u, nullptr, instance_mask, d_tex1, ctr, cursor); \
         else k_primary_persistent<C, TL><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, cam, width, height, instance_mask, (PackedHitInfo*)d_tex1, ctx->tune, ctr, cursor); \
     } while (0)
         if (cnt) { if (tl) MPT_LAUNCH_PRIMARY_P(true, true); else MPT_LAUNCH_PRIMARY_P(true, false); }
@@ -2337,7 +2364,7 @@ MPT_API mpt_status mpt_trace(mpt_context* ctx, const void* d_rays, uint64_t n, u
         const uint32_t query_blocks = uint32_t(ctx->sm_count) * query_blocks_per_sm(ctx);
 #define MPT_LAUNCH_TRACE_P(C, TL)                                                                                                                       \
     do {                                                                                                                                              \
-        if (ctx->query_pooled) k_query_pooled<C, TL, false><<<query_blocks, kThreads, 0, st>>>(ctx->view, (const float4*)d_rays, CameraParams{}, 0u, 0u, uint32_t(n), instance_mask, d_hits, ctr, cursor); \
+        if (ctx->query_pooled) k_query_pooled<C, TL, kQueryTrace><<<query_blocks, kThreads, 0, st>>>(ctx->view, (const float4*)d_rays, nullptr, nullptr, CameraParams{}, 0u, 0u, uint32_t(n), nullptr, instance_mask, d_hits, ctr, cursor); \
         else k_trace_persistent<C, TL><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, (const float4*)d_rays, uint32_t(n), instance_mask, (uint32_t*)d_hits, ctx->tune, ctr, cursor); \
     } while (0)
         if (cnt) { if (tl) MPT_LAUNCH_TRACE_P(true, true); else MPT_LAUNCH_TRACE_P(true, false); }
