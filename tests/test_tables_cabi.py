@@ -149,3 +149,31 @@ def test_c_tables_feed_the_host_accel_build():
     assert np.array_equal(got, ref.nodes.view(np.uint8).reshape(-1))
     lib().mpt_host_accel_free(h)
     c.close()
+
+
+def test_uv_half_conversion_matches_ieee_round_to_nearest_even():
+    """half2(uv) of the vertex path (gltf_scene.cpp:113): the C++ float -> binary16 conversion against numpy's on every binary16 value, its
+    two float32 neighbours, the midpoints between consecutive halves (the ties), the subnormal range, overflow and random bit patterns."""
+    h = np.arange(0x10000, dtype=np.uint32).astype(np.uint16)
+    exact = h.view(np.float16).astype(np.float32)
+    exact = exact[np.isfinite(exact)]
+    near = np.concatenate([np.nextafter(exact, np.float32(np.inf)), np.nextafter(exact, np.float32(-np.inf))])
+    s = np.sort(exact)
+    mid = ((s[:-1].astype(np.float64) + s[1:].astype(np.float64)) * 0.5).astype(np.float32)      # exactly representable in float32
+    rng = np.random.default_rng(5)
+    bits = rng.integers(0, 1 << 32, 400000, dtype=np.uint64).astype(np.uint32)
+    rnd = bits.view(np.float32)
+    rnd = rnd[np.isfinite(rnd)]
+    small = (rng.random(100000).astype(np.float32) - np.float32(0.5)) * np.float32(2.5e-4)      # around the subnormal halves
+    big = np.array([65504.0, 65519.9, 65520.0, 65536.0, 1e9, -65520.0, -1e9, 0.0, -0.0, 5.9604645e-08, 2.9802322e-08, 2.98023226e-08], np.float32)
+    v = np.concatenate([exact, near, mid, rnd, small, big]).astype(np.float32)
+    if len(v) % 2:
+        v = v[:-1]
+    uv = np.ascontiguousarray(v.reshape(-1, 2))
+    n = len(uv)
+    pos = np.zeros((n, 3), np.float32)
+    nrm = np.tile(np.array([[0, 0, 1]], np.float32), (n, 1))
+    got = c_pack_vertices(pos, nrm, uv)["uv"]
+    with np.errstate(over="ignore"):
+        ref = uv.astype(np.float16).view(np.uint16)
+    assert np.array_equal(got, ref), np.argwhere(got != ref)[:5]
