@@ -2,8 +2,8 @@
  *
  * What a host that is not merian does to swap the path tracer in: loader output (float vertex attributes, scene-graph nodes) ->
  * mptt_build (include/mpt_tables.h: merian::Scene's grouping, GeometryData order and vertex path) -> mpt_scene_upload (BVH8 build on the
- * host cores) -> material buffer in the reference's entry layout (material_system.cpp:140-195: MaterialHeader {u16 type id, u16 alpha
- * texture} + payload) -> mpt_env_set -> one frame into host memory (mpt_render_host) -> PFM (mpt_pfm_save, the Image Write node's format).
+ * host cores) -> mptt_materials_build (the reference's material buffer: MaterialHeader {u16 type id, u16 alpha texture} + payload,
+ * material_system.cpp:140-195) -> mpt_materials_upload -> mpt_env_set -> one frame into host memory (mpt_render_host) -> PFM (mpt_pfm_save, the Image Write node's format).
  *
  * Scene: a floor, a back wall and a box under a uniform sky; 160x120, 64 spp, max path length 5.
  *   gcc -std=c99 -Iinclude examples/standalone_host.c -Lmerian_b200/csrc -lmpt -Wl,-rpath,$PWD/merian_b200/csrc -lm -o standalone_host
@@ -87,11 +87,20 @@ int main(int argc, char** argv) {
     if (mptt_build(meshes, 3, nodes, 2, &tables) != MPT_OK) return fail("mptt_build", mpt_last_error(NULL));
     if (mpt_scene_upload(ctx, mptt_scene_desc(tables)) != MPT_OK) return fail("mpt_scene_upload", mpt_last_error(ctx));
 
-    /* ---- materials: three DiffuseMaterial entries (diffuse-material.slang:8-12: float4 base colour), 4-byte header + 16-byte payload */
-    struct { uint16_t type_id, alpha_texture; float base_color[4]; } entries[3] = {
-        {0, MPT_TEXTURE_NONE, {0.7f, 0.7f, 0.7f, 1.f}}, {0, MPT_TEXTURE_NONE, {0.2f, 0.4f, 0.7f, 1.f}}, {0, MPT_TEXTURE_NONE, {0.8f, 0.3f, 0.2f, 1.f}}};
-    const mpt_material_type types[1] = {{MPT_MATERIAL_DIFFUSE, 0}};
-    if (mpt_materials_upload(ctx, entries, (uint32_t)sizeof(entries[0]), 3, types, 1) != MPT_OK) return fail("mpt_materials_upload", mpt_last_error(ctx));
+    /* ---- materials: the reference's entry layout (MaterialHeader + payload, material_system.cpp:140-195) from typed descriptions */
+    mpt_src_material mats[3];
+    memset(mats, 0, sizeof(mats));
+    const float colours[3][4] = {{0.7f, 0.7f, 0.7f, 1.f}, {0.2f, 0.4f, 0.7f, 1.f}, {0.8f, 0.3f, 0.2f, 1.f}};
+    for (int m = 0; m < 3; m++) {
+        mats[m].model = MPT_MATERIAL_DIFFUSE;
+        memcpy(mats[m].base_color_factor, colours[m], sizeof(colours[m]));
+        mats[m].base_color_texture = MPT_TEXTURE_NONE;
+    }
+    mpt_material_table* mtab = NULL;
+    mpt_material_table_view mv;
+    if (mptt_materials_build(mats, 3, &mtab) != MPT_OK || mptt_materials_get(mtab, &mv) != MPT_OK) return fail("mptt_materials_build", mpt_last_error(NULL));
+    if (mpt_materials_upload(ctx, mv.entries, mv.entry_size, mv.material_count, mv.types, mv.type_count) != MPT_OK)
+        return fail("mpt_materials_upload", mpt_last_error(ctx));
 
     /* ---- a uniform sky: 8x4 lat-long texels */
     static float sky[8 * 4 * 4];
@@ -134,6 +143,7 @@ int main(int argc, char** argv) {
     if (mpt_pfm_save(out_path, image, IMG_W, IMG_H, 4) != MPT_OK) return fail("mpt_pfm_save", mpt_last_error(NULL));
     printf("wrote %s\n", out_path);
     free(image);
+    mptt_materials_free(mtab);
     mptt_free(tables);
     mpt_destroy(ctx);
     return 0;

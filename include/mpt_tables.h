@@ -67,6 +67,46 @@ MPT_API void mptt_free(mpt_tables* t);
 MPT_API mpt_status mptt_pack_vertices(const float* positions, const float* normals, const float* uvs, const float* tangents, uint32_t vertex_count,
                                       const float* transform, mpt_packed_vertex* out);
 
+/* ---- material buffer (the host side of SURVEY.md 8(a) A6) ---------------------------------------------------------------------------
+ * MaterialSystem::add_material / repack_host_buffer (src/merian-shaders/shading/materials/material_system.cpp:124-195): every material
+ * becomes one entry = MaterialHeader {u16 material_model_type_id, u16 alpha_texture_id} + the model's serialised payload, all entries
+ * padded to the largest one; type ids are handed out in first-registration order of (model, feature set). Payloads:
+ * DiffuseMaterial = float4 base colour (diffuse-material.slang:8-12); GltfMaterial = the core block followed by the blocks of the
+ * enabled extensions in the order transmission, volume, clearcoat, sheen, iridescence, anisotropy
+ * (include/merian-shaders/shading/materials/gltf_material.hpp:93-146). Texture ids: MPT_TEXTURE_NONE = no texture. */
+typedef struct mpt_src_material {
+    uint32_t model;                  /* MPT_MATERIAL_DIFFUSE | MPT_MATERIAL_GLTF */
+    float base_color_factor[4];
+    uint32_t base_color_texture;     /* = the header's alpha_texture_id */
+    /* ---- glTF metallic-roughness only */
+    float emissive_factor[3];
+    float metallic_factor, roughness_factor, normal_scale, occlusion_strength, ior;
+    uint32_t metallic_roughness_texture, normal_texture, occlusion_texture, emissive_texture;
+    uint32_t features;               /* MPT_GLTF_* bits: which of the blocks below exist */
+    float transmission_weight;
+    float volume_absorption[3];
+    float clearcoat_weight, clearcoat_roughness;
+    uint32_t clearcoat_texture, clearcoat_roughness_texture;
+    float sheen_color[3], sheen_roughness;
+    uint32_t sheen_color_texture, sheen_roughness_texture;
+    float iridescence_factor, iridescence_ior, iridescence_thickness_min, iridescence_thickness_max;
+    uint32_t iridescence_texture, iridescence_thickness_texture;
+    float anisotropy_strength, anisotropy_rotation;
+    uint32_t anisotropy_texture;
+} mpt_src_material;
+
+typedef struct mpt_material_table mpt_material_table;
+typedef struct mpt_material_table_view { /* the arguments of mpt_materials_upload */
+    const void* entries;
+    uint32_t entry_size, material_count;
+    const mpt_material_type* types;
+    uint32_t type_count;
+} mpt_material_table_view;
+
+MPT_API mpt_status mptt_materials_build(const mpt_src_material* materials, uint32_t material_count, mpt_material_table** out);
+MPT_API mpt_status mptt_materials_get(const mpt_material_table* table, mpt_material_table_view* out);
+MPT_API void mptt_materials_free(mpt_material_table* table);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,23 @@ class SrcMesh(C.Structure):  # mpt_src_mesh, include/mpt_tables.h
                 ("flags", C.c_uint32), ("instance_mask", C.c_uint32)]
 
 
+class SrcMaterial(C.Structure):  # mpt_src_material, include/mpt_tables.h
+    _fields_ = [("model", C.c_uint32), ("base_color_factor", C.c_float * 4), ("base_color_texture", C.c_uint32),
+                ("emissive_factor", C.c_float * 3), ("metallic_factor", C.c_float), ("roughness_factor", C.c_float), ("normal_scale", C.c_float),
+                ("occlusion_strength", C.c_float), ("ior", C.c_float),
+                ("metallic_roughness_texture", C.c_uint32), ("normal_texture", C.c_uint32), ("occlusion_texture", C.c_uint32), ("emissive_texture", C.c_uint32),
+                ("features", C.c_uint32), ("transmission_weight", C.c_float), ("volume_absorption", C.c_float * 3),
+                ("clearcoat_weight", C.c_float), ("clearcoat_roughness", C.c_float), ("clearcoat_texture", C.c_uint32), ("clearcoat_roughness_texture", C.c_uint32),
+                ("sheen_color", C.c_float * 3), ("sheen_roughness", C.c_float), ("sheen_color_texture", C.c_uint32), ("sheen_roughness_texture", C.c_uint32),
+                ("iridescence_factor", C.c_float), ("iridescence_ior", C.c_float), ("iridescence_thickness_min", C.c_float), ("iridescence_thickness_max", C.c_float),
+                ("iridescence_texture", C.c_uint32), ("iridescence_thickness_texture", C.c_uint32),
+                ("anisotropy_strength", C.c_float), ("anisotropy_rotation", C.c_float), ("anisotropy_texture", C.c_uint32)]
+
+
+class MaterialTableView(C.Structure):  # mpt_material_table_view
+    _fields_ = [("entries", C.c_void_p), ("entry_size", C.c_uint32), ("material_count", C.c_uint32), ("types", C.c_void_p), ("type_count", C.c_uint32)]
+
+
 class SrcNode(C.Structure):  # mpt_src_node
     _fields_ = [("transform", C.c_float * 16), ("meshes", C.c_void_p), ("mesh_count", C.c_uint32)]
 

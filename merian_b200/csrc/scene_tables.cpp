@@ -314,3 +314,88 @@ MPT_API mpt_status mptt_build(const mpt_src_mesh* meshes, uint32_t mesh_count, c
 MPT_API const mpt_scene_desc* mptt_scene_desc(const mpt_tables* t) { return t ? &t->desc : nullptr; }
 
 MPT_API void mptt_free(mpt_tables* t) { delete t; }
+
+// ---------------------------------------------------------------------------------------------------------------- material buffer
+// MaterialSystem::add_material / repack_host_buffer (material_system.cpp:124-195), payloads of diffuse-material.slang:8-12 and
+// gltf_material.hpp:93-146.
+struct mpt_material_table {
+    std::vector<uint8_t> entries;
+    std::vector<mpt_material_type> types;
+    uint32_t entry_size = 0, count = 0;
+};
+
+namespace {
+struct Payload {
+    std::vector<uint8_t> b;
+    void f32(float v) { const size_t n = b.size(); b.resize(n + 4); std::memcpy(&b[n], &v, 4); }
+    void u16(uint32_t v) { const uint16_t h = uint16_t(v); const size_t n = b.size(); b.resize(n + 2); std::memcpy(&b[n], &h, 2); }
+};
+} // namespace
+
+MPT_API mpt_status mptt_materials_build(const mpt_src_material* materials, uint32_t material_count, mpt_material_table** out) try {
+    if (!out || (!materials && material_count)) return tables_fail(MPT_ERR_INVALID_ARGUMENT, "mptt_materials_build: NULL argument");
+    *out = nullptr;
+    std::unique_ptr<mpt_material_table> T(new mpt_material_table);
+    std::vector<Payload> payloads(material_count);
+    std::vector<uint32_t> type_of(material_count), alpha_tex(material_count);
+    size_t max_payload = 0;
+    for (uint32_t i = 0; i < material_count; i++) {
+        const mpt_src_material& m = materials[i];
+        if (m.model != MPT_MATERIAL_DIFFUSE && m.model != MPT_MATERIAL_GLTF) return tables_fail(MPT_ERR_INVALID_ARGUMENT, "mptt_materials_build: unknown material model");
+        const uint32_t features = m.model == MPT_MATERIAL_GLTF ? (m.features & 63u) : 0u;
+        uint32_t tid = 0;
+        for (; tid < T->types.size(); tid++) // type ids in first-registration order (material_system.cpp:124-139)
+            if (T->types[tid].model == m.model && T->types[tid].features == features) break;
+        if (tid == T->types.size()) T->types.push_back(mpt_material_type{m.model, features});
+        if (tid > 0xFFFFu || m.base_color_texture > 0xFFFFu) return tables_fail(MPT_ERR_LIMIT, "mptt_materials_build: type / texture ids are 16 bit");
+        type_of[i] = tid;
+        alpha_tex[i] = m.base_color_texture;
+        Payload& p = payloads[i];
+        for (int k = 0; k < 4; k++) p.f32(m.base_color_factor[k]);
+        if (m.model == MPT_MATERIAL_GLTF) {
+            for (int k = 0; k < 3; k++) p.f32(m.emissive_factor[k]);
+            p.f32(m.metallic_factor); p.f32(m.roughness_factor); p.f32(m.normal_scale); p.f32(m.occlusion_strength); p.f32(m.ior);
+            p.u16(m.metallic_roughness_texture); p.u16(m.normal_texture); p.u16(m.occlusion_texture); p.u16(m.emissive_texture);
+            if (features & MPT_GLTF_TRANSMISSION) p.f32(m.transmission_weight);
+            if (features & MPT_GLTF_VOLUME) for (int k = 0; k < 3; k++) p.f32(m.volume_absorption[k]);
+            if (features & MPT_GLTF_CLEARCOAT) { p.f32(m.clearcoat_weight); p.f32(m.clearcoat_roughness); p.u16(m.clearcoat_texture); p.u16(m.clearcoat_roughness_texture); }
+            if (features & MPT_GLTF_SHEEN) {
+                for (int k = 0; k < 3; k++) p.f32(m.sheen_color[k]);
+                p.f32(m.sheen_roughness); p.u16(m.sheen_color_texture); p.u16(m.sheen_roughness_texture);
+            }
+            if (features & MPT_GLTF_IRIDESCENCE) {
+                p.f32(m.iridescence_factor); p.f32(m.iridescence_ior); p.f32(m.iridescence_thickness_min); p.f32(m.iridescence_thickness_max);
+                p.u16(m.iridescence_texture); p.u16(m.iridescence_thickness_texture);
+            }
+            if (features & MPT_GLTF_ANISOTROPY) { p.f32(m.anisotropy_strength); p.f32(m.anisotropy_rotation); p.u16(m.anisotropy_texture); }
+        }
+        max_payload = std::max(max_payload, p.b.size());
+    }
+    T->entry_size = uint32_t(4 + ((max_payload + 3) / 4) * 4); // header + payload_size_in_uints * 4
+    T->count = material_count;
+    T->entries.assign(size_t(T->entry_size) * material_count, uint8_t(0));
+    for (uint32_t i = 0; i < material_count; i++) {
+        uint8_t* e = &T->entries[size_t(i) * T->entry_size];
+        const uint16_t hdr[2] = {uint16_t(type_of[i]), uint16_t(alpha_tex[i])};
+        std::memcpy(e, hdr, 4);
+        std::memcpy(e + 4, payloads[i].b.data(), payloads[i].b.size());
+    }
+    *out = T.release();
+    return MPT_OK;
+} catch (const std::bad_alloc&) {
+    return tables_fail(MPT_ERR_LIMIT, "mptt_materials_build: out of host memory");
+} catch (...) { // no C++ exception crosses the C ABI
+    return tables_fail(MPT_ERR_INVALID_ARGUMENT, "mptt_materials_build: unexpected exception");
+}
+
+MPT_API mpt_status mptt_materials_get(const mpt_material_table* t, mpt_material_table_view* out) {
+    if (!t || !out) return tables_fail(MPT_ERR_INVALID_ARGUMENT, "mptt_materials_get: NULL argument");
+    out->entries = t->entries.data();
+    out->entry_size = t->entry_size;
+    out->material_count = t->count;
+    out->types = t->types.data();
+    out->type_count = uint32_t(t->types.size());
+    return MPT_OK;
+}
+
+MPT_API void mptt_materials_free(mpt_material_table* t) { delete t; }

@@ -177,3 +177,74 @@ def test_uv_half_conversion_matches_ieee_round_to_nearest_even():
     with np.errstate(over="ignore"):
         ref = uv.astype(np.float16).view(np.uint16)
     assert np.array_equal(got, ref), np.argwhere(got != ref)[:5]
+
+
+def _src_material(m):
+    """A scene.py material as the mpt_src_material of include/mpt_tables.h."""
+    from merian_b200.scene import GltfMaterial
+    N = abi.TEXTURE_NONE
+    s = abi.SrcMaterial()
+    s.base_color_factor[:] = list(m.base_color_factor)
+    s.base_color_texture = m.base_color_texture
+    if not isinstance(m, GltfMaterial):
+        s.model = abi.MATERIAL_DIFFUSE
+        return s
+    s.model = abi.MATERIAL_GLTF
+    s.emissive_factor[:] = list(m.emissive_factor)
+    s.metallic_factor, s.roughness_factor, s.normal_scale, s.occlusion_strength, s.ior = m.metallic_factor, m.roughness_factor, m.normal_scale, m.occlusion_strength, m.ior
+    s.metallic_roughness_texture, s.normal_texture, s.occlusion_texture, s.emissive_texture = m.metallic_roughness_texture, m.normal_texture, m.occlusion_texture, m.emissive_texture
+    s.features = m.features()
+    if m.transmission is not None:
+        s.transmission_weight = m.transmission.get("weight", 0.0)
+    if m.volume is not None:
+        s.volume_absorption[:] = list(m.volume.get("absorption", (0, 0, 0)))
+    if m.clearcoat is not None:
+        c = m.clearcoat
+        s.clearcoat_weight, s.clearcoat_roughness, s.clearcoat_texture, s.clearcoat_roughness_texture = c.get("weight", 0.0), c.get("roughness", 0.0), c.get("texture", N), c.get("roughness_texture", N)
+    if m.sheen is not None:
+        c = m.sheen
+        s.sheen_color[:] = list(c.get("color", (0, 0, 0)))
+        s.sheen_roughness, s.sheen_color_texture, s.sheen_roughness_texture = c.get("roughness", 0.0), c.get("color_texture", N), c.get("roughness_texture", N)
+    if m.iridescence is not None:
+        c = m.iridescence
+        s.iridescence_factor, s.iridescence_ior = c.get("factor", 0.0), c.get("ior", 1.3)
+        s.iridescence_thickness_min, s.iridescence_thickness_max = c.get("thickness_min", 100.0), c.get("thickness_max", 400.0)
+        s.iridescence_texture, s.iridescence_thickness_texture = c.get("texture", N), c.get("thickness_texture", N)
+    if m.anisotropy is not None:
+        c = m.anisotropy
+        s.anisotropy_strength, s.anisotropy_rotation, s.anisotropy_texture = c.get("strength", 0.0), c.get("rotation", 0.0), c.get("texture", N)
+    return s
+
+
+def test_material_buffer_matches_the_numpy_restatement():
+    """mptt_materials_build against scene.build_material_buffer (material_system.cpp:124-195, gltf_material.hpp:93-146): entry bytes, entry
+    size and the type table in first-registration order, on a list that mixes both models and every extension block."""
+    import ctypes as C
+    from merian_b200._lib import lib
+    from merian_b200.scene import GltfMaterial, build_material_buffer
+    mats = [GltfMaterial(base_color_factor=(0.8, 0.3, 0.2, 1), metallic_factor=0.0, roughness_factor=0.5, emissive_factor=(0.1, 0.2, 0.3), base_color_texture=3),
+            DiffuseMaterial((0.25, 0.5, 0.75, 1.0)),
+            GltfMaterial(metallic_factor=1.0, roughness_factor=0.25, normal_texture=7, ior=1.33, clearcoat={"weight": 0.7, "roughness": 0.15, "texture": 2},
+                         sheen={"color": (0.6, 0.5, 0.4), "roughness": 0.5, "roughness_texture": 9}),
+            GltfMaterial(transmission={"weight": 0.9}, volume={"absorption": (0.1, 0.2, 0.3)}),
+            GltfMaterial(iridescence={"factor": 0.6, "ior": 1.35, "thickness_min": 150.0, "thickness_max": 350.0, "thickness_texture": 4},
+                         anisotropy={"strength": 0.4, "rotation": 1.2, "texture": 5}),
+            DiffuseMaterial((1, 1, 1, 1), base_color_texture=1),
+            GltfMaterial(base_color_factor=(0.1, 0.1, 0.1, 1), metallic_factor=0.3),                       # same type as the first
+            GltfMaterial(transmission={"weight": 0.5}, volume={"absorption": (1, 2, 3)}, clearcoat={"weight": 1.0}, sheen={"color": (1, 1, 1)},
+                         iridescence={"factor": 1.0}, anisotropy={"strength": 1.0})]
+    ref_entries, ref_size, ref_types = build_material_buffer(mats)
+    src = (abi.SrcMaterial * len(mats))(*[_src_material(m) for m in mats])
+    h = C.c_void_p()
+    assert lib().mptt_materials_build(C.cast(src, C.c_void_p), len(mats), C.byref(h)) == abi.MPT_OK
+    view = abi.MaterialTableView()
+    assert lib().mptt_materials_get(h, C.byref(view)) == abi.MPT_OK
+    assert (view.entry_size, view.material_count, view.type_count) == (ref_size, len(mats), len(ref_types))
+    got = bytes((C.c_char * (view.entry_size * view.material_count)).from_address(view.entries))
+    assert got == ref_entries
+    types = (abi.MaterialType * view.type_count).from_address(view.types)
+    assert [(t.model, t.features) for t in types] == [tuple(t) for t in ref_types]
+    lib().mptt_materials_free(h)
+    bad = abi.SrcMaterial()
+    bad.model = 7
+    assert lib().mptt_materials_build(C.byref(bad), 1, C.byref(h)) != abi.MPT_OK
