@@ -9,7 +9,7 @@
  *   gcc -std=c99 -Iinclude examples/standalone_host.c -Lmerian_b200/csrc -lmpt -Wl,-rpath,$PWD/merian_b200/csrc -lm -o standalone_host
  *   ./standalone_host out.pfm     (exit code 2 + the library's message when there is no sm_100 device: there is no CPU fallback)
  * tests/test_standalone_host.py builds and runs it, and compares the image with the same scene rendered through the Python mirror. */
-#include <math.h>
+#include <math.h> /* cosf, sinf for the node transform */
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -109,23 +109,9 @@ int main(int argc, char** argv) {
 
     /* ---- camera: Camera::write_to (camera.cpp:349-368) */
     mpt_camera cam;
-    memset(&cam, 0, sizeof(cam));
     const float eye[3] = {0.0f, 1.4f, 4.0f}, tgt[3] = {0.0f, 0.6f, 0.0f}, upv[3] = {0, 1, 0};
-    float fwd[3] = {tgt[0] - eye[0], tgt[1] - eye[1], tgt[2] - eye[2]};
-    const float focus = sqrtf(fwd[0] * fwd[0] + fwd[1] * fwd[1] + fwd[2] * fwd[2]);
-    for (int k = 0; k < 3; k++) fwd[k] /= focus;
-    float rgt[3] = {fwd[1] * upv[2] - fwd[2] * upv[1], fwd[2] * upv[0] - fwd[0] * upv[2], fwd[0] * upv[1] - fwd[1] * upv[0]};
-    const float rl = sqrtf(rgt[0] * rgt[0] + rgt[1] * rgt[1] + rgt[2] * rgt[2]);
-    for (int k = 0; k < 3; k++) rgt[k] /= rl;
-    const float upc[3] = {rgt[1] * fwd[2] - rgt[2] * fwd[1], rgt[2] * fwd[0] - rgt[0] * fwd[2], rgt[0] * fwd[1] - rgt[1] * fwd[0]};
-    const float aspect = (float)IMG_W / (float)IMG_H, half_tan = tanf(45.0f * 3.14159265358979f / 180.0f * 0.5f);
-    for (int k = 0; k < 3; k++) {
-        cam.position[k] = eye[k]; cam.target[k] = tgt[k]; cam.up[k] = upv[k];
-        cam.U[k] = rgt[k] * (half_tan * aspect * focus);
-        cam.V[k] = upc[k] * (half_tan * focus);
-        cam.W[k] = fwd[k] * focus;
-    }
-    cam.near_plane = 0.01f; cam.far_plane = 1e4f; cam.aspect_ratio = aspect;
+    if (mptt_camera_look_at(eye, tgt, upv, 45.0f, (float)IMG_W / (float)IMG_H, 0.01f, 1e4f, 0.0f, NULL, &cam) != MPT_OK)
+        return fail("mptt_camera_look_at", mpt_last_error(NULL));
 
     /* ---- one frame into host memory (mpt_render_host: H2D of nothing here, render, D2H of the irradiance image). A host that keeps device
      * memory drives the node object instead (include/mpt_node.h: mptn_load_config with the reference's property keys, mptn_process). */

@@ -107,6 +107,13 @@ MPT_API mpt_status mptt_materials_build(const mpt_src_material* materials, uint3
 MPT_API mpt_status mptt_materials_get(const mpt_material_table* table, mpt_material_table_view* out);
 MPT_API void mptt_materials_free(mpt_material_table* table);
 
+/* ---- camera (the host side of SURVEY.md 8(a) A4) ------------------------------------------------------------------------------------
+ * Camera::write_to (src/merian/utils/camera/camera.cpp:349-368): the basis the shaders read — W = forward x focus distance (the distance to
+ * `target`, camera.cpp:255-260), U = right x tan(yfov / 2) x aspect x focus, V = up x tan(yfov / 2) x focus. jitter: sub-pixel offset in
+ * pixels (Camera::advance_jitter, camera.cpp:318-347; NULL = none). aperture_radius 0 = pinhole. */
+MPT_API mpt_status mptt_camera_look_at(const float position[3], const float target[3], const float up[3], float yfov_degrees, float aspect,
+                                       float near_plane, float far_plane, float aperture_radius, const float jitter[2], mpt_camera* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -399,3 +399,36 @@ MPT_API mpt_status mptt_materials_get(const mpt_material_table* t, mpt_material_
 }
 
 MPT_API void mptt_materials_free(mpt_material_table* t) { delete t; }
+
+// ---------------------------------------------------------------------------------------------------------------- camera
+MPT_API mpt_status mptt_camera_look_at(const float position[3], const float target[3], const float up[3], float yfov_degrees, float aspect,
+                                       float near_plane, float far_plane, float aperture_radius, const float jitter[2], mpt_camera* out) {
+    if (!position || !target || !up || !out) return tables_fail(MPT_ERR_INVALID_ARGUMENT, "mptt_camera_look_at: NULL argument");
+    float fwd[3] = {target[0] - position[0], target[1] - position[1], target[2] - position[2]};
+    const float focus = std::sqrt((fwd[0] * fwd[0] + fwd[1] * fwd[1]) + fwd[2] * fwd[2]); // focus_distance_on_target, camera.cpp:255-260
+    if (!(focus > 0.f)) return tables_fail(MPT_ERR_INVALID_ARGUMENT, "mptt_camera_look_at: position and target coincide");
+    for (float& f : fwd) f /= focus;
+    float rgt[3] = {fwd[1] * up[2] - fwd[2] * up[1], fwd[2] * up[0] - fwd[0] * up[2], fwd[0] * up[1] - fwd[1] * up[0]};
+    const float rl = std::sqrt((rgt[0] * rgt[0] + rgt[1] * rgt[1]) + rgt[2] * rgt[2]);
+    if (!(rl > 0.f)) return tables_fail(MPT_ERR_INVALID_ARGUMENT, "mptt_camera_look_at: up is parallel to the viewing direction");
+    for (float& r : rgt) r /= rl;
+    const float upc[3] = {rgt[1] * fwd[2] - rgt[2] * fwd[1], rgt[2] * fwd[0] - rgt[0] * fwd[2], rgt[0] * fwd[1] - rgt[1] * fwd[0]};
+    const float half_tan = std::tan(yfov_degrees * 0.017453292519943295f * 0.5f);
+    const float su = (half_tan * aspect) * focus, sv = half_tan * focus;
+    std::memset(out, 0, sizeof(*out));
+    for (int k = 0; k < 3; k++) {
+        out->position[k] = position[k];
+        out->target[k] = target[k];
+        out->up[k] = up[k];
+        out->U[k] = rgt[k] * su;
+        out->V[k] = upc[k] * sv;
+        out->W[k] = fwd[k] * focus;
+    }
+    out->near_plane = near_plane;
+    out->far_plane = far_plane;
+    out->aspect_ratio = aspect;
+    out->aperture_radius = aperture_radius;
+    out->jitter[0] = jitter ? jitter[0] : 0.f;
+    out->jitter[1] = jitter ? jitter[1] : 0.f;
+    return MPT_OK;
+}

@@ -248,3 +248,25 @@ def test_material_buffer_matches_the_numpy_restatement():
     bad = abi.SrcMaterial()
     bad.model = 7
     assert lib().mptt_materials_build(C.byref(bad), 1, C.byref(h)) != abi.MPT_OK
+
+
+def test_camera_look_at_matches_the_python_mirror():
+    """mptt_camera_look_at (Camera::write_to, camera.cpp:349-368) against scene.CameraDesc.to_abi: the same basis up to the last bit of
+    tan / sqrt between libm and numpy."""
+    import ctypes as C
+    from merian_b200._lib import lib
+    from merian_b200.scene import CameraDesc
+    rng = np.random.default_rng(2)
+    f3 = lambda v: (C.c_float * 3)(*[float(x) for x in v])
+    for _ in range(20):
+        pos, tgt = rng.normal(size=3) * 5, rng.normal(size=3) * 2
+        fov, aspect = float(rng.uniform(20, 100)), float(rng.uniform(0.5, 2.5))
+        ref = CameraDesc(position=tuple(pos), target=tuple(tgt), up=(0, 1, 0), yfov_deg=fov, aspect=aspect, near=0.05, far=500.0).to_abi(0)
+        got = abi.Camera()
+        assert lib().mptt_camera_look_at(f3(pos), f3(tgt), f3((0, 1, 0)), fov, aspect, 0.05, 500.0, 0.0, None, C.byref(got)) == abi.MPT_OK
+        for name in ("position", "target", "up", "U", "V", "W"):
+            np.testing.assert_allclose(np.array(getattr(got, name)[:]), np.array(getattr(ref, name)[:]), rtol=3e-6, atol=1e-6)
+        assert (got.near_plane, got.far_plane, got.aperture_radius) == (ref.near_plane, ref.far_plane, 0.0) and abs(got.aspect_ratio - ref.aspect_ratio) < 1e-6
+    bad = abi.Camera()
+    assert lib().mptt_camera_look_at(f3((0, 0, 0)), f3((0, 0, 0)), f3((0, 1, 0)), 45.0, 1.0, 0.1, 10.0, 0.0, None, C.byref(bad)) != abi.MPT_OK
+    assert lib().mptt_camera_look_at(f3((0, 0, 0)), f3((0, 2, 0)), f3((0, 1, 0)), 45.0, 1.0, 0.1, 10.0, 0.0, None, C.byref(bad)) != abi.MPT_OK
