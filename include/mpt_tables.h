@@ -114,6 +114,41 @@ MPT_API void mptt_materials_free(mpt_material_table* table);
 MPT_API mpt_status mptt_camera_look_at(const float position[3], const float target[3], const float up[3], float yfov_degrees, float aspect,
                                        float near_plane, float far_plane, float aperture_radius, const float jitter[2], mpt_camera* out);
 
+/* ---- glTF ingestion -----------------------------------------------------------------------------------------------
+ * GLTFScene::load (src/merian-shaders/scene/gltf_scene.cpp:831-897) without a Vulkan Scene: a .gltf / .glb file becomes the source tables
+ * above — one mesh per TRIANGLES primitive with its flags (:607-694), nodes with GLOBAL transforms in DFS order (:146-196, 696-716),
+ * materials with the KHR extension gates (:265-536), textures in first-use order with the sRGB / linear decision of the slot that uses
+ * them (:538-604), the first perspective camera (:719-775). Images are NOT decoded (the reference uses stb_image, which is not vendored
+ * here): every texture comes as the encoded bytes found in the file (PNG, JPEG, ...) plus its sampler state; the caller decodes to RGBA8
+ * and calls mpt_texture_upload_ex(texture id = position in `textures`). Float attributes only, like the reference (:127-146).
+ * The Python mirror is merian_b200/gltf.py (tests/test_gltf_cabi.py compares the two). */
+typedef struct mpt_gltf mpt_gltf;
+typedef struct mpt_gltf_texture {
+    const uint8_t* encoded;  /* the image file as stored (bufferView, data URI or external file) */
+    uint64_t encoded_size;
+    uint32_t srgb;           /* 1: colour data (MPT_TEX_RGBA8_SRGB), 0: linear data (MPT_TEX_RGBA8_UNORM) */
+    uint32_t wrap_u, wrap_v; /* MPT_WRAP_* */
+    uint32_t filter;         /* MPT_FILTER_* */
+    uint32_t mipmap;         /* MPT_MIPMAP_* */
+} mpt_gltf_texture;
+typedef struct mpt_gltf_view {
+    const mpt_src_mesh* meshes;
+    uint32_t mesh_count;
+    const mpt_src_node* nodes;
+    uint32_t node_count;
+    const mpt_src_material* materials;
+    uint32_t material_count;
+    const mpt_gltf_texture* textures;
+    uint32_t texture_count;
+    uint32_t has_camera;     /* 0: the file has no perspective camera in its default scene (the caller supplies one) */
+    mpt_camera camera;       /* jitter 0; glTF cameras jitter with the R2 sequence over 16 frames (gltf_scene.cpp:773-774): set camera.jitter per frame */
+    float yfov_degrees, aspect, znear, zfar;
+} mpt_gltf_view;
+
+MPT_API mpt_status mptt_gltf_load(const char* path, mpt_gltf** out);
+MPT_API mpt_status mptt_gltf_get(const mpt_gltf* gltf, mpt_gltf_view* out); /* pointers stay valid until mptt_gltf_free */
+MPT_API void mptt_gltf_free(mpt_gltf* gltf);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,7 +28,7 @@ EXPORTS = ["mpt_abi_version", "mpt_create", "mpt_destroy", "mpt_last_error", "mp
            "mptn_accumulate_create", "mptn_accumulate_destroy", "mptn_accumulate_last_error", "mptn_accumulate_load_config",
            "mptn_accumulate_dump_config", "mptn_accumulate_request_clear", "mptn_accumulate_process", "mptn_process_accumulate",
            # include/mpt_tables.h
-           "mptt_build", "mptt_scene_desc", "mptt_free", "mptt_pack_vertices", "mptt_materials_build", "mptt_materials_get", "mptt_materials_free", "mptt_camera_look_at"]
+           "mptt_build", "mptt_scene_desc", "mptt_free", "mptt_pack_vertices", "mptt_materials_build", "mptt_materials_get", "mptt_materials_free", "mptt_camera_look_at", "mptt_gltf_load", "mptt_gltf_get", "mptt_gltf_free"]
 
 
 class MptError(RuntimeError):
@@ -69,6 +69,10 @@ def lib():
         l.mptt_materials_free.argtypes = [C.c_void_p]
         l.mptt_materials_free.restype = None
         l.mptt_camera_look_at.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.POINTER(abi.Camera)]
+        l.mptt_gltf_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+        l.mptt_gltf_get.argtypes = [C.c_void_p, C.c_void_p]
+        l.mptt_gltf_free.argtypes = [C.c_void_p]
+        l.mptt_gltf_free.restype = None
         l.mptt_pack_vertices.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
         l.mpt_set_scene_frame.argtypes = [C.c_void_p, C.c_uint32]
         l.mpt_scene_set_prev_transforms.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]

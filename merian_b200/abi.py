@@ -105,6 +105,11 @@ class MaterialTableView(C.Structure):  # mpt_material_table_view
     _fields_ = [("entries", C.c_void_p), ("entry_size", C.c_uint32), ("material_count", C.c_uint32), ("types", C.c_void_p), ("type_count", C.c_uint32)]
 
 
+class GltfTexture(C.Structure):  # mpt_gltf_texture
+    _fields_ = [("encoded", C.c_void_p), ("encoded_size", C.c_uint64), ("srgb", C.c_uint32), ("wrap_u", C.c_uint32), ("wrap_v", C.c_uint32),
+                ("filter", C.c_uint32), ("mipmap", C.c_uint32)]
+
+
 class SrcNode(C.Structure):  # mpt_src_node
     _fields_ = [("transform", C.c_float * 16), ("meshes", C.c_void_p), ("mesh_count", C.c_uint32)]
 
@@ -119,6 +124,12 @@ class Camera(C.Structure):  # camera.slang:6-24
                 ("near_plane", C.c_float), ("far_plane", C.c_float), ("aspect_ratio", C.c_float),
                 ("aperture_radius", C.c_float), ("jitter", C.c_float * 2)]
 
+
+
+class GltfView(C.Structure):  # mpt_gltf_view
+    _fields_ = [("meshes", C.c_void_p), ("mesh_count", C.c_uint32), ("nodes", C.c_void_p), ("node_count", C.c_uint32),
+                ("materials", C.c_void_p), ("material_count", C.c_uint32), ("textures", C.c_void_p), ("texture_count", C.c_uint32),
+                ("has_camera", C.c_uint32), ("camera", Camera), ("yfov_degrees", C.c_float), ("aspect", C.c_float), ("znear", C.c_float), ("zfar", C.c_float)]
 
 class RenderParams(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("frame", C.c_uint32), ("spp", C.c_int32),
