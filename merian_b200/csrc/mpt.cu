@@ -924,8 +924,13 @@ __global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS) k_primary_per
 // Modes 0 and 1: the records carry the ray's own interval (TraversalP<..., TMIN_ZERO = false>): b.w = tmin, d.w = tmax, a.w = the ray /
 // pixel index. Mode 2: continuation-ray records (b.w = the triangle the ray leaves, a.w = the shadow-queue index).
 constexpr int kQueryTrace = 0, kQueryPrimary = 1, kQueryShadow = 2;
+// Single-level scenes without counters: 8 blocks per SM / 64 registers like the plain extend kernel (primary visibility +1.7 %, incoherent
+// rays +0.4 %, NEE frame +0.7 % against 7 blocks / 72 registers, `profiles/r02z_q8_ab.txt`); the other variants keep 7.
+#ifndef MPT_QUERY_PLAIN_MIN_BLOCKS
+#define MPT_QUERY_PLAIN_MIN_BLOCKS 8
+#endif
 template <bool COUNT, bool TWO_LEVEL, int MODE>
-__global__ void __launch_bounds__(kThreads, MPT_EXTEND_MIN_BLOCKS)
+__global__ void __launch_bounds__(kThreads, (!COUNT && !TWO_LEVEL) ? MPT_QUERY_PLAIN_MIN_BLOCKS : MPT_EXTEND_MIN_BLOCKS)
 k_query_pooled(const __grid_constant__ SceneView S, const float4* __restrict__ rays, const float4* __restrict__ rays_d, const float4* __restrict__ contrib,
                CameraParams cam, uint32_t w, uint32_t h, uint32_t n_host, const uint32_t* __restrict__ n_dev, uint32_t mask, void* __restrict__ out, Counters* ctr,
                uint32_t* fetch) {
@@ -1487,7 +1492,7 @@ struct mpt_context {
     DevBuf tri_attr, geometries, prim_to_tri, instances, tlas_prims, tlas_boxes, xform, xform_it, xform_prev;
     uint32_t instance_count = 0; // of the uploaded scene
     uint32_t single_instance_mask = 0xFFu; // single-level scenes: the 8-bit mask of the one instance (a masked-out scene takes the legacy extend kernel)
-    uint32_t query_blocks_per_sm = 0;      // resident blocks of k_query_pooled (0 = not asked yet)
+    uint32_t query_blocks_per_sm = 0, query_plain_blocks_per_sm = 0; // resident blocks of k_query_pooled (0 = not asked yet)
     bool query_pooled = true;              // MPT_QUERY_LEGACY=1: the per-lane-fetch forms of mpt_trace / mpt_primary_visibility (A/B runs)
     DevBuf materials, material_types, texture_table, env_pixels, env_alias, env_pmf;
     bool env_sampling_ready = false;
@@ -1628,13 +1633,16 @@ mpt_status ensure_pool(mpt_context* ctx, size_t slots, bool need_medium, bool ne
     return MPT_OK;
 }
 
-uint32_t query_blocks_per_sm(mpt_context* ctx) {
+// resident blocks per SM of k_query_pooled: the plain variants (single-level scene, no counters) and the others have different launch bounds
+uint32_t query_blocks_per_sm(mpt_context* ctx, bool plain = false) {
     if (!ctx->query_blocks_per_sm) {
         int occ = 0;
-        ctx->query_blocks_per_sm = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_query_pooled<false, false, kQueryTrace>, kThreads, 0) == cudaSuccess && occ > 0)
+        ctx->query_blocks_per_sm = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_query_pooled<true, true, kQueryTrace>, kThreads, 0) == cudaSuccess && occ > 0)
                                        ? uint32_t(occ) : 7u;
+        ctx->query_plain_blocks_per_sm = (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_query_pooled<false, false, kQueryTrace>, kThreads, 0) == cudaSuccess && occ > 0)
+                                             ? uint32_t(occ) : ctx->query_blocks_per_sm;
     }
-    return ctx->query_blocks_per_sm;
+    return plain ? ctx->query_plain_blocks_per_sm : ctx->query_blocks_per_sm;
 }
 
 mpt_status next_cursor(mpt_context* ctx, cudaStream_t st, uint32_t** out) {
@@ -1775,7 +1783,7 @@ mpt_status run_passes(mpt_context* ctx, const CameraParams& cam, const mpt_rende
             if (NEE) { // shadow rays of the vertex shaded last: before the extend so that both add to rad[] in stream order
                 const bool tl_s = ctx->view.accel.two_level != 0;
                 if (ctx->query_pooled && (tl_s || (ctx->single_instance_mask & P.instance_mask & 0xFFu) != 0u)) { // (masked-out scene: see the extend launch)
-                    const uint32_t qb = uint32_t(ctx->sm_count) * query_blocks_per_sm(ctx);
+                    const uint32_t qb = uint32_t(ctx->sm_count) * query_blocks_per_sm(ctx, !tl_s);
                     if (tl_s) k_query_pooled<false, true, kQueryShadow><<<qb, kThreads, 0, st>>>(ctx->view, pb.sq_o, pb.sq_d, pb.sq_c, CameraParams{}, 0u, 0u, 0u, &ctr->scount[b], P.instance_mask, pb.rad, ctr, &ctr->sfetch[b]);
                     else k_query_pooled<false, false, kQueryShadow><<<qb, kThreads, 0, st>>>(ctx->view, pb.sq_o, pb.sq_d, pb.sq_c, CameraParams{}, 0u, 0u, 0u, &ctr->scount[b], P.instance_mask, pb.rad, ctr, &ctr->sfetch[b]);
                 } else if (tl_s) k_shadow<true><<<persistent_blocks, kThreads, 0, st>>>(ctx->view, pb, uint32_t(b), P.instance_mask, ctx->tune, ctr);
@@ -2288,7 +2296,7 @@ MPT_API mpt_status mpt_primary_visibility(mpt_context* ctx, const mpt_camera* ca
         Counters* ctr = ctx->counters.as<Counters>();
         uint32_t* cursor = nullptr;
         { const mpt_status cs = next_cursor(ctx, st, &cursor); if (cs != MPT_OK) return cs; }
-        const uint32_t query_blocks = uint32_t(ctx->sm_count) * query_blocks_per_sm(ctx);
+        const uint32_t query_blocks = uint32_t(ctx->sm_count) * query_blocks_per_sm(ctx, !cnt && !tl);
 #define MPT_LAUNCH_PRIMARY_P(C, TL)                                                                                                                     \
     do {                                                                                                                                              \
         if (ctx->query_pooled) k_query_pooled<C, TL, kQueryPrimary><<<query_blocks, kThreads, 0, st>>>(ctx->view, nullptr, nullptr, nullptr, cam, width, height, tiles * 32u, nullptr, instance_mask, d_tex1, ctr, cursor); \
@@ -2361,7 +2369,7 @@ MPT_API mpt_status mpt_trace(mpt_context* ctx, const void* d_rays, uint64_t n, u
         Counters* ctr = ctx->counters.as<Counters>();
         uint32_t* cursor = nullptr;
         { const mpt_status cs = next_cursor(ctx, st, &cursor); if (cs != MPT_OK) return cs; }
-        const uint32_t query_blocks = uint32_t(ctx->sm_count) * query_blocks_per_sm(ctx);
+        const uint32_t query_blocks = uint32_t(ctx->sm_count) * query_blocks_per_sm(ctx, !cnt && !tl);
 #define MPT_LAUNCH_TRACE_P(C, TL)                                                                                                                       \
     do {                                                                                                                                              \
         if (ctx->query_pooled) k_query_pooled<C, TL, kQueryTrace><<<query_blocks, kThreads, 0, st>>>(ctx->view, (const float4*)d_rays, nullptr, nullptr, CameraParams{}, 0u, 0u, uint32_t(n), nullptr, instance_mask, d_hits, ctr, cursor); \
